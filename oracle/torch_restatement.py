@@ -1,0 +1,183 @@
+"""torch-CPU restatement of the Python-level reference code on the hot path.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+The reference modules themselves cannot be imported here: ``mmdet3d`` hard-
+imports mmcv/mmdet/mmseg (mmdetection3d/mmdet3d/__init__.py:2-5), none of
+which are installed.  Each function below performs the same torch operations,
+in the same order and dtype, as the cited reference lines, so that on CPU
+tensors it produces the bits the reference would.
+"""
+import torch
+
+
+def backproject_depth_to_points(depths, intrinsics, cam2lidar_rts,
+                                max_depth=None, confs=None, conf_thresh=None,
+                                sky_masks=None):
+    """reconstruction_backbone.py:285-386 without the colour branch.
+
+    depths (B,N,H,W), intrinsics (B,N,3,3), cam2lidar_rts (B,N,4,4).
+    Optional conf / sky masks follow the commented block at :341-346 whose live
+    form is tools/inference_nuscenes.py:399-414.
+    Returns list_B of (P_b, 3) tensors.
+    """
+    B, N, H, W = depths.shape
+    dt = depths.dtype
+    u = torch.arange(W, dtype=dt)
+    v = torch.arange(H, dtype=dt)
+    vv, uu = torch.meshgrid(v, u, indexing="ij")                       # :312-314
+    out = []
+    for b in range(B):
+        per_cam = []
+        for n in range(N):
+            z = depths[b, n]
+            K = intrinsics[b, n]
+            fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]        # :325-326
+            x = (uu - cx) * z / fx                                      # :329-331
+            y = (vv - cy) * z / fy
+            pts = torch.stack([x.reshape(-1), y.reshape(-1), z.reshape(-1)], dim=1)
+            zf = z.reshape(-1)
+            valid = (zf > 0) & torch.isfinite(zf)                       # :338
+            if max_depth is not None:
+                valid = valid & (zf <= max_depth)                       # :339-340
+            if confs is not None and conf_thresh is not None:
+                valid = valid & (confs[b, n].reshape(-1) >= conf_thresh)
+            if sky_masks is not None:
+                valid = valid & (~sky_masks[b, n].reshape(-1))
+            pts = pts[valid]                                            # :348
+            if pts.numel() > 0:
+                M = cam2lidar_rts[b, n]
+                pts = pts @ M[:3, :3].T + M[3, :3]                      # :370
+                per_cam.append(pts)
+        out.append(torch.cat(per_cam, dim=0) if per_cam
+                   else torch.zeros((0, 3), dtype=dt))                  # :376-381
+    return out
+
+
+def filter_point_by_range(points, point_cloud_range):
+    """respoint_post_processing.py:190-199: inclusive on both ends."""
+    x0, y0, z0, x1, y1, z1 = point_cloud_range
+    m = ((points[:, 0] >= x0) & (points[:, 0] <= x1) &
+         (points[:, 1] >= y0) & (points[:, 1] <= y1) &
+         (points[:, 2] >= z0) & (points[:, 2] <= z1))
+    return points[m], torch.nonzero(m, as_tuple=False).squeeze(1)
+
+
+def conf_threshold(conf, sky, percentile):
+    """tools/inference_nuscenes.py:351-361 (numpy percentile, linear interp).
+
+    conf (N,H,W) float, sky (N,H,W) bool or None."""
+    import numpy as np
+    c = conf.numpy() if torch.is_tensor(conf) else np.asarray(conf)
+    if sky is not None:
+        s = sky.numpy() if torch.is_tensor(sky) else np.asarray(sky)
+        px = c[~s] if (~s).sum() > 10 else c.flatten()
+    else:
+        px = c.flatten()
+    return float(np.percentile(px, percentile))
+
+
+def hard_simple_vfe(features, num_points, num_features):
+    """voxel_encoder.py:45-46."""
+    mean = features[:, :, :num_features].sum(dim=1, keepdim=False) / \
+        num_points.type_as(features).view(-1, 1)
+    return mean.contiguous()
+
+
+def voxelization_forward(ref_layer, points, voxel_size, coors_range,
+                         max_points, max_voxels):
+    """voxelize.py:52-70 driving the compiled reference op (oracle/_ref)."""
+    if max_points == -1 or max_voxels == -1:
+        coors = points.new_zeros(size=(points.size(0), 3), dtype=torch.int)
+        ref_layer.dynamic_voxelize(points, coors, voxel_size, coors_range, 3)
+        return coors
+    voxels = points.new_zeros(size=(max_voxels, max_points, points.size(1)))
+    coors = points.new_zeros(size=(max_voxels, 3), dtype=torch.int)
+    num = points.new_zeros(size=(max_voxels,), dtype=torch.int)
+    n = ref_layer.hard_voxelize(points, voxels, coors, num, voxel_size,
+                                coors_range, max_points, max_voxels, 3, True)
+    return voxels[:n], coors[:n], num[:n]
+
+
+def dynamic_point_to_voxel_forward(feats, coors, reduce_type):
+    """scatter_points_cuda.cu:183-239 with torch-CPU ops (faithful unique_dim).
+
+    Returns [voxel_feats, voxel_coors, point2voxel_map int32, count int32].
+    Sums run through index_add_ in fp32 (point order on one thread)."""
+    if reduce_type not in ("sum", "mean", "max"):
+        raise RuntimeError("do not support reduce type " + reduce_type)
+    N, C = feats.shape
+    if N == 0:                                                          # :192-196
+        return [feats.clone().detach(), coors.clone().detach(),
+                coors.new_empty((0,), dtype=torch.int32),
+                coors.new_empty((0,), dtype=torch.int32)]
+    clean = coors.masked_fill(coors.lt(0).any(-1, True), -1)            # :202
+    out_coors, cmap, cnt = torch.unique(clean, dim=0, sorted=True,
+                                        return_inverse=True,
+                                        return_counts=True)             # :204-205
+    if bool(out_coors[0, 0].lt(0)):                                     # :207-212
+        out_coors = out_coors[1:]
+        cnt = cnt[1:]
+        cmap = cmap - 1
+    cmap = cmap.to(torch.int32)
+    cnt = cnt.to(torch.int32)
+    M = out_coors.size(0)
+    keep = cmap >= 0
+    idx = cmap[keep].long()
+    if reduce_type == "max":
+        red = feats.new_full((M, C), float("-inf"))
+        red.scatter_reduce_(0, idx.view(-1, 1).expand(-1, C), feats[keep],
+                            reduce="amax", include_self=True)
+    else:
+        red = feats.new_zeros((M, C))
+        red.index_add_(0, idx, feats[keep])
+        if reduce_type == "mean":
+            red /= cnt.unsqueeze(-1).to(red.dtype)                      # :233-234
+    return [red, out_coors, cmap, cnt]
+
+
+def dynamic_point_to_voxel_backward(grad_voxel, feats, voxel_feats, cmap, cnt,
+                                    reduce_type):
+    """scatter_points_cuda.cu:105-179,241-308 -> grad_feats (N,C)."""
+    N, C = feats.shape
+    g = torch.zeros_like(feats)                                         # :259
+    M = voxel_feats.size(0)
+    if N == 0 or M == 0:
+        return g
+    keep = cmap >= 0
+    idx = cmap[keep].long()
+    if reduce_type == "sum":
+        g[keep] = grad_voxel[idx]
+    elif reduce_type == "mean":
+        g[keep] = grad_voxel[idx] / cnt[idx].to(g.dtype).unsqueeze(-1)
+    else:
+        # lowest point index attaining the max per (voxel, feature) (:149-152)
+        pts = torch.nonzero(keep).squeeze(1)
+        hit = feats[pts] == voxel_feats[idx]
+        src = torch.full((M, C), N, dtype=torch.long)
+        pidx = pts.view(-1, 1).expand(-1, C)
+        cand = torch.where(hit, pidx, torch.full_like(pidx, N))
+        src.scatter_reduce_(0, idx.view(-1, 1).expand(-1, C), cand,
+                            reduce="amin", include_self=True)
+        cols = torch.arange(C).view(1, -1).expand(M, -1)
+        ok = src < N
+        g[src[ok], cols[ok]] = grad_voxel[ok]
+    return g
+
+
+def dynamic_scatter_batched(feats, coors, reduce_type):
+    """scatter_points.py:78-99: (N,4) [b,z,y,x] coors -> per-batch scatter, cat."""
+    if coors.size(-1) == 3:
+        r = dynamic_point_to_voxel_forward(feats.contiguous(),
+                                           coors.contiguous(), reduce_type)
+        return r[0], r[1]
+    batch_size = int(coors[-1, 0]) + 1
+    vs, cs = [], []
+    for i in range(batch_size):
+        inds = torch.where(coors[:, 0] == i)
+        r = dynamic_point_to_voxel_forward(feats[inds].contiguous(),
+                                           coors[inds][:, 1:].contiguous(),
+                                           reduce_type)
+        cs.append(torch.nn.functional.pad(r[1], (1, 0), mode="constant", value=i))
+        vs.append(r[0])
+    return torch.cat(vs, dim=0), torch.cat(cs, dim=0)

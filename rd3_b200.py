@@ -1,0 +1,15 @@
+"""Import alias: ``import rd3_b200`` loads the package that lives in
+``3d-reconstruction-detection_b200/`` (a directory name Python cannot import
+directly because of the leading digit and the hyphens)."""
+import importlib.util
+import os
+import sys
+
+_PKG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                        "3d-reconstruction-detection_b200")
+_spec = importlib.util.spec_from_file_location(
+    __name__, os.path.join(_PKG_DIR, "__init__.py"),
+    submodule_search_locations=[_PKG_DIR])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)
