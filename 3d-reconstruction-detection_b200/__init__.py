@@ -1,5 +1,24 @@
 """rd3_b200 -- B200-native depth->voxel path (unproject, voxelize, scatter, VFE).
 
-Importable as ``rd3_b200`` (see /rd3_b200.py at the repo root).
+Importable as ``rd3_b200`` (see /rd3_b200.py at the repo root).  The public
+names mirror the reference's operator API for this path:
+
+    Voxelization, voxelization            mmdet3d/ops/voxel/voxelize.py
+    DynamicScatter, dynamic_scatter       mmdet3d/ops/voxel/scatter_points.py
+    voxel_layer (4 functions)             mmdet3d/ops/voxel/src/voxelization.cpp
+    HardSimpleVFE                         mmdet3d/models/voxel_encoders/voxel_encoder.py
+    backproject_depth_to_points           plugin ReconstructionBackbone._backproject_depth_to_points
+    DepthToVoxels                         the fused, batched path (no reference equivalent)
+
+All compute runs in librd3_b200.so (hand-written sm_100a CUDA, C ABI in
+include/rd3_b200.h).  There is no CPU or PyTorch fallback.
 """
 __version__ = "0.1.0"
+
+from . import voxel_layer  # noqa: F401
+from .voxelize import Voxelization, voxelization  # noqa: F401
+from .scatter_points import DynamicScatter, dynamic_scatter  # noqa: F401
+from .voxel_encoder import HardSimpleVFE, hard_simple_vfe  # noqa: F401
+from .backproject import (DepthToPointsMixin, backproject_depth_to_points,  # noqa: F401
+                          unproject_padded)
+from .fused import DepthToVoxels  # noqa: F401

@@ -1,0 +1,130 @@
+"""ctypes binding of librd3_b200.so (the C ABI in include/rd3_b200.h).
+
+There is no fallback: if the library is missing or a call fails, a RuntimeError
+is raised.  Nothing in this package computes on the CPU.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librd3_b200.so")
+
+_c = ctypes
+_vp, _i32, _i64, _sz, _f32 = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_size_t, _c.c_float
+_F3, _F6, _I3 = _c.c_float * 3, _c.c_float * 6, _c.c_int32 * 3
+
+
+class DepthParams(ctypes.Structure):
+    """struct rd3_depth_params"""
+    _fields_ = [("B", _c.c_int32), ("ncam", _c.c_int32), ("H", _c.c_int32), ("W", _c.c_int32),
+                ("use_max_depth", _c.c_int32), ("max_depth", _c.c_float),
+                ("conf_thresh", _c.c_float), ("use_range", _c.c_int32),
+                ("range", _c.c_float * 6)]
+
+
+# name -> (restype, argtypes); must list every symbol include/rd3_b200.h declares
+SIGNATURES = {
+    "rd3_version": (_i32, []),
+    "rd3_status_string": (_c.c_char_p, [_i32]),
+    "rd3_last_cuda_error": (_c.c_char_p, []),
+    "rd3_grid_size": (_i32, [_F3, _F6, _I3]),
+    "rd3_dynamic_voxelize": (_i32, [_vp, _i64, _i32, _F3, _F6, _vp, _vp]),
+    "rd3_hard_voxelize_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "rd3_hard_voxelize": (_i32, [_vp, _i64, _i32, _F3, _F6, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
+                                 _i32, _vp, _vp, _sz, _vp]),
+    "rd3_hard_simple_vfe": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "rd3_unproject_workspace_bytes": (_sz, [_c.POINTER(DepthParams)]),
+    "rd3_unproject": (_i32, [_vp, _vp, _vp, _vp, _vp, _c.POINTER(DepthParams), _vp, _vp, _vp, _vp,
+                             _sz, _vp]),
+    "rd3_depth_to_voxels_workspace_bytes": (_sz, [_c.POINTER(DepthParams), _i32, _i32]),
+    "rd3_depth_to_voxels": (_i32, [_vp, _vp, _vp, _vp, _vp, _c.POINTER(DepthParams), _F3, _F6, _i32,
+                                   _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rd3_coors_extent": (_i32, [_vp, _i64, _vp, _vp]),
+    "rd3_dynamic_scatter_workspace_bytes": (_sz, [_i64, _i32, _I3]),
+    "rd3_dynamic_scatter_forward": (_i32, [_vp, _vp, _i64, _i32, _I3, _i32, _vp, _vp, _vp, _vp, _vp,
+                                           _vp, _vp, _sz, _vp]),
+    "rd3_dynamic_scatter_backward_workspace_bytes": (_sz, [_i64, _i32]),
+    "rd3_dynamic_scatter_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32,
+                                            _vp, _sz, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """Load librd3_b200.so once.  Raises if it was not built (no fallback)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        "rd3_b200: %s not found. Build it with "
+                        "`python 3d-reconstruction-detection_b200/build.py` "
+                        "(there is no CPU/PyTorch fallback)." % LIB_PATH)
+                L = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(L, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = L
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        L = lib()
+        msg = L.rd3_status_string(status).decode()
+        if status == 4:
+            msg += ": " + L.rd3_last_cuda_error().decode()
+        raise RuntimeError("rd3_b200.%s failed: %s" % (what, msg))
+
+
+def ptr(t):
+    return _vp(t.data_ptr()) if t is not None else _vp(0)
+
+
+def stream_of(t):
+    return _vp(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def f3(v):
+    return _F3(*[float(x) for x in v])
+
+
+def f6(v):
+    return _F6(*[float(x) for x in v])
+
+
+def i3(v):
+    return _I3(*[int(x) for x in v])
+
+
+def require_cuda(t, name, dtype=None):
+    if not torch.is_tensor(t) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (rd3_b200 has no CPU path)" % name)
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+
+
+# grow-only scratch buffer per (device, stream)
+_workspaces = {}
+
+
+def workspace(device, nbytes):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def release_workspaces():
+    _workspaces.clear()

@@ -1,0 +1,159 @@
+// rd3_common.cuh -- shared device helpers for the sm_100a depth->voxel kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rd3_b200.h"
+
+#ifndef __CUDA_ARCH_LIST__
+#endif
+
+namespace rd3 {
+
+constexpr uint32_t kEmpty32 = 0xFFFFFFFFu;
+constexpr unsigned long long kEmpty64 = 0xFFFFFFFFFFFFFFFFull;
+
+// ordered first-flag scan geometry: one CTA scans kChunkWords flag words
+constexpr int kChunkWords = 256;                 // 8192 points per chunk
+constexpr int kChunkPoints = kChunkWords * 32;
+constexpr int kChunkShift = 13;                  // log2(kChunkPoints)
+constexpr int kScanThreads = 256;
+
+void set_last_cuda_error(cudaError_t e);
+int check_launch();
+
+#define RD3_CUDA_TRY(expr)                       \
+  do {                                           \
+    cudaError_t _e = (expr);                     \
+    if (_e != cudaSuccess) {                     \
+      rd3::set_last_cuda_error(_e);              \
+      return RD3_ERR_CUDA;                       \
+    }                                            \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------
+// Voxel grid (x,y,z order, like voxel_size / coors_range of the reference).
+// ---------------------------------------------------------------------------
+struct VoxelGrid {
+  float lo[3];
+  float vs[3];
+  int32_t grid[3];
+};
+
+// host: grid = round((max-min)/vs) in fp32  (voxelization_cpu.cpp:121-124)
+int make_grid(const float voxel_size[3], const float coors_range[6], VoxelGrid *g,
+              uint64_t *volume);
+
+// One point -> (cx,cy,cz).  Bit-exact restatement of voxelization_cpu.cpp:21-38:
+// c = floor((p - min) / vs) with IEEE fp32 subtract and TRUE division, tested
+// x then y then z, inside iff 0 <= c < grid.  NaN/Inf/huge fail (the reference's
+// int conversion yields INT_MIN there).
+__device__ __forceinline__ bool voxel_coor(float px, float py, float pz,
+                                           const VoxelGrid &g, int &cx, int &cy,
+                                           int &cz) {
+  float f = floorf(__fdiv_rn(__fsub_rn(px, g.lo[0]), g.vs[0]));
+  if (!(f >= 0.0f && f < 2147483648.0f)) return false;
+  cx = (int)f;
+  if (cx >= g.grid[0]) return false;
+  f = floorf(__fdiv_rn(__fsub_rn(py, g.lo[1]), g.vs[1]));
+  if (!(f >= 0.0f && f < 2147483648.0f)) return false;
+  cy = (int)f;
+  if (cy >= g.grid[1]) return false;
+  f = floorf(__fdiv_rn(__fsub_rn(pz, g.lo[2]), g.vs[2]));
+  if (!(f >= 0.0f && f < 2147483648.0f)) return false;
+  cz = (int)f;
+  if (cz >= g.grid[2]) return false;
+  return true;
+}
+
+// linear voxel id in (z,y,x) order == lexicographic order of the output coors
+__device__ __forceinline__ uint32_t voxel_key(int cx, int cy, int cz, const VoxelGrid &g) {
+  return ((uint32_t)cz * (uint32_t)g.grid[1] + (uint32_t)cy) * (uint32_t)g.grid[0] + (uint32_t)cx;
+}
+
+__device__ __forceinline__ void key_to_zyx(uint32_t key, const VoxelGrid &g, int &cz, int &cy, int &cx) {
+  cx = (int)(key % (uint32_t)g.grid[0]);
+  uint32_t r = key / (uint32_t)g.grid[0];
+  cy = (int)(r % (uint32_t)g.grid[1]);
+  cz = (int)(r / (uint32_t)g.grid[1]);
+}
+
+// ---------------------------------------------------------------------------
+// Per-camera calibration staged in shared memory (16 floats per camera).
+//   [0]=fx [1]=fy [2]=cx [3]=cy  [4..12]=R row-major (M[:3,:3])  [13..15]=t (M[3,:3])
+// ---------------------------------------------------------------------------
+constexpr int kCalibFloats = 16;
+constexpr int kMaxCams = 16;
+
+struct DepthParams {
+  int32_t ncam, H, W;
+  int32_t HW;            // H*W
+  int32_t npix;          // ncam*H*W
+  int32_t use_max_depth;
+  float max_depth;
+  int32_t use_conf;
+  float conf_thresh;
+  int32_t use_sky;
+  int32_t use_range;
+  float range[6];
+};
+
+__device__ __forceinline__ void stage_calibration(float *s_cal, const float *intr,
+                                                  const float *c2l, int ncam) {
+  for (int i = threadIdx.x; i < ncam * kCalibFloats; i += blockDim.x) {
+    int cam = i / kCalibFloats, j = i % kCalibFloats;
+    const float *K = intr + cam * 9;
+    const float *M = c2l + cam * 16;
+    float v;
+    if (j == 0) v = K[0];
+    else if (j == 1) v = K[4];
+    else if (j == 2) v = K[2];
+    else if (j == 3) v = K[5];
+    else if (j < 13) { int r = (j - 4) / 3, c = (j - 4) % 3; v = M[r * 4 + c]; }
+    else v = M[12 + (j - 13)];
+    s_cal[i] = v;
+  }
+}
+
+// Pixel -> ego-frame point.  reconstruction_backbone.py:329-334,338-340,370.
+// Every fp32 operation is a separately rounded IEEE op; the only fused ops are
+// the two FMAs of the 3x3 product, in the order torch-CPU's sgemm evaluates it
+// (oracle/rd3_oracle.c: orc_unproject).
+__device__ __forceinline__ bool unproject_pixel(float z, float conf, bool sky, int u, int v,
+                                                const float *cal, const DepthParams &p,
+                                                float &ox, float &oy, float &oz) {
+  bool valid = (z > 0.0f) && (fabsf(z) <= 3.402823466e+38f);   // z > 0 & isfinite
+  if (p.use_max_depth) valid = valid && (z <= p.max_depth);
+  if (p.use_conf) valid = valid && (conf >= p.conf_thresh);
+  if (p.use_sky) valid = valid && !sky;
+  if (!valid) return false;
+  float x = __fdiv_rn(__fmul_rn(__fsub_rn((float)u, cal[2]), z), cal[0]);
+  float y = __fdiv_rn(__fmul_rn(__fsub_rn((float)v, cal[3]), z), cal[1]);
+  ox = __fadd_rn(__fmaf_rn(z, cal[6], __fmaf_rn(y, cal[5], __fmul_rn(x, cal[4]))), cal[13]);
+  oy = __fadd_rn(__fmaf_rn(z, cal[9], __fmaf_rn(y, cal[8], __fmul_rn(x, cal[7]))), cal[14]);
+  oz = __fadd_rn(__fmaf_rn(z, cal[12], __fmaf_rn(y, cal[11], __fmul_rn(x, cal[10]))), cal[15]);
+  if (p.use_range) {
+    if (!(ox >= p.range[0] && ox <= p.range[3] && oy >= p.range[1] && oy <= p.range[4] &&
+          oz >= p.range[2] && oz <= p.range[5]))
+      return false;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// warp / block scan helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int warp_inclusive_scan(int v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int n = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += n;
+  }
+  return v;
+}
+
+}  // namespace rd3

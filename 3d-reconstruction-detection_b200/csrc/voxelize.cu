@@ -1,0 +1,179 @@
+// voxelize.cu -- C-ABI entry points for dynamic / hard voxelization of a point
+// array and the standalone HardSimpleVFE, plus library-wide helpers.
+#include <math.h>
+#include <string.h>
+
+#include "hard_voxel.cuh"
+
+namespace rd3 {
+
+static thread_local cudaError_t g_last_error = cudaSuccess;
+
+void set_last_cuda_error(cudaError_t e) { g_last_error = e; }
+
+int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e);
+    return RD3_ERR_CUDA;
+  }
+  return RD3_OK;
+}
+
+int make_grid(const float voxel_size[3], const float coors_range[6], VoxelGrid *g,
+              uint64_t *volume) {
+  for (int i = 0; i < 3; ++i) {
+    if (!(voxel_size[i] > 0.0f)) return RD3_ERR_INVALID_ARGUMENT;
+    g->lo[i] = coors_range[i];
+    g->vs[i] = voxel_size[i];
+    // voxelization_cpu.cpp:121-124: round() of the fp32 quotient
+    const float q = (coors_range[3 + i] - coors_range[i]) / voxel_size[i];
+    const float r = roundf(q);
+    if (!(r >= 1.0f && r < 2147483648.0f)) return RD3_ERR_INVALID_ARGUMENT;
+    g->grid[i] = (int32_t)r;
+  }
+  uint64_t vol = 1;
+  for (int i = 0; i < 3; ++i) {
+    vol *= (uint64_t)g->grid[i];
+    if (vol > 0xFFFFFFFEull) {
+      *volume = 0;
+      return RD3_ERR_UNSUPPORTED;   // grid[] is still valid
+    }
+  }
+  *volume = vol;
+  return RD3_OK;
+}
+
+// ---------------------------------------------------------------------------
+// dynamic_voxelize: one thread per point.  For C == 3 a warp's 32 points are
+// 384 contiguous bytes in and out; for C == 4 each point is one 128-bit load.
+// ---------------------------------------------------------------------------
+template <int CT>
+__global__ void __launch_bounds__(256) dynamic_voxelize_kernel(const float *__restrict__ pts,
+                                                               int64_t N, int C, VoxelGrid g,
+                                                               int32_t *__restrict__ coors) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float x, y, z;
+  if (CT == 4) {
+    const float4 p = __ldg(reinterpret_cast<const float4 *>(pts) + i);
+    x = p.x; y = p.y; z = p.z;
+  } else {
+    const float *p = pts + i * C;
+    x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+  }
+  int cx, cy, cz;
+  const bool ok = voxel_coor(x, y, z, g, cx, cy, cz);
+  int32_t *o = coors + i * 3;
+  o[0] = ok ? cz : -1;
+  o[1] = ok ? cy : -1;
+  o[2] = ok ? cx : -1;
+}
+
+// ---------------------------------------------------------------------------
+// HardSimpleVFE: one thread per (voxel, feature); sequential slot order.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hard_simple_vfe_kernel(const float *__restrict__ voxels,
+                                                              const int32_t *__restrict__ num,
+                                                              int64_t M, int K, int C, int F,
+                                                              float *__restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M * F) return;
+  const int64_t m = t / F;
+  const int f = (int)(t - m * F);
+  const float *v = voxels + m * K * C + f;
+  float s = 0.0f;
+  for (int k = 0; k < K; ++k) s = __fadd_rn(s, __ldg(v + (int64_t)k * C));
+  out[t] = __fdiv_rn(s, (float)__ldg(num + m));
+}
+
+}  // namespace rd3
+
+using namespace rd3;
+
+extern "C" {
+
+int rd3_version(void) { return 100; }
+
+const char *rd3_status_string(int status) {
+  switch (status) {
+    case RD3_OK: return "ok";
+    case RD3_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case RD3_ERR_WORKSPACE: return "workspace too small";
+    case RD3_ERR_UNSUPPORTED: return "unsupported configuration";
+    case RD3_ERR_CUDA: return "CUDA error";
+    default: return "unknown status";
+  }
+}
+
+const char *rd3_last_cuda_error(void) { return cudaGetErrorString(g_last_error); }
+
+int rd3_grid_size(const float voxel_size[3], const float coors_range[6], int32_t grid[3]) {
+  if (!voxel_size || !coors_range || !grid) return RD3_ERR_INVALID_ARGUMENT;
+  VoxelGrid g;
+  uint64_t vol;
+  int st = make_grid(voxel_size, coors_range, &g, &vol);
+  if (st != RD3_OK && st != RD3_ERR_UNSUPPORTED) return st;
+  for (int i = 0; i < 3; ++i) grid[i] = g.grid[i];
+  return RD3_OK;
+}
+
+int rd3_dynamic_voxelize(const float *points, int64_t N, int C, const float voxel_size[3],
+                         const float coors_range[6], int32_t *coors, rd3_stream_t stream) {
+  if (N < 0 || C < 3 || !voxel_size || !coors_range) return RD3_ERR_INVALID_ARGUMENT;
+  if (N == 0) return RD3_OK;
+  if (!points || !coors) return RD3_ERR_INVALID_ARGUMENT;
+  VoxelGrid g;
+  uint64_t vol;
+  int st = make_grid(voxel_size, coors_range, &g, &vol);
+  if (st == RD3_ERR_UNSUPPORTED) st = RD3_OK;  // no linear key needed here
+  if (st != RD3_OK) return st;
+  const unsigned blocks = (unsigned)ceil_div(N, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (C == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0)
+    dynamic_voxelize_kernel<4><<<blocks, 256, 0, s>>>(points, N, C, g, coors);
+  else
+    dynamic_voxelize_kernel<0><<<blocks, 256, 0, s>>>(points, N, C, g, coors);
+  return check_launch();
+}
+
+size_t rd3_hard_voxelize_workspace_bytes(int64_t N, int max_points, int max_voxels) {
+  if (N < 0 || max_points <= 0 || max_voxels <= 0) return 0;
+  return hv_plan(N, 1, max_points, max_voxels).total;
+}
+
+int rd3_hard_voxelize(const float *points, int64_t N, int C, const float voxel_size[3],
+                      const float coors_range[6], int max_points, int max_voxels, float *voxels,
+                      int32_t *coors, int32_t *num_points_per_voxel, int32_t *d_voxel_num,
+                      float *voxel_mean, int F, int32_t *point2voxel, void *workspace,
+                      size_t workspace_bytes, rd3_stream_t stream) {
+  if (N < 0 || C < 3 || max_points <= 0 || max_voxels <= 0 || !voxel_size || !coors_range ||
+      !voxels || !coors || !num_points_per_voxel || !d_voxel_num || !workspace)
+    return RD3_ERR_INVALID_ARGUMENT;
+  if (N > 0 && !points) return RD3_ERR_INVALID_ARGUMENT;
+  if (voxel_mean && (F < 1 || F > C)) return RD3_ERR_INVALID_ARGUMENT;
+  if (N >= ((int64_t)1 << 30)) return RD3_ERR_UNSUPPORTED;
+  VoxelGrid g;
+  uint64_t vol;
+  int st = make_grid(voxel_size, coors_range, &g, &vol);
+  if (st != RD3_OK) return st;
+  const HvPlan plan = hv_plan(N, 1, max_points, max_voxels);
+  if (workspace_bytes < plan.total) return RD3_ERR_WORKSPACE;
+  PointsSource src{points, N, C};
+  HvOut out{voxels, coors, num_points_per_voxel, voxel_mean, d_voxel_num, point2voxel,
+            voxel_mean ? F : 0};
+  return hv_run(src, g, vol, plan, workspace, out, (cudaStream_t)stream);
+}
+
+int rd3_hard_simple_vfe(const float *voxels, const int32_t *num_points, int64_t M, int max_points,
+                        int C, int F, float *out, rd3_stream_t stream) {
+  if (M < 0 || max_points <= 0 || C <= 0 || F <= 0 || F > C) return RD3_ERR_INVALID_ARGUMENT;
+  if (M == 0) return RD3_OK;
+  if (!voxels || !num_points || !out) return RD3_ERR_INVALID_ARGUMENT;
+  const unsigned blocks = (unsigned)ceil_div(M * F, 256);
+  hard_simple_vfe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(voxels, num_points, M,
+                                                                    max_points, C, F, out);
+  return check_launch();
+}
+
+}  // extern "C"

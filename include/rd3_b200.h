@@ -1,0 +1,201 @@
+/*
+ * rd3_b200.h -- C ABI of the B200-native depth->voxel path.
+ *
+ * One shared library (librd3_b200.so, sm_100a only), plain pointers and sizes,
+ * no torch types, no exceptions, no implicit synchronisation: every entry point
+ * enqueues its kernels on the caller's stream and returns an int status
+ * (RD3_OK == 0).  All pointers are DEVICE pointers unless a parameter says
+ * "host".  Data-dependent counts are written to device memory; the caller
+ * decides when to read them back.
+ *
+ * Each entry point names the reference interface it replaces
+ * (paths relative to the reference repository root):
+ *
+ *   pybind module `voxel_layer`
+ *       mmdetection3d/mmdet3d/ops/voxel/src/voxelization.cpp:6-11
+ *       dispatch: mmdetection3d/mmdet3d/ops/voxel/src/voxelization.h:58-140
+ *   HardSimpleVFE.forward
+ *       mmdetection3d/mmdet3d/models/voxel_encoders/voxel_encoder.py:30-47
+ *   ReconstructionBackbone._backproject_depth_to_points
+ *       projects/mmdet3d_plugin/models/backbone/reconstruction_backbone.py:285-386
+ *
+ * There is no CPU fallback anywhere behind this header.
+ */
+#ifndef RD3_B200_H_
+#define RD3_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define RD3_API __attribute__((visibility("default")))
+#else
+#define RD3_API
+#endif
+
+/* cudaStream_t without dragging cuda_runtime.h into C callers */
+typedef void *rd3_stream_t;
+
+enum {
+  RD3_OK = 0,
+  RD3_ERR_INVALID_ARGUMENT = 1, /* null pointer, negative size, NDim != 3 ...        */
+  RD3_ERR_WORKSPACE = 2,        /* workspace smaller than *_workspace_bytes() says   */
+  RD3_ERR_UNSUPPORTED = 3,      /* e.g. voxel grid with more than 2^32-2 cells       */
+  RD3_ERR_CUDA = 4              /* a CUDA call failed; see rd3_last_cuda_error()     */
+};
+
+enum { RD3_REDUCE_SUM = 0, RD3_REDUCE_MEAN = 1, RD3_REDUCE_MAX = 2 };
+
+RD3_API int rd3_version(void);
+RD3_API const char *rd3_status_string(int status);
+/* cudaGetErrorString of the last CUDA failure seen by this library (host string). */
+RD3_API const char *rd3_last_cuda_error(void);
+
+/* grid = round((max - min) / voxel_size) in fp32, x,y,z order.
+ * Replaces the inline computation at voxelization_cpu.cpp:121-124 /
+ * voxelize.py:113-121.  Host-only helper (voxel_size, coors_range, grid: host). */
+RD3_API int rd3_grid_size(const float voxel_size[3], const float coors_range[6], int32_t grid[3]);
+
+/* ---------------------------------------------------------------------------
+ * dynamic_voxelize   (voxelization.h:83-94 -> voxelization_cpu.cpp:146-171)
+ *   points (N, C>=3) fp32 row-major -> coors (N, 3) int32 = (z,y,x), or
+ *   (-1,-1,-1) when the point falls outside [min, min+grid*vs) on any axis
+ *   (CPU semantics; the reference GPU kernel's partial -1 prefix is not kept).
+ *   voxel_size / coors_range: host arrays.
+ * ------------------------------------------------------------------------- */
+RD3_API int rd3_dynamic_voxelize(const float *points, int64_t N, int C,
+                         const float voxel_size[3], const float coors_range[6],
+                         int32_t *coors, rd3_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * hard_voxelize      (voxelization.h:58-81 -> voxelization_cpu.cpp:107-144)
+ *   Deterministic; reproduces the sequential CPU scan bit for bit:
+ *   voxels numbered in order of their first point, a new voxel is dropped once
+ *   max_voxels exist, a voxel keeps its first max_points points in point order.
+ *
+ *   voxels (max_voxels, max_points, C), coors (max_voxels, 3) zyx,
+ *   num_points_per_voxel (max_voxels): rows [0, voxel_num) are fully written
+ *   (unused slots = 0); rows beyond are left untouched (the reference's caller
+ *   pre-zeroes them, voxelize.py:57-61).
+ *   d_voxel_num: device int32[1], the value the reference returns as `int`.
+ *   Optional outputs (may be NULL):
+ *     voxel_mean (max_voxels, F): HardSimpleVFE fused (sum of slots / count).
+ *     point2voxel (N): voxel id of each point, -1 if out of range / dropped.
+ * ------------------------------------------------------------------------- */
+RD3_API size_t rd3_hard_voxelize_workspace_bytes(int64_t N, int max_points, int max_voxels);
+
+RD3_API int rd3_hard_voxelize(const float *points, int64_t N, int C,
+                      const float voxel_size[3], const float coors_range[6],
+                      int max_points, int max_voxels, float *voxels,
+                      int32_t *coors, int32_t *num_points_per_voxel,
+                      int32_t *d_voxel_num, float *voxel_mean, int F,
+                      int32_t *point2voxel, void *workspace,
+                      size_t workspace_bytes, rd3_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * HardSimpleVFE.forward   (voxel_encoder.py:45-46)
+ *   out (M, F) = voxels[:, :, :F].sum(dim=1) / float(num_points)
+ * ------------------------------------------------------------------------- */
+RD3_API int rd3_hard_simple_vfe(const float *voxels, const int32_t *num_points, int64_t M,
+                        int max_points, int C, int F, float *out,
+                        rd3_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Depth maps -> ego-frame points
+ *   (reconstruction_backbone.py:285-386; live masks of
+ *    tools/inference_nuscenes.py:399-414; inclusive range filter of
+ *    projects/mmdet3d_plugin/datasets/pipelines/respoint_post_processing.py:190-195)
+ *
+ *   depth (B, ncam, H, W) fp32; intrinsics (B, ncam, 3, 3); cam2lidar
+ *   (B, ncam, 4, 4) with the translation in row 3; conf (B, ncam, H, W) fp32 or
+ *   NULL; sky (B, ncam, H, W) uint8/bool or NULL.
+ *   valid = z > 0 && isfinite(z) [&& z <= max_depth] [&& conf >= conf_thresh]
+ *           [&& !sky] [&& range_min <= p <= range_max].
+ *   x = ((u-cx)*z)/fx, y = ((v-cy)*z)/fy, p = fma-chain(R, (x,y,z)) + t.
+ * ------------------------------------------------------------------------- */
+typedef struct rd3_depth_params {
+  int32_t B, ncam, H, W;
+  int32_t use_max_depth;  /* 0/1 */
+  float max_depth;
+  float conf_thresh;      /* used when conf != NULL */
+  int32_t use_range;      /* 0/1: inclusive filter on the transformed point */
+  float range[6];         /* x0 y0 z0 x1 y1 z1 */
+} rd3_depth_params;
+
+/* Order-preserving compaction (cameras in index order, pixels row-major).
+ *   out_points (B, ncam*H*W, 3): first d_counts[b] rows of sample b are valid.
+ *   out_pix (B, ncam*H*W) int32 or NULL: flat pixel index of each emitted point.
+ *   d_counts: device int32[B]. */
+RD3_API size_t rd3_unproject_workspace_bytes(const rd3_depth_params *p);
+
+RD3_API int rd3_unproject(const float *depth, const float *intrinsics,
+                  const float *cam2lidar, const float *conf, const uint8_t *sky,
+                  const rd3_depth_params *p, float *out_points, int32_t *out_pix,
+                  int32_t *d_counts, void *workspace, size_t workspace_bytes,
+                  rd3_stream_t stream);
+
+/* Fused: depth -> hard voxels (+ voxel mean) for B samples in one pass; the
+ * point cloud is never written to memory.  Output of sample b is bit-identical
+ * to rd3_unproject(b) followed by rd3_hard_voxelize + rd3_hard_simple_vfe.
+ *   voxels (B, max_voxels, max_points, 3), coors (B, max_voxels, 3),
+ *   num_points_per_voxel (B, max_voxels), voxel_mean (B, max_voxels, 3) or
+ *   NULL, d_voxel_num device int32[B]. */
+RD3_API size_t rd3_depth_to_voxels_workspace_bytes(const rd3_depth_params *p,
+                                           int max_points, int max_voxels);
+
+RD3_API int rd3_depth_to_voxels(const float *depth, const float *intrinsics,
+                        const float *cam2lidar, const float *conf,
+                        const uint8_t *sky, const rd3_depth_params *p,
+                        const float voxel_size[3], const float coors_range[6],
+                        int max_points, int max_voxels, float *voxels,
+                        int32_t *coors, int32_t *num_points_per_voxel,
+                        float *voxel_mean, int32_t *d_voxel_num,
+                        void *workspace, size_t workspace_bytes,
+                        rd3_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * dynamic_point_to_voxel_forward
+ *   (voxelization.h:108-121 -> scatter_points_cuda.cu:183-239)
+ *   feats (N, C) fp32, coors (N, 3) int32.  Rows with any negative component
+ *   are dropped (map -1).  Voxels come out in lexicographic (c0,c1,c2) order.
+ *   dims (host int32[3]): exclusive upper bound of every valid coordinate
+ *   (e.g. the voxel grid (gz,gy,gx)); a valid coordinate >= dims sets
+ *   *d_status (device int32[1]) to 1 and the outputs are then undefined --
+ *   call rd3_coors_extent and retry.
+ *   Outputs sized for the worst case: voxel_feats (N, C), voxel_coors (N, 3),
+ *   point2voxel (N), voxel_count (N); d_num_voxels device int32[1].
+ * ------------------------------------------------------------------------- */
+RD3_API int rd3_coors_extent(const int32_t *coors, int64_t N, int32_t *d_extent3,
+                     rd3_stream_t stream);
+
+RD3_API size_t rd3_dynamic_scatter_workspace_bytes(int64_t N, int C, const int32_t dims[3]);
+
+RD3_API int rd3_dynamic_scatter_forward(const float *feats, const int32_t *coors, int64_t N,
+                                int C, const int32_t dims[3], int reduce_type,
+                                float *voxel_feats, int32_t *voxel_coors,
+                                int32_t *point2voxel, int32_t *voxel_count,
+                                int32_t *d_num_voxels, int32_t *d_status,
+                                void *workspace, size_t workspace_bytes,
+                                rd3_stream_t stream);
+
+/* dynamic_point_to_voxel_backward
+ *   (voxelization.h:123-140 -> scatter_points_cuda.cu:241-308)
+ *   grad_feats (N, C) is fully written (zeros for dropped points).
+ *   max: the gradient goes to the lowest-index point attaining the maximum. */
+RD3_API size_t rd3_dynamic_scatter_backward_workspace_bytes(int64_t M, int C);
+
+RD3_API int rd3_dynamic_scatter_backward(float *grad_feats, const float *grad_voxel_feats,
+                                 const float *feats, const float *voxel_feats,
+                                 const int32_t *point2voxel,
+                                 const int32_t *voxel_count, int64_t N, int64_t M,
+                                 int C, int reduce_type, void *workspace,
+                                 size_t workspace_bytes, rd3_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RD3_B200_H_ */

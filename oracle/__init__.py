@@ -140,6 +140,15 @@ def hard_simple_vfe(voxels, num, num_features=None, f64=False):
     return out
 
 
+def _f32_ceil(x):
+    """smallest fp32 >= x: `conf_f32 >= thr_f64` (numpy, tools/inference_nuscenes.py:401)
+    evaluated exactly, expressed as an fp32 threshold."""
+    f = np.float32(x)
+    if float(f) < float(x):
+        f = np.nextafter(f, np.float32(np.inf))
+    return float(f)
+
+
 def unproject(depth, intrinsics, cam2lidar, max_depth=None, conf=None,
               conf_thresh=0.0, sky=None, range_filter=None, return_pix=False):
     """One sample: depth (ncam,H,W) -> ego points (P,3) fp32.
@@ -161,7 +170,7 @@ def unproject(depth, intrinsics, cam2lidar, max_depth=None, conf=None,
     P = lib().orc_unproject(_ptr(d, _f32p), ncam, H, W, _ptr(K, _f32p),
                             _ptr(M, _f32p), int(max_depth is not None),
                             float(max_depth if max_depth is not None else 0.0),
-                            _ptr(cf, _f32p), float(conf_thresh),
+                            _ptr(cf, _f32p), _f32_ceil(conf_thresh),
                             _ptr(sk, _u8p), _ptr(rf, _f32p), _ptr(pts, _f32p),
                             _ptr(pix, _i32p), cap)
     if return_pix:

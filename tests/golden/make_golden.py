@@ -1,0 +1,79 @@
+"""Generate tests/golden/*.npz from the REFERENCE itself, in the build container.
+
+Run here (needs /root/reference for oracle/_ref and torch for the restatement of
+the Python-level reference code); the resulting small fixtures are committed and
+travel to the GPU box, where /root/reference does not exist.
+
+    python tests/golden/make_golden.py
+
+Sources of truth:
+  hard/dynamic voxelization : oracle/_ref = the reference's voxelization_cpu.cpp compiled unmodified
+  unprojection              : torch-CPU ops of reconstruction_backbone.py:305-386 (oracle/torch_restatement.py)
+  DynamicScatter            : torch-CPU ops of scatter_points_cuda.cu:183-239 (ibid.)
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import oracle  # noqa: E402
+from oracle import torch_restatement as tr  # noqa: E402
+from rd3_b200 import synthetic  # noqa: E402
+from test_oracle import _adversarial_points, kat_points  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    ref = oracle.ref_voxel_layer()
+    assert ref is not None, "build oracle/_ref first (python oracle/build_ref.py)"
+
+    # 1. the reference's known-answer input through the reference's own op
+    pts = torch.from_numpy(kat_points())
+    v, c, n = tr.voxelization_forward(ref, pts, [0.5, 0.5, 0.5], [0, -40, -3, 70.4, 40, 1], 1000, 20000)
+    np.savez_compressed(os.path.join(OUT, "kat_hard.npz"), points=pts.numpy(), coors=c.numpy(),
+                        num=n.numpy(), voxels_sum=v.sum(dim=1).numpy())
+
+    # 2. adversarial cloud, nuScenes grid, both truncations active
+    vs, pcr, mp, mv = [0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3], 3, 2000
+    p = _adversarial_points(20000, pcr, vs, seed=42)
+    v, c, n = tr.voxelization_forward(ref, torch.from_numpy(p), vs, pcr, mp, mv)
+    dc = tr.voxelization_forward(ref, torch.from_numpy(p), vs, pcr, -1, -1)
+    np.savez_compressed(os.path.join(OUT, "adversarial_hard.npz"), points=p, voxel_size=vs, pcr=pcr,
+                        max_points=mp, max_voxels=mv, voxels=v.numpy(), coors=c.numpy(), num=n.numpy(),
+                        dyn_coors=dc.numpy())
+
+    # 3. unprojection (+ masks) of 2 small frames
+    b = synthetic.make_batch([100, 101], 28, 48)
+    thr = tr.conf_threshold(b["conf"][0], b["sky"][0], synthetic.CONF_PERCENTILE)
+    plain = tr.backproject_depth_to_points(b["depth"], b["intrinsics"], b["cam2lidar"],
+                                           max_depth=synthetic.MAX_DEPTH)
+    masked = tr.backproject_depth_to_points(b["depth"], b["intrinsics"], b["cam2lidar"],
+                                            max_depth=synthetic.MAX_DEPTH, confs=b["conf"],
+                                            conf_thresh=np.float64(thr), sky_masks=b["sky"])
+    masked = [tr.filter_point_by_range(m, synthetic.FILTER_RANGE)[0] for m in masked]
+    np.savez_compressed(os.path.join(OUT, "unproject.npz"), frame_ids=[100, 101], hw=[28, 48],
+                        conf_thresh=thr, plain0=plain[0].numpy(), plain1=plain[1].numpy(),
+                        masked0=masked[0].numpy(), masked1=masked[1].numpy())
+
+    # 4. DynamicScatter
+    g = torch.Generator().manual_seed(99)
+    feats = torch.rand(5000, 4, generator=g) * 100 - 50
+    coors = torch.randint(-1, 12, (5000, 3), generator=g, dtype=torch.int32)
+    d = dict(feats=feats.numpy(), coors=coors.numpy())
+    for red in ("sum", "mean", "max"):
+        rf, rc, rm, rn = tr.dynamic_point_to_voxel_forward(feats, coors, red)
+        d[red + "_feats"] = rf.numpy()
+        d["voxel_coors"], d["map"], d["count"] = rc.numpy(), rm.numpy(), rn.numpy()
+    np.savez_compressed(os.path.join(OUT, "dynamic_scatter.npz"), **d)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

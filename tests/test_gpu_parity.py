@@ -1,0 +1,430 @@
+"""Parity of the sm_100a path against the oracle.  Needs a CUDA device (-m gpu).
+
+Bar: integer outputs (voxel coords, counts, point->voxel maps, voxel payload
+copies) bit-exact; floating-point reductions within 1e-6 relative.
+Nothing here reads /root/reference (it does not exist on the GPU box).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import torch_restatement as tr
+import rd3_b200
+from rd3_b200 import synthetic, voxel_layer
+from test_oracle import CASES, KAT_COORS, KAT_NUM, _adversarial_points, kat_points
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEV = "cuda:0"
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def gpu_hard(points, vs, pcr, mp, mv, mean_F=None, want_p2v=False):
+    p = torch.from_numpy(np.ascontiguousarray(points, np.float32)).to(DEV)
+    N, C = p.shape
+    # poisoned buffers: every row < voxel_num must be fully overwritten
+    voxels = torch.full((mv, mp, C), 777.0, device=DEV)
+    coors = torch.full((mv, 3), -7, dtype=torch.int32, device=DEV)
+    num = torch.full((mv,), -7, dtype=torch.int32, device=DEV)
+    mean = torch.full((mv, mean_F), 777.0, device=DEV) if mean_F else None
+    p2v = torch.full((N,), -7, dtype=torch.int32, device=DEV) if want_p2v else None
+    n = voxel_layer.hard_voxelize(p, voxels, coors, num, vs, pcr, mp, mv, 3, True,
+                                  voxel_mean=mean, point2voxel=p2v)
+    out = [voxels[:n].cpu().numpy(), coors[:n].cpu().numpy(), num[:n].cpu().numpy()]
+    # rows beyond voxel_num untouched
+    assert (coors[n:] == -7).all() and (num[n:] == -7).all()
+    if mean_F:
+        out.append(mean[:n].cpu().numpy())
+    if want_p2v:
+        out.append(p2v.cpu().numpy())
+    return out
+
+
+def check_hard(points, vs, pcr, mp, mv):
+    C = points.shape[1]
+    v, c, n, mean, p2v = gpu_hard(points, vs, pcr, mp, mv, mean_F=min(C, 4), want_p2v=True)
+    ov, oc, on, op2v = oracle.hard_voxelize(points, vs, pcr, mp, mv, return_point2voxel=True)
+    assert len(c) == len(oc)
+    assert np.array_equal(c, oc)
+    assert np.array_equal(n, on)
+    assert np.array_equal(bits(v), bits(ov))
+    assert np.array_equal(p2v, op2v)
+    om = oracle.hard_simple_vfe(ov, on, min(C, 4))
+    assert np.array_equal(bits(mean), bits(om))          # same sequential order -> same bits
+    o64 = oracle.hard_simple_vfe(ov, on, min(C, 4), f64=True)
+    scale = np.abs(ov).max() if ov.size else 1.0
+    assert np.allclose(mean, o64, rtol=1e-6, atol=1e-6 * scale)
+    return len(c)
+
+
+def frame_points(cfg, frame=0, scene="mixture"):
+    H, W = synthetic.CONFIGS[cfg]["hw"]
+    f = synthetic.make_frame(frame, H, W, scene=scene)
+    pts = oracle.unproject(f["depth"].numpy(), f["intrinsics"].numpy(), f["cam2lidar"].numpy(),
+                           max_depth=synthetic.MAX_DEPTH)
+    return f, pts
+
+
+# ----------------------------------------------------------------------------------------------
+# library / boundary
+# ----------------------------------------------------------------------------------------------
+def test_no_cpu_path():
+    with pytest.raises(RuntimeError):
+        rd3_b200.Voxelization([0.5] * 3, [0, -40, -3, 70.4, 40, 1], 35)(torch.rand(10, 4))
+    with pytest.raises(RuntimeError):
+        voxel_layer.dynamic_point_to_voxel_forward(torch.rand(4, 3, device=DEV),
+                                                   torch.zeros(4, 3, dtype=torch.int32, device=DEV), "min")
+
+
+# ----------------------------------------------------------------------------------------------
+# a3 dynamic_voxelize
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("vs,pcr,mp,mv", CASES)
+def test_dynamic_voxelize_adversarial(vs, pcr, mp, mv):
+    pts = _adversarial_points(40000, pcr, vs, seed=mp)
+    for C in (3, 4, 5):
+        p = pts[:, :C] if C <= 4 else np.concatenate([pts, pts[:, :1]], axis=1)
+        p = np.ascontiguousarray(p)
+        vox = rd3_b200.Voxelization(vs, pcr, -1)
+        got = vox(torch.from_numpy(p).to(DEV)).cpu().numpy()
+        assert np.array_equal(got, oracle.dynamic_voxelize(p, vs, pcr))
+
+
+def test_dynamic_voxelize_c3_full_size():
+    cfg = synthetic.CONFIGS["C3"]
+    _, pts = frame_points("C3")
+    got = rd3_b200.Voxelization(cfg["voxel_size"], cfg["pcr"], -1)(torch.from_numpy(pts).to(DEV))
+    exp = oracle.dynamic_voxelize(pts, cfg["voxel_size"], cfg["pcr"])
+    assert np.array_equal(got.cpu().numpy(), exp)
+    assert (exp[:, 0] >= 0).sum() > 100000
+
+
+# ----------------------------------------------------------------------------------------------
+# a4 hard_voxelize (+ fused a9)
+# ----------------------------------------------------------------------------------------------
+def test_hard_known_answer():
+    """mmdetection3d/tests/test_models/test_voxel_encoder/test_voxel_generator.py:7-22"""
+    v, c, n = gpu_hard(kat_points(), [0.5, 0.5, 0.5], [0, -40, -3, 70.4, 40, 1], 1000, 20000)
+    assert v.shape == (8, 1000, 4)
+    assert np.array_equal(c, KAT_COORS)
+    assert np.array_equal(n, KAT_NUM)
+    g = np.load(os.path.join(GOLD, "kat_hard.npz"))
+    assert np.allclose(v.sum(axis=1), g["voxels_sum"], rtol=1e-5)
+
+
+def test_hard_golden_adversarial():
+    g = np.load(os.path.join(GOLD, "adversarial_hard.npz"))
+    vs, pcr = g["voxel_size"].tolist(), g["pcr"].tolist()
+    v, c, n = gpu_hard(g["points"], vs, pcr, int(g["max_points"]), int(g["max_voxels"]))
+    assert np.array_equal(c, g["coors"]) and np.array_equal(n, g["num"])
+    assert np.array_equal(bits(v), bits(g["voxels"]))
+    dyn = rd3_b200.Voxelization(vs, pcr, -1)(torch.from_numpy(g["points"]).to(DEV))
+    assert np.array_equal(dyn.cpu().numpy(), g["dyn_coors"])
+
+
+@pytest.mark.parametrize("vs,pcr,mp,mv", CASES)
+def test_hard_adversarial(vs, pcr, mp, mv):
+    pts = _adversarial_points(60000, pcr, vs, seed=mp + 1)
+    assert check_hard(pts, vs, pcr, mp, mv) > 0
+    assert check_hard(np.ascontiguousarray(pts[:, :3]), vs, pcr, mp, mv) > 0
+
+
+def test_hard_edge_cases():
+    vs, pcr = [0.5, 0.5, 0.5], [0, -40, -3, 70.4, 40, 1]
+    # empty input
+    assert check_hard(np.zeros((0, 4), np.float32), vs, pcr, 5, 100) == 0
+    # nothing in range
+    assert check_hard(np.full((1000, 3), 1e6, np.float32), vs, pcr, 5, 100) == 0
+    # one voxel, many points (max_points truncation under heavy contention), reversed chunks
+    p = np.tile(np.array([[1.1, 1.1, 0.1, 0.0]], np.float32), (200000, 1))
+    p[:, 3] = np.arange(200000)
+    assert check_hard(p, vs, pcr, 7, 100) == 1
+    # max_voxels = 1, max_points = 1
+    pts = _adversarial_points(30000, pcr, vs, seed=5)
+    assert check_hard(pts, vs, pcr, 1, 1) == 1
+    # ragged: N not a multiple of anything
+    assert check_hard(pts[:8193], vs, pcr, 3, 50) == 50
+    assert check_hard(pts[:31], vs, pcr, 3, 50) > 0
+
+
+@pytest.mark.parametrize("cfg,scene", [("C1", "mixture"), ("C2", "mixture"), ("C2", "ground"),
+                                       ("C4", "mixture"), ("C4", "ground")])
+def test_hard_full_size(cfg, scene):
+    """BASELINE.json configs at full size: ~0.85 M / 2.7 M pixel frames."""
+    c = synthetic.CONFIGS[cfg]
+    _, pts = frame_points(cfg, scene=scene)
+    for mv in c["max_voxels"]:
+        m = check_hard(pts, list(c["voxel_size"]), list(c["pcr"]), c["max_points"], mv)
+        assert m > 1000
+
+
+def test_hard_deterministic_and_order_independent_of_scheduling():
+    c = synthetic.CONFIGS["C4"]
+    _, pts = frame_points("C1", scene="ground")
+    a = gpu_hard(pts, list(c["voxel_size"]), list(c["pcr"]), c["max_points"], 30000)
+    for _ in range(3):
+        b = gpu_hard(pts, list(c["voxel_size"]), list(c["pcr"]), c["max_points"], 30000)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+
+
+def test_voxelization_module_train_eval_max_voxels():
+    c = synthetic.CONFIGS["C1"]
+    _, pts = frame_points("C1")
+    vox = rd3_b200.Voxelization(list(c["voxel_size"]), list(c["pcr"]), c["max_points"], (2000, 3000)).to(DEV)
+    assert vox.grid_size.tolist() == [1440, 1440, 40]
+    p = torch.from_numpy(pts).to(DEV)
+    vox.train()
+    v, co, n = vox(p)
+    assert v.shape == (2000, 10, 3) and co.shape == (2000, 3) and n.shape == (2000,)
+    vox.eval()
+    v2, co2, n2 = vox(p)
+    assert v2.shape[0] == 3000
+    assert torch.equal(co2[:2000], co) and torch.equal(v2[:2000], v)
+    assert co.dtype == torch.int32 and n.dtype == torch.int32
+
+
+# ----------------------------------------------------------------------------------------------
+# a9 HardSimpleVFE
+# ----------------------------------------------------------------------------------------------
+def test_hard_simple_vfe():
+    g = np.random.default_rng(0)
+    M, K, C = 24000, 10, 5
+    n = g.integers(1, K + 1, size=M).astype(np.int32)
+    v = (g.random((M, K, C)) * 10 + 20).astype(np.float32)
+    for m in range(M):
+        v[m, n[m]:] = 0
+    vfe = rd3_b200.HardSimpleVFE(num_features=4)
+    out = vfe(torch.from_numpy(v).to(DEV), torch.from_numpy(n).to(DEV), None)
+    assert out.shape == (M, 4)                         # test_voxel_encoders.py:27-34 shape check
+    assert np.array_equal(bits(out.cpu().numpy()), bits(oracle.hard_simple_vfe(v, n, 4)))
+    ref = tr.hard_simple_vfe(torch.from_numpy(v), torch.from_numpy(n), 4).numpy()
+    assert np.allclose(out.cpu().numpy(), ref, rtol=1e-6, atol=0)
+
+
+# ----------------------------------------------------------------------------------------------
+# a1/a2 unprojection
+# ----------------------------------------------------------------------------------------------
+def test_unproject_golden():
+    g = np.load(os.path.join(GOLD, "unproject.npz"))
+    H, W = g["hw"].tolist()
+    b = synthetic.make_batch(g["frame_ids"].tolist(), H, W)
+    d = {k: v.to(DEV) for k, v in b.items()}
+    pts, cols = rd3_b200.backproject_depth_to_points(d["depth"], d["intrinsics"], None, d["cam2lidar"],
+                                                     max_depth=synthetic.MAX_DEPTH)
+    assert cols == [None, None]
+    for i in range(2):
+        assert np.array_equal(bits(pts[i].cpu().numpy()), bits(g["plain%d" % i]))
+    pts, _ = rd3_b200.backproject_depth_to_points(
+        d["depth"], d["intrinsics"], None, d["cam2lidar"], max_depth=synthetic.MAX_DEPTH,
+        multi_batch_confs=d["conf"], conf_thresh=float(g["conf_thresh"]),
+        multi_batch_sky_masks=d["sky"], range_filter=synthetic.FILTER_RANGE)
+    for i in range(2):
+        assert np.array_equal(bits(pts[i].cpu().numpy()), bits(g["masked%d" % i]))
+
+
+@pytest.mark.parametrize("hw,scene", [((280, 504), "mixture"), ((504, 896), "ground"), ((37, 53), "mixture")])
+def test_unproject_vs_oracle(hw, scene):
+    H, W = hw
+    b = synthetic.make_batch([3, 4], H, W, scene=scene)
+    d = {k: v.to(DEV) for k, v in b.items()}
+    thr = tr.conf_threshold(b["conf"][0], b["sky"][0], synthetic.CONF_PERCENTILE)
+    for masks in (False, True):
+        kw = dict(max_depth=synthetic.MAX_DEPTH)
+        okw = dict(max_depth=synthetic.MAX_DEPTH)
+        if masks:
+            kw.update(multi_batch_confs=d["conf"], conf_thresh=thr, multi_batch_sky_masks=d["sky"],
+                      range_filter=synthetic.FILTER_RANGE)
+        pts, _ = rd3_b200.backproject_depth_to_points(d["depth"], d["intrinsics"], None, d["cam2lidar"], **kw)
+        for i in range(2):
+            if masks:
+                okw.update(conf=b["conf"][i].numpy(), conf_thresh=thr, sky=b["sky"][i].numpy(),
+                           range_filter=synthetic.FILTER_RANGE)
+            o = oracle.unproject(b["depth"][i].numpy(), b["intrinsics"][i].numpy(),
+                                 b["cam2lidar"][i].numpy(), **okw)
+            got = pts[i].cpu().numpy()
+            assert got.shape == o.shape
+            assert np.array_equal(bits(got), bits(o))
+
+
+def test_unproject_mixin_and_colors():
+    class Backbone(rd3_b200.DepthToPointsMixin):
+        max_depth = synthetic.MAX_DEPTH
+    H, W = 28, 48
+    b = synthetic.make_batch([8], H, W)
+    g = torch.Generator().manual_seed(0)
+    imgs = torch.randint(0, 256, (1, 6, 3, H, W), generator=g).float()
+    pts, cols = Backbone()._backproject_depth_to_points(b["depth"].to(DEV), b["intrinsics"].to(DEV),
+                                                        imgs.to(DEV), b["cam2lidar"].to(DEV))
+    o, pix = oracle.unproject(b["depth"][0].numpy(), b["intrinsics"][0].numpy(), b["cam2lidar"][0].numpy(),
+                              max_depth=synthetic.MAX_DEPTH, return_pix=True)
+    assert np.array_equal(bits(pts[0].cpu().numpy()), bits(o))
+    flat = imgs[0].permute(0, 2, 3, 1).reshape(-1, 3).numpy()
+    assert np.allclose(cols[0].cpu().numpy(), flat[pix] / 255.0, rtol=1e-6)
+    # all-invalid depth -> empty (0,3) tensor
+    z = torch.zeros(1, 6, H, W, device=DEV)
+    pts, cols = Backbone()._backproject_depth_to_points(z, b["intrinsics"].to(DEV), None, b["cam2lidar"].to(DEV))
+    assert tuple(pts[0].shape) == (0, 3)
+
+
+# ----------------------------------------------------------------------------------------------
+# fused depth -> voxels (C2, C4)
+# ----------------------------------------------------------------------------------------------
+def check_fused(cfg, frames, scene, masks, training):
+    c = synthetic.CONFIGS[cfg]
+    H, W = c["hw"]
+    b = synthetic.make_batch(frames, H, W, scene=scene)
+    d = {k: v.to(DEV) for k, v in b.items()}
+    rf = synthetic.FILTER_RANGE if masks else None
+    mod = rd3_b200.DepthToVoxels(c["voxel_size"], c["pcr"], c["max_points"], c["max_voxels"],
+                                 max_depth=synthetic.MAX_DEPTH, range_filter=rf).to(DEV)
+    mod.train(training)
+    mv = c["max_voxels"][0 if training else 1]
+    thr = tr.conf_threshold(b["conf"][0], b["sky"][0], synthetic.CONF_PERCENTILE) if masks else None
+    r = mod(d["depth"], d["intrinsics"], d["cam2lidar"], confs=d["conf"] if masks else None,
+            conf_thresh=thr, sky_masks=d["sky"] if masks else None)
+    vn = r["voxel_num"].cpu().numpy()
+    for i in range(len(frames)):
+        okw = dict(max_depth=synthetic.MAX_DEPTH)
+        if masks:
+            okw.update(conf=b["conf"][i].numpy(), conf_thresh=thr, sky=b["sky"][i].numpy(), range_filter=rf)
+        pts = oracle.unproject(b["depth"][i].numpy(), b["intrinsics"][i].numpy(), b["cam2lidar"][i].numpy(), **okw)
+        ov, oc, on = oracle.hard_voxelize(pts, list(c["voxel_size"]), list(c["pcr"]), c["max_points"], mv)
+        m = int(vn[i])
+        assert m == len(oc)
+        assert np.array_equal(r["coors"][i, :m].cpu().numpy(), oc)
+        assert np.array_equal(r["num_points"][i, :m].cpu().numpy(), on)
+        assert np.array_equal(bits(r["voxels"][i, :m].cpu().numpy()), bits(ov))
+        om = oracle.hard_simple_vfe(ov, on, 3)
+        assert np.array_equal(bits(r["voxel_mean"][i, :m].cpu().numpy()), bits(om))
+    feats, coors4, bs = mod.to_sparse_encoder_inputs(r)
+    assert bs == len(frames) and coors4.shape[1] == 4 and feats.shape[0] == coors4.shape[0] == vn.sum()
+    assert coors4[-1, 0].item() == len(frames) - 1
+    return vn
+
+
+@pytest.mark.parametrize("cfg,scene,masks,training", [
+    ("C2", "mixture", False, True), ("C2", "ground", True, False),
+    ("C4", "mixture", True, True), ("C4", "ground", False, False),
+    ("C1", "mixture", True, True)])
+def test_fused_depth_to_voxels(cfg, scene, masks, training):
+    vn = check_fused(cfg, [0, 1, 2], scene, masks, training)
+    assert (vn > 1000).all()
+
+
+# ----------------------------------------------------------------------------------------------
+# a6/a7/a8 DynamicScatter
+# ----------------------------------------------------------------------------------------------
+def check_scatter(feats, coors, red, dims=None):
+    f, c = torch.from_numpy(feats).to(DEV), torch.from_numpy(coors).to(DEV)
+    vf, vc, p2v, cnt = voxel_layer.dynamic_point_to_voxel_forward(f, c, red, dims)
+    of, oc, om, on = oracle.dynamic_scatter(feats, coors, red)
+    assert np.array_equal(vc.cpu().numpy(), oc)
+    assert np.array_equal(p2v.cpu().numpy(), om)
+    assert np.array_equal(cnt.cpu().numpy(), on)
+    got = vf.cpu().numpy()
+    if red == "max":
+        assert np.array_equal(bits(got), bits(of))
+    else:
+        # 1e-6 relative to the magnitude of the summands (the oracle is the fp64-accumulated value)
+        scale = np.abs(feats).max()
+        assert np.allclose(got, of, rtol=1e-6, atol=1e-6 * scale)
+    return len(oc)
+
+
+def test_dynamic_scatter_golden():
+    g = np.load(os.path.join(GOLD, "dynamic_scatter.npz"))
+    f, c = torch.from_numpy(g["feats"]).to(DEV), torch.from_numpy(g["coors"]).to(DEV)
+    for red in ("sum", "mean", "max"):
+        vf, vc, p2v, cnt = voxel_layer.dynamic_point_to_voxel_forward(f, c, red)
+        assert np.array_equal(vc.cpu().numpy(), g["voxel_coors"])
+        assert np.array_equal(p2v.cpu().numpy(), g["map"])
+        assert np.array_equal(cnt.cpu().numpy(), g["count"])
+        # the golden sums are torch-CPU fp32 index_add_ (order dependent): 1e-5 of the summand scale
+        assert np.allclose(vf.cpu().numpy(), g[red + "_feats"], rtol=1e-5, atol=50 * 1e-5 if red == "sum" else 1e-4)
+
+
+@pytest.mark.parametrize("red", ["sum", "mean", "max"])
+def test_dynamic_scatter_reference_test_cases(red):
+    """mmdetection3d/tests/test_models/test_voxel_encoder/test_dynamic_scatter.py:9-130 (forward part)"""
+    g = torch.Generator().manual_seed(1)
+    # empty input (:18-32)
+    ef = torch.empty((0, 3), device=DEV)
+    ec = torch.empty((0, 3), dtype=torch.int32, device=DEV)
+    r = voxel_layer.dynamic_point_to_voxel_forward(ef, ec, red)
+    assert r[0].shape == ef.shape and r[1].shape == ec.shape and r[2].numel() == 0 and r[3].numel() == 0
+    # all points invalid (:35-50)
+    feats = (torch.rand(200000, 3, generator=g) * 100 - 50).numpy()
+    coors = torch.randint(-1, 0, (200000, 3), generator=g, dtype=torch.int32).numpy()
+    assert check_scatter(feats, coors, red) == 0
+    # random with / without negatives (:53-118)
+    for low in (-1, 0):
+        coors = torch.randint(low, 20, (200000, 3), generator=g, dtype=torch.int32).numpy()
+        m = check_scatter(feats, coors, red)
+        u = torch.from_numpy(coors).unique(dim=0, sorted=True)
+        assert m == int((u.min(dim=-1).values >= 0).sum())
+    # C = 1 and C = 7; hint too small -> transparent retry
+    f7 = (torch.rand(5000, 7, generator=g) * 2 - 1).numpy()
+    c7 = torch.randint(-2, 300, (5000, 3), generator=g, dtype=torch.int32).numpy()
+    check_scatter(f7, c7, red)
+    check_scatter(f7, c7, red, dims=[10, 10, 10])
+    check_scatter(np.ascontiguousarray(f7[:, :1]), c7, red, dims=[300, 300, 300])
+
+
+@pytest.mark.parametrize("red", ["mean", "max"])
+def test_dynamic_scatter_c3_full_size(red):
+    """C3: dynamic voxelization + DynamicScatter on the 1440x1440x40 grid, ~2.7 M points."""
+    c = synthetic.CONFIGS["C3"]
+    _, pts = frame_points("C3", scene="ground" if red == "max" else "mixture")
+    p = torch.from_numpy(pts).to(DEV)
+    coors = rd3_b200.Voxelization(c["voxel_size"], c["pcr"], -1)(p)
+    ds = rd3_b200.DynamicScatter(c["voxel_size"], c["pcr"], red == "mean")
+    vf, vc = ds(p, coors)
+    of, oc, om, on = oracle.dynamic_scatter(pts, coors.cpu().numpy(), red)
+    assert np.array_equal(vc.cpu().numpy(), oc)
+    if red == "max":
+        assert np.array_equal(bits(vf.cpu().numpy()), bits(of))
+    else:
+        assert np.allclose(vf.cpu().numpy(), of, rtol=1e-6, atol=1e-6 * 54)
+    assert len(oc) > 100000
+
+
+def test_dynamic_scatter_batched_and_backward():
+    g = torch.Generator().manual_seed(3)
+    N = 30000
+    feats = torch.rand(N, 4, generator=g) * 100 - 50
+    coors = torch.randint(-1, 9, (N, 3), generator=g, dtype=torch.int32)
+    batch = torch.sort(torch.randint(0, 3, (N,), generator=g, dtype=torch.int32)).values
+    coors4 = torch.cat([batch.view(-1, 1), coors], dim=1)
+    for avg in (True, False):
+        red = "mean" if avg else "max"
+        ds = rd3_b200.DynamicScatter([0.32, 0.32, 6], [-74.88, -74.88, -2, 74.88, 74.88, 4], avg)
+        f = feats.clone().to(DEV).requires_grad_()
+        vf, vc = ds(f, coors4.to(DEV))
+        rf, rc = tr.dynamic_scatter_batched(feats, coors4, red)
+        assert torch.equal(vc.cpu(), rc)
+        assert torch.allclose(vf.detach().cpu(), rf, rtol=1e-6, atol=5e-5)
+        # backward vs restated reference backward (scatter_points_cuda.cu:241-308)
+        gout = torch.rand(vf.shape, generator=g)
+        vf.backward(gout.to(DEV))
+        exp = torch.zeros_like(feats)
+        off = 0
+        for i in range(3):
+            m = coors4[:, 0] == i
+            r = tr.dynamic_point_to_voxel_forward(feats[m].contiguous(), coors[m].contiguous(), red)
+            M = r[0].shape[0]
+            exp[m] = tr.dynamic_point_to_voxel_backward(gout[off:off + M], feats[m], r[0], r[2], r[3], red)
+            off += M
+        assert torch.allclose(f.grad.cpu(), exp, rtol=1e-6, atol=1e-7)
+    # all-invalid input -> zero grad (test_dynamic_scatter.py:35-50)
+    f = feats.clone().to(DEV).requires_grad_()
+    neg = torch.full((N, 3), -1, dtype=torch.int32, device=DEV)
+    out, _ = rd3_b200.DynamicScatter([1, 1, 1], [0, 0, 0, 1, 1, 1], True)(f, neg)
+    out.sum().backward()
+    assert (f.grad == 0).all()
