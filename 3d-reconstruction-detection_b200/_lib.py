@@ -30,6 +30,8 @@ SIGNATURES = {
     "rd3_version": (_i32, []),
     "rd3_status_string": (_c.c_char_p, [_i32]),
     "rd3_last_cuda_error": (_c.c_char_p, []),
+    "rd3_profile_enable": (_i32, [_i32]),
+    "rd3_profile_read": (_i32, [_c.POINTER(_c.c_double * 7), _c.POINTER(_c.c_int)]),
     "rd3_grid_size": (_i32, [_F3, _F6, _I3]),
     "rd3_dynamic_voxelize": (_i32, [_vp, _i64, _i32, _F3, _F6, _vp, _vp]),
     "rd3_hard_voxelize_workspace_bytes": (_sz, [_i64, _i32, _i32]),
@@ -124,6 +126,21 @@ def workspace(device, nbytes):
         ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+PROFILE_STAGES = ("memset", "insert", "flags", "scan", "slots", "emit", "meta")
+
+
+def profile_enable(on=True):
+    check(lib().rd3_profile_enable(int(on)), "profile_enable")
+
+
+def profile_read():
+    """-> (dict stage -> summed ms, calls)"""
+    ms = (_c.c_double * 7)()
+    calls = _c.c_int(0)
+    check(lib().rd3_profile_read(_c.byref(ms), _c.byref(calls)), "profile_read")
+    return dict(zip(PROFILE_STAGES, list(ms))), calls.value
 
 
 def release_workspaces():

@@ -12,6 +12,16 @@
 
 namespace rd3 {
 
+// calibration table: (B, ncam, kCalibFloats), one block per frame
+__global__ void calib_kernel(const float *intr, const float *c2l, int ncam, float *table) {
+  __shared__ float s_cal[kMaxCams * kCalibFloats];
+  const int b = blockIdx.x;
+  stage_calibration(s_cal, intr + (int64_t)b * ncam * 9, c2l + (int64_t)b * ncam * 16, ncam);
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncam * kCalibFloats; i += blockDim.x)
+    table[(int64_t)b * ncam * kCalibFloats + i] = s_cal[i];
+}
+
 // U1: validity flags + chunk-local exclusive prefix.  grid (nchunks, B).
 __global__ void __launch_bounds__(kScanThreads)
     up_flags_kernel(DepthSource src, uint32_t *flags, int32_t *wordprefix, int32_t *chunk_total,
@@ -28,8 +38,12 @@ __global__ void __launch_bounds__(kScanThreads)
     const int64_t i = ((int64_t)(word0 + it) << 5) + lane;
     bool valid = false;
     if (i < src.p.npix) {
-      float x, y, z;
-      valid = src.load(b, i, s_cal, x, y, z);
+      const int64_t gi = (int64_t)b * src.p.npix + i;
+      const float d = __ldg(src.depth + gi);
+      if (src.depth_ok(d, gi)) {
+        float x, y, z;
+        valid = !src.p.use_range || src.point(b, i, 0, s_cal, nullptr, x, y, z);
+      }
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, valid);
     if (lane == it) my_word = bal;
@@ -54,7 +68,7 @@ __global__ void __launch_bounds__(256)
   const uint32_t bit = 1u << (i & 31);
   if (!(word & bit)) return;
   float x, y, z;
-  src.load(b, i, s_cal, x, y, z);
+  src.point(b, i, 0, s_cal, nullptr, x, y, z);
   const int pos = __ldg(chunk_base + (int64_t)b * nchunks + (i >> kChunkShift)) +
                   __ldg(wordprefix + wi) + __popc(word & (bit - 1u));
   const int64_t o = (int64_t)b * src.p.npix + pos;
@@ -94,6 +108,7 @@ static int make_depth_source(const float *depth, const float *intrinsics, const 
   src->sky = sky;
   src->intr = intrinsics;
   src->c2l = cam2lidar;
+  src->cal_table = nullptr;
   DepthParams &d = src->p;
   d.ncam = p->ncam; d.H = p->H; d.W = p->W; d.HW = p->H * p->W; d.npix = (int32_t)npix;
   d.use_max_depth = p->use_max_depth; d.max_depth = p->max_depth;
@@ -101,6 +116,9 @@ static int make_depth_source(const float *depth, const float *intrinsics, const 
   d.use_sky = sky != nullptr;
   d.use_range = p->use_range;
   for (int i = 0; i < 6; ++i) d.range[i] = p->range[i];
+  d.div_hw = make_fastdiv((uint32_t)d.HW);
+  d.div_w = make_fastdiv((uint32_t)d.W);
+  src->vec_ok = ((npix & 3) == 0) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0);
   return RD3_OK;
 }
 
@@ -141,7 +159,8 @@ int rd3_unproject(const float *depth, const float *intrinsics, const float *cam2
 size_t rd3_depth_to_voxels_workspace_bytes(const rd3_depth_params *p, int max_points,
                                            int max_voxels) {
   if (!p || p->B <= 0 || max_points <= 0 || max_voxels <= 0) return 0;
-  return hv_plan((int64_t)p->ncam * p->H * p->W, p->B, max_points, max_voxels).total;
+  return hv_plan((int64_t)p->ncam * p->H * p->W, p->B, max_points, max_voxels).total +
+         align_up((size_t)p->B * p->ncam * kCalibFloats * 4);
 }
 
 int rd3_depth_to_voxels(const float *depth, const float *intrinsics, const float *cam2lidar,
@@ -161,7 +180,11 @@ int rd3_depth_to_voxels(const float *depth, const float *intrinsics, const float
   st = make_grid(voxel_size, coors_range, &g, &vol);
   if (st != RD3_OK) return st;
   const HvPlan plan = hv_plan(src.p.npix, p->B, max_points, max_voxels);
-  if (workspace_bytes < plan.total) return RD3_ERR_WORKSPACE;
+  const size_t cal_bytes = align_up((size_t)p->B * p->ncam * kCalibFloats * 4);
+  if (workspace_bytes < plan.total + cal_bytes) return RD3_ERR_WORKSPACE;
+  float *cal_table = (float *)((char *)workspace + plan.total);
+  calib_kernel<<<p->B, 128, 0, (cudaStream_t)stream>>>(intrinsics, cam2lidar, p->ncam, cal_table);
+  src.cal_table = cal_table;
   HvOut out{voxels, coors, num_points_per_voxel, voxel_mean, d_voxel_num, nullptr,
             voxel_mean ? 3 : 0};
   return hv_run(src, g, vol, plan, workspace, out, (cudaStream_t)stream);

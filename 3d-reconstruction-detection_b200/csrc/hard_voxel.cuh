@@ -7,25 +7,39 @@
 //   * a voxel keeps its first max_points points in point order (:91-97)
 // None of the reference's GPU formulation (O(N^2) scan + <<<1,1>>> kernel,
 // voxelization_cuda.cu:105-180) is reused.  Everything order-related is derived
-// from explicit point indices, so the result does not depend on scheduling:
+// from explicit point indices, so the result does not depend on scheduling.
 //
-//   K1 insert  : voxel key -> hash/direct table entry {key, min point index}
-//                (64-bit atomicMin; read-before-atomic skips most atomics)
-//   K2 flags   : point i is a voxel's FIRST point iff entry.min == i; one ballot
-//                word per 32 points + per-chunk exclusive popcount scan
-//   K2s        : scan of chunk totals (one CTA per frame) -> voxel_num
-//   K3 slots   : voxel rank r = #first-points before entry.min; if r < max_voxels
-//                insert i into the sorted per-voxel slot array S[r][0..K) with a
-//                cascade of atomicMin (keeps the K smallest indices, sorted)
-//   K4 emit    : voxels[r][k][:] = features(S[r][k]) (zeros for empty slots)
-//   K5 meta    : coors[r], num_points[r], fused HardSimpleVFE mean[r]
+//   K1 insert (R rounds over consecutive index ranges of S points):
+//        block = 1024 points; three in-block compactions keep lanes dense:
+//        valid pixels -> unproject + voxel key -> in-range keys -> table op.
+//        Table entry {key:32 | min point index:32}; 64-bit CAS claims a slot,
+//        64-bit atomicMin lowers the index.  A round only INSERTS while fewer
+//        than max_voxels voxels were claimed by the previous rounds; later
+//        rounds only look keys up.  Voxels first seen after that point have
+//        rank >= max_voxels and are dropped by the reference anyway, so the
+//        table never holds more than max_voxels + S keys, whatever N is.
+//        Points whose voxel is in the table are appended to a candidate list.
+//   K2a first : every table entry marks bit[min index] in a per-frame bitmask
+//   K2b scan  : per-chunk exclusive popcount prefix; K2s chunk totals -> voxel_num
+//   K3 slots  : per candidate: rank r = #first-points before its voxel's first
+//        point; if r < max_voxels insert its index into S[r][0..K) with a cascade
+//        of atomicMin that keeps the K smallest indices, sorted.
+//   K4 emit   : a CTA owns V voxels; gathers (or re-unprojects) the slot points
+//        into a shared-memory tile, then writes voxels (coalesced), coors, count
+//        and the HardSimpleVFE mean from the tile.
 //
-// The pipeline is templated on the point source: a (N,C) point array, or DA3
-// depth maps unprojected on the fly (the point cloud never exists in memory).
+// Templated on the point source: a (N,C) point array, or DA3 depth maps
+// unprojected on the fly (the point cloud never exists in memory).
 #pragma once
 #include "rd3_common.cuh"
 
 namespace rd3 {
+
+constexpr int kInsThreads = 256;
+constexpr int kInsPoints = 1024;      // points per insert CTA (4 per thread)
+constexpr int kTilePoints = 128;      // points per warp tile
+constexpr int kTileShift = 7;
+constexpr int kMaxRounds = 64;
 
 // ---------------------------------------------------------------------------
 // point sources
@@ -34,26 +48,44 @@ struct PointsSource {
   const float *pts;   // (B, N, C)
   int64_t N;
   int C;
-  static constexpr bool kNeedsSmem = false;
+  static constexpr bool kIsDepth = false;
 
+  __device__ __forceinline__ void stage(float *, int) const {}
   __device__ __forceinline__ void prepare(float *, int) const {}
-  // load xyz of point i of frame b; false if the point does not exist
-  __device__ __forceinline__ bool load(int b, int64_t i, const float *, float &x, float &y,
-                                       float &z) const {
+  int host_num_feats() const { return C; }
+  __device__ __forceinline__ int num_feats() const { return C; }
+
+  // stage A: which of the 4 points starting at i exist (cheap validity)
+  __device__ __forceinline__ unsigned valid4(int b, int64_t i, float *) const {
+    unsigned m = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) m |= (i + q < N) ? (1u << q) : 0u;
+    return m;
+  }
+  // stage B: coordinates of point i
+  __device__ __forceinline__ bool point(int b, int64_t i, int, const float *, const float *,
+                                        float &x, float &y, float &z) const {
     const float *p = pts + ((int64_t)b * N + i) * C;
-    x = __ldg(p);
-    y = __ldg(p + 1);
-    z = __ldg(p + 2);
+    x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
     return true;
   }
-  __host__ __device__ __forceinline__ int num_feats() const { return C; }
-  int host_num_feats() const { return C; }
-  __device__ __forceinline__ void feats3(int b, int64_t i, const float *, float &x, float &y,
-                                         float &z) const {
-    load(b, i, nullptr, x, y, z);
+  // stage B: voxel cell of point i.  cell_fast: 1 inside / 0 outside / 2 undecided (-> cell_exact)
+  __device__ __forceinline__ int cell_fast(int b, int64_t i, int lid, const float *s_cal, const float *s_z,
+                                           const VoxelGrid &g, int &cx, int &cy, int &cz) const {
+    float x, y, z;
+    point(b, i, lid, s_cal, s_z, x, y, z);
+    return voxel_coor_fast(x, y, z, 0.0f, g, cx, cy, cz);
   }
-  __device__ __forceinline__ float feat(int b, int64_t i, int c, const float *) const {
-    return __ldg(pts + ((int64_t)b * N + i) * C + c);
+  __device__ __forceinline__ bool cell_exact(int b, int64_t i, int lid, const float *s_cal, const float *s_z,
+                                             const VoxelGrid &g, int &cx, int &cy, int &cz) const {
+    float x, y, z;
+    point(b, i, lid, s_cal, s_z, x, y, z);
+    return voxel_coor(x, y, z, g, cx, cy, cz);
+  }
+  // emit: all features of point i into dst[0..C)
+  __device__ __forceinline__ void gather(int b, int64_t i, const float *, float *dst) const {
+    const float *p = pts + ((int64_t)b * N + i) * C;
+    for (int c = 0; c < C; ++c) dst[c] = __ldg(p + c);
   }
 };
 
@@ -63,36 +95,95 @@ struct DepthSource {
   const uint8_t *sky;      // (B, npix) or null
   const float *intr;       // (B, ncam, 9)
   const float *c2l;        // (B, ncam, 16)
+  const float *cal_table;  // (B, ncam, kCalibFloats) precomputed by calib_kernel, or null
   DepthParams p;
-  static constexpr bool kNeedsSmem = true;
+  int vec_ok;              // 16-byte aligned float4 loads are legal
+  static constexpr bool kIsDepth = true;
 
+  // copy this frame's calibration into shared memory (no barrier)
+  __device__ __forceinline__ void stage(float *s_cal, int b) const {
+    if (cal_table) {
+      const float *src = cal_table + (int64_t)b * p.ncam * kCalibFloats;
+      for (int i = threadIdx.x; i < p.ncam * kCalibFloats; i += blockDim.x) s_cal[i] = __ldg(src + i);
+    } else {
+      stage_calibration(s_cal, intr + (int64_t)b * p.ncam * 9, c2l + (int64_t)b * p.ncam * 16, p.ncam);
+    }
+  }
   __device__ __forceinline__ void prepare(float *s_cal, int b) const {
-    stage_calibration(s_cal, intr + (int64_t)b * p.ncam * 9, c2l + (int64_t)b * p.ncam * 16, p.ncam);
+    stage(s_cal, b);
     __syncthreads();
   }
-  __device__ __forceinline__ bool load(int b, int64_t i, const float *s_cal, float &x, float &y,
-                                       float &z) const {
-    const int64_t g = (int64_t)b * p.npix + i;
-    const float d = __ldg(depth + g);
-    const float cf = p.use_conf ? __ldg(conf + g) : 0.0f;
-    const bool sk = p.use_sky ? (__ldg(sky + g) != 0) : false;
-    const int pix = (int)i;
-    const int cam = pix / p.HW;
-    const int rem = pix - cam * p.HW;
-    const int v = rem / p.W;
-    const int u = rem - v * p.W;
-    return unproject_pixel(d, cf, sk, u, v, s_cal + cam * kCalibFloats, p, x, y, z);
-  }
-  __host__ __device__ __forceinline__ int num_feats() const { return 3; }
   int host_num_feats() const { return 3; }
-  __device__ __forceinline__ void feats3(int b, int64_t i, const float *s_cal, float &x, float &y,
-                                         float &z) const {
-    load(b, i, s_cal, x, y, z);
+  __device__ __forceinline__ int num_feats() const { return 3; }
+
+  __device__ __forceinline__ bool depth_ok(float z, int64_t gidx) const {
+    bool ok = (z > 0.0f) && (z <= 3.402823466e+38f);            // z > 0 & isfinite (:338)
+    if (p.use_max_depth) ok = ok && (z <= p.max_depth);          // :339-340
+    if (ok && p.use_conf) ok = __ldg(conf + gidx) >= p.conf_thresh;
+    if (ok && p.use_sky) ok = __ldg(sky + gidx) == 0;
+    return ok;
   }
-  __device__ __forceinline__ float feat(int b, int64_t i, int c, const float *s_cal) const {
+  __device__ __forceinline__ unsigned valid4(int b, int64_t i, float *s_z4) const {
+    const int64_t g = (int64_t)b * p.npix + i;
+    float z[4];
+    if (vec_ok && i + 3 < p.npix) {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(depth + g));
+      z[0] = v.x; z[1] = v.y; z[2] = v.z; z[3] = v.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) z[q] = (i + q < p.npix) ? __ldg(depth + g + q) : 0.0f;
+    }
+    unsigned m = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      s_z4[q] = z[q];
+      m |= depth_ok(z[q], g + q) ? (1u << q) : 0u;
+    }
+    return m;
+  }
+  // pixel index -> (cam, v, u) -> ego-frame point; s_z: block-staged depth (lid-indexed) or null
+  __device__ __forceinline__ bool point(int b, int64_t i, int lid, const float *s_cal,
+                                        const float *s_z, float &x, float &y, float &z) const {
+    const float d = s_z ? s_z[lid] : __ldg(depth + (int64_t)b * p.npix + i);
+    const uint32_t pix = (uint32_t)i;
+    const uint32_t cam = fast_div(pix, p.div_hw);
+    const uint32_t rem = pix - cam * (uint32_t)p.HW;
+    const uint32_t v = fast_div(rem, p.div_w);
+    const uint32_t u = rem - v * (uint32_t)p.W;
+    return unproject_point(d, (int)u, (int)v, s_cal + cam * kCalibFloats, p, x, y, z);
+  }
+  // stage B: voxel cell of pixel i.  cell_fast decides the cell with reciprocal arithmetic and
+  // a rigorous error bound (1 inside / 0 outside); pixels within that bound of a cell or
+  // range-filter boundary return 2 and are re-done by cell_exact with the IEEE divisions.
+  __device__ __forceinline__ int cell_fast(int b, int64_t i, int lid, const float *s_cal, const float *s_z,
+                                           const VoxelGrid &g, int &cx, int &cy, int &cz) const {
+    const float d = s_z[lid];
+    const uint32_t pix = (uint32_t)i;
+    const uint32_t cam = fast_div(pix, p.div_hw);
+    const uint32_t rem = pix - cam * (uint32_t)p.HW;
+    const uint32_t v = fast_div(rem, p.div_w);
+    const uint32_t u = rem - v * (uint32_t)p.W;
+    float x, y, z, err;
+    unproject_point_approx(d, (int)u, (int)v, s_cal + cam * kCalibFloats, x, y, z, err);
+    int r = voxel_coor_fast(x, y, z, err, g, cx, cy, cz);
+    if (r == 1 && p.use_range) {
+      // inclusive range filter (respoint_post_processing.py:190-195) applies to the exact point
+      const bool in_sure = x - p.range[0] >= err && p.range[3] - x >= err && y - p.range[1] >= err &&
+                           p.range[4] - y >= err && z - p.range[2] >= err && p.range[5] - z >= err;
+      const bool out_sure = p.range[0] - x > err || x - p.range[3] > err || p.range[1] - y > err ||
+                            y - p.range[4] > err || p.range[2] - z > err || z - p.range[5] > err;
+      r = out_sure ? 0 : (in_sure ? 1 : 2);
+    }
+    return r;
+  }
+  __device__ __forceinline__ bool cell_exact(int b, int64_t i, int lid, const float *s_cal, const float *s_z,
+                                             const VoxelGrid &g, int &cx, int &cy, int &cz) const {
     float x, y, z;
-    load(b, i, s_cal, x, y, z);
-    return c == 0 ? x : (c == 1 ? y : z);
+    if (!point(b, i, lid, s_cal, s_z, x, y, z)) return false;
+    return voxel_coor(x, y, z, g, cx, cy, cz);
+  }
+  __device__ __forceinline__ void gather(int b, int64_t i, const float *s_cal, float *dst) const {
+    point(b, i, 0, s_cal, nullptr, dst[0], dst[1], dst[2]);
   }
 };
 
@@ -100,12 +191,15 @@ struct DepthSource {
 // per-call work description (device pointers, all with a leading frame dim)
 // ---------------------------------------------------------------------------
 struct HvWork {
-  unsigned long long *table;  // [B][cap]        {key:32 | min point idx:32}, empty = ~0
-  int32_t *pslot;             // [B][N]          table slot of each point, -1 if outside
-  uint32_t *flags;            // [B][nwords]     bit i: point i is the first of its voxel
-  int32_t *wordprefix;        // [B][nwords]     exclusive popcount prefix inside the chunk
-  int32_t *chunk_base;        // [B][nchunks]    totals, then exclusive bases after K2s
+  unsigned long long *table;  // [B][cap]   {key:32 | min point idx:32}, empty = ~0
   uint32_t *slots;            // [B][max_voxels*K] sorted point indices, empty = ~0
+  uint32_t *flags;            // [B][nwords] bit i: point i is the first of a voxel
+  int32_t *wordprefix;        // [B][nwords] exclusive popcount prefix inside the chunk
+  int32_t *chunk_base;        // [B][nchunks] totals, then exclusive bases after K2s
+  int32_t *round_claims;      // [B][kMaxRounds] voxels claimed per insert round
+  uint8_t *cand_cnt;          // [B][ntiles] candidates of each 128-point tile (0..128)
+  uint2 *cand;                // [B][N] (point idx, table slot); tile t owns [t*128, t*128+128)
+  int ntiles;
   int64_t N;
   int64_t cap;
   uint32_t cap_mask;
@@ -123,7 +217,7 @@ struct HvOut {
   int32_t *num;           // [B][max_voxels]
   float *mean;            // [B][max_voxels][F] or null
   int32_t *voxel_num;     // [B]
-  int32_t *point2voxel;   // [B][N] or null
+  int32_t *point2voxel;   // [B][N] or null (pre-filled with -1)
   int F;
 };
 
@@ -131,18 +225,19 @@ __device__ __forceinline__ uint32_t hash_key(uint32_t key, int log2cap) {
   return (key * 2654435769u) >> (32 - log2cap);
 }
 
-// Insert (key, idx); returns the table slot of the key.  Slot ownership is
-// permanent (CAS from empty); the payload only ever decreases (atomicMin), so
-// a stale read can only cause a redundant atomic, never a wrong skip.
+// Insert (key, idx).  Slot ownership is permanent (CAS from empty); the payload
+// only ever decreases (atomicMin), so a stale read can only cause a redundant
+// atomic, never a wrong skip.  *claimed = 1 iff this call created the entry.
 __device__ __forceinline__ uint32_t table_insert(unsigned long long *table, const HvWork &w,
-                                                 uint32_t key, uint32_t idx) {
+                                                 uint32_t key, uint32_t idx, int *claimed) {
   uint32_t slot = w.direct ? key : hash_key(key, w.log2cap);
   const unsigned long long mine = ((unsigned long long)key << 32) | idx;
+  *claimed = 0;
   while (true) {
     unsigned long long e = __ldcg(table + slot);
     if (e == kEmpty64) {
       const unsigned long long old = atomicCAS(table + slot, kEmpty64, mine);
-      if (old == kEmpty64) return slot;
+      if (old == kEmpty64) { *claimed = 1; return slot; }
       e = old;
     }
     if ((uint32_t)(e >> 32) == key) {
@@ -153,28 +248,184 @@ __device__ __forceinline__ uint32_t table_insert(unsigned long long *table, cons
   }
 }
 
-// K1 ------------------------------------------------------------------------
-template <class Src>
-__global__ void __launch_bounds__(256) hv_insert_kernel(Src src, VoxelGrid g, HvWork w) {
-  __shared__ float s_cal[Src::kNeedsSmem ? kMaxCams * kCalibFloats : 1];
-  const int b = blockIdx.y;
-  src.prepare(s_cal, b);
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= w.N) return;
-  float x, y, z;
-  int32_t ps = -1;
-  if (src.load(b, i, s_cal, x, y, z)) {
-    int cx, cy, cz;
-    if (voxel_coor(x, y, z, g, cx, cy, cz)) {
-      ps = (int32_t)table_insert(w.table + (int64_t)b * w.cap, w, voxel_key(cx, cy, cz, g), (uint32_t)i);
-    }
+// Lookup only; returns kEmpty32 when the key is absent.
+__device__ __forceinline__ uint32_t table_find(const unsigned long long *table, const HvWork &w,
+                                               uint32_t key) {
+  uint32_t slot = w.direct ? key : hash_key(key, w.log2cap);
+  while (true) {
+    const unsigned long long e = __ldcg(table + slot);
+    if (e == kEmpty64) return kEmpty32;
+    if ((uint32_t)(e >> 32) == key) return slot;
+    slot = (slot + 1) & w.cap_mask;
   }
-  w.pslot[(int64_t)b * w.N + i] = ps;
 }
 
-// Shared tail of the ordered-flag kernels: lane L of warp wv holds the 32-bit flag
-// word (chunk*kChunkWords + wv*32 + L).  Stores the word, its exclusive popcount
-// prefix inside the chunk, and the chunk total.
+// K1 ------------------------------------------------------------------------
+// grid (ceil((end-begin)/1024), B), 256 threads; every WARP owns a tile of 128
+// consecutive points and runs its three stages without block barriers:
+//   A  4 points per lane (one 16-byte load), cheap validity, ballot compaction
+//   B  dense lanes: voxel cell by the conservative reciprocal path; the few
+//      undecided ones are redone with exact IEEE arithmetic, again on dense lanes
+//   C  dense lanes: table insert (or lookup once max_voxels voxels exist);
+//      hits go to the tile's own region of the candidate list (no global counter)
+template <class Src>
+__global__ void __launch_bounds__(kInsThreads)
+    hv_insert_kernel(Src src, VoxelGrid g, HvWork w, int64_t begin, int64_t end, int round) {
+  constexpr int kWarps = kInsThreads / 32;
+  __shared__ float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 1];
+  __shared__ float s_zb[Src::kIsDepth ? kInsPoints : 4];
+  __shared__ uint32_t s_keyb[kInsPoints];
+  __shared__ uint8_t s_l1b[kInsPoints], s_l2b[kInsPoints], s_undb[kInsPoints];
+  __shared__ int s_prev;
+
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const int64_t block_base = begin + (int64_t)blockIdx.x * kInsPoints;
+  if (block_base >= end) return;
+  if (wv == 0) {
+    // voxels claimed by the previous rounds: insert vs lookup-only for the whole round
+    int c = 0;
+    for (int r = lane; r < round; r += 32) c += __ldcg(w.round_claims + b * kMaxRounds + r);
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (lane == 0) s_prev = c;
+  }
+  src.stage(s_cal, b);
+  __syncthreads();
+  const bool lookup_only = s_prev >= w.max_voxels;
+
+  const int64_t base = block_base + wv * kTilePoints;     // this warp's tile
+  if (base >= end) return;
+  float *s_z = s_zb + (Src::kIsDepth ? wv * kTilePoints : 0);
+  uint32_t *s_key = s_keyb + wv * kTilePoints;
+  uint8_t *s_l1 = s_l1b + wv * kTilePoints, *s_l2 = s_l2b + wv * kTilePoints;
+  uint8_t *s_und = s_undb + wv * kTilePoints;
+
+  // ---- stage A --------------------------------------------------------------------
+  const int64_t i0 = base + 4 * lane;
+  unsigned m = 0;
+  if (i0 < end) {
+    m = src.valid4(b, i0, s_z + (Src::kIsDepth ? 4 * lane : 0));
+    if (i0 + 3 >= end) m &= (1u << (int)(end - i0)) - 1u;
+  }
+  int nv = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const bool on = (m >> q) & 1u;
+    const unsigned bal = __ballot_sync(0xffffffffu, on);
+    if (on) s_l1[nv + __popc(bal & lt)] = (uint8_t)(4 * lane + q);
+    nv += __popc(bal);
+  }
+  __syncwarp();
+
+  // ---- stage B --------------------------------------------------------------------
+  int n2 = 0, nu = 0;
+#pragma unroll 1
+  for (int j0 = 0; j0 < nv; j0 += 32) {
+    const int j = j0 + lane;
+    int r = 0, lid = 0, cx, cy, cz;
+    if (j < nv) {
+      lid = s_l1[j];
+      r = src.cell_fast(b, base + lid, lid, s_cal, s_z, g, cx, cy, cz);
+    }
+    const unsigned b1 = __ballot_sync(0xffffffffu, r == 1);
+    const unsigned b2 = __ballot_sync(0xffffffffu, r == 2);
+    if (r == 1) {
+      const int at = n2 + __popc(b1 & lt);
+      s_l2[at] = (uint8_t)lid;
+      s_key[at] = voxel_key(cx, cy, cz, g);
+    } else if (r == 2) {
+      s_und[nu + __popc(b2 & lt)] = (uint8_t)lid;
+    }
+    n2 += __popc(b1);
+    nu += __popc(b2);
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int j0 = 0; j0 < nu; j0 += 32) {       // rare: within the error bound of a boundary
+    const int j = j0 + lane;
+    bool in = false;
+    int lid = 0, cx, cy, cz;
+    if (j < nu) {
+      lid = s_und[j];
+      in = src.cell_exact(b, base + lid, lid, s_cal, s_z, g, cx, cy, cz);
+    }
+    const unsigned b1 = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const int at = n2 + __popc(b1 & lt);
+      s_l2[at] = (uint8_t)lid;
+      s_key[at] = voxel_key(cx, cy, cz, g);
+    }
+    n2 += __popc(b1);
+  }
+  __syncwarp();
+
+  // ---- stage C --------------------------------------------------------------------
+  unsigned long long *table = w.table + (int64_t)b * w.cap;
+  uint2 *cand = w.cand + (int64_t)b * w.N + base;
+  int nc = 0, claims = 0;
+#pragma unroll 1
+  for (int j0 = 0; j0 < n2; j0 += 32) {
+    const int j = j0 + lane;
+    uint32_t slot = kEmpty32, idx = 0;
+    if (j < n2) {
+      idx = (uint32_t)(base + s_l2[j]);
+      if (lookup_only) {
+        slot = table_find(table, w, s_key[j]);
+      } else {
+        int c;
+        slot = table_insert(table, w, s_key[j], idx, &c);
+        claims += c;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, slot != kEmpty32);
+    if (slot != kEmpty32) cand[nc + __popc(bal & lt)] = make_uint2(idx, slot);
+    nc += __popc(bal);
+  }
+  if (lane == 0) w.cand_cnt[(int64_t)b * w.ntiles + (base >> kTileShift)] = (uint8_t)nc;
+  if (!lookup_only) {
+    for (int d = 16; d > 0; d >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, d);
+    if (lane == 0 && claims) atomicAdd(w.round_claims + b * kMaxRounds + round, claims);
+  }
+}
+
+// K2a -----------------------------------------------------------------------
+// every table entry marks its voxel's first point.  grid (cap/256, B).
+static __global__ void __launch_bounds__(256) hv_first_kernel(HvWork w) {
+  const int b = blockIdx.y;
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= w.cap) return;
+  const unsigned long long e = w.table[(int64_t)b * w.cap + s];
+  if (e == kEmpty64) return;
+  const uint32_t first = (uint32_t)e;
+  atomicOr(w.flags + (int64_t)b * w.nwords + (first >> 5), 1u << (first & 31));
+}
+
+// K2b -----------------------------------------------------------------------
+// grid (nchunks, B), kScanThreads threads, one flag word each.
+static __global__ void __launch_bounds__(kScanThreads) hv_flagscan_kernel(HvWork w) {
+  __shared__ int s_warp[kScanThreads / 32];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const int64_t wi = (int64_t)b * w.nwords + (int64_t)blockIdx.x * kChunkWords + threadIdx.x;
+  const int cnt = __popc(w.flags[wi]);
+  const int inc = warp_inclusive_scan(cnt);
+  if (lane == 31) s_warp[wv] = inc;
+  __syncthreads();
+  int base = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < kScanThreads / 32; ++k) {
+    const int t = s_warp[k];
+    if (k < wv) base += t;
+    total += t;
+  }
+  w.wordprefix[wi] = base + inc - cnt;
+  if (threadIdx.x == 0) w.chunk_base[(int64_t)b * w.nchunks + blockIdx.x] = total;
+}
+
+// Shared tail of the ordered-flag kernels (depth.cu): lane L of warp wv holds the
+// 32-bit flag word (chunk*kChunkWords + wv*32 + L).  Stores the word, its exclusive
+// popcount prefix inside the chunk, and the chunk total.
 __device__ __forceinline__ void chunk_scan_store(uint32_t my_word, int *s_warp, uint32_t *flags,
                                                  int32_t *wordprefix, int32_t *chunk_total) {
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
@@ -195,36 +446,11 @@ __device__ __forceinline__ void chunk_scan_store(uint32_t my_word, int *s_warp, 
   if (threadIdx.x == 0) chunk_total[blockIdx.x] = total;
 }
 
-// K2 ------------------------------------------------------------------------
-// grid (nchunks, B), 256 threads: warp wv owns words [wv*32, wv*32+32) of the chunk.
-static __global__ void __launch_bounds__(kScanThreads) hv_flags_kernel(HvWork w) {
-  __shared__ int s_warp[kScanThreads / 32];
-  const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-  const unsigned long long *table = w.table + (int64_t)b * w.cap;
-  const int32_t *pslot = w.pslot + (int64_t)b * w.N;
-  const int word0 = blockIdx.x * kChunkWords + wv * 32;
-  uint32_t my_word = 0;
-#pragma unroll 4
-  for (int it = 0; it < 32; ++it) {
-    const int64_t i = ((int64_t)(word0 + it) << 5) + lane;
-    bool first = false;
-    if (i < w.N) {
-      const int32_t ps = __ldg(pslot + i);
-      if (ps >= 0) first = ((uint32_t)__ldg(table + ps) == (uint32_t)i);
-    }
-    const uint32_t bal = __ballot_sync(0xffffffffu, first);
-    if (lane == it) my_word = bal;
-  }
-  chunk_scan_store(my_word, s_warp, w.flags + (int64_t)b * w.nwords, w.wordprefix + (int64_t)b * w.nwords,
-                   w.chunk_base + (int64_t)b * w.nchunks);
-}
-
 // K2s -----------------------------------------------------------------------
 // one CTA per frame: exclusive scan of the chunk totals in place; the frame's
 // total (clamped) goes to out_total[b].
 static __global__ void __launch_bounds__(1024) scan_chunks_kernel(int32_t *chunk_base, int nchunks,
-                                                           int32_t *out_total, int clamp) {
+                                                                  int32_t *out_total, int clamp) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   const int b = blockIdx.x;
@@ -283,95 +509,106 @@ __device__ __forceinline__ void slot_insert(uint32_t *S, int K, uint32_t idx) {
 }
 
 // K3 ------------------------------------------------------------------------
+// grid (ceil(ntiles/8), B), 256 threads: one warp per 128-point tile region.
 static __global__ void __launch_bounds__(256) hv_slots_kernel(HvWork w, int32_t *point2voxel) {
   const int b = blockIdx.y;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= w.N) return;
-  const int32_t ps = __ldg(w.pslot + (int64_t)b * w.N + i);
-  int r = -1;
-  if (ps >= 0) {
-    const uint32_t first_idx = (uint32_t)__ldg(w.table + (int64_t)b * w.cap + ps);
-    r = voxel_rank(w, b, first_idx);
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= w.ntiles) return;
+  const int n = w.cand_cnt[(int64_t)b * w.ntiles + t];
+  const uint2 *cand = w.cand + (int64_t)b * w.N + ((int64_t)t << kTileShift);
+  const unsigned long long *table = w.table + (int64_t)b * w.cap;
+  for (int j = threadIdx.x & 31; j < n; j += 32) {
+    const uint2 c = __ldg(cand + j);
+    const uint32_t first_idx = (uint32_t)__ldg(table + c.y);
+    const int r = voxel_rank(w, b, first_idx);
     if (r < w.max_voxels) {
-      slot_insert(w.slots + ((int64_t)b * w.max_voxels + r) * w.K, w.K, (uint32_t)i);
-    } else {
-      r = -1;
+      slot_insert(w.slots + ((int64_t)b * w.max_voxels + r) * w.K, w.K, c.x);
+      if (point2voxel) point2voxel[(int64_t)b * w.N + c.x] = r;
     }
   }
-  if (point2voxel) point2voxel[(int64_t)b * w.N + i] = r;
 }
 
 // K4 ------------------------------------------------------------------------
-// one thread per output float of voxels[b][r][k][c]; coalesced stores.
+// A CTA owns V consecutive voxels.  dynamic smem: tile[V*K*C] floats + idx[V*K] + list[V*K] u16.
 template <class Src>
-__global__ void __launch_bounds__(256) hv_emit_kernel(Src src, HvWork w, HvOut o) {
-  __shared__ float s_cal[Src::kNeedsSmem ? kMaxCams * kCalibFloats : 1];
+__global__ void __launch_bounds__(256) hv_emit_kernel(Src src, VoxelGrid g, HvWork w, HvOut o, int V) {
+  extern __shared__ float s_dyn[];
+  __shared__ float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 1];
+  __shared__ int s_count;
   const int b = blockIdx.y;
+  const int vn = o.voxel_num[b];
+  const int r0 = blockIdx.x * V;
+  if (r0 >= vn) return;
+  src.prepare(s_cal, b);
   const int C = src.num_feats();
-  const int64_t per_frame = (int64_t)w.max_voxels * w.K * C;
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int vn = o.voxel_num[b];
-  // whole block beyond the last valid voxel: nothing to do (uniform exit)
-  if ((int64_t)blockIdx.x * blockDim.x >= (int64_t)vn * w.K * C) return;
-  src.prepare(s_cal, b);
-  if (e >= (int64_t)vn * w.K * C) return;
-  const int64_t rk = e / C;
-  const int c = (int)(e - rk * C);
-  const uint32_t idx = __ldg(w.slots + (int64_t)b * w.max_voxels * w.K + rk);
-  float v = 0.0f;
-  if (idx != kEmpty32) v = src.feat(b, idx, c, s_cal);
-  o.voxels[(int64_t)b * per_frame + e] = v;
-}
+  const int K = w.K;
+  const int nvox = min(V, vn - r0);
+  const int items = nvox * K;
+  float *tile = s_dyn;
+  uint32_t *s_idx = reinterpret_cast<uint32_t *>(s_dyn + (size_t)V * K * C);
+  const uint32_t *S = w.slots + ((int64_t)b * w.max_voxels + r0) * K;
 
-// K5 ------------------------------------------------------------------------
-// one thread per voxel: coors (from its first point), count, HardSimpleVFE mean
-// (voxel_encoder.py:45-46: sum over ALL slots in slot order, then one division).
-template <class Src>
-__global__ void __launch_bounds__(256) hv_meta_kernel(Src src, VoxelGrid g, HvWork w, HvOut o) {
-  __shared__ float s_cal[Src::kNeedsSmem ? kMaxCams * kCalibFloats : 1];
-  const int b = blockIdx.y;
-  const int vn = o.voxel_num[b];
-  if ((int64_t)blockIdx.x * blockDim.x >= vn) return;
-  src.prepare(s_cal, b);
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= vn) return;
-  const uint32_t *S = w.slots + ((int64_t)b * w.max_voxels + r) * w.K;
-  const int64_t vr = (int64_t)b * w.max_voxels + r;
-  int cnt = 0;
-  float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-  const int F = o.F;
-  for (int k = 0; k < w.K; ++k) {
-    const uint32_t idx = __ldg(S + k);
-    if (idx == kEmpty32) break;
-    ++cnt;
-    float x, y, z;
-    src.feats3(b, idx, s_cal, x, y, z);
-    if (k == 0) {
-      int cx, cy, cz;
-      voxel_coor(x, y, z, g, cx, cy, cz);
-      o.coors[vr * 3 + 0] = cz;
-      o.coors[vr * 3 + 1] = cy;
-      o.coors[vr * 3 + 2] = cx;
-    }
-    if (o.mean) {
-      sx = __fadd_rn(sx, x);
-      sy = __fadd_rn(sy, y);
-      sz = __fadd_rn(sz, z);
-      // features beyond xyz (points source with C > 3)
-      for (int f = 3; f < F; ++f) {
-        float *m = o.mean + vr * F + f;
-        const float a = src.feat(b, idx, f, s_cal);
-        *m = (k == 0) ? a : __fadd_rn(*m, a);
+  // pass 1: slot indices; zero the tile; compact the non-empty items so that the
+  // (expensive) gather / re-unprojection below runs on dense lanes
+  uint16_t *s_list = reinterpret_cast<uint16_t *>(s_idx + (size_t)V * K);
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  for (int it0 = 0; it0 < items; it0 += blockDim.x) {
+    const int it = it0 + threadIdx.x;
+    uint32_t idx = kEmpty32;
+    if (it < items) {
+      idx = __ldg(S + it);
+      s_idx[it] = idx;
+      if (idx == kEmpty32) {
+        float *dst = tile + (size_t)it * C;
+        for (int c = 0; c < C; ++c) dst[c] = 0.0f;
       }
     }
+    const unsigned bal = __ballot_sync(0xffffffffu, idx != kEmpty32);
+    int wbase = 0;
+    if ((threadIdx.x & 31) == 0 && bal) wbase = atomicAdd(&s_count, __popc(bal));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (idx != kEmpty32) s_list[wbase + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = (uint16_t)it;
   }
-  o.num[vr] = cnt;
+  __syncthreads();
+  const int nfull = s_count;
+  for (int j = threadIdx.x; j < nfull; j += blockDim.x) {
+    const int it = s_list[j];
+    src.gather(b, s_idx[it], s_cal, tile + (size_t)it * C);
+  }
+  __syncthreads();
+
+  // voxels: contiguous nvox*K*C floats
+  float *vout = o.voxels + ((int64_t)b * w.max_voxels + r0) * K * C;
+  for (int e = threadIdx.x; e < items * C; e += blockDim.x) vout[e] = tile[e];
+
+  // per-voxel meta: coords from the first point, count
+  int *s_cnt = reinterpret_cast<int *>(s_list + (((size_t)V * K + 7) & ~(size_t)7));
+  for (int v = threadIdx.x; v < nvox; v += blockDim.x) {
+    int cnt = 0;
+    while (cnt < K && s_idx[v * K + cnt] != kEmpty32) ++cnt;
+    s_cnt[v] = cnt;
+    const float *p0 = tile + (size_t)v * K * C;
+    int cx = 0, cy = 0, cz = 0;
+    if (voxel_coor_fast(p0[0], p0[1], p0[2], 0.0f, g, cx, cy, cz) == 2)
+      voxel_coor(p0[0], p0[1], p0[2], g, cx, cy, cz);
+    const int64_t vr = (int64_t)b * w.max_voxels + r0 + v;
+    o.coors[vr * 3 + 0] = cz;
+    o.coors[vr * 3 + 1] = cy;
+    o.coors[vr * 3 + 2] = cx;
+    o.num[vr] = cnt;
+  }
+  // HardSimpleVFE (voxel_encoder.py:45-46): sum over ALL slots in slot order, one division
   if (o.mean) {
-    const float n = (float)cnt;
-    if (F > 0) o.mean[vr * F + 0] = __fdiv_rn(sx, n);
-    if (F > 1) o.mean[vr * F + 1] = __fdiv_rn(sy, n);
-    if (F > 2) o.mean[vr * F + 2] = __fdiv_rn(sz, n);
-    for (int f = 3; f < F; ++f) o.mean[vr * F + f] = __fdiv_rn(o.mean[vr * F + f], n);
+    __syncthreads();
+    const int F = o.F;
+    for (int t = threadIdx.x; t < nvox * F; t += blockDim.x) {
+      const int v = t / F, f = t - v * F;
+      const float *p = tile + (size_t)v * K * C + f;
+      float s = 0.0f;
+      for (int k = 0; k < K; ++k) s = __fadd_rn(s, p[(size_t)k * C]);
+      o.mean[((int64_t)b * w.max_voxels + r0 + v) * F + f] = __fdiv_rn(s, (float)s_cnt[v]);
+    }
   }
 }
 
@@ -383,31 +620,44 @@ struct HvPlan {
   int B;
   int K;
   int max_voxels;
+  int64_t S;          // points per insert round (multiple of kInsPoints)
+  int rounds;
   int64_t cap;
   int log2cap;
-  int nwords, nchunks;
-  size_t off_table, off_slots, off_pslot, off_flags, off_prefix, off_chunk, total;
+  int nwords, nchunks, ntiles;
+  // [table | slots] are set to 0xFF with one memset, [flags | round_claims] to 0 with another
+  size_t off_table, off_slots, off_flags, off_claims, off_ccount, off_prefix, off_chunk, off_cand, total;
 };
 
 inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels) {
   HvPlan p;
   p.N = N; p.B = B; p.K = K; p.max_voxels = max_voxels;
-  // capacity: power of two >= 1.25 N (worst case: every point its own voxel -> load <= 0.8)
-  int64_t want = N + N / 4 + 1;
+  const int64_t n1 = N > 0 ? N : 1;
+  // round length: at most 8 rounds unless that makes rounds shorter than 64 Ki points
+  int64_t S = ceil_div(ceil_div(n1, 8), kInsPoints) * kInsPoints;
+  if (S < 65536) S = 65536;
+  p.S = S;
+  p.rounds = (int)ceil_div(n1, S);
+  // the table never holds more than max_voxels + S keys (see header), nor more than N
+  int64_t keys = (int64_t)max_voxels + S;
+  if (keys > n1) keys = n1;
+  int64_t want = 2 * keys;
   int lg = 10;
   while (((int64_t)1 << lg) < want) ++lg;
   p.log2cap = lg;
   p.cap = (int64_t)1 << lg;
-  p.nchunks = (int)ceil_div(N > 0 ? N : 1, kChunkPoints);
+  p.nchunks = (int)ceil_div(n1, kChunkPoints);
   p.nwords = p.nchunks * kChunkWords;
+  p.ntiles = (int)ceil_div(n1, kTilePoints);
   size_t off = 0;
-  // table and slots are adjacent: one memset(0xFF) initialises both
   p.off_table = off; off += align_up((size_t)B * p.cap * 8);
   p.off_slots = off; off += align_up((size_t)B * max_voxels * K * 4);
-  p.off_pslot = off; off += align_up((size_t)B * (N > 0 ? N : 1) * 4);
   p.off_flags = off; off += align_up((size_t)B * p.nwords * 4);
+  p.off_claims = off; off += align_up((size_t)B * kMaxRounds * 4);
+  p.off_ccount = off; off += align_up((size_t)B * p.ntiles);
   p.off_prefix = off; off += align_up((size_t)B * p.nwords * 4);
   p.off_chunk = off; off += align_up((size_t)B * p.nchunks * 4);
+  p.off_cand = off; off += align_up((size_t)B * n1 * 8);
   p.total = off;
   return p;
 }
@@ -419,31 +669,54 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   HvWork w;
   w.table = (unsigned long long *)(base + p.off_table);
   w.slots = (uint32_t *)(base + p.off_slots);
-  w.pslot = (int32_t *)(base + p.off_pslot);
   w.flags = (uint32_t *)(base + p.off_flags);
+  w.round_claims = (int32_t *)(base + p.off_claims);
+  w.cand_cnt = (uint8_t *)(base + p.off_ccount);
+  w.ntiles = p.ntiles;
   w.wordprefix = (int32_t *)(base + p.off_prefix);
   w.chunk_base = (int32_t *)(base + p.off_chunk);
+  w.cand = (uint2 *)(base + p.off_cand);
   w.N = p.N; w.cap = p.cap; w.cap_mask = (uint32_t)(p.cap - 1); w.log2cap = p.log2cap;
   w.direct = (volume <= (uint64_t)p.cap) ? 1 : 0;
   w.nwords = p.nwords; w.nchunks = p.nchunks; w.K = p.K; w.max_voxels = p.max_voxels;
 
-  RD3_CUDA_TRY(cudaMemsetAsync(base + p.off_table, 0xFF, p.off_pslot - p.off_table, stream));
-  if (p.N > 0) {
-    dim3 gp((unsigned)ceil_div(p.N, 256), p.B);
-    hv_insert_kernel<Src><<<gp, 256, 0, stream>>>(src, g, w);
+  prof_mark(stream, 0);
+  RD3_CUDA_TRY(cudaMemsetAsync(base + p.off_table, 0xFF, p.off_flags - p.off_table, stream));
+  RD3_CUDA_TRY(cudaMemsetAsync(base + p.off_flags, 0, p.off_ccount - p.off_flags, stream));
+  if (out.point2voxel && p.N > 0)
+    RD3_CUDA_TRY(cudaMemsetAsync(out.point2voxel, 0xFF, (size_t)p.B * p.N * 4, stream));
+  prof_mark(stream, 1);
+  for (int r = 0; r < p.rounds && p.N > 0; ++r) {
+    const int64_t begin = (int64_t)r * p.S;
+    const int64_t end = begin + p.S < p.N ? begin + p.S : p.N;
+    dim3 grid((unsigned)ceil_div(end - begin, kInsPoints), p.B);
+    hv_insert_kernel<Src><<<grid, kInsThreads, 0, stream>>>(src, g, w, begin, end, r);
   }
-  hv_flags_kernel<<<dim3(p.nchunks, p.B), kScanThreads, 0, stream>>>(w);
+  prof_mark(stream, 2);
+  hv_first_kernel<<<dim3((unsigned)ceil_div(p.cap, 256), p.B), 256, 0, stream>>>(w);
+  hv_flagscan_kernel<<<dim3(p.nchunks, p.B), kScanThreads, 0, stream>>>(w);
+  prof_mark(stream, 3);
   scan_chunks_kernel<<<p.B, 1024, 0, stream>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels);
-  if (p.N > 0) {
-    dim3 gp((unsigned)ceil_div(p.N, 256), p.B);
-    hv_slots_kernel<<<gp, 256, 0, stream>>>(w, out.point2voxel);
+  prof_mark(stream, 4);
+  if (p.N > 0)
+    hv_slots_kernel<<<dim3((unsigned)ceil_div(p.ntiles, 8), p.B), 256, 0, stream>>>(w, out.point2voxel);
+  prof_mark(stream, 5);
+  {
+    const int C = src.host_num_feats();
+    int V = 1024 / p.K;            // ~1024 slot items per CTA: amortises the calibration staging
+    if (V < 1) V = 1;
+    if (V > 128) V = 128;
+    while (V > 1 && (size_t)V * p.K * (C + 1) * 4 > 40 * 1024) V /= 2;
+    const size_t smem = (size_t)V * p.K * (C + 1) * 4 + align_up((size_t)V * p.K * 2, 16) + (size_t)V * 4;
+    if (smem > 200 * 1024) return RD3_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024)
+      RD3_CUDA_TRY(cudaFuncSetAttribute(hv_emit_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, V), p.B), 256, smem, stream>>>(src, g, w,
+                                                                                              out, V);
   }
-  const int C = src.host_num_feats();
-  const int64_t elems = (int64_t)p.max_voxels * p.K * C;
-  if (elems > 0) {
-    hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(elems, 256), p.B), 256, 0, stream>>>(src, w, out);
-    hv_meta_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, 256), p.B), 256, 0, stream>>>(src, g, w, out);
-  }
+  prof_mark(stream, 6);
+  prof_mark(stream, 7);
   return check_launch();
 }
 

@@ -22,6 +22,11 @@ constexpr int kScanThreads = 256;
 void set_last_cuda_error(cudaError_t e);
 int check_launch();
 
+// Optional per-stage timing of the hard-voxel pipeline with CUDA events on the
+// launching stream (rd3_profile_enable / rd3_profile_read).  No-op when disabled.
+constexpr int kProfStages = 7;   // memset, insert, flags, scan, slots, emit, meta
+void prof_mark(cudaStream_t stream, int boundary);   // boundary 0..kProfStages
+
 #define RD3_CUDA_TRY(expr)                       \
   do {                                           \
     cudaError_t _e = (expr);                     \
@@ -40,8 +45,30 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 struct VoxelGrid {
   float lo[3];
   float vs[3];
+  float rvs[3];      // RN(1 / vs): only used by the conservative fast path
+  float lo_abs_max;  // max |lo[i]|
   int32_t grid[3];
 };
+
+// Exact unsigned division by a launch-invariant divisor (Granlund-Montgomery,
+// branch-free form): q = n / d for every 32-bit n, d >= 1.
+struct FastDiv {
+  uint32_t d, m, l;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t l = 1;
+  while (l < 32 && (1ull << l) < d) ++l;
+  f.l = l;
+  f.m = d <= 1 ? 0u : (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv &f) {
+  if (f.d == 1) return n;
+  const uint32_t q = __umulhi(f.m, n);
+  return (((n - q) >> 1) + q) >> (f.l - 1);
+}
 
 // host: grid = round((max-min)/vs) in fp32  (voxelization_cpu.cpp:121-124)
 int make_grid(const float voxel_size[3], const float coors_range[6], VoxelGrid *g,
@@ -69,6 +96,36 @@ __device__ __forceinline__ bool voxel_coor(float px, float py, float pz,
   return true;
 }
 
+// Conservative fast path for the same predicate.  f' = RN(RN(p - lo) * RN(1/vs))
+// differs from the exact quotient f by at most 2^-22 |f'| (three roundings of
+// 2^-24 each, with slack); `abs_err` bounds an additional absolute error of the
+// INPUT coordinate (0 for stored points; the reciprocal-based unprojection passes
+// its own bound).  If f' is farther than tol from every integer, floor(f') ==
+// floor(f) and the cell (or the out-of-range verdict) is exact.
+// Returns 1 inside, 0 outside, 2 undecided (caller must run voxel_coor()).
+__device__ __forceinline__ int voxel_coor_fast(float px, float py, float pz, float abs_err,
+                                               const VoxelGrid &g, int &cx, int &cy, int &cz) {
+  const float p[3] = {px, py, pz};
+  int c[3];
+  bool undecided = false, outside = false;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float f = __fmul_rn(__fsub_rn(p[j], g.lo[j]), g.rvs[j]);
+    const float fl = floorf(f);
+    // 2^-21 |f'| + input error in cells + an absolute floor (denormal inputs, exact integers)
+    const float tol = fmaf(abs_err, g.rvs[j], fmaf(4.76837158e-7f, fabsf(f), 1e-30f));
+    const float lo_gap = f - fl, hi_gap = (fl + 1.0f) - f;
+    // NaN / huge values fail both comparisons -> undecided -> exact path
+    if (!(lo_gap >= tol && hi_gap >= tol && fabsf(f) < 4194304.0f)) undecided = true;
+    if (!(fl >= 0.0f && fl < (float)g.grid[j])) outside = true;
+    c[j] = (int)fl;
+  }
+  if (undecided) return 2;
+  if (outside) return 0;
+  cx = c[0]; cy = c[1]; cz = c[2];
+  return 1;
+}
+
 // linear voxel id in (z,y,x) order == lexicographic order of the output coors
 __device__ __forceinline__ uint32_t voxel_key(int cx, int cy, int cz, const VoxelGrid &g) {
   return ((uint32_t)cz * (uint32_t)g.grid[1] + (uint32_t)cy) * (uint32_t)g.grid[0] + (uint32_t)cx;
@@ -85,7 +142,7 @@ __device__ __forceinline__ void key_to_zyx(uint32_t key, const VoxelGrid &g, int
 // Per-camera calibration staged in shared memory (16 floats per camera).
 //   [0]=fx [1]=fy [2]=cx [3]=cy  [4..12]=R row-major (M[:3,:3])  [13..15]=t (M[3,:3])
 // ---------------------------------------------------------------------------
-constexpr int kCalibFloats = 16;
+constexpr int kCalibFloats = 20;   // +[16]=RN(1/fx) [17]=RN(1/fy) [18]=max|R| [19]=max|t|
 constexpr int kMaxCams = 16;
 
 struct DepthParams {
@@ -99,6 +156,7 @@ struct DepthParams {
   int32_t use_sky;
   int32_t use_range;
   float range[6];
+  FastDiv div_hw, div_w;   // pixel index -> (cam, v, u)
 };
 
 __device__ __forceinline__ void stage_calibration(float *s_cal, const float *intr,
@@ -113,7 +171,16 @@ __device__ __forceinline__ void stage_calibration(float *s_cal, const float *int
     else if (j == 2) v = K[2];
     else if (j == 3) v = K[5];
     else if (j < 13) { int r = (j - 4) / 3, c = (j - 4) % 3; v = M[r * 4 + c]; }
-    else v = M[12 + (j - 13)];
+    else if (j < 16) v = M[12 + (j - 13)];
+    else if (j == 16) v = __frcp_rn(K[0]);
+    else if (j == 17) v = __frcp_rn(K[4]);
+    else if (j == 18) {
+      v = 0.0f;
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) v = fmaxf(v, fabsf(M[r * 4 + c]));
+    } else {
+      v = fmaxf(fabsf(M[12]), fmaxf(fabsf(M[13]), fabsf(M[14])));
+    }
     s_cal[i] = v;
   }
 }
@@ -121,26 +188,39 @@ __device__ __forceinline__ void stage_calibration(float *s_cal, const float *int
 // Pixel -> ego-frame point.  reconstruction_backbone.py:329-334,338-340,370.
 // Every fp32 operation is a separately rounded IEEE op; the only fused ops are
 // the two FMAs of the 3x3 product, in the order torch-CPU's sgemm evaluates it
-// (oracle/rd3_oracle.c: orc_unproject).
-__device__ __forceinline__ bool unproject_pixel(float z, float conf, bool sky, int u, int v,
-                                                const float *cal, const DepthParams &p,
-                                                float &ox, float &oy, float &oz) {
-  bool valid = (z > 0.0f) && (fabsf(z) <= 3.402823466e+38f);   // z > 0 & isfinite
-  if (p.use_max_depth) valid = valid && (z <= p.max_depth);
-  if (p.use_conf) valid = valid && (conf >= p.conf_thresh);
-  if (p.use_sky) valid = valid && !sky;
-  if (!valid) return false;
-  float x = __fdiv_rn(__fmul_rn(__fsub_rn((float)u, cal[2]), z), cal[0]);
-  float y = __fdiv_rn(__fmul_rn(__fsub_rn((float)v, cal[3]), z), cal[1]);
+// (oracle/rd3_oracle.c: orc_unproject).  `z` already passed the depth/conf/sky masks.
+__device__ __forceinline__ bool unproject_point(float z, int u, int v, const float *cal,
+                                                const DepthParams &p, float &ox, float &oy,
+                                                float &oz) {
+  const float x = __fdiv_rn(__fmul_rn(__fsub_rn((float)u, cal[2]), z), cal[0]);
+  const float y = __fdiv_rn(__fmul_rn(__fsub_rn((float)v, cal[3]), z), cal[1]);
   ox = __fadd_rn(__fmaf_rn(z, cal[6], __fmaf_rn(y, cal[5], __fmul_rn(x, cal[4]))), cal[13]);
   oy = __fadd_rn(__fmaf_rn(z, cal[9], __fmaf_rn(y, cal[8], __fmul_rn(x, cal[7]))), cal[14]);
   oz = __fadd_rn(__fmaf_rn(z, cal[12], __fmaf_rn(y, cal[11], __fmul_rn(x, cal[10]))), cal[15]);
-  if (p.use_range) {
+  if (p.use_range) {                       // respoint_post_processing.py:190-195, inclusive
     if (!(ox >= p.range[0] && ox <= p.range[3] && oy >= p.range[1] && oy <= p.range[4] &&
           oz >= p.range[2] && oz <= p.range[5]))
       return false;
   }
   return true;
+}
+
+// Reciprocal-based unprojection used ONLY to decide the voxel cell: identical to
+// unproject_point() except that the two divisions become multiplications by
+// RN(1/fx), RN(1/fy).  |x' - x| <= 2^-22 |x'| (same for y); pushing that and the
+// (at most 4) differing roundings through the 3x3 product gives
+//   |o' - o| <= 3 * 2^-22 * S,  S = (|x'| + |y'| + |z|) * max|R| + max|t|;
+// err = 2^-19 * S is returned (2.7x slack).
+__device__ __forceinline__ void unproject_point_approx(float z, int u, int v, const float *cal,
+                                                       float &ox, float &oy, float &oz,
+                                                       float &err) {
+  const float x = __fmul_rn(__fmul_rn(__fsub_rn((float)u, cal[2]), z), cal[16]);
+  const float y = __fmul_rn(__fmul_rn(__fsub_rn((float)v, cal[3]), z), cal[17]);
+  ox = __fadd_rn(__fmaf_rn(z, cal[6], __fmaf_rn(y, cal[5], __fmul_rn(x, cal[4]))), cal[13]);
+  oy = __fadd_rn(__fmaf_rn(z, cal[9], __fmaf_rn(y, cal[8], __fmul_rn(x, cal[7]))), cal[14]);
+  oz = __fadd_rn(__fmaf_rn(z, cal[12], __fmaf_rn(y, cal[11], __fmul_rn(x, cal[10]))), cal[15]);
+  // analysis gives 3 * 2^-22 * S; 2^-19 * S (+ a floor for denormal products) is used
+  err = fmaf(1.90734863e-6f, fmaf(fabsf(x) + fabsf(y) + fabsf(z), cal[18], cal[19]), 1e-30f);
 }
 
 // ---------------------------------------------------------------------------

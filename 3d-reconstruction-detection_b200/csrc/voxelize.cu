@@ -20,6 +20,29 @@ int check_launch() {
   return RD3_OK;
 }
 
+// ---- per-stage profiler ------------------------------------------------------
+namespace {
+constexpr int kProfMaxCalls = 1024;
+struct Profiler {
+  bool enabled = false;
+  int calls = 0;
+  bool in_call = false;
+  cudaEvent_t ev[kProfMaxCalls][kProfStages + 1];
+  bool created = false;
+} g_prof;
+}  // namespace
+
+void prof_mark(cudaStream_t stream, int boundary) {
+  if (!g_prof.enabled) return;
+  if (boundary == 0) g_prof.in_call = g_prof.calls < kProfMaxCalls;
+  if (!g_prof.in_call) return;
+  cudaEventRecord(g_prof.ev[g_prof.calls][boundary], stream);
+  if (boundary == kProfStages) {
+    ++g_prof.calls;
+    g_prof.in_call = false;
+  }
+}
+
 int make_grid(const float voxel_size[3], const float coors_range[6], VoxelGrid *g,
               uint64_t *volume) {
   for (int i = 0; i < 3; ++i) {
@@ -31,7 +54,9 @@ int make_grid(const float voxel_size[3], const float coors_range[6], VoxelGrid *
     const float r = roundf(q);
     if (!(r >= 1.0f && r < 2147483648.0f)) return RD3_ERR_INVALID_ARGUMENT;
     g->grid[i] = (int32_t)r;
+    g->rvs[i] = (float)(1.0 / (double)voxel_size[i]);
   }
+  g->lo_abs_max = fmaxf(fabsf(g->lo[0]), fmaxf(fabsf(g->lo[1]), fabsf(g->lo[2])));
   uint64_t vol = 1;
   for (int i = 0; i < 3; ++i) {
     vol *= (uint64_t)g->grid[i];
@@ -107,6 +132,33 @@ const char *rd3_status_string(int status) {
 }
 
 const char *rd3_last_cuda_error(void) { return cudaGetErrorString(g_last_error); }
+
+int rd3_profile_enable(int on) {
+  if (on && !g_prof.created) {
+    for (int c = 0; c < kProfMaxCalls; ++c)
+      for (int b = 0; b <= kProfStages; ++b) RD3_CUDA_TRY(cudaEventCreate(&g_prof.ev[c][b]));
+    g_prof.created = true;
+  }
+  g_prof.enabled = on != 0;
+  g_prof.calls = 0;
+  g_prof.in_call = false;
+  return RD3_OK;
+}
+
+int rd3_profile_read(double *stage_ms, int *calls) {
+  if (!stage_ms || !calls) return RD3_ERR_INVALID_ARGUMENT;
+  for (int s = 0; s < kProfStages; ++s) stage_ms[s] = 0.0;
+  *calls = g_prof.calls;
+  for (int c = 0; c < g_prof.calls; ++c) {
+    RD3_CUDA_TRY(cudaEventSynchronize(g_prof.ev[c][kProfStages]));
+    for (int s = 0; s < kProfStages; ++s) {
+      float ms = 0.0f;
+      RD3_CUDA_TRY(cudaEventElapsedTime(&ms, g_prof.ev[c][s], g_prof.ev[c][s + 1]));
+      stage_ms[s] += ms;
+    }
+  }
+  return RD3_OK;
+}
 
 int rd3_grid_size(const float voxel_size[3], const float coors_range[6], int32_t grid[3]) {
   if (!voxel_size || !coors_range || !grid) return RD3_ERR_INVALID_ARGUMENT;

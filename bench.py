@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- fused depth unprojection + hard voxelization (+ voxel mean) throughput.
+
+Workload (BASELINE.json configs[1], "C2"): per GPU a batch of synthetic nuScenes-
+shaped frames, 6 cameras x 504 x 896 DA3 depth (2 709 504 pixels/frame), voxel
+(0.075, 0.075, 0.2) m, range (-54,-54,-5,54,54,3), max_points 10, max_voxels
+120 000, max_depth 100.  One "step" = one pass of the hot path
+over the whole batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a path
+    python bench.py --impl reference [--gpus N --steps K --warmup W] # reference CPU path, host cores
+
+Prints ONE JSON line (rank 0).  `value` is pixels(points)/s over all GPUs with the
+inputs resident in HBM; `e2e` is the same through the public API from pinned HOST
+buffers with every host<->device copy inside the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "points_per_sec_unproject_voxelize_scatter"
+UNIT = "points/s"
+WORKLOAD = "C2"
+
+
+# --------------------------------------------------------------------------------------
+# reference / CPU baseline (the ONLY place bench.py touches oracle/)
+# --------------------------------------------------------------------------------------
+def _cpu_worker_init(hw, cfg_name, frame_ids, nthreads):
+    global _W
+    import torch
+    torch.set_num_threads(nthreads)
+    import oracle
+    from oracle import torch_restatement as tr
+    from rd3_b200 import synthetic
+    ref = oracle.ref_voxel_layer()
+    frames = [synthetic.make_frame(i, hw[0], hw[1], with_conf=False) for i in frame_ids]
+    _W = dict(torch=torch, oracle=oracle, tr=tr, ref=ref, frames=frames,
+              cfg=synthetic.CONFIGS[cfg_name], max_depth=synthetic.MAX_DEPTH)
+
+
+def _cpu_one_frame(f):
+    """The reference's CPU path for one frame: torch-CPU unprojection
+    (reconstruction_backbone.py:305-386) -> hard_voxelize_cpu (the reference's own C++,
+    oracle/_ref; or the C port when that was never built) -> HardSimpleVFE."""
+    W = _W
+    torch, tr, cfg = W["torch"], W["tr"], W["cfg"]
+    pts = tr.backproject_depth_to_points(f["depth"][None], f["intrinsics"][None], f["cam2lidar"][None],
+                                         max_depth=W["max_depth"])[0]
+    mv = cfg["max_voxels"][0]
+    if W["ref"] is not None:
+        v, c, n = tr.voxelization_forward(W["ref"], pts.contiguous(), list(cfg["voxel_size"]),
+                                          list(cfg["pcr"]), cfg["max_points"], mv)
+    else:
+        v, c, n = W["oracle"].hard_voxelize(pts.numpy(), list(cfg["voxel_size"]), list(cfg["pcr"]),
+                                            cfg["max_points"], mv)
+        v, n = torch.from_numpy(v), torch.from_numpy(n)
+    mean = tr.hard_simple_vfe(v, n, 3)
+    return int(mean.shape[0])
+
+
+def _cpu_worker_run(_):
+    t0 = time.perf_counter()
+    m = [_cpu_one_frame(f) for f in _W["frames"]]
+    return time.perf_counter() - t0, m
+
+
+class CpuReference:
+    """Process-parallel reference path: one frame per worker per step (hard_voxelize_cpu is
+    single-threaded by construction, so the host is filled with independent frames)."""
+
+    def __init__(self, cfg_name, workers=None, frames_per_worker=1):
+        import multiprocessing as mp
+        from rd3_b200 import synthetic
+        import oracle
+        ncpu = os.cpu_count() or 1
+        self.workers = workers or max(1, min(ncpu, 32))
+        self.frames_per_worker = frames_per_worker
+        self.kind = "reference" if oracle.ref_voxel_layer() is not None else "port"
+        hw = synthetic.CONFIGS[cfg_name]["hw"]
+        self.pix_per_frame = 6 * hw[0] * hw[1]
+        ctx = mp.get_context("spawn")
+        self.pools = []
+        for w in range(self.workers):
+            ids = [10000 + w * frames_per_worker + k for k in range(frames_per_worker)]
+            self.pools.append(ctx.Pool(1, initializer=_cpu_worker_init, initargs=(hw, cfg_name, ids, 1)))
+        # make sure every worker finished its init before anything is timed
+        for p in self.pools:
+            p.apply(int, (0,))
+
+    def step(self):
+        """Run one bounded sample on all workers; returns (wall seconds, frames)."""
+        t0 = time.perf_counter()
+        res = [p.apply_async(_cpu_worker_run, (0,)) for p in self.pools]
+        out = [r.get() for r in res]
+        wall = time.perf_counter() - t0
+        return wall, self.workers * self.frames_per_worker, out
+
+    def close(self):
+        for p in self.pools:
+            p.terminate()
+
+    def describe(self):
+        return "%d frames (one 6x504x896 frame per worker process, %d workers): torch-CPU unprojection + %s hard_voxelize_cpu + HardSimpleVFE" % (
+            self.workers * self.frames_per_worker, self.workers,
+            "the reference's compiled" if self.kind == "reference" else "C-port")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ref = CpuReference(WORKLOAD, workers=args.cpu_workers)
+    for _ in range(args.warmup):
+        ref.step()
+    t = 0.0
+    frames = 0
+    for _ in range(args.steps):
+        w, f, _o = ref.step()
+        t += w
+        frames += f
+    ref.close()
+    value = frames * ref.pix_per_frame / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "frames_per_sec": frames / t,
+        "config": {"workload": WORKLOAD + ": fused depth unprojection + hard voxelization, 6x504x896 depth, "
+                               "voxel 0.075/0.075/0.2, max_points 10, max_voxels 120000",
+                   "frames_per_step": ref.workers},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.workers, "kind": ref.kind,
+                         "sample": ref.describe()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--cpu-workers", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="also time the NCCL all_gather of the outputs")
+    ap.add_argument("--profile-only", action="store_true",
+                    help="few steps, no e2e / cpu baseline (the command profiled under ncu)")
+    args = ap.parse_args()
+    if args.warmup < 3 and not args.profile_only:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import rd3_b200
+    from rd3_b200 import _lib, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = synthetic.CONFIGS[WORKLOAD]
+    H, W = cfg["hw"]
+    B = args.frames
+    K, mv = cfg["max_points"], cfg["max_voxels"][0]
+    npix = 6 * H * W
+
+    # weak scaling: every rank owns B frames (frame ids disjoint across ranks)
+    host = synthetic.make_batch([rank * B + i for i in range(B)], H, W, with_conf=False)
+    depth_h = host["depth"].pin_memory()
+    intr_h, c2l_h = host["intrinsics"].pin_memory(), host["cam2lidar"].pin_memory()
+    depth, intr, c2l = depth_h.to(dev), intr_h.to(dev), c2l_h.to(dev)
+
+    mod = rd3_b200.DepthToVoxels(cfg["voxel_size"], cfg["pcr"], K, cfg["max_voxels"],
+                                 max_depth=synthetic.MAX_DEPTH).to(dev).train()
+
+    def step():
+        return mod(depth, intr, c2l)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        r = step()
+    barrier()
+    vn = r["voxel_num"].tolist()
+    M_total = int(sum(vn))
+
+    # ---- device-resident timed region ------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    time.sleep(0.3)
+    _lib.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    stage_ms, calls = _lib.profile_read()
+    _lib.profile_enable(False)
+    clk = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = world * B * npix / (ms_per_step * 1e-3)
+
+    # ---- optional: NCCL gather of the outputs (north_star: only collective on the path) --
+    gather_ms = None
+    if args.gather and world > 1:
+        outs = [r["voxel_mean"], r["coors"], r["num_points"], r["voxel_num"]]
+        bufs = [torch.empty((world,) + tuple(o.shape), dtype=o.dtype, device=dev) for o in outs]
+        for _ in range(2):
+            for o, bf in zip(outs, bufs):
+                dist.all_gather_into_tensor(bf, o)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for o, bf in zip(outs, bufs):
+            dist.all_gather_into_tensor(bf, o)
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather_ms = float(tg.item())
+
+    # ---- roofline of the dominant kernel + of the whole fused path ---------------------
+    hbm_peak, peak_src = 6650.0, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    C = F = 3
+    # ALGORITHMIC bytes per launch (DESIGN.md "Kernels"): compulsory reads+writes only
+    alg = {
+        "insert": B * npix * 4,                                 # depth read
+        "flags": 0, "scan": 0, "slots": 0, "memset": 0,         # scratch-only stages
+        "emit": M_total * K * C * 4,                            # voxels written
+        "meta": M_total * (12 + 4 + 4 * F),                     # coors + num + mean written
+    }
+    path_bytes = B * npix * 4 + M_total * (K * 4 * C + 16) + M_total * 4 * F
+    kern = {k: v for k, v in stage_ms.items() if k != "memset"}
+    dom = max(kern, key=kern.get) if calls else "insert"
+    dom_ms = stage_ms[dom] / max(calls, 1)
+    dom_achieved = alg[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    path_achieved = path_bytes / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "hv_%s_kernel" % dom, "achieved": dom_achieved, "peak": hbm_peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": dom_achieved / hbm_peak, "traffic": None,
+                "ms_per_launch": dom_ms, "algorithmic_bytes_per_launch": alg[dom]}
+    traffic_file = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            tr_ = json.load(open(traffic_file))
+            if tr_.get("kernel") == roofline["kernel"]:
+                roofline["traffic"] = tr_.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    path_roofline = {"bound": "hbm", "achieved": path_achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": path_achieved / hbm_peak, "algorithmic_bytes_per_step": path_bytes,
+                     "stage_ms_per_step": {k: v / max(calls, 1) for k, v in stage_ms.items()}}
+
+    # ---- e2e: public API from pinned host buffers, copies inside the timed region ------
+    e2e = None
+    if not args.no_e2e and not args.profile_only:
+        chunk = 8 if B % 8 == 0 else B
+        nchunks = B // chunk
+        nstreams = min(3, nchunks)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
+        mods = [rd3_b200.DepthToVoxels(cfg["voxel_size"], cfg["pcr"], K, cfg["max_voxels"],
+                                       max_depth=synthetic.MAX_DEPTH).to(dev).train() for _ in range(nstreams)]
+        d_in = [torch.empty((chunk, 6, H, W), device=dev) for _ in range(nstreams)]
+        h_out = dict(voxels=torch.empty((B, mv, K, 3), pin_memory=True),
+                     coors=torch.empty((B, mv, 3), dtype=torch.int32, pin_memory=True),
+                     num_points=torch.empty((B, mv), dtype=torch.int32, pin_memory=True),
+                     voxel_mean=torch.empty((B, mv, 3), pin_memory=True),
+                     voxel_num=torch.empty((B,), dtype=torch.int32, pin_memory=True))
+        h2d = depth_h.numel() * 4 + intr_h.numel() * 4 + c2l_h.numel() * 4
+        d2h = sum(v.numel() * v.element_size() for v in h_out.values())
+
+        def e2e_step():
+            for ci in range(nchunks):
+                s = streams[ci % nstreams]
+                sl = slice(ci * chunk, (ci + 1) * chunk)
+                with torch.cuda.stream(s):
+                    d_in[ci % nstreams].copy_(depth_h[sl], non_blocking=True)
+                    k_d = intr_h[sl].to(dev, non_blocking=True)
+                    m_d = c2l_h[sl].to(dev, non_blocking=True)
+                    rr = mods[ci % nstreams](d_in[ci % nstreams], k_d, m_d)
+                    for name, hbuf in h_out.items():
+                        hbuf[sl].copy_(rr[name], non_blocking=True)
+            for s in streams:
+                s.synchronize()
+
+        n_e2e = max(2, min(args.steps, 5))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * npix * n_e2e / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
+               "frames_per_sec": world * B * n_e2e / float(dt.item()),
+               "how": "pinned host depth/calibration -> %d-frame chunks on %d streams (H2D, fused kernels, D2H of "
+                      "voxels+coors+num+mean+count) through rd3_b200.DepthToVoxels" % (chunk, nstreams)}
+        assert torch.equal(h_out["voxel_num"], r["voxel_num"].cpu())
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) --------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile_only:
+        ref = CpuReference(WORKLOAD, workers=args.cpu_workers)
+        ref.step()
+        tt, ff = 0.0, 0
+        while tt < 10.0 and ff < 8 * ref.workers:
+            w, f, _o = ref.step()
+            tt += w
+            ff += f
+        ref.close()
+        cpu_baseline = {"value": ff * npix / tt, "unit": UNIT, "cores": ref.workers, "kind": ref.kind,
+                        "frames_per_sec": ff / tt, "sample": ref.describe() + ", %d frames in %.1f s" % (ff, tt)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "frames_per_sec": world * B / (ms_per_step * 1e-3),
+            "config": {"workload": WORKLOAD + ": fused depth unprojection + hard voxelization + voxel mean, "
+                                   "6x504x896 depth, voxel 0.075/0.075/0.2, max_points 10, max_voxels 120000, "
+                                   "max_depth 100",
+                       "frames_per_gpu_per_step": B, "pixels_per_frame": npix,
+                       "voxels_per_frame_mean": M_total / B,
+                       "l2": "inputs larger than L2 (%.0f MB depth per step per GPU vs 126 MB L2)" % (B * npix * 4 / 1e6),
+                       "parallelism": "frames sharded by sample, %d per GPU, no data-path collective" % B},
+            "clocks": clk, "gpu_launches": 6 * args.steps,
+            "roofline": roofline, "path_roofline": path_roofline,
+            "e2e": e2e, "cpu_baseline": cpu_baseline,
+        }
+        if gather_ms is not None:
+            line["gather_ms"] = gather_ms
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

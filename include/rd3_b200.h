@@ -55,6 +55,16 @@ RD3_API const char *rd3_status_string(int status);
 /* cudaGetErrorString of the last CUDA failure seen by this library (host string). */
 RD3_API const char *rd3_last_cuda_error(void);
 
+/* Per-stage timing of the hard-voxel pipeline (rd3_hard_voxelize and
+ * rd3_depth_to_voxels) with CUDA events recorded on the launching stream between
+ * its kernels.  Stages: 0 memset, 1 insert, 2 flags, 3 chunk scan, 4 slots,
+ * 5 emit, 6 meta.  rd3_profile_enable(1) resets the counters; rd3_profile_read
+ * waits for the recorded events and returns the summed milliseconds per stage
+ * (host double[7]) and the number of calls covered (at most 1024). */
+#define RD3_PROFILE_STAGES 7
+RD3_API int rd3_profile_enable(int on);
+RD3_API int rd3_profile_read(double *stage_ms, int *calls);
+
 /* grid = round((max - min) / voxel_size) in fp32, x,y,z order.
  * Replaces the inline computation at voxelization_cpu.cpp:121-124 /
  * voxelize.py:113-121.  Host-only helper (voxel_size, coors_range, grid: host). */
