@@ -114,6 +114,10 @@ static int make_depth_source(const float *depth, const float *intrinsics, const 
   d.use_max_depth = p->use_max_depth; d.max_depth = p->max_depth;
   d.use_conf = conf != nullptr; d.conf_thresh = p->conf_thresh;
   d.use_sky = sky != nullptr;
+  d.use_masks = d.use_conf || d.use_sky;
+  d.zmax = 3.402823466e+38f;
+  if (p->use_max_depth && p->max_depth < d.zmax) d.zmax = p->max_depth;   // NaN max_depth: comparison false
+  if (p->use_max_depth && !(p->max_depth == p->max_depth)) d.zmax = -1.0f; // z <= NaN is never true
   d.use_range = p->use_range;
   for (int i = 0; i < 6; ++i) d.range[i] = p->range[i];
   d.div_hw = make_fastdiv((uint32_t)d.HW);

@@ -31,6 +31,8 @@
 // Templated on the point source: a (N,C) point array, or DA3 depth maps
 // unprojected on the fly (the point cloud never exists in memory).
 #pragma once
+#include <stdlib.h>
+
 #include "rd3_common.cuh"
 
 namespace rd3 {
@@ -69,9 +71,12 @@ struct PointsSource {
     x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
     return true;
   }
+  struct TileOrigin {};
+  __device__ __forceinline__ TileOrigin tile_origin(int64_t) const { return TileOrigin(); }
   // stage B: voxel cell of point i.  cell_fast: 1 inside / 0 outside / 2 undecided (-> cell_exact)
-  __device__ __forceinline__ int cell_fast(int b, int64_t i, int lid, const float *s_cal, const float *s_z,
-                                           const VoxelGrid &g, int &cx, int &cy, int &cz) const {
+  __device__ __forceinline__ int cell_fast(int b, int64_t i, int lid, const TileOrigin &, const float *s_cal,
+                                           const float *s_z, const VoxelGrid &g, int &cx, int &cy,
+                                           int &cz) const {
     float x, y, z;
     point(b, i, lid, s_cal, s_z, x, y, z);
     return voxel_coor_fast(x, y, z, 0.0f, g, cx, cy, cz);
@@ -117,11 +122,24 @@ struct DepthSource {
   __device__ __forceinline__ int num_feats() const { return 3; }
 
   __device__ __forceinline__ bool depth_ok(float z, int64_t gidx) const {
-    bool ok = (z > 0.0f) && (z <= 3.402823466e+38f);            // z > 0 & isfinite (:338)
-    if (p.use_max_depth) ok = ok && (z <= p.max_depth);          // :339-340
-    if (ok && p.use_conf) ok = __ldg(conf + gidx) >= p.conf_thresh;
-    if (ok && p.use_sky) ok = __ldg(sky + gidx) == 0;
+    // z > 0 & isfinite(z) [& z <= max_depth] (:338-340); p.zmax = min(max_depth, FLT_MAX)
+    bool ok = (z > 0.0f) && (z <= p.zmax);
+    if (p.use_masks) {
+      if (ok && p.use_conf) ok = __ldg(conf + gidx) >= p.conf_thresh;
+      if (ok && p.use_sky) ok = __ldg(sky + gidx) == 0;
+    }
     return ok;
+  }
+  // (cam, v, u) of the first pixel of a tile; lanes then offset by their local id
+  struct TileOrigin { uint32_t cam, v, u; };
+  __device__ __forceinline__ TileOrigin tile_origin(int64_t base) const {
+    TileOrigin t;
+    const uint32_t pix = (uint32_t)base;
+    t.cam = fast_div(pix, p.div_hw);
+    const uint32_t rem = pix - t.cam * (uint32_t)p.HW;
+    t.v = fast_div(rem, p.div_w);
+    t.u = rem - t.v * (uint32_t)p.W;
+    return t;
   }
   __device__ __forceinline__ unsigned valid4(int b, int64_t i, float *s_z4) const {
     const int64_t g = (int64_t)b * p.npix + i;
@@ -155,14 +173,23 @@ struct DepthSource {
   // stage B: voxel cell of pixel i.  cell_fast decides the cell with reciprocal arithmetic and
   // a rigorous error bound (1 inside / 0 outside); pixels within that bound of a cell or
   // range-filter boundary return 2 and are re-done by cell_exact with the IEEE divisions.
-  __device__ __forceinline__ int cell_fast(int b, int64_t i, int lid, const float *s_cal, const float *s_z,
+  __device__ __forceinline__ int cell_fast(int b, int64_t i, int lid, const TileOrigin &t0,
+                                           const float *s_cal, const float *s_z,
                                            const VoxelGrid &g, int &cx, int &cy, int &cz) const {
     const float d = s_z[lid];
-    const uint32_t pix = (uint32_t)i;
-    const uint32_t cam = fast_div(pix, p.div_hw);
-    const uint32_t rem = pix - cam * (uint32_t)p.HW;
-    const uint32_t v = fast_div(rem, p.div_w);
-    const uint32_t u = rem - v * (uint32_t)p.W;
+    uint32_t cam = t0.cam, v = t0.v, u = t0.u + (uint32_t)lid;
+    if (p.W >= kTilePoints) {            // at most one row wrap inside a 128-pixel tile
+      if (u >= (uint32_t)p.W) {
+        u -= (uint32_t)p.W;
+        if (++v >= (uint32_t)p.H) { v = 0; ++cam; }
+      }
+    } else {
+      const uint32_t pix = (uint32_t)i;
+      cam = fast_div(pix, p.div_hw);
+      const uint32_t rem = pix - cam * (uint32_t)p.HW;
+      v = fast_div(rem, p.div_w);
+      u = rem - v * (uint32_t)p.W;
+    }
     float x, y, z, err;
     unproject_point_approx(d, (int)u, (int)v, s_cal + cam * kCalibFloats, x, y, z, err);
     int r = voxel_coor_fast(x, y, z, err, g, cx, cy, cz);
@@ -201,6 +228,7 @@ struct HvWork {
   uint2 *cand;                // [B][N] (point idx, table slot); tile t owns [t*128, t*128+128)
   int ntiles;
   int64_t N;
+  int b0;                     // first frame of the group this launch works on
   int64_t cap;
   uint32_t cap_mask;
   int log2cap;
@@ -278,7 +306,7 @@ __global__ void __launch_bounds__(kInsThreads)
   __shared__ uint8_t s_l1b[kInsPoints], s_l2b[kInsPoints], s_undb[kInsPoints];
   __shared__ int s_prev;
 
-  const int b = blockIdx.y;
+  const int b = blockIdx.y + w.b0;
   const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const int64_t block_base = begin + (int64_t)blockIdx.x * kInsPoints;
@@ -319,6 +347,7 @@ __global__ void __launch_bounds__(kInsThreads)
   __syncwarp();
 
   // ---- stage B --------------------------------------------------------------------
+  const typename Src::TileOrigin t0 = src.tile_origin(base);
   int n2 = 0, nu = 0;
 #pragma unroll 1
   for (int j0 = 0; j0 < nv; j0 += 32) {
@@ -326,7 +355,7 @@ __global__ void __launch_bounds__(kInsThreads)
     int r = 0, lid = 0, cx, cy, cz;
     if (j < nv) {
       lid = s_l1[j];
-      r = src.cell_fast(b, base + lid, lid, s_cal, s_z, g, cx, cy, cz);
+      r = src.cell_fast(b, base + lid, lid, t0, s_cal, s_z, g, cx, cy, cz);
     }
     const unsigned b1 = __ballot_sync(0xffffffffu, r == 1);
     const unsigned b2 = __ballot_sync(0xffffffffu, r == 2);
@@ -392,7 +421,7 @@ __global__ void __launch_bounds__(kInsThreads)
 // K2a -----------------------------------------------------------------------
 // every table entry marks its voxel's first point.  grid (cap/256, B).
 static __global__ void __launch_bounds__(256) hv_first_kernel(HvWork w) {
-  const int b = blockIdx.y;
+  const int b = blockIdx.y + w.b0;
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= w.cap) return;
   const unsigned long long e = w.table[(int64_t)b * w.cap + s];
@@ -405,7 +434,7 @@ static __global__ void __launch_bounds__(256) hv_first_kernel(HvWork w) {
 // grid (nchunks, B), kScanThreads threads, one flag word each.
 static __global__ void __launch_bounds__(kScanThreads) hv_flagscan_kernel(HvWork w) {
   __shared__ int s_warp[kScanThreads / 32];
-  const int b = blockIdx.y;
+  const int b = blockIdx.y + w.b0;
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
   const int64_t wi = (int64_t)b * w.nwords + (int64_t)blockIdx.x * kChunkWords + threadIdx.x;
   const int cnt = __popc(w.flags[wi]);
@@ -450,10 +479,11 @@ __device__ __forceinline__ void chunk_scan_store(uint32_t my_word, int *s_warp, 
 // one CTA per frame: exclusive scan of the chunk totals in place; the frame's
 // total (clamped) goes to out_total[b].
 static __global__ void __launch_bounds__(1024) scan_chunks_kernel(int32_t *chunk_base, int nchunks,
-                                                                  int32_t *out_total, int clamp) {
+                                                                  int32_t *out_total, int clamp,
+                                                                  int b0 = 0) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x + b0;
   int32_t *cb = chunk_base + (int64_t)b * nchunks;
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_carry = 0;
@@ -511,7 +541,7 @@ __device__ __forceinline__ void slot_insert(uint32_t *S, int K, uint32_t idx) {
 // K3 ------------------------------------------------------------------------
 // grid (ceil(ntiles/8), B), 256 threads: one warp per 128-point tile region.
 static __global__ void __launch_bounds__(256) hv_slots_kernel(HvWork w, int32_t *point2voxel) {
-  const int b = blockIdx.y;
+  const int b = blockIdx.y + w.b0;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= w.ntiles) return;
   const int n = w.cand_cnt[(int64_t)b * w.ntiles + t];
@@ -535,7 +565,7 @@ __global__ void __launch_bounds__(256) hv_emit_kernel(Src src, VoxelGrid g, HvWo
   extern __shared__ float s_dyn[];
   __shared__ float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 1];
   __shared__ int s_count;
-  const int b = blockIdx.y;
+  const int b = blockIdx.y + w.b0;
   const int vn = o.voxel_num[b];
   const int r0 = blockIdx.x * V;
   if (r0 >= vn) return;
@@ -680,43 +710,58 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   w.direct = (volume <= (uint64_t)p.cap) ? 1 : 0;
   w.nwords = p.nwords; w.nchunks = p.nchunks; w.K = p.K; w.max_voxels = p.max_voxels;
 
-  prof_mark(stream, 0);
-  RD3_CUDA_TRY(cudaMemsetAsync(base + p.off_table, 0xFF, p.off_flags - p.off_table, stream));
-  RD3_CUDA_TRY(cudaMemsetAsync(base + p.off_flags, 0, p.off_ccount - p.off_flags, stream));
+  // Frames are processed in groups small enough that a group's table, slot arrays and
+  // candidate lists stay resident in the 126 MB L2 from the memset to the emit kernel:
+  // the random table / slot accesses then never go to HBM.
+  const size_t per_frame = (size_t)p.cap * 8 + (size_t)p.max_voxels * p.K * 4 + (size_t)p.nwords * 8;
+  int G = (int)((48u << 20) / (per_frame ? per_frame : 1));
+  if (const char *e = getenv("RD3_GROUP")) G = atoi(e);
+  if (G < 1) G = 1;
+  if (G > p.B) G = p.B;
+  const int C = src.host_num_feats();
+  int V = 1024 / p.K;            // ~1024 slot items per CTA: amortises the calibration staging
+  if (V < 1) V = 1;
+  if (V > 128) V = 128;
+  while (V > 1 && (size_t)V * p.K * (C + 1) * 4 > 40 * 1024) V /= 2;
+  const size_t smem = (size_t)V * p.K * (C + 1) * 4 + align_up((size_t)V * p.K * 2, 16) + (size_t)V * 4;
+  if (smem > 200 * 1024) return RD3_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    RD3_CUDA_TRY(cudaFuncSetAttribute(hv_emit_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
   if (out.point2voxel && p.N > 0)
     RD3_CUDA_TRY(cudaMemsetAsync(out.point2voxel, 0xFF, (size_t)p.B * p.N * 4, stream));
-  prof_mark(stream, 1);
-  for (int r = 0; r < p.rounds && p.N > 0; ++r) {
-    const int64_t begin = (int64_t)r * p.S;
-    const int64_t end = begin + p.S < p.N ? begin + p.S : p.N;
-    dim3 grid((unsigned)ceil_div(end - begin, kInsPoints), p.B);
-    hv_insert_kernel<Src><<<grid, kInsThreads, 0, stream>>>(src, g, w, begin, end, r);
+
+  for (int b0 = 0; b0 < p.B; b0 += G) {
+    const int nb = (p.B - b0 < G) ? p.B - b0 : G;
+    w.b0 = b0;
+    prof_mark(stream, 0);
+    RD3_CUDA_TRY(cudaMemsetAsync(w.table + (size_t)b0 * p.cap, 0xFF, (size_t)nb * p.cap * 8, stream));
+    RD3_CUDA_TRY(cudaMemsetAsync(w.slots + (size_t)b0 * p.max_voxels * p.K, 0xFF,
+                                 (size_t)nb * p.max_voxels * p.K * 4, stream));
+    RD3_CUDA_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords, 0, (size_t)nb * p.nwords * 4, stream));
+    RD3_CUDA_TRY(cudaMemsetAsync(w.round_claims + (size_t)b0 * kMaxRounds, 0, (size_t)nb * kMaxRounds * 4,
+                                 stream));
+    prof_mark(stream, 1);
+    for (int r = 0; r < p.rounds && p.N > 0; ++r) {
+      const int64_t begin = (int64_t)r * p.S;
+      const int64_t end = begin + p.S < p.N ? begin + p.S : p.N;
+      dim3 grid((unsigned)ceil_div(end - begin, kInsPoints), nb);
+      hv_insert_kernel<Src><<<grid, kInsThreads, 0, stream>>>(src, g, w, begin, end, r);
+    }
+    prof_mark(stream, 2);
+    hv_first_kernel<<<dim3((unsigned)ceil_div(p.cap, 256), nb), 256, 0, stream>>>(w);
+    hv_flagscan_kernel<<<dim3(p.nchunks, nb), kScanThreads, 0, stream>>>(w);
+    prof_mark(stream, 3);
+    scan_chunks_kernel<<<nb, 1024, 0, stream>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels, b0);
+    prof_mark(stream, 4);
+    if (p.N > 0)
+      hv_slots_kernel<<<dim3((unsigned)ceil_div(p.ntiles, 8), nb), 256, 0, stream>>>(w, out.point2voxel);
+    prof_mark(stream, 5);
+    hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, V), nb), 256, smem, stream>>>(src, g, w, out,
+                                                                                             V);
+    prof_mark(stream, 6);
+    prof_mark(stream, 7);
   }
-  prof_mark(stream, 2);
-  hv_first_kernel<<<dim3((unsigned)ceil_div(p.cap, 256), p.B), 256, 0, stream>>>(w);
-  hv_flagscan_kernel<<<dim3(p.nchunks, p.B), kScanThreads, 0, stream>>>(w);
-  prof_mark(stream, 3);
-  scan_chunks_kernel<<<p.B, 1024, 0, stream>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels);
-  prof_mark(stream, 4);
-  if (p.N > 0)
-    hv_slots_kernel<<<dim3((unsigned)ceil_div(p.ntiles, 8), p.B), 256, 0, stream>>>(w, out.point2voxel);
-  prof_mark(stream, 5);
-  {
-    const int C = src.host_num_feats();
-    int V = 1024 / p.K;            // ~1024 slot items per CTA: amortises the calibration staging
-    if (V < 1) V = 1;
-    if (V > 128) V = 128;
-    while (V > 1 && (size_t)V * p.K * (C + 1) * 4 > 40 * 1024) V /= 2;
-    const size_t smem = (size_t)V * p.K * (C + 1) * 4 + align_up((size_t)V * p.K * 2, 16) + (size_t)V * 4;
-    if (smem > 200 * 1024) return RD3_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024)
-      RD3_CUDA_TRY(cudaFuncSetAttribute(hv_emit_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, V), p.B), 256, smem, stream>>>(src, g, w,
-                                                                                              out, V);
-  }
-  prof_mark(stream, 6);
-  prof_mark(stream, 7);
   return check_launch();
 }
 

@@ -46,7 +46,9 @@ struct VoxelGrid {
   float lo[3];
   float vs[3];
   float rvs[3];      // RN(1 / vs): only used by the conservative fast path
-  float lo_abs_max;  // max |lo[i]|
+  float rvs_max;     // max rvs[i]
+  float tolc;        // 2^-21 * (max grid + 2) + 1e-30: rounding slack of the fast path, in cells
+  int32_t fast_ok;   // max grid + 2 < 2^20 (else the fast path is disabled)
   int32_t grid[3];
 };
 
@@ -97,32 +99,36 @@ __device__ __forceinline__ bool voxel_coor(float px, float py, float pz,
 }
 
 // Conservative fast path for the same predicate.  f' = RN(RN(p - lo) * RN(1/vs))
-// differs from the exact quotient f by at most 2^-22 |f'| (three roundings of
-// 2^-24 each, with slack); `abs_err` bounds an additional absolute error of the
-// INPUT coordinate (0 for stored points; the reciprocal-based unprojection passes
-// its own bound).  If f' is farther than tol from every integer, floor(f') ==
-// floor(f) and the cell (or the out-of-range verdict) is exact.
+// differs from the exact quotient f = RN(RN(p - lo) / vs) by at most 2^-21 |f'|
+// (five roundings of 2^-24 each, with slack); `abs_err` bounds an additional
+// absolute error of the INPUT coordinate (0 for stored points; the reciprocal-
+// based unprojection passes its own bound).  With
+//     tol = abs_err * max(1/vs) + 2^-21 * (max grid + 2) + 1e-30
+// a point whose three f' are all farther than tol from every integer has
+// floor(f') == floor(f) whenever 0 <= floor(f') < grid, and is outside exactly
+// when floor(f') is (for |f'| beyond the grid the error stays below |f'| - grid
+// because max grid + 2 < 2^20).  NaN, huge values and exact integers fail the
+// distance test and are undecided.
 // Returns 1 inside, 0 outside, 2 undecided (caller must run voxel_coor()).
 __device__ __forceinline__ int voxel_coor_fast(float px, float py, float pz, float abs_err,
                                                const VoxelGrid &g, int &cx, int &cy, int &cz) {
-  const float p[3] = {px, py, pz};
-  int c[3];
-  bool undecided = false, outside = false;
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const float f = __fmul_rn(__fsub_rn(p[j], g.lo[j]), g.rvs[j]);
-    const float fl = floorf(f);
-    // 2^-21 |f'| + input error in cells + an absolute floor (denormal inputs, exact integers)
-    const float tol = fmaf(abs_err, g.rvs[j], fmaf(4.76837158e-7f, fabsf(f), 1e-30f));
-    const float lo_gap = f - fl, hi_gap = (fl + 1.0f) - f;
-    // NaN / huge values fail both comparisons -> undecided -> exact path
-    if (!(lo_gap >= tol && hi_gap >= tol && fabsf(f) < 4194304.0f)) undecided = true;
-    if (!(fl >= 0.0f && fl < (float)g.grid[j])) outside = true;
-    c[j] = (int)fl;
-  }
-  if (undecided) return 2;
-  if (outside) return 0;
-  cx = c[0]; cy = c[1]; cz = c[2];
+  if (!g.fast_ok) return 2;
+  const float fx = __fmul_rn(__fsub_rn(px, g.lo[0]), g.rvs[0]);
+  const float fy = __fmul_rn(__fsub_rn(py, g.lo[1]), g.rvs[1]);
+  const float fz = __fmul_rn(__fsub_rn(pz, g.lo[2]), g.rvs[2]);
+  const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+  const float tx = fminf(fx - flx, (flx + 1.0f) - fx);
+  const float ty = fminf(fy - fly, (fly + 1.0f) - fy);
+  const float tz = fminf(fz - flz, (flz + 1.0f) - fz);
+  // fminf drops NaNs, so test them through the sum (NaN + x = NaN fails the comparison)
+  const float t = fminf(tx, fminf(ty, tz));
+  const float tol = fmaf(abs_err, g.rvs_max, g.tolc);
+  if (!(t >= tol) || !((fx + fy) + fz == (fx + fy) + fz)) return 2;
+  const int ix = (int)flx, iy = (int)fly, iz = (int)flz;
+  if ((unsigned)ix >= (unsigned)g.grid[0] || (unsigned)iy >= (unsigned)g.grid[1] ||
+      (unsigned)iz >= (unsigned)g.grid[2])
+    return 0;
+  cx = ix; cy = iy; cz = iz;
   return 1;
 }
 
@@ -151,6 +157,8 @@ struct DepthParams {
   int32_t npix;          // ncam*H*W
   int32_t use_max_depth;
   float max_depth;
+  float zmax;            // min(max_depth, FLT_MAX): z <= zmax  <=>  isfinite(z) [&& z <= max_depth]
+  int32_t use_masks;     // use_conf || use_sky
   int32_t use_conf;
   float conf_thresh;
   int32_t use_sky;

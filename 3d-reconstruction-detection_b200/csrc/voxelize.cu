@@ -56,7 +56,13 @@ int make_grid(const float voxel_size[3], const float coors_range[6], VoxelGrid *
     g->grid[i] = (int32_t)r;
     g->rvs[i] = (float)(1.0 / (double)voxel_size[i]);
   }
-  g->lo_abs_max = fmaxf(fabsf(g->lo[0]), fmaxf(fabsf(g->lo[1]), fabsf(g->lo[2])));
+  g->rvs_max = fmaxf(g->rvs[0], fmaxf(g->rvs[1], g->rvs[2]));
+  {
+    int gmax = g->grid[0] > g->grid[1] ? g->grid[0] : g->grid[1];
+    if (g->grid[2] > gmax) gmax = g->grid[2];
+    g->fast_ok = (gmax < (1 << 20) - 2) ? 1 : 0;
+    g->tolc = 4.76837158e-7f * (float)(gmax + 2) + 1e-30f;
+  }
   uint64_t vol = 1;
   for (int i = 0; i < 3; ++i) {
     vol *= (uint64_t)g->grid[i];

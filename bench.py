@@ -214,6 +214,8 @@ def main():
     ap.add_argument("--cpu-workers", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scene", default="mixture", choices=["mixture", "ground"],
+                    help="synthetic depth: SURVEY 8(d) per-pixel mixture (default) or a structured ground+walls scene")
     ap.add_argument("--gather", action="store_true", help="also time the NCCL all_gather of the outputs")
     ap.add_argument("--profile-only", action="store_true",
                     help="few steps, no e2e / cpu baseline (the command profiled under ncu)")
@@ -245,7 +247,7 @@ def main():
     npix = 6 * H * W
 
     # weak scaling: every rank owns B frames (frame ids disjoint across ranks)
-    host = synthetic.make_batch([rank * B + i for i in range(B)], H, W, with_conf=False)
+    host = synthetic.make_batch([rank * B + i for i in range(B)], H, W, with_conf=False, scene=args.scene)
     depth_h = host["depth"].pin_memory()
     intr_h, c2l_h = host["intrinsics"].pin_memory(), host["cam2lidar"].pin_memory()
     depth, intr, c2l = depth_h.to(dev), intr_h.to(dev), c2l_h.to(dev)
@@ -327,7 +329,7 @@ def main():
     path_bytes = B * npix * 4 + M_total * (K * 4 * C + 16) + M_total * 4 * F
     kern = {k: v for k, v in stage_ms.items() if k != "memset"}
     dom = max(kern, key=kern.get) if calls else "insert"
-    dom_ms = stage_ms[dom] / max(calls, 1)
+    dom_ms = stage_ms[dom] / max(args.steps, 1)
     dom_achieved = alg[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     path_achieved = path_bytes / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "hv_%s_kernel" % dom, "achieved": dom_achieved, "peak": hbm_peak,
@@ -343,7 +345,7 @@ def main():
             pass
     path_roofline = {"bound": "hbm", "achieved": path_achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": path_achieved / hbm_peak, "algorithmic_bytes_per_step": path_bytes,
-                     "stage_ms_per_step": {k: v / max(calls, 1) for k, v in stage_ms.items()}}
+                     "stage_ms_per_step": {k: v / max(args.steps, 1) for k, v in stage_ms.items()}}
 
     # ---- e2e: public API from pinned host buffers, copies inside the timed region ------
     e2e = None
@@ -417,7 +419,7 @@ def main():
             "config": {"workload": WORKLOAD + ": fused depth unprojection + hard voxelization + voxel mean, "
                                    "6x504x896 depth, voxel 0.075/0.075/0.2, max_points 10, max_voxels 120000, "
                                    "max_depth 100",
-                       "frames_per_gpu_per_step": B, "pixels_per_frame": npix,
+                       "scene": args.scene, "frames_per_gpu_per_step": B, "pixels_per_frame": npix,
                        "voxels_per_frame_mean": M_total / B,
                        "l2": "inputs larger than L2 (%.0f MB depth per step per GPU vs 126 MB L2)" % (B * npix * 4 / 1e6),
                        "parallelism": "frames sharded by sample, %d per GPU, no data-path collective" % B},
