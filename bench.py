@@ -296,7 +296,7 @@ def main():
     gather_ms = None
     if args.gather and world > 1:
         outs = [r["voxel_mean"], r["coors"], r["num_points"], r["voxel_num"]]
-        bufs = [torch.empty((world,) + tuple(o.shape), dtype=o.dtype, device=dev) for o in outs]
+        bufs = [torch.empty((world * o.shape[0],) + tuple(o.shape[1:]), dtype=o.dtype, device=dev) for o in outs]
         for _ in range(2):
             for o, bf in zip(outs, bufs):
                 dist.all_gather_into_tensor(bf, o)

@@ -1,0 +1,149 @@
+"""Host-side logic that needs no GPU: sharding, the gloo (world_size 2) output gather,
+threshold conversion, module attributes, the mmdet3d patch, the product/oracle firewall."""
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import rd3_b200
+from rd3_b200 import parallel, synthetic
+from rd3_b200.backproject import f32_ceil
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_f32_ceil_is_the_exact_fp64_threshold():
+    g = np.random.default_rng(0)
+    for x in list(g.random(2000) * 10) + [0.0, 1.5, -0.1, 1e-50, -1e-50, 3.4e38, 1.30000001]:
+        f = f32_ceil(x)
+        assert np.float32(f) == np.float64(f)              # representable in fp32
+        assert np.float64(f) >= np.float64(x)
+        below = np.nextafter(np.float32(f), np.float32(-np.inf))
+        assert np.float64(below) < np.float64(x)
+        # predicate equivalence on neighbouring fp32 values
+        for c in (below, np.float32(f), np.nextafter(np.float32(f), np.float32(np.inf))):
+            assert (np.float64(c) >= np.float64(x)) == (np.float32(c) >= np.float32(f))
+
+
+def test_shard_range_partitions_the_batch():
+    for n in (0, 1, 7, 64, 65):
+        for w in (1, 2, 3, 4, 8):
+            spans = [parallel.shard_range(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == parallel.shard_sizes(n, w)
+    with pytest.raises(ValueError):
+        parallel.shard_range(4, 2, 2)
+
+
+def _fake_result(frame_ids, mv=6, k=2):
+    """deterministic stand-in for DepthToVoxels output of the given global frames"""
+    b = len(frame_ids)
+    ids = torch.tensor(frame_ids, dtype=torch.float32).view(b, 1, 1, 1)
+    return dict(voxels=ids.expand(b, mv, k, 3).clone() + torch.arange(mv).view(1, mv, 1, 1),
+                coors=(ids.view(b, 1, 1).expand(b, mv, 3) * 10).to(torch.int32),
+                num_points=torch.full((b, mv), k, dtype=torch.int32),
+                voxel_mean=ids.view(b, 1, 1).expand(b, mv, 3).clone(),
+                voxel_num=torch.tensor([1 + (i % mv) for i in frame_ids], dtype=torch.int32))
+
+
+def _gloo_worker(rank, world, port, total, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = parallel.shard_range(total, world, rank)
+    local = _fake_result(list(range(lo, hi)))
+    full = parallel.gather_voxel_outputs(local, num_frames_total=total)
+    ref = _fake_result(list(range(total)))
+    ok = all(torch.equal(full[k], ref[k]) for k in ref)
+    full2 = parallel.gather_voxel_outputs(local)              # sizes discovered by all_gather
+    ok = ok and all(torch.equal(full2[k], ref[k]) for k in ref)
+    feats, coors, bs = parallel.to_sparse_encoder_inputs(full)
+    ok = ok and bs == total and coors.shape[1] == 4 and int(coors[-1, 0]) == total - 1
+    ok = ok and feats.shape[0] == int(ref["voxel_num"].sum())
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [4, 5])
+def test_gloo_world2_gather_matches_single_process(total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + total
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_module_attributes_mirror_reference():
+    v = rd3_b200.Voxelization([0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3], 10, (120000, 160000))
+    assert v.grid_size.tolist() == [1440, 1440, 40]
+    assert [int(x) for x in v.pcd_shape] == [1, 1440, 1440]
+    assert v.max_voxels == (120000, 160000) and v.max_num_points == 10
+    assert rd3_b200.Voxelization([0.5] * 3, [0, -40, -3, 70.4, 40, 1], 35).max_voxels == (20000, 20000)
+    assert "max_num_points=10" in repr(v)
+    d = rd3_b200.DynamicScatter([0.32, 0.32, 6], [-74.88, -74.88, -2, 74.88, 74.88, 4], True)
+    assert d.average_points and "average_points=True" in repr(d)
+    assert rd3_b200.HardSimpleVFE().num_features == 4
+
+
+def test_synthetic_inputs_are_deterministic_and_shaped():
+    a = synthetic.make_frame(3, 28, 48)
+    b = synthetic.make_frame(3, 28, 48)
+    for k in a:
+        assert torch.equal(a[k], b[k], ) or (torch.isnan(a[k]) == torch.isnan(b[k])).all()
+    d = a["depth"]
+    assert d.shape == (6, 28, 48) and torch.isnan(d).any() and torch.isinf(d).any() and (d == 0).any()
+    assert (a["conf"] >= 1).all() and a["sky"].dtype == torch.bool
+    assert torch.equal(a["cam2lidar"][:, :3, 3], torch.zeros(6, 3))       # translation lives in ROW 3
+    c = synthetic.make_frame(4, 28, 48)
+    assert not torch.equal(torch.nan_to_num(c["depth"]), torch.nan_to_num(d))
+
+
+def test_patch_mmdet3d_rebinds_standin_modules(monkeypatch):
+    names = ["mmdet3d", "mmdet3d.ops", "mmdet3d.ops.voxel", "mmdet3d.ops.voxel.voxelize",
+             "mmdet3d.ops.voxel.scatter_points", "mmdet3d.models", "mmdet3d.models.voxel_encoders",
+             "mmdet3d.models.voxel_encoders.voxel_encoder"]
+    mods = {n: types.ModuleType(n) for n in names}
+    for n, m in mods.items():
+        monkeypatch.setitem(sys.modules, n, m)
+    vz, sp = mods["mmdet3d.ops.voxel.voxelize"], mods["mmdet3d.ops.voxel.scatter_points"]
+    for a in ("hard_voxelize", "dynamic_voxelize", "Voxelization", "voxelization"):
+        setattr(vz, a, None)
+    for a in ("dynamic_point_to_voxel_forward", "dynamic_point_to_voxel_backward", "DynamicScatter", "dynamic_scatter"):
+        setattr(sp, a, None)
+    for a in ("Voxelization", "voxelization", "DynamicScatter", "dynamic_scatter"):
+        setattr(mods["mmdet3d.ops"], a, None)
+
+    class HardSimpleVFE:
+        num_features = 4
+    mods["mmdet3d.models.voxel_encoders.voxel_encoder"].HardSimpleVFE = HardSimpleVFE
+    done = rd3_b200.patch_mmdet3d()
+    assert vz.Voxelization is rd3_b200.Voxelization and vz.hard_voxelize is rd3_b200.voxel_layer.hard_voxelize
+    assert sp.DynamicScatter is rd3_b200.DynamicScatter
+    assert mods["mmdet3d.ops"].Voxelization is rd3_b200.Voxelization
+    assert "mmdet3d.models.voxel_encoders.voxel_encoder.HardSimpleVFE.forward" in done
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the package may import or load it."""
+    pkg = os.path.join(ROOT, "3d-reconstruction-detection_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
+                assert "librd3_oracle" not in src and "ref_voxel_layer" not in src, f
+                assert "/root/reference" not in src, f
