@@ -12,11 +12,43 @@
 
 namespace rd3 {
 
-// calibration table: (B, ncam, kCalibFloats), one block per frame
-__global__ void calib_kernel(const float *intr, const float *c2l, int ncam, float *table) {
+// calibration table: (B, ncam, kCalibFloats), one block per frame.  With a voxel grid
+// (has_grid) it also holds the direct pixel->cell map and its error-bound constants
+// (rd3_common.cuh: pixel_cell_fast), derived in fp64 and rounded once.
+__global__ void calib_kernel(const float *intr, const float *c2l, int ncam, int H, int W,
+                             VoxelGrid g, int has_grid, CellRange rg, float *table) {
   __shared__ float s_cal[kMaxCams * kCalibFloats];
   const int b = blockIdx.x;
-  stage_calibration(s_cal, intr + (int64_t)b * ncam * 9, c2l + (int64_t)b * ncam * 16, ncam);
+  const float *Kb = intr + (int64_t)b * ncam * 9;
+  const float *Mb = c2l + (int64_t)b * ncam * 16;
+  stage_calibration(s_cal, Kb, Mb, ncam);
+  __syncthreads();
+  if (has_grid && threadIdx.x < ncam) {
+    const int cam = threadIdx.x;
+    const float *K = Kb + cam * 9, *M = Mb + cam * 16;
+    float *k = s_cal + cam * kCalibFloats + kCalDirect;
+    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    const double ex = fmax(fabs(cx), fabs((double)(W - 1) - cx)) / fabs(fx);
+    const double ey = fmax(fabs(cy), fabs((double)(H - 1) - cy)) / fabs(fy);
+    double Qc = 0.0, Pc = 0.0;
+    for (int a = 0; a < 3; ++a) {
+      const double rv = 1.0 / (double)g.vs[a];
+      const double r0 = M[a * 4 + 0], r1 = M[a * 4 + 1], r2 = M[a * 4 + 2], t = M[12 + a];
+      const float A = (float)(r0 / fx * rv), Bc = (float)(r1 / fy * rv);
+      const float C = (float)((r2 - r0 * cx / fx - r1 * cy / fy) * rv);
+      const float T = (float)((t - (double)g.lo[a]) * rv);
+      k[a * 4 + 0] = A; k[a * 4 + 1] = Bc; k[a * 4 + 2] = C; k[a * 4 + 3] = T;
+      const double D = fabs((double)A) * (W - 1) + fabs((double)Bc) * (H - 1) + fabs((double)C);
+      const double Q = (fabs(r0) * ex + fabs(r1) * ey + fabs(r2)) * rv;
+      const double P1 = fabs(t) * rv;
+      double P = fabs((double)T) + 10.0 * P1 + 3.0 * fabs((double)g.lo[a]) * rv;
+      if (rg.on) P += fabs((double)rg.lo[a]) + fabs((double)rg.hi[a]);
+      Qc = fmax(Qc, 3.0 * D + 10.0 * Q);
+      Pc = fmax(Pc, P);
+    }
+    k[12] = (float)(Qc * 1.000001);
+    k[13] = (float)(Pc * 1.000001);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < ncam * kCalibFloats; i += blockDim.x)
     table[(int64_t)b * ncam * kCalibFloats + i] = s_cal[i];
@@ -42,7 +74,7 @@ __global__ void __launch_bounds__(kScanThreads)
       const float d = __ldg(src.depth + gi);
       if (src.depth_ok(d, gi)) {
         float x, y, z;
-        valid = !src.p.use_range || src.point(b, i, 0, s_cal, nullptr, x, y, z);
+        valid = !src.p.use_range || src.point(b, i, s_cal, x, y, z);
       }
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, valid);
@@ -68,7 +100,7 @@ __global__ void __launch_bounds__(256)
   const uint32_t bit = 1u << (i & 31);
   if (!(word & bit)) return;
   float x, y, z;
-  src.point(b, i, 0, s_cal, nullptr, x, y, z);
+  src.point(b, i, s_cal, x, y, z);
   const int pos = __ldg(chunk_base + (int64_t)b * nchunks + (i >> kChunkShift)) +
                   __ldg(wordprefix + wi) + __popc(word & (bit - 1u));
   const int64_t o = (int64_t)b * src.p.npix + pos;
@@ -109,6 +141,7 @@ static int make_depth_source(const float *depth, const float *intrinsics, const 
   src->intr = intrinsics;
   src->c2l = cam2lidar;
   src->cal_table = nullptr;
+  src->rg.on = 0;
   DepthParams &d = src->p;
   d.ncam = p->ncam; d.H = p->H; d.W = p->W; d.HW = p->H * p->W; d.npix = (int32_t)npix;
   d.use_max_depth = p->use_max_depth; d.max_depth = p->max_depth;
@@ -187,7 +220,14 @@ int rd3_depth_to_voxels(const float *depth, const float *intrinsics, const float
   const size_t cal_bytes = align_up((size_t)p->B * p->ncam * kCalibFloats * 4);
   if (workspace_bytes < plan.total + cal_bytes) return RD3_ERR_WORKSPACE;
   float *cal_table = (float *)((char *)workspace + plan.total);
-  calib_kernel<<<p->B, 128, 0, (cudaStream_t)stream>>>(intrinsics, cam2lidar, p->ncam, cal_table);
+  // inclusive range filter in cell units (pixel_cell_fast)
+  src.rg.on = p->use_range;
+  for (int a = 0; a < 3; ++a) {
+    src.rg.lo[a] = (float)(((double)p->range[a] - (double)g.lo[a]) / (double)g.vs[a]);
+    src.rg.hi[a] = (float)(((double)p->range[3 + a] - (double)g.lo[a]) / (double)g.vs[a]);
+  }
+  calib_kernel<<<p->B, 128, 0, (cudaStream_t)stream>>>(intrinsics, cam2lidar, p->ncam, p->H, p->W, g, 1,
+                                                       src.rg, cal_table);
   src.cal_table = cal_table;
   HvOut out{voxels, coors, num_points_per_voxel, voxel_mean, d_voxel_num, nullptr,
             voxel_mean ? 3 : 0};

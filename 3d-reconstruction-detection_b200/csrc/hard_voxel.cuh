@@ -57,35 +57,28 @@ struct PointsSource {
   int host_num_feats() const { return C; }
   __device__ __forceinline__ int num_feats() const { return C; }
 
-  // stage A: which of the 4 points starting at i exist (cheap validity)
-  __device__ __forceinline__ unsigned valid4(int b, int64_t i, float *) const {
-    unsigned m = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) m |= (i + q < N) ? (1u << q) : 0u;
-    return m;
+  // stage AB: a lane walks its 4 consecutive points
+  struct Cursor { const float *p; };
+  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t, const float *) const {
+    Cursor c;
+    c.p = pts + ((int64_t)b * N + i0) * C;
+    return c;
   }
-  // stage B: coordinates of point i
-  __device__ __forceinline__ bool point(int b, int64_t i, int, const float *, const float *,
-                                        float &x, float &y, float &z) const {
+  // cell of the cursor's point: 1 inside / 0 outside / 2 undecided (-> cell_exact); then advance
+  __device__ __forceinline__ int cell_next(Cursor &c, bool exists, const float *, const VoxelGrid &g,
+                                           int &cx, int &cy, int &cz) const {
+    int r = 0;
+    if (exists) {
+      const float x = __ldg(c.p), y = __ldg(c.p + 1), z = __ldg(c.p + 2);
+      r = voxel_coor_fast(x, y, z, 0.0f, g, cx, cy, cz);
+    }
+    c.p += C;
+    return r;
+  }
+  __device__ __forceinline__ bool cell_exact(int b, int64_t i, const float *, const VoxelGrid &g,
+                                             int &cx, int &cy, int &cz) const {
     const float *p = pts + ((int64_t)b * N + i) * C;
-    x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
-    return true;
-  }
-  struct TileOrigin {};
-  __device__ __forceinline__ TileOrigin tile_origin(int64_t) const { return TileOrigin(); }
-  // stage B: voxel cell of point i.  cell_fast: 1 inside / 0 outside / 2 undecided (-> cell_exact)
-  __device__ __forceinline__ int cell_fast(int b, int64_t i, int lid, const TileOrigin &, const float *s_cal,
-                                           const float *s_z, const VoxelGrid &g, int &cx, int &cy,
-                                           int &cz) const {
-    float x, y, z;
-    point(b, i, lid, s_cal, s_z, x, y, z);
-    return voxel_coor_fast(x, y, z, 0.0f, g, cx, cy, cz);
-  }
-  __device__ __forceinline__ bool cell_exact(int b, int64_t i, int lid, const float *s_cal, const float *s_z,
-                                             const VoxelGrid &g, int &cx, int &cy, int &cz) const {
-    float x, y, z;
-    point(b, i, lid, s_cal, s_z, x, y, z);
-    return voxel_coor(x, y, z, g, cx, cy, cz);
+    return voxel_coor(__ldg(p), __ldg(p + 1), __ldg(p + 2), g, cx, cy, cz);
   }
   // emit: all features of point i into dst[0..C)
   __device__ __forceinline__ void gather(int b, int64_t i, const float *, float *dst) const {
@@ -102,6 +95,7 @@ struct DepthSource {
   const float *c2l;        // (B, ncam, 16)
   const float *cal_table;  // (B, ncam, kCalibFloats) precomputed by calib_kernel, or null
   DepthParams p;
+  CellRange rg;            // range filter in cell units (fused path)
   int vec_ok;              // 16-byte aligned float4 loads are legal
   static constexpr bool kIsDepth = true;
 
@@ -130,87 +124,74 @@ struct DepthSource {
     }
     return ok;
   }
-  // (cam, v, u) of the first pixel of a tile; lanes then offset by their local id
-  struct TileOrigin { uint32_t cam, v, u; };
-  __device__ __forceinline__ TileOrigin tile_origin(int64_t base) const {
-    TileOrigin t;
-    const uint32_t pix = (uint32_t)base;
-    t.cam = fast_div(pix, p.div_hw);
-    const uint32_t rem = pix - t.cam * (uint32_t)p.HW;
-    t.v = fast_div(rem, p.div_w);
-    t.u = rem - t.v * (uint32_t)p.W;
-    return t;
-  }
-  __device__ __forceinline__ unsigned valid4(int b, int64_t i, float *s_z4) const {
-    const int64_t g = (int64_t)b * p.npix + i;
-    float z[4];
-    if (vec_ok && i + 3 < p.npix) {
-      const float4 v = __ldg(reinterpret_cast<const float4 *>(depth + g));
-      z[0] = v.x; z[1] = v.y; z[2] = v.z; z[3] = v.w;
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) z[q] = (i + q < p.npix) ? __ldg(depth + g + q) : 0.0f;
-    }
-    unsigned m = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      s_z4[q] = z[q];
-      m |= depth_ok(z[q], g + q) ? (1u << q) : 0u;
-    }
-    return m;
-  }
-  // pixel index -> (cam, v, u) -> ego-frame point; s_z: block-staged depth (lid-indexed) or null
-  __device__ __forceinline__ bool point(int b, int64_t i, int lid, const float *s_cal,
-                                        const float *s_z, float &x, float &y, float &z) const {
-    const float d = s_z ? s_z[lid] : __ldg(depth + (int64_t)b * p.npix + i);
-    const uint32_t pix = (uint32_t)i;
-    const uint32_t cam = fast_div(pix, p.div_hw);
+  // pixel index -> (cam, v, u)
+  __device__ __forceinline__ void pixel_cvu(uint32_t pix, uint32_t &cam, uint32_t &v, uint32_t &u) const {
+    cam = fast_div(pix, p.div_hw);
     const uint32_t rem = pix - cam * (uint32_t)p.HW;
-    const uint32_t v = fast_div(rem, p.div_w);
-    const uint32_t u = rem - v * (uint32_t)p.W;
-    return unproject_point(d, (int)u, (int)v, s_cal + cam * kCalibFloats, p, x, y, z);
+    v = fast_div(rem, p.div_w);
+    u = rem - v * (uint32_t)p.W;
   }
-  // stage B: voxel cell of pixel i.  cell_fast decides the cell with reciprocal arithmetic and
-  // a rigorous error bound (1 inside / 0 outside); pixels within that bound of a cell or
-  // range-filter boundary return 2 and are re-done by cell_exact with the IEEE divisions.
-  __device__ __forceinline__ int cell_fast(int b, int64_t i, int lid, const TileOrigin &t0,
-                                           const float *s_cal, const float *s_z,
-                                           const VoxelGrid &g, int &cx, int &cy, int &cz) const {
-    const float d = s_z[lid];
-    uint32_t cam = t0.cam, v = t0.v, u = t0.u + (uint32_t)lid;
-    if (p.W >= kTilePoints) {            // at most one row wrap inside a 128-pixel tile
-      if (u >= (uint32_t)p.W) {
-        u -= (uint32_t)p.W;
-        if (++v >= (uint32_t)p.H) { v = 0; ++cam; }
-      }
+  // stage AB: a lane walks its 4 consecutive pixels
+  struct Cursor {
+    float z[4];
+    unsigned valid;        // depth/conf/sky mask of the 4 pixels
+    uint32_t cam, v, u;
+    int q;
+  };
+  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *) const {
+    Cursor c;
+    const int64_t gi = (int64_t)b * p.npix + i0;
+    if (vec_ok && i0 + 3 < end) {
+      const float4 t = __ldg(reinterpret_cast<const float4 *>(depth + gi));
+      c.z[0] = t.x; c.z[1] = t.y; c.z[2] = t.z; c.z[3] = t.w;
     } else {
-      const uint32_t pix = (uint32_t)i;
-      cam = fast_div(pix, p.div_hw);
-      const uint32_t rem = pix - cam * (uint32_t)p.HW;
-      v = fast_div(rem, p.div_w);
-      u = rem - v * (uint32_t)p.W;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c.z[q] = (i0 + q < end) ? __ldg(depth + gi + q) : 0.0f;
     }
-    float x, y, z, err;
-    unproject_point_approx(d, (int)u, (int)v, s_cal + cam * kCalibFloats, x, y, z, err);
-    int r = voxel_coor_fast(x, y, z, err, g, cx, cy, cz);
-    if (r == 1 && p.use_range) {
-      // inclusive range filter (respoint_post_processing.py:190-195) applies to the exact point
-      const bool in_sure = x - p.range[0] >= err && p.range[3] - x >= err && y - p.range[1] >= err &&
-                           p.range[4] - y >= err && z - p.range[2] >= err && p.range[5] - z >= err;
-      const bool out_sure = p.range[0] - x > err || x - p.range[3] > err || p.range[1] - y > err ||
-                            y - p.range[4] > err || p.range[2] - z > err || z - p.range[5] > err;
-      r = out_sure ? 0 : (in_sure ? 1 : 2);
+    c.valid = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c.valid |= (i0 + q < end && depth_ok(c.z[q], gi + q)) ? (1u << q) : 0u;
+    pixel_cvu((uint32_t)i0, c.cam, c.v, c.u);
+    c.q = 0;
+    return c;
+  }
+  // cell of the cursor's pixel: 1 inside / 0 outside or masked / 2 undecided; then advance.
+  // The direct pixel->cell map (pixel_cell_fast) decides all but the pixels within its error
+  // bound of a cell / range-filter boundary; those are redone by cell_exact.
+  __device__ __forceinline__ int cell_next(Cursor &c, bool, const float *s_cal, const VoxelGrid &g,
+                                           int &cx, int &cy, int &cz) const {
+    int r = 0;
+    if ((c.valid >> c.q) & 1u) {
+      float z = c.z[0];
+      z = c.q == 1 ? c.z[1] : z;
+      z = c.q == 2 ? c.z[2] : z;
+      z = c.q == 3 ? c.z[3] : z;
+      r = g.fast_ok ? pixel_cell_fast(z, (float)c.u, (float)c.v, s_cal + c.cam * kCalibFloats, g, rg, cx, cy, cz)
+                    : 2;
+    }
+    ++c.q;
+    if (++c.u == (uint32_t)p.W) {
+      c.u = 0;
+      if (++c.v == (uint32_t)p.H) { c.v = 0; ++c.cam; }
     }
     return r;
   }
-  __device__ __forceinline__ bool cell_exact(int b, int64_t i, int lid, const float *s_cal, const float *s_z,
-                                             const VoxelGrid &g, int &cx, int &cy, int &cz) const {
+  // pixel index -> exact ego-frame point (reference arithmetic); false if the range filter drops it
+  __device__ __forceinline__ bool point(int b, int64_t i, const float *s_cal, float &x, float &y,
+                                        float &z) const {
+    const float d = __ldg(depth + (int64_t)b * p.npix + i);
+    uint32_t cam, v, u;
+    pixel_cvu((uint32_t)i, cam, v, u);
+    return unproject_point(d, (int)u, (int)v, s_cal + cam * kCalibFloats, p, x, y, z);
+  }
+  __device__ __forceinline__ bool cell_exact(int b, int64_t i, const float *s_cal, const VoxelGrid &g,
+                                             int &cx, int &cy, int &cz) const {
     float x, y, z;
-    if (!point(b, i, lid, s_cal, s_z, x, y, z)) return false;
+    if (!point(b, i, s_cal, x, y, z)) return false;
     return voxel_coor(x, y, z, g, cx, cy, cz);
   }
   __device__ __forceinline__ void gather(int b, int64_t i, const float *s_cal, float *dst) const {
-    point(b, i, 0, s_cal, nullptr, dst[0], dst[1], dst[2]);
+    point(b, i, s_cal, dst[0], dst[1], dst[2]);
   }
 };
 
@@ -289,21 +270,19 @@ __device__ __forceinline__ uint32_t table_find(const unsigned long long *table, 
 }
 
 // K1 ------------------------------------------------------------------------
-// grid (ceil((end-begin)/1024), B), 256 threads; every WARP owns a tile of 128
-// consecutive points and runs its three stages without block barriers:
-//   A  4 points per lane (one 16-byte load), cheap validity, ballot compaction
-//   B  dense lanes: voxel cell by the conservative reciprocal path; the few
-//      undecided ones are redone with exact IEEE arithmetic, again on dense lanes
+// grid (ceil((end-begin)/1024), frames), 256 threads; every WARP owns a tile of 128
+// consecutive points and runs its stages without block barriers:
+//   AB each lane walks its 4 consecutive points (one 16-byte load): validity, voxel cell
+//      by the conservative fast path; in-range keys and the few undecided points are
+//      ballot-compacted; the undecided ones are redone with exact IEEE arithmetic
 //   C  dense lanes: table insert (or lookup once max_voxels voxels exist);
 //      hits go to the tile's own region of the candidate list (no global counter)
 template <class Src>
 __global__ void __launch_bounds__(kInsThreads)
     hv_insert_kernel(Src src, VoxelGrid g, HvWork w, int64_t begin, int64_t end, int round) {
-  constexpr int kWarps = kInsThreads / 32;
   __shared__ float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 1];
-  __shared__ float s_zb[Src::kIsDepth ? kInsPoints : 4];
   __shared__ uint32_t s_keyb[kInsPoints];
-  __shared__ uint8_t s_l1b[kInsPoints], s_l2b[kInsPoints], s_undb[kInsPoints];
+  __shared__ uint8_t s_l2b[kInsPoints], s_undb[kInsPoints];
   __shared__ int s_prev;
 
   const int b = blockIdx.y + w.b0;
@@ -324,60 +303,39 @@ __global__ void __launch_bounds__(kInsThreads)
 
   const int64_t base = block_base + wv * kTilePoints;     // this warp's tile
   if (base >= end) return;
-  float *s_z = s_zb + (Src::kIsDepth ? wv * kTilePoints : 0);
   uint32_t *s_key = s_keyb + wv * kTilePoints;
-  uint8_t *s_l1 = s_l1b + wv * kTilePoints, *s_l2 = s_l2b + wv * kTilePoints;
-  uint8_t *s_und = s_undb + wv * kTilePoints;
+  uint8_t *s_l2 = s_l2b + wv * kTilePoints, *s_und = s_undb + wv * kTilePoints;
 
-  // ---- stage A --------------------------------------------------------------------
+  // ---- stage AB ---------------------------------------------------------------------
   const int64_t i0 = base + 4 * lane;
-  unsigned m = 0;
-  if (i0 < end) {
-    m = src.valid4(b, i0, s_z + (Src::kIsDepth ? 4 * lane : 0));
-    if (i0 + 3 >= end) m &= (1u << (int)(end - i0)) - 1u;
-  }
-  int nv = 0;
+  typename Src::Cursor cur = src.cursor(b, i0 < end ? i0 : base, end, s_cal);
+  int n2 = 0, nu = 0;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const bool on = (m >> q) & 1u;
-    const unsigned bal = __ballot_sync(0xffffffffu, on);
-    if (on) s_l1[nv + __popc(bal & lt)] = (uint8_t)(4 * lane + q);
-    nv += __popc(bal);
-  }
-  __syncwarp();
-
-  // ---- stage B --------------------------------------------------------------------
-  const typename Src::TileOrigin t0 = src.tile_origin(base);
-  int n2 = 0, nu = 0;
-#pragma unroll 1
-  for (int j0 = 0; j0 < nv; j0 += 32) {
-    const int j = j0 + lane;
-    int r = 0, lid = 0, cx, cy, cz;
-    if (j < nv) {
-      lid = s_l1[j];
-      r = src.cell_fast(b, base + lid, lid, t0, s_cal, s_z, g, cx, cy, cz);
-    }
+    int cx, cy, cz;
+    int r = src.cell_next(cur, i0 + q < end, s_cal, g, cx, cy, cz);
+    if (i0 + q >= end) r = 0;
     const unsigned b1 = __ballot_sync(0xffffffffu, r == 1);
     const unsigned b2 = __ballot_sync(0xffffffffu, r == 2);
     if (r == 1) {
       const int at = n2 + __popc(b1 & lt);
-      s_l2[at] = (uint8_t)lid;
+      s_l2[at] = (uint8_t)(4 * lane + q);
       s_key[at] = voxel_key(cx, cy, cz, g);
     } else if (r == 2) {
-      s_und[nu + __popc(b2 & lt)] = (uint8_t)lid;
+      s_und[nu + __popc(b2 & lt)] = (uint8_t)(4 * lane + q);
     }
     n2 += __popc(b1);
     nu += __popc(b2);
   }
   __syncwarp();
 #pragma unroll 1
-  for (int j0 = 0; j0 < nu; j0 += 32) {       // rare: within the error bound of a boundary
+  for (int j0 = 0; j0 < nu; j0 += 32) {       // within the error bound of a boundary: exact arithmetic
     const int j = j0 + lane;
     bool in = false;
     int lid = 0, cx, cy, cz;
     if (j < nu) {
       lid = s_und[j];
-      in = src.cell_exact(b, base + lid, lid, s_cal, s_z, g, cx, cy, cz);
+      in = src.cell_exact(b, base + lid, s_cal, g, cx, cy, cz);
     }
     const unsigned b1 = __ballot_sync(0xffffffffu, in);
     if (in) {
@@ -389,7 +347,7 @@ __global__ void __launch_bounds__(kInsThreads)
   }
   __syncwarp();
 
-  // ---- stage C --------------------------------------------------------------------
+  // ---- stage C ----------------------------------------------------------------------
   unsigned long long *table = w.table + (int64_t)b * w.cap;
   uint2 *cand = w.cand + (int64_t)b * w.N + base;
   int nc = 0, claims = 0;

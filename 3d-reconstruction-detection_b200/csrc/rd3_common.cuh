@@ -148,7 +148,9 @@ __device__ __forceinline__ void key_to_zyx(uint32_t key, const VoxelGrid &g, int
 // Per-camera calibration staged in shared memory (16 floats per camera).
 //   [0]=fx [1]=fy [2]=cx [3]=cy  [4..12]=R row-major (M[:3,:3])  [13..15]=t (M[3,:3])
 // ---------------------------------------------------------------------------
-constexpr int kCalibFloats = 20;   // +[16]=RN(1/fx) [17]=RN(1/fy) [18]=max|R| [19]=max|t|
+constexpr int kCalibFloats = 36;   // +[16]=RN(1/fx) [17]=RN(1/fy) [18]=max|R| [19]=max|t|
+                                   // +[20..31] direct cell map A,B,C,T per axis  [32]=Qc [33]=Pc
+constexpr int kCalDirect = 20;
 constexpr int kMaxCams = 16;
 
 struct DepthParams {
@@ -186,8 +188,10 @@ __device__ __forceinline__ void stage_calibration(float *s_cal, const float *int
       v = 0.0f;
       for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) v = fmaxf(v, fabsf(M[r * 4 + c]));
-    } else {
+    } else if (j == 19) {
       v = fmaxf(fabsf(M[12]), fmaxf(fabsf(M[13]), fabsf(M[14])));
+    } else {
+      v = 0.0f;        // direct cell map: filled by calib_kernel when a voxel grid is known
     }
     s_cal[i] = v;
   }
@@ -229,6 +233,58 @@ __device__ __forceinline__ void unproject_point_approx(float z, int u, int v, co
   oz = __fadd_rn(__fmaf_rn(z, cal[12], __fmaf_rn(y, cal[11], __fmul_rn(x, cal[10]))), cal[15]);
   // analysis gives 3 * 2^-22 * S; 2^-19 * S (+ a floor for denormal products) is used
   err = fmaf(1.90734863e-6f, fmaf(fabsf(x) + fabsf(y) + fabsf(z), cal[18], cal[19]), 1e-30f);
+}
+
+// Direct pixel -> cell map used ONLY to decide the voxel cell (fused path).
+// With per-camera, per-axis constants (fp64-derived, rounded once to fp32)
+//   A = R[a][0] / (fx vs_a)      B = R[a][1] / (fy vs_a)
+//   C = (R[a][2] - R[a][0] cx/fx - R[a][1] cy/fy) / vs_a      T = (t_a - lo_a) / vs_a
+// the cell coordinate is  f'_a = fma(z, fma(A, u, fma(B, v, C)), T)   (3 FMAs per axis).
+// Against the reference chain f_ref = RN(RN(o_ref - lo)/vs) (o_ref = its fp32 unprojection):
+//   |o_ref - o*| <= 7 eps S*            (3 roundings in x,y; 4 in the 3x3 product)
+//   |f_ref - f*| <= 7 eps S* / vs + 2 eps |f|
+//   |f'   - f*| <= eps (3 z D + |T| + |f'|),   D = |A|(W-1) + |B|(H-1) + |C|
+// with eps = 2^-24 and S*/vs <= z Q + P1 (Q = (|R0| ex + |R1| ey + |R2|)/vs, ex/ey = ray
+// extents, P1 = |t|/vs).  Hence |f' - f_ref| <= eps (z (3D + 10Q) + |T| + 10 P1 + 3 |lo|/vs)
+// and   tol = 2^-23 (z Qc + Pc) + 1e-30   (2x slack; Qc, Pc = maxima over the three axes,
+// Pc also covers the rounding of the range-filter limits).  If every f'_a is at least tol
+// away from the nearest integer then floor(f'_a) == floor(f_ref_a): the cell and the
+// in/out verdict are the reference's.  Everything else is redone exactly.
+struct CellRange {          // inclusive range filter expressed in cell units, per axis
+  float lo[3], hi[3];
+  int32_t on;
+};
+
+__device__ __forceinline__ int pixel_cell_fast(float z, float uf, float vf, const float *cal,
+                                               const VoxelGrid &g, const CellRange &rg, int &cx,
+                                               int &cy, int &cz) {
+  const float *k = cal + kCalDirect;
+  const float fx = __fmaf_rn(z, __fmaf_rn(k[0], uf, __fmaf_rn(k[1], vf, k[2])), k[3]);
+  const float fy = __fmaf_rn(z, __fmaf_rn(k[4], uf, __fmaf_rn(k[5], vf, k[6])), k[7]);
+  const float fz = __fmaf_rn(z, __fmaf_rn(k[8], uf, __fmaf_rn(k[9], vf, k[10])), k[11]);
+  const float tol = __fmaf_rn(1.1920929e-7f, __fmaf_rn(z, k[12], k[13]), 1e-30f);
+  const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+  const float tx = fminf(fx - flx, (flx + 1.0f) - fx);
+  const float ty = fminf(fy - fly, (fly + 1.0f) - fy);
+  const float tz = fminf(fz - flz, (flz + 1.0f) - fz);
+  const float t = fminf(tx, fminf(ty, tz));
+  const float sum = (fx + fy) + fz;
+  if (!(t >= tol) || !(sum == sum)) return 2;          // near a boundary, NaN, or huge
+  const int ix = (int)flx, iy = (int)fly, iz = (int)flz;
+  if ((unsigned)ix >= (unsigned)g.grid[0] || (unsigned)iy >= (unsigned)g.grid[1] ||
+      (unsigned)iz >= (unsigned)g.grid[2])
+    return 0;
+  if (rg.on) {
+    const bool in_sure = fx - rg.lo[0] >= tol && rg.hi[0] - fx >= tol && fy - rg.lo[1] >= tol &&
+                         rg.hi[1] - fy >= tol && fz - rg.lo[2] >= tol && rg.hi[2] - fz >= tol;
+    if (!in_sure) {
+      const bool out_sure = rg.lo[0] - fx > tol || fx - rg.hi[0] > tol || rg.lo[1] - fy > tol ||
+                            fy - rg.hi[1] > tol || rg.lo[2] - fz > tol || fz - rg.hi[2] > tol;
+      return out_sure ? 0 : 2;
+    }
+  }
+  cx = ix; cy = iy; cz = iz;
+  return 1;
 }
 
 // ---------------------------------------------------------------------------
