@@ -377,15 +377,19 @@ __global__ void __launch_bounds__(kInsThreads)
 }
 
 // K2a -----------------------------------------------------------------------
-// every table entry marks its voxel's first point.  grid (cap/256, B).
+// every table entry marks its voxel's first point.  grid (gx, frames), grid-stride over the
+// table so that the launch has a few thousand fat blocks instead of cap/256 per frame.
 static __global__ void __launch_bounds__(256) hv_first_kernel(HvWork w) {
   const int b = blockIdx.y + w.b0;
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= w.cap) return;
-  const unsigned long long e = w.table[(int64_t)b * w.cap + s];
-  if (e == kEmpty64) return;
-  const uint32_t first = (uint32_t)e;
-  atomicOr(w.flags + (int64_t)b * w.nwords + (first >> 5), 1u << (first & 31));
+  const unsigned long long *table = w.table + (int64_t)b * w.cap;
+  uint32_t *flags = w.flags + (int64_t)b * w.nwords;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < w.cap;
+       s += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long e = __ldg(table + s);
+    if (e == kEmpty64) continue;
+    const uint32_t first = (uint32_t)e;
+    atomicOr(flags + (first >> 5), 1u << (first & 31));
+  }
 }
 
 // K2b -----------------------------------------------------------------------
@@ -481,13 +485,15 @@ __device__ __forceinline__ int voxel_rank(const HvWork &w, int b, uint32_t first
 }
 
 // Keep the K smallest point indices of a voxel, sorted, with atomicMin only.
-// Invariant: a value reaches slot k only after losing against slots < k, so the
-// non-empty prefix is strictly increasing at all times; the final content is
-// independent of arrival order.
-__device__ __forceinline__ void slot_insert(uint32_t *S, int K, uint32_t idx) {
-  if (__ldcg(S + K - 1) < idx) return;   // K smaller indices already present
+// Slot 0 is reserved for the voxel's first point (known from the table), which is
+// stored without an atomic; every other point cascades through slots 1..K-1:
+// a value reaches slot k only after losing against the slots before it, so the
+// non-empty prefix is strictly increasing at all times and the final content is
+// independent of arrival order.  `s_last` is a (possibly stale, hence larger) copy of
+// slot K-1: if it is already smaller than idx, K smaller indices exist.
+__device__ __forceinline__ void slot_insert_tail(uint32_t *S, int K, uint32_t idx) {
   uint32_t cur = idx;
-  for (int k = 0; k < K; ++k) {
+  for (int k = 1; k < K; ++k) {
     const uint32_t s = __ldcg(S + k);
     if (s < cur) continue;               // stale reads are larger: conservative
     const uint32_t old = atomicMin(S + k, cur);
@@ -497,20 +503,40 @@ __device__ __forceinline__ void slot_insert(uint32_t *S, int K, uint32_t idx) {
 }
 
 // K3 ------------------------------------------------------------------------
-// grid (ceil(ntiles/8), B), 256 threads: one warp per 128-point tile region.
+// grid (ceil(ntiles/8), frames), 256 threads: one warp per 128-point tile region.
+// Neighbouring pixels often share a voxel: lanes holding the same table slot form a
+// group (__match_any_sync); only the group leader walks table -> rank -> last slot and
+// broadcasts the result, and a whole group leaves after one load when the voxel is full.
 static __global__ void __launch_bounds__(256) hv_slots_kernel(HvWork w, int32_t *point2voxel) {
   const int b = blockIdx.y + w.b0;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= w.ntiles) return;
   const int n = w.cand_cnt[(int64_t)b * w.ntiles + t];
+  if (n == 0) return;
+  const int lane = threadIdx.x & 31;
   const uint2 *cand = w.cand + (int64_t)b * w.N + ((int64_t)t << kTileShift);
   const unsigned long long *table = w.table + (int64_t)b * w.cap;
-  for (int j = threadIdx.x & 31; j < n; j += 32) {
-    const uint2 c = __ldg(cand + j);
-    const uint32_t first_idx = (uint32_t)__ldg(table + c.y);
-    const int r = voxel_rank(w, b, first_idx);
-    if (r < w.max_voxels) {
-      slot_insert(w.slots + ((int64_t)b * w.max_voxels + r) * w.K, w.K, c.x);
+  for (int j0 = 0; j0 < n; j0 += 32) {
+    const int j = j0 + lane;
+    const bool on = j < n;
+    const uint2 c = on ? __ldg(cand + j) : make_uint2(0u, kEmpty32 - lane);   // distinct dummies
+    const unsigned grp = __match_any_sync(0xffffffffu, c.y);
+    const int leader = __ffs(grp) - 1;
+    uint32_t first_idx = 0, last = 0;
+    int r = w.max_voxels;
+    if (on && lane == leader) {
+      first_idx = (uint32_t)__ldg(table + c.y);
+      r = voxel_rank(w, b, first_idx);
+      if (r < w.max_voxels && w.K > 1)
+        last = __ldcg(w.slots + ((int64_t)b * w.max_voxels + r) * w.K + (w.K - 1));
+    }
+    first_idx = __shfl_sync(0xffffffffu, first_idx, leader);
+    last = __shfl_sync(0xffffffffu, last, leader);
+    r = __shfl_sync(0xffffffffu, r, leader);
+    if (on && r < w.max_voxels) {
+      uint32_t *S = w.slots + ((int64_t)b * w.max_voxels + r) * w.K;
+      if (c.x == first_idx) S[0] = c.x;                       // the voxel's first point
+      else if (w.K > 1 && !(last < c.x)) slot_insert_tail(S, w.K, c.x);
       if (point2voxel) point2voxel[(int64_t)b * w.N + c.x] = r;
     }
   }
@@ -707,7 +733,13 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
       hv_insert_kernel<Src><<<grid, kInsThreads, 0, stream>>>(src, g, w, begin, end, r);
     }
     prof_mark(stream, 2);
-    hv_first_kernel<<<dim3((unsigned)ceil_div(p.cap, 256), nb), 256, 0, stream>>>(w);
+    {
+      int gx = (int)ceil_div(p.cap, 256 * 8);
+      const int lim = (148 * 16 + nb - 1) / nb;
+      if (gx > lim) gx = lim;
+      if (gx < 1) gx = 1;
+      hv_first_kernel<<<dim3(gx, nb), 256, 0, stream>>>(w);
+    }
     hv_flagscan_kernel<<<dim3(p.nchunks, nb), kScanThreads, 0, stream>>>(w);
     prof_mark(stream, 3);
     scan_chunks_kernel<<<nb, 1024, 0, stream>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels, b0);
