@@ -57,23 +57,22 @@ struct PointsSource {
   int host_num_feats() const { return C; }
   __device__ __forceinline__ int num_feats() const { return C; }
 
-  // stage AB: a lane walks its 4 consecutive points
-  struct Cursor { const float *p; };
-  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t, const float *) const {
+  // stage AB: a lane owns 4 consecutive points
+  struct Cursor { const float *p; int npx; };
+  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *) const {
     Cursor c;
     c.p = pts + ((int64_t)b * N + i0) * C;
+    const int64_t left = end - i0;
+    c.npx = left >= 4 ? 4 : (left > 0 ? (int)left : 0);
     return c;
   }
-  // cell of the cursor's point: 1 inside / 0 outside / 2 undecided (-> cell_exact); then advance
-  __device__ __forceinline__ int cell_next(Cursor &c, bool exists, const float *, const VoxelGrid &g,
-                                           int &cx, int &cy, int &cz) const {
-    int r = 0;
-    if (exists) {
-      const float x = __ldg(c.p), y = __ldg(c.p + 1), z = __ldg(c.p + 2);
-      r = voxel_coor_fast(x, y, z, 0.0f, g, cx, cy, cz);
-    }
-    c.p += C;
-    return r;
+  // cell of the lane's Q-th point: 1 inside / 0 outside / 2 undecided (-> cell_exact)
+  template <int Q>
+  __device__ __forceinline__ int cell_q(const Cursor &c, const float *, const VoxelGrid &g, int &cx, int &cy,
+                                        int &cz) const {
+    if (Q >= c.npx) return 0;
+    const float *q = c.p + Q * C;
+    return voxel_coor_fast(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.0f, g, cx, cy, cz);
   }
   __device__ __forceinline__ bool cell_exact(int b, int64_t i, const float *, const VoxelGrid &g,
                                              int &cx, int &cy, int &cz) const {
@@ -131,50 +130,45 @@ struct DepthSource {
     v = fast_div(rem, p.div_w);
     u = rem - v * (uint32_t)p.W;
   }
-  // stage AB: a lane walks its 4 consecutive pixels
+  // stage AB: a lane owns 4 consecutive pixels
   struct Cursor {
     float z[4];
     unsigned valid;        // depth/conf/sky mask of the 4 pixels
-    uint32_t cam, v, u;
-    int q;
+    uint32_t cam, v, u;    // of the first pixel
+    uint32_t pix0;
+    bool wraps;            // the 4 pixels cross a row boundary (only when W % 4 != 0)
   };
   __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *) const {
     Cursor c;
     const int64_t gi = (int64_t)b * p.npix + i0;
-    if (vec_ok && i0 + 3 < end) {
+    const int64_t left = end - i0;
+    const int npx = left >= 4 ? 4 : (left > 0 ? (int)left : 0);
+    if (vec_ok && npx == 4) {
       const float4 t = __ldg(reinterpret_cast<const float4 *>(depth + gi));
       c.z[0] = t.x; c.z[1] = t.y; c.z[2] = t.z; c.z[3] = t.w;
     } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) c.z[q] = (i0 + q < end) ? __ldg(depth + gi + q) : 0.0f;
+      for (int q = 0; q < 4; ++q) c.z[q] = (q < npx) ? __ldg(depth + gi + q) : 0.0f;
     }
     c.valid = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) c.valid |= (i0 + q < end && depth_ok(c.z[q], gi + q)) ? (1u << q) : 0u;
-    pixel_cvu((uint32_t)i0, c.cam, c.v, c.u);
-    c.q = 0;
+    for (int q = 0; q < 4; ++q) c.valid |= (q < npx && depth_ok(c.z[q], gi + q)) ? (1u << q) : 0u;
+    c.pix0 = (uint32_t)i0;
+    pixel_cvu(c.pix0, c.cam, c.v, c.u);
+    c.wraps = c.u + 3 >= (uint32_t)p.W;
     return c;
   }
-  // cell of the cursor's pixel: 1 inside / 0 outside or masked / 2 undecided; then advance.
+  // cell of the lane's Q-th pixel: 1 inside / 0 outside or masked / 2 undecided.
   // The direct pixel->cell map (pixel_cell_fast) decides all but the pixels within its error
   // bound of a cell / range-filter boundary; those are redone by cell_exact.
-  __device__ __forceinline__ int cell_next(Cursor &c, bool, const float *s_cal, const VoxelGrid &g,
-                                           int &cx, int &cy, int &cz) const {
-    int r = 0;
-    if ((c.valid >> c.q) & 1u) {
-      float z = c.z[0];
-      z = c.q == 1 ? c.z[1] : z;
-      z = c.q == 2 ? c.z[2] : z;
-      z = c.q == 3 ? c.z[3] : z;
-      r = g.fast_ok ? pixel_cell_fast(z, (float)c.u, (float)c.v, s_cal + c.cam * kCalibFloats, g, rg, cx, cy, cz)
-                    : 2;
-    }
-    ++c.q;
-    if (++c.u == (uint32_t)p.W) {
-      c.u = 0;
-      if (++c.v == (uint32_t)p.H) { c.v = 0; ++c.cam; }
-    }
-    return r;
+  template <int Q>
+  __device__ __forceinline__ int cell_q(const Cursor &c, const float *s_cal, const VoxelGrid &g, int &cx,
+                                        int &cy, int &cz) const {
+    if (!((c.valid >> Q) & 1u)) return 0;
+    if (!g.fast_ok) return 2;
+    uint32_t cam = c.cam, v = c.v, u = c.u + Q;
+    if (c.wraps) pixel_cvu(c.pix0 + Q, cam, v, u);
+    return pixel_cell_fast(c.z[Q], (float)u, (float)v, s_cal + cam * kCalibFloats, g, rg, cx, cy, cz);
   }
   // pixel index -> exact ego-frame point (reference arithmetic); false if the range filter drops it
   __device__ __forceinline__ bool point(int b, int64_t i, const float *s_cal, float &x, float &y,
@@ -308,13 +302,9 @@ __global__ void __launch_bounds__(kInsThreads)
 
   // ---- stage AB ---------------------------------------------------------------------
   const int64_t i0 = base + 4 * lane;
-  typename Src::Cursor cur = src.cursor(b, i0 < end ? i0 : base, end, s_cal);
+  typename Src::Cursor cur = src.cursor(b, i0, end, s_cal);
   int n2 = 0, nu = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    int cx, cy, cz;
-    int r = src.cell_next(cur, i0 + q < end, s_cal, g, cx, cy, cz);
-    if (i0 + q >= end) r = 0;
+  auto put = [&](int r, int q, int cx, int cy, int cz) {
     const unsigned b1 = __ballot_sync(0xffffffffu, r == 1);
     const unsigned b2 = __ballot_sync(0xffffffffu, r == 2);
     if (r == 1) {
@@ -326,6 +316,17 @@ __global__ void __launch_bounds__(kInsThreads)
     }
     n2 += __popc(b1);
     nu += __popc(b2);
+  };
+  {
+    int cx = 0, cy = 0, cz = 0;
+    int r = src.template cell_q<0>(cur, s_cal, g, cx, cy, cz);
+    put(r, 0, cx, cy, cz);
+    r = src.template cell_q<1>(cur, s_cal, g, cx, cy, cz);
+    put(r, 1, cx, cy, cz);
+    r = src.template cell_q<2>(cur, s_cal, g, cx, cy, cz);
+    put(r, 2, cx, cy, cz);
+    r = src.template cell_q<3>(cur, s_cal, g, cx, cy, cz);
+    put(r, 3, cx, cy, cz);
   }
   __syncwarp();
 #pragma unroll 1
@@ -527,12 +528,16 @@ static __global__ void __launch_bounds__(256) hv_slots_kernel(HvWork w, int32_t 
     if (on && lane == leader) {
       first_idx = (uint32_t)__ldg(table + c.y);
       r = voxel_rank(w, b, first_idx);
-      if (r < w.max_voxels && w.K > 1)
-        last = __ldcg(w.slots + ((int64_t)b * w.max_voxels + r) * w.K + (w.K - 1));
     }
     first_idx = __shfl_sync(0xffffffffu, first_idx, leader);
-    last = __shfl_sync(0xffffffffu, last, leader);
     r = __shfl_sync(0xffffffffu, r, leader);
+    // the last slot is only needed by points that are not their voxel's first point
+    const bool tail = on && r < w.max_voxels && w.K > 1 && c.x != first_idx;
+    const unsigned tails = __ballot_sync(0xffffffffu, tail);
+    if (tails & grp) {
+      if (lane == leader) last = __ldcg(w.slots + ((int64_t)b * w.max_voxels + r) * w.K + (w.K - 1));
+      last = __shfl_sync(grp, last, leader);
+    }
     if (on && r < w.max_voxels) {
       uint32_t *S = w.slots + ((int64_t)b * w.max_voxels + r) * w.K;
       if (c.x == first_idx) S[0] = c.x;                       // the voxel's first point
@@ -694,14 +699,6 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   w.direct = (volume <= (uint64_t)p.cap) ? 1 : 0;
   w.nwords = p.nwords; w.nchunks = p.nchunks; w.K = p.K; w.max_voxels = p.max_voxels;
 
-  // Frames are processed in groups small enough that a group's table, slot arrays and
-  // candidate lists stay resident in the 126 MB L2 from the memset to the emit kernel:
-  // the random table / slot accesses then never go to HBM.
-  const size_t per_frame = (size_t)p.cap * 8 + (size_t)p.max_voxels * p.K * 4 + (size_t)p.nwords * 8;
-  int G = (int)((48u << 20) / (per_frame ? per_frame : 1));
-  if (const char *e = getenv("RD3_GROUP")) G = atoi(e);
-  if (G < 1) G = 1;
-  if (G > p.B) G = p.B;
   const int C = src.host_num_feats();
   int V = 1024 / p.K;            // ~1024 slot items per CTA: amortises the calibration staging
   if (V < 1) V = 1;
@@ -715,42 +712,66 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   if (out.point2voxel && p.N > 0)
     RD3_CUDA_TRY(cudaMemsetAsync(out.point2voxel, 0xFF, (size_t)p.B * p.N * 4, stream));
 
-  for (int b0 = 0; b0 < p.B; b0 += G) {
-    const int nb = (p.B - b0 < G) ? p.B - b0 : G;
+  // Frames are independent: the batch is split into up to kMaxLanes sub-batches that run the
+  // whole kernel sequence on their own streams (forked from / joined to the caller's stream),
+  // so that the issue-bound insert kernel of one sub-batch overlaps the latency-bound
+  // first/slots kernels and memsets of another.  With the stage profiler on, one lane is used.
+  StreamLanes *lanes = nullptr;
+  int nl = 1;
+  if (!prof_enabled() && p.B >= 2) {
+    nl = stream_lane_count();
+    if (nl > p.B) nl = p.B;
+    if (nl > 1) {
+      lanes = get_stream_lanes();
+      if (!lanes) nl = 1;
+    }
+  }
+  if (nl > 1) RD3_CUDA_TRY(cudaEventRecord(lanes->fork, stream));
+  for (int l = 0; l < nl; ++l) {
+    const int b0 = (int)((int64_t)p.B * l / nl), b1 = (int)((int64_t)p.B * (l + 1) / nl);
+    const int nb = b1 - b0;
+    cudaStream_t st = stream;
+    if (l > 0) {
+      st = lanes->s[l - 1];
+      RD3_CUDA_TRY(cudaStreamWaitEvent(st, lanes->fork, 0));
+    }
     w.b0 = b0;
-    prof_mark(stream, 0);
-    RD3_CUDA_TRY(cudaMemsetAsync(w.table + (size_t)b0 * p.cap, 0xFF, (size_t)nb * p.cap * 8, stream));
+    prof_mark(st, 0);
+    RD3_CUDA_TRY(cudaMemsetAsync(w.table + (size_t)b0 * p.cap, 0xFF, (size_t)nb * p.cap * 8, st));
     RD3_CUDA_TRY(cudaMemsetAsync(w.slots + (size_t)b0 * p.max_voxels * p.K, 0xFF,
-                                 (size_t)nb * p.max_voxels * p.K * 4, stream));
-    RD3_CUDA_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords, 0, (size_t)nb * p.nwords * 4, stream));
+                                 (size_t)nb * p.max_voxels * p.K * 4, st));
+    RD3_CUDA_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords, 0, (size_t)nb * p.nwords * 4, st));
     RD3_CUDA_TRY(cudaMemsetAsync(w.round_claims + (size_t)b0 * kMaxRounds, 0, (size_t)nb * kMaxRounds * 4,
-                                 stream));
-    prof_mark(stream, 1);
+                                 st));
+    prof_mark(st, 1);
     for (int r = 0; r < p.rounds && p.N > 0; ++r) {
       const int64_t begin = (int64_t)r * p.S;
       const int64_t end = begin + p.S < p.N ? begin + p.S : p.N;
       dim3 grid((unsigned)ceil_div(end - begin, kInsPoints), nb);
-      hv_insert_kernel<Src><<<grid, kInsThreads, 0, stream>>>(src, g, w, begin, end, r);
+      hv_insert_kernel<Src><<<grid, kInsThreads, 0, st>>>(src, g, w, begin, end, r);
     }
-    prof_mark(stream, 2);
+    prof_mark(st, 2);
     {
       int gx = (int)ceil_div(p.cap, 256 * 8);
       const int lim = (148 * 16 + nb - 1) / nb;
       if (gx > lim) gx = lim;
       if (gx < 1) gx = 1;
-      hv_first_kernel<<<dim3(gx, nb), 256, 0, stream>>>(w);
+      hv_first_kernel<<<dim3(gx, nb), 256, 0, st>>>(w);
     }
-    hv_flagscan_kernel<<<dim3(p.nchunks, nb), kScanThreads, 0, stream>>>(w);
-    prof_mark(stream, 3);
-    scan_chunks_kernel<<<nb, 1024, 0, stream>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels, b0);
-    prof_mark(stream, 4);
+    hv_flagscan_kernel<<<dim3(p.nchunks, nb), kScanThreads, 0, st>>>(w);
+    prof_mark(st, 3);
+    scan_chunks_kernel<<<nb, 1024, 0, st>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels, b0);
+    prof_mark(st, 4);
     if (p.N > 0)
-      hv_slots_kernel<<<dim3((unsigned)ceil_div(p.ntiles, 8), nb), 256, 0, stream>>>(w, out.point2voxel);
-    prof_mark(stream, 5);
-    hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, V), nb), 256, smem, stream>>>(src, g, w, out,
-                                                                                             V);
-    prof_mark(stream, 6);
-    prof_mark(stream, 7);
+      hv_slots_kernel<<<dim3((unsigned)ceil_div(p.ntiles, 8), nb), 256, 0, st>>>(w, out.point2voxel);
+    prof_mark(st, 5);
+    hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, V), nb), 256, smem, st>>>(src, g, w, out, V);
+    prof_mark(st, 6);
+    prof_mark(st, 7);
+    if (l > 0) {
+      RD3_CUDA_TRY(cudaEventRecord(lanes->join[l - 1], st));
+      RD3_CUDA_TRY(cudaStreamWaitEvent(stream, lanes->join[l - 1], 0));
+    }
   }
   return check_launch();
 }

@@ -26,6 +26,17 @@ int check_launch();
 // launching stream (rd3_profile_enable / rd3_profile_read).  No-op when disabled.
 constexpr int kProfStages = 7;   // memset, insert, flags, scan, slots, emit, meta
 void prof_mark(cudaStream_t stream, int boundary);   // boundary 0..kProfStages
+bool prof_enabled();
+
+// Internal side streams for the frame sub-batches of the hard-voxel pipeline (created once
+// per device, non-blocking, event fork/join with the caller's stream).
+constexpr int kMaxLanes = 4;
+struct StreamLanes {
+  cudaStream_t s[kMaxLanes - 1];
+  cudaEvent_t fork, join[kMaxLanes - 1];
+};
+StreamLanes *get_stream_lanes();   // nullptr if creation failed
+int stream_lane_count();           // RD3_STREAMS (1..kMaxLanes), default 3
 
 #define RD3_CUDA_TRY(expr)                       \
   do {                                           \

@@ -1,6 +1,7 @@
 // voxelize.cu -- C-ABI entry points for dynamic / hard voxelization of a point
 // array and the standalone HardSimpleVFE, plus library-wide helpers.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "hard_voxel.cuh"
@@ -41,6 +42,40 @@ void prof_mark(cudaStream_t stream, int boundary) {
     ++g_prof.calls;
     g_prof.in_call = false;
   }
+}
+
+bool prof_enabled() { return g_prof.enabled; }
+
+namespace {
+struct LaneSet {
+  bool tried = false, ok = false;
+  StreamLanes lanes;
+};
+LaneSet g_lanes[64];
+}  // namespace
+
+StreamLanes *get_stream_lanes() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  LaneSet &L = g_lanes[dev];
+  if (!L.tried) {
+    L.tried = true;
+    bool ok = cudaEventCreateWithFlags(&L.lanes.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < kMaxLanes - 1; ++i) {
+      ok = cudaStreamCreateWithFlags(&L.lanes.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&L.lanes.join[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    L.ok = ok;
+  }
+  return L.ok ? &L.lanes : nullptr;
+}
+
+int stream_lane_count() {
+  int n = 3;
+  if (const char *e = getenv("RD3_STREAMS")) n = atoi(e);
+  if (n < 1) n = 1;
+  if (n > kMaxLanes) n = kMaxLanes;
+  return n;
 }
 
 int make_grid(const float voxel_size[3], const float coors_range[6], VoxelGrid *g,
