@@ -30,6 +30,8 @@ if ROOT not in sys.path:
 METRIC = "points_per_sec_unproject_voxelize_scatter"
 UNIT = "points/s"
 WORKLOAD = "C2"
+WORKLOAD_DESC = ("C2: fused depth unprojection + hard voxelization + voxel mean, 6x504x896 depth, "
+                 "voxel 0.075/0.075/0.2, max_points 10, max_voxels 120000, max_depth 100")
 
 
 # --------------------------------------------------------------------------------------
@@ -135,9 +137,8 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "frames_per_sec": frames / t,
-        "config": {"workload": WORKLOAD + ": fused depth unprojection + hard voxelization, 6x504x896 depth, "
-                               "voxel 0.075/0.075/0.2, max_points 10, max_voxels 120000",
-                   "frames_per_step": ref.workers},
+        "config": {"workload": WORKLOAD_DESC, "scene": "mixture", "frames_per_step": ref.workers,
+                   "note": "bounded sample of the same workload: one frame per host core per step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.workers, "kind": ref.kind,
                          "sample": ref.describe()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -164,7 +165,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -207,7 +208,7 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
@@ -431,9 +432,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "frames_per_sec": world * B / (ms_per_step * 1e-3),
-            "config": {"workload": WORKLOAD + ": fused depth unprojection + hard voxelization + voxel mean, "
-                                   "6x504x896 depth, voxel 0.075/0.075/0.2, max_points 10, max_voxels 120000, "
-                                   "max_depth 100",
+            "config": {"workload": WORKLOAD_DESC,
                        "scene": args.scene, "frames_per_gpu_per_step": B, "pixels_per_frame": npix,
                        "voxels_per_frame_mean": M_total / B,
                        "l2": "inputs larger than L2 (%.0f MB depth per step per GPU vs 126 MB L2)" % (B * npix * 4 / 1e6),
