@@ -564,13 +564,19 @@ __global__ void __launch_bounds__(256) hv_emit_kernel(Src src, VoxelGrid g, HvWo
   const int nvox = min(V, vn - r0);
   const int items = nvox * K;
   float *tile = s_dyn;
-  uint32_t *s_idx = reinterpret_cast<uint32_t *>(s_dyn + (size_t)V * K * C);
+  uint32_t *s_idx = reinterpret_cast<uint32_t *>(s_dyn + (((size_t)V * K * C + 3) & ~(size_t)3));
   const uint32_t *S = w.slots + ((int64_t)b * w.max_voxels + r0) * K;
 
   // pass 1: slot indices; zero the tile; compact the non-empty items so that the
   // (expensive) gather / re-unprojection below runs on dense lanes
   uint16_t *s_list = reinterpret_cast<uint16_t *>(s_idx + (size_t)V * K);
   if (threadIdx.x == 0) s_count = 0;
+  {
+    // zero the whole tile with 16-byte stores; the gather below overwrites the non-empty items
+    float4 *t4 = reinterpret_cast<float4 *>(tile);
+    const int n4 = (items * C + 3) >> 2;      // the tile is allocated for V*K*C >= items*C, padded below
+    for (int e = threadIdx.x; e < n4; e += blockDim.x) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   __syncthreads();
   for (int it0 = 0; it0 < items; it0 += blockDim.x) {
     const int it = it0 + threadIdx.x;
@@ -578,10 +584,6 @@ __global__ void __launch_bounds__(256) hv_emit_kernel(Src src, VoxelGrid g, HvWo
     if (it < items) {
       idx = __ldg(S + it);
       s_idx[it] = idx;
-      if (idx == kEmpty32) {
-        float *dst = tile + (size_t)it * C;
-        for (int c = 0; c < C; ++c) dst[c] = 0.0f;
-      }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, idx != kEmpty32);
     int wbase = 0;
@@ -599,7 +601,15 @@ __global__ void __launch_bounds__(256) hv_emit_kernel(Src src, VoxelGrid g, HvWo
 
   // voxels: contiguous nvox*K*C floats
   float *vout = o.voxels + ((int64_t)b * w.max_voxels + r0) * K * C;
-  for (int e = threadIdx.x; e < items * C; e += blockDim.x) vout[e] = tile[e];
+  const int nfl = items * C;
+  if ((reinterpret_cast<uintptr_t>(vout) & 15) == 0) {
+    const float4 *t4 = reinterpret_cast<const float4 *>(tile);
+    float4 *v4 = reinterpret_cast<float4 *>(vout);
+    for (int e = threadIdx.x; e < (nfl >> 2); e += blockDim.x) v4[e] = t4[e];
+    for (int e = (nfl & ~3) + threadIdx.x; e < nfl; e += blockDim.x) vout[e] = tile[e];
+  } else {
+    for (int e = threadIdx.x; e < nfl; e += blockDim.x) vout[e] = tile[e];
+  }
 
   // per-voxel meta: coords from the first point, count
   int *s_cnt = reinterpret_cast<int *>(s_list + (((size_t)V * K + 7) & ~(size_t)7));
@@ -704,7 +714,8 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   if (V < 1) V = 1;
   if (V > 128) V = 128;
   while (V > 1 && (size_t)V * p.K * (C + 1) * 4 > 40 * 1024) V /= 2;
-  const size_t smem = (size_t)V * p.K * (C + 1) * 4 + align_up((size_t)V * p.K * 2, 16) + (size_t)V * 4;
+  const size_t smem = align_up((size_t)V * p.K * C * 4, 16) + (size_t)V * p.K * 4 +
+                      align_up((size_t)V * p.K * 2, 16) + (size_t)V * 4;
   if (smem > 200 * 1024) return RD3_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
     RD3_CUDA_TRY(cudaFuncSetAttribute(hv_emit_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize,
