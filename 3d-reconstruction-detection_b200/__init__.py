@@ -24,3 +24,4 @@ from .backproject import (DepthToPointsMixin, backproject_depth_to_points,  # no
 from .fused import DepthToVoxels  # noqa: F401
 from .parallel import gather_voxel_outputs, shard_range, shard_sizes  # noqa: F401
 from .patch import patch_mmdet3d  # noqa: F401
+from .pipelines import FilterPointByRange, VoxelDownsample  # noqa: F401

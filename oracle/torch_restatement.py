@@ -181,3 +181,21 @@ def dynamic_scatter_batched(feats, coors, reduce_type):
         cs.append(torch.nn.functional.pad(r[1], (1, 0), mode="constant", value=i))
         vs.append(r[0])
     return torch.cat(vs, dim=0), torch.cat(cs, dim=0)
+
+
+def voxel_downsample(ref_layer, points, voxel_size, point_cloud_range, colors=None):
+    """respoint_post_processing.py:29-98 on CPU tensors, driving the compiled reference op."""
+    pcr = point_cloud_range
+    if pcr is None:
+        pcr = (points.min(dim=0).values - 1.0).tolist() + (points.max(dim=0).values + 1.0).tolist()
+    vs = [voxel_size] * 3 if isinstance(voxel_size, (int, float)) else list(voxel_size)
+    voxels, coors, num = voxelization_forward(ref_layer, points.contiguous(), vs, list(pcr), 100, 200000)
+    if voxels.shape[0] == 0:
+        return points, colors, torch.arange(points.shape[0])
+    centers = torch.stack([voxels[i, :int(num[i])].mean(dim=0) for i in range(voxels.shape[0])], dim=0)
+    idx = torch.arange(centers.shape[0])
+    vcol = None
+    if colors is not None:
+        idx = torch.argmin(torch.cdist(centers, points, compute_mode='donot_use_mm_for_euclid_dist'), dim=1)
+        vcol = colors[idx]
+    return centers, vcol, idx

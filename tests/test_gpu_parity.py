@@ -428,3 +428,29 @@ def test_dynamic_scatter_batched_and_backward():
     out, _ = rd3_b200.DynamicScatter([1, 1, 1], [0, 0, 0, 1, 1, 1], True)(f, neg)
     out.sum().backward()
     assert (f.grad == 0).all()
+
+
+# ----------------------------------------------------------------------------------------------
+# §8(f) next rows: pipeline steps of the plugin
+# ----------------------------------------------------------------------------------------------
+def test_voxel_downsample_and_range_filter(ref_layer):
+    _, pts = frame_points("C1", scene="ground")
+    pts = pts[:60000]
+    g = torch.Generator().manual_seed(0)
+    cols = torch.rand(len(pts), 3, generator=g)
+    p = torch.from_numpy(pts)
+    out = rd3_b200.FilterPointByRange(synthetic.FILTER_RANGE)({'points': p.to(DEV), 'colors': cols.to(DEV)})
+    rp, ri = tr.filter_point_by_range(p, synthetic.FILTER_RANGE)
+    assert torch.equal(out['points'].cpu(), rp) and torch.equal(out['indices'].cpu(), ri)
+    fp, fc = out['points'], out['colors']
+    ds = rd3_b200.VoxelDownsample(voxel_size=0.5, point_cloud_range=list(synthetic.FILTER_RANGE))
+    r = ds({'points': fp, 'colors': fc})
+    ec, ecol, eidx = tr.voxel_downsample(ref_layer, fp.cpu(), 0.5, list(synthetic.FILTER_RANGE), fc.cpu())
+    assert r['points'].shape == ec.shape
+    assert torch.allclose(r['points'].cpu(), ec, rtol=1e-6, atol=1e-5)
+    # nearest-point colours: identical except where two points are equidistant to rounding
+    same = (r['indices'].cpu() == eidx).float().mean().item()
+    assert same > 0.999
+    r2 = rd3_b200.VoxelDownsample(voxel_size=[0.5, 0.5, 0.5])({'points': fp})          # auto range, no colours
+    ec2, _, _ = tr.voxel_downsample(ref_layer, fp.cpu(), 0.5, None)
+    assert torch.allclose(r2['points'].cpu(), ec2, rtol=1e-6, atol=1e-5) and r2['colors'] is None
