@@ -362,7 +362,8 @@ def main():
     kern = {k: v for k, v in stage_ms.items() if k != "memset"}
     dom = max(kern, key=kern.get) if calls else "insert"
     # launches of the dominant kernel per step (insert: one per round; others: one)
-    S_round = max(-(-(-(-npix // 8)) // 1024) * 1024, 65536)
+    fill = -(-(-(-(148 * 8 * 1024) // B)) // 1024) * 1024          # mirrors hv_plan()
+    S_round = max(-(-(-(-npix // 8)) // 1024) * 1024, fill, 65536)
     rounds = -(-npix // S_round)
     lanes = max(1, min(int(os.environ.get("RD3_STREAMS", "3")), 4, B))
     dom_launches = rounds if dom == "insert" else 1

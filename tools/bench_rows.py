@@ -1,0 +1,149 @@
+#!/usr/bin/env python
+"""Per-row timings of SURVEY.md §8(a) on one GPU: every operator of the path at its
+BASELINE.json configuration, CUDA events, inputs resident in HBM, against the
+algorithmic bytes of SURVEY §8(d).  Secondary to bench.py (which measures the
+headline C2 metric); output is a small table + JSON for profiles/.
+
+    python tools/bench_rows.py [--iters 20] [--scene mixture|ground] [--json out.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import rd3_b200  # noqa: E402
+from rd3_b200 import synthetic, voxel_layer  # noqa: E402
+
+PEAK = 6551.4
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timeit(fn, iters, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.add_(1.0)                       # > L2: evict between iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--scene", default="mixture")
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    flush = torch.zeros(64 << 20, device=dev)            # 256 MB
+    rows = []
+
+    def add(name, cfg, units, unit_name, alg_bytes, ms):
+        med, best = ms
+        rows.append(dict(row=name, config=cfg, units=units, unit=unit_name, alg_MB=alg_bytes / 1e6,
+                         ms_median=med, ms_best=best, GBps=alg_bytes / med / 1e6,
+                         frac_of_hbm=alg_bytes / med / 1e6 / PEAK, Munits_per_s=units / med / 1e3))
+
+    # ---- C2-shaped inputs ------------------------------------------------------------
+    c2 = synthetic.CONFIGS["C2"]
+    H, W = c2["hw"]
+    B = 8
+    b = synthetic.make_batch(list(range(B)), H, W, scene=args.scene)
+    d = {k: v.to(dev) for k, v in b.items()}
+    npix = 6 * H * W
+
+    # a1 unprojection (module interface, padded output, no sync)
+    fn = lambda: rd3_b200.unproject_padded(d["depth"], d["intrinsics"], d["cam2lidar"], max_depth=synthetic.MAX_DEPTH)
+    pts, counts = fn()
+    P = int(counts.sum())
+    add("a1 unproject", "8 x 6x504x896, max_depth", B * npix, "pixel", B * npix * 4 + P * 12, timeit(fn, args.iters, flush))
+    thr = 1.4
+    fn = lambda: rd3_b200.unproject_padded(d["depth"], d["intrinsics"], d["cam2lidar"], max_depth=synthetic.MAX_DEPTH,
+                                           confs=d["conf"], conf_thresh=thr, sky_masks=d["sky"],
+                                           range_filter=synthetic.FILTER_RANGE)
+    pts2, counts2 = fn()
+    P2 = int(counts2.sum())
+    add("a1+a2 unproject+masks+range", "8 x 6x504x896", B * npix, "pixel", B * npix * 9 + P2 * 12,
+        timeit(fn, args.iters, flush))
+
+    # one frame's cloud for the point-array operators
+    n0 = int(counts[0])
+    cloud = pts[0, :n0].contiguous()
+    N, C = cloud.shape
+
+    # a3 dynamic voxelize
+    vox_dyn = rd3_b200.Voxelization(c2["voxel_size"], c2["pcr"], -1)
+    coors = vox_dyn(cloud)
+    add("a3 dynamic_voxelize", "C3 grid 1440x1440x40, N=%d" % N, N, "point", N * 24, timeit(lambda: vox_dyn(cloud), args.iters, flush))
+
+    # a4 hard voxelize (+a5 wrapper) C1/C2 grid and C4 pillars
+    for name, cfg in (("C2", c2), ("C4", synthetic.CONFIGS["C4"])):
+        K, mv = cfg["max_points"], cfg["max_voxels"][0]
+        voxels = torch.empty((mv, K, C), device=dev)
+        co = torch.empty((mv, 3), dtype=torch.int32, device=dev)
+        nu = torch.empty((mv,), dtype=torch.int32, device=dev)
+        mean = torch.empty((mv, C), device=dev)
+        fnh = lambda: voxel_layer.hard_voxelize(cloud, voxels, co, nu, list(cfg["voxel_size"]), list(cfg["pcr"]), K, mv,
+                                                voxel_mean=mean)
+        M = fnh()
+        add("a4+a9 hard_voxelize+mean (%s)" % name, "N=%d, M=%d, K=%d (incl. count D2H)" % (N, M, K), N, "point",
+            N * 12 + M * (K * 12 + 16) + M * 12, timeit(fnh, args.iters, flush))
+        vfe = rd3_b200.HardSimpleVFE(3)
+        vv, nn = voxels[:M].contiguous(), nu[:M].contiguous()
+        add("a9 HardSimpleVFE (%s)" % name, "M=%d, K=%d" % (M, K), M, "voxel", M * (K * 12 + 4 + 12),
+            timeit(lambda: vfe(vv, nn, None), args.iters, flush))
+
+    # a6/a7 DynamicScatter mean / max (C3)
+    for avg in (True, False):
+        ds = rd3_b200.DynamicScatter(c2["voxel_size"], c2["pcr"], avg)
+        vf, vc = ds(cloud, coors)
+        M = vf.shape[0]
+        add("a6 DynamicScatter %s (C3)" % ("mean" if avg else "max"), "N=%d, M=%d (incl. M D2H)" % (N, M), N, "point",
+            N * 28 + M * 28, timeit(lambda: ds(cloud, coors), args.iters, flush))
+    # a8 backward
+    f = cloud.clone().requires_grad_()
+    ds = rd3_b200.DynamicScatter(c2["voxel_size"], c2["pcr"], True)
+    vf, vc = ds(f, coors)
+    g = torch.ones_like(vf)
+
+    def bwd():
+        f.grad = None
+        vf.backward(g, retain_graph=True)
+    add("a8 DynamicScatter backward mean", "N=%d, M=%d" % (N, vf.shape[0]), N, "point", N * 16 + vf.shape[0] * 16,
+        timeit(bwd, args.iters, flush))
+
+    # fused C2 / C4 (batched, 8 frames)
+    for name, cfg in (("C2", c2), ("C4", synthetic.CONFIGS["C4"])):
+        mod = rd3_b200.DepthToVoxels(cfg["voxel_size"], cfg["pcr"], cfg["max_points"], cfg["max_voxels"],
+                                     max_depth=synthetic.MAX_DEPTH).to(dev).train()
+        r = mod(d["depth"], d["intrinsics"], d["cam2lidar"])
+        M = int(r["voxel_num"].sum())
+        K = cfg["max_points"]
+        add("fused depth->voxels (%s)" % name, "8 frames, M=%d" % M, B * npix, "pixel", B * npix * 4 + M * (K * 12 + 28),
+            timeit(lambda: mod(d["depth"], d["intrinsics"], d["cam2lidar"]), args.iters, flush))
+
+    print("%-38s %-40s %10s %9s %9s %8s %10s" % ("row", "config", "alg MB", "ms(med)", "GB/s", "of HBM", "Munit/s"))
+    for r in rows:
+        print("%-38s %-40s %10.1f %9.3f %9.1f %7.1f%% %10.1f" % (r["row"], r["config"][:40], r["alg_MB"], r["ms_median"],
+                                                                 r["GBps"], 100 * r["frac_of_hbm"], r["Munits_per_s"]))
+    if args.json:
+        json.dump(dict(peak_gbs=PEAK, scene=args.scene, rows=rows), open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
