@@ -662,8 +662,11 @@ inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels) {
   HvPlan p;
   p.N = N; p.B = B; p.K = K; p.max_voxels = max_voxels;
   const int64_t n1 = N > 0 ? N : 1;
-  // round length: at most 8 rounds unless that makes rounds shorter than 64 Ki points
+  // round length: at most 8 rounds, but a round should keep the whole GPU busy
+  // (>= ~1.2 M points over all frames), so small batches use fewer, longer rounds
   int64_t S = ceil_div(ceil_div(n1, 8), kInsPoints) * kInsPoints;
+  const int64_t fill = ceil_div(ceil_div((int64_t)148 * 8 * kInsPoints, B > 0 ? B : 1), kInsPoints) * kInsPoints;
+  if (S < fill) S = fill;
   if (S < 65536) S = 65536;
   p.S = S;
   p.rounds = (int)ceil_div(n1, S);
