@@ -35,6 +35,7 @@ SIGNATURES = {
     "rd3_grid_size": (_i32, [_F3, _F6, _I3]),
     "rd3_dynamic_voxelize": (_i32, [_vp, _i64, _i32, _F3, _F6, _vp, _vp]),
     "rd3_hard_voxelize_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "rd3_hard_voxel_rounds": (_i32, [_i64, _i32]),
     "rd3_hard_voxelize": (_i32, [_vp, _i64, _i32, _F3, _F6, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
                                  _i32, _vp, _vp, _sz, _vp]),
     "rd3_hard_simple_vfe": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),

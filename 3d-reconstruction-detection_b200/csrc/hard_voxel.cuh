@@ -38,8 +38,12 @@
 namespace rd3 {
 
 constexpr int kInsThreads = 256;
-constexpr int kInsPoints = 1024;      // points per insert CTA (4 per thread)
-constexpr int kTilePoints = 128;      // points per warp tile
+constexpr int kTilePoints = 128;      // points per warp tile (4 per lane)
+#ifndef RD3_TILES_PER_WARP
+#define RD3_TILES_PER_WARP 1
+#endif
+constexpr int kTilesPerWarp = RD3_TILES_PER_WARP;   // tiles a warp walks: amortises the CTA prologue
+constexpr int kInsPoints = (kInsThreads / 32) * kTilePoints * kTilesPerWarp;   // points per insert CTA
 constexpr int kTileShift = 7;
 constexpr int kMaxRounds = 64;
 
@@ -275,8 +279,8 @@ template <class Src>
 __global__ void __launch_bounds__(kInsThreads)
     hv_insert_kernel(Src src, VoxelGrid g, HvWork w, int64_t begin, int64_t end, int round) {
   __shared__ float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 1];
-  __shared__ uint32_t s_keyb[kInsPoints];
-  __shared__ uint8_t s_l2b[kInsPoints], s_undb[kInsPoints];
+  __shared__ uint32_t s_keyb[(kInsThreads / 32) * kTilePoints];
+  __shared__ uint8_t s_l2b[(kInsThreads / 32) * kTilePoints], s_undb[(kInsThreads / 32) * kTilePoints];
   __shared__ int s_prev;
 
   const int b = blockIdx.y + w.b0;
@@ -295,10 +299,15 @@ __global__ void __launch_bounds__(kInsThreads)
   __syncthreads();
   const bool lookup_only = s_prev >= w.max_voxels;
 
-  const int64_t base = block_base + wv * kTilePoints;     // this warp's tile
-  if (base >= end) return;
   uint32_t *s_key = s_keyb + wv * kTilePoints;
   uint8_t *s_l2 = s_l2b + wv * kTilePoints, *s_und = s_undb + wv * kTilePoints;
+  unsigned long long *table = w.table + (int64_t)b * w.cap;
+  int claims = 0;
+#pragma unroll 1
+  for (int tw = 0; tw < kTilesPerWarp; ++tw) {
+  // consecutive warps take consecutive tiles (coalesced depth reads across the CTA)
+  const int64_t base = block_base + (int64_t)(tw * (kInsThreads / 32) + wv) * kTilePoints;
+  if (base >= end) break;
 
   // ---- stage AB ---------------------------------------------------------------------
   const int64_t i0 = base + 4 * lane;
@@ -349,9 +358,8 @@ __global__ void __launch_bounds__(kInsThreads)
   __syncwarp();
 
   // ---- stage C ----------------------------------------------------------------------
-  unsigned long long *table = w.table + (int64_t)b * w.cap;
   uint2 *cand = w.cand + (int64_t)b * w.N + base;
-  int nc = 0, claims = 0;
+  int nc = 0;
 #pragma unroll 1
   for (int j0 = 0; j0 < n2; j0 += 32) {
     const int j = j0 + lane;
@@ -371,6 +379,8 @@ __global__ void __launch_bounds__(kInsThreads)
     nc += __popc(bal);
   }
   if (lane == 0) w.cand_cnt[(int64_t)b * w.ntiles + (base >> kTileShift)] = (uint8_t)nc;
+  __syncwarp();
+  }   // tiles of this warp
   if (!lookup_only) {
     for (int d = 16; d > 0; d >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, d);
     if (lane == 0 && claims) atomicAdd(w.round_claims + b * kMaxRounds + round, claims);

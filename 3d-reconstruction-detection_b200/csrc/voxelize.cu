@@ -235,6 +235,11 @@ size_t rd3_hard_voxelize_workspace_bytes(int64_t N, int max_points, int max_voxe
   return hv_plan(N, 1, max_points, max_voxels).total;
 }
 
+int rd3_hard_voxel_rounds(int64_t N, int B) {
+  if (N < 0 || B <= 0) return 0;
+  return hv_plan(N, B, 1, 1).rounds;
+}
+
 int rd3_hard_voxelize(const float *points, int64_t N, int C, const float voxel_size[3],
                       const float coors_range[6], int max_points, int max_voxels, float *voxels,
                       int32_t *coors, int32_t *num_points_per_voxel, int32_t *d_voxel_num,

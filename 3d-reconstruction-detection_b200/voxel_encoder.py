@@ -22,11 +22,29 @@ def hard_simple_vfe(features, num_points, num_features):
     return out
 
 
-class HardSimpleVFE(nn.Module):
-    """Simple voxel feature encoder used in SECOND: the mean of the points of a voxel.
+class _HardSimpleVFEFn(torch.autograd.Function):
+    """forward = the sm_100a kernel; backward = d(sum_k x[m,k,f] / n[m]) = grad[m,f] / n[m] for
+    every slot k and f < F (what autograd derives for voxel_encoder.py:45-46)."""
 
-    Forward-only kernel (the reference's module is used under no_grad for the
-    pseudo-point branch and has no parameters)."""
+    @staticmethod
+    def forward(ctx, features, num_points, num_features):
+        ctx.save_for_backward(num_points)
+        ctx.shape = features.shape
+        return hard_simple_vfe(features, num_points, num_features)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (num_points,) = ctx.saved_tensors
+        M, K, C = ctx.shape
+        F = grad_out.shape[1]
+        g = grad_out / num_points.to(grad_out.dtype).view(-1, 1)
+        grad = grad_out.new_zeros((M, K, C))
+        grad[:, :, :F] = g.unsqueeze(1)
+        return grad, None, None
+
+
+class HardSimpleVFE(nn.Module):
+    """Simple voxel feature encoder used in SECOND: the mean of the points of a voxel."""
 
     def __init__(self, num_features=4):
         super(HardSimpleVFE, self).__init__()
@@ -35,5 +53,9 @@ class HardSimpleVFE(nn.Module):
 
     def forward(self, features, num_points, coors=None):
         out_half = features.dtype == torch.half
-        out = hard_simple_vfe(features.float().contiguous(), num_points.contiguous(), self.num_features)
+        feats = features.float().contiguous()
+        if feats.requires_grad and torch.is_grad_enabled():
+            out = _HardSimpleVFEFn.apply(feats, num_points.contiguous(), self.num_features)
+        else:
+            out = hard_simple_vfe(feats, num_points.contiguous(), self.num_features)
         return out.half() if out_half else out

@@ -362,9 +362,7 @@ def main():
     kern = {k: v for k, v in stage_ms.items() if k != "memset"}
     dom = max(kern, key=kern.get) if calls else "insert"
     # launches of the dominant kernel per step (insert: one per round; others: one)
-    fill = -(-(-(-(148 * 8 * 1024) // B)) // 1024) * 1024          # mirrors hv_plan()
-    S_round = max(-(-(-(-npix // 8)) // 1024) * 1024, fill, 65536)
-    rounds = -(-npix // S_round)
+    rounds = _lib.lib().rd3_hard_voxel_rounds(npix, B)
     lanes = max(1, min(int(os.environ.get("RD3_STREAMS", "3")), 4, B))
     dom_launches = rounds if dom == "insert" else 1
     dom_ms = stage_ms[dom] / dom_launches

@@ -97,6 +97,9 @@ RD3_API int rd3_dynamic_voxelize(const float *points, int64_t N, int C,
  *     point2voxel (N): voxel id of each point, -1 if out of range / dropped.
  * ------------------------------------------------------------------------- */
 RD3_API size_t rd3_hard_voxelize_workspace_bytes(int64_t N, int max_points, int max_voxels);
+/* number of insert-kernel launches (index-ordered rounds) a call with N points per frame and
+ * B frames makes; kernel launches per call = lanes * (rounds + 5) [+ 1 calibration kernel]. */
+RD3_API int rd3_hard_voxel_rounds(int64_t N, int B);
 
 RD3_API int rd3_hard_voxelize(const float *points, int64_t N, int C,
                       const float voxel_size[3], const float coors_range[6],

@@ -454,3 +454,115 @@ def test_voxel_downsample_and_range_filter(ref_layer):
     r2 = rd3_b200.VoxelDownsample(voxel_size=[0.5, 0.5, 0.5])({'points': fp})          # auto range, no colours
     ec2, _, _ = tr.voxel_downsample(ref_layer, fp.cpu(), 0.5, None)
     assert torch.allclose(r2['points'].cpu(), ec2, rtol=1e-6, atol=1e-5) and r2['colors'] is None
+
+
+# ----------------------------------------------------------------------------------------------
+# randomized stress: odd shapes, tiny images, K = 1, small max_voxels, masks on/off, B > 1
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_fused_randomized(seed):
+    g = np.random.default_rng(1000 + seed)
+    H, W = int(g.integers(5, 70)), int(g.integers(3, 140))
+    ncam = int(g.integers(1, 7))
+    B = int(g.integers(1, 4))
+    K = int(g.choice([1, 2, 5, 10, 33]))
+    mv = int(g.choice([1, 7, 300, 5000]))
+    vs = [float(g.choice([0.075, 0.2, 0.5, 1.3])), float(g.choice([0.075, 0.2, 0.5])), float(g.choice([0.2, 1.0, 8.0]))]
+    pcr = [-54.0, -54.0, -5.0, 54.0, 54.0, 3.0]
+    masks = bool(g.integers(0, 2))
+    scene = "ground" if g.integers(0, 2) else "mixture"
+    frames = [synthetic.make_frame(int(g.integers(0, 10000)), H, W, num_cams=ncam, scene=scene) for _ in range(B)]
+    b = {k: torch.stack([f[k] for f in frames]) for k in frames[0]}
+    d = {k: v.to(DEV) for k, v in b.items()}
+    rf = synthetic.FILTER_RANGE if masks else None
+    mod = rd3_b200.DepthToVoxels(vs, pcr, K, mv, max_depth=synthetic.MAX_DEPTH, range_filter=rf).to(DEV)
+    thr = 1.3 if masks else None
+    r = mod(d["depth"], d["intrinsics"], d["cam2lidar"], confs=d["conf"] if masks else None, conf_thresh=thr,
+            sky_masks=d["sky"] if masks else None)
+    vn = r["voxel_num"].cpu().numpy()
+    for i in range(B):
+        okw = dict(max_depth=synthetic.MAX_DEPTH)
+        if masks:
+            okw.update(conf=b["conf"][i].numpy(), conf_thresh=thr, sky=b["sky"][i].numpy(), range_filter=rf)
+        pts = oracle.unproject(b["depth"][i].numpy(), b["intrinsics"][i].numpy(), b["cam2lidar"][i].numpy(), **okw)
+        ov, oc, on = oracle.hard_voxelize(pts, vs, pcr, K, mv)
+        m = int(vn[i])
+        assert m == len(oc), (seed, i, m, len(oc))
+        assert np.array_equal(r["coors"][i, :m].cpu().numpy(), oc)
+        assert np.array_equal(r["num_points"][i, :m].cpu().numpy(), on)
+        assert np.array_equal(bits(r["voxels"][i, :m].cpu().numpy()), bits(ov))
+        # the same cloud through the points API must give the same thing
+        if len(pts):
+            v2, c2, n2 = gpu_hard(pts, vs, pcr, K, mv)
+            assert np.array_equal(c2, oc) and np.array_equal(n2, on) and np.array_equal(bits(v2), bits(ov))
+
+
+def test_cell_boundary_stress():
+    """Depth planes chosen so that many unprojected points land (to rounding) ON voxel boundaries:
+    the reciprocal fast path must hand every such pixel to the exact arithmetic."""
+    H, W = 64, 128
+    f = synthetic.make_frame(77, H, W, num_cams=2)
+    K_, M_ = f["intrinsics"].clone(), f["cam2lidar"].clone()
+    # axis-aligned camera looking along +x with zero translation: x_lidar = z_cam
+    for n in range(2):
+        M_[n] = torch.eye(4)
+        M_[n, :3, :3] = torch.tensor([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])
+    g = torch.Generator().manual_seed(5)
+    k = torch.randint(1, 700, (2, H, W), generator=g).float()
+    depth = k * 0.075                      # exact multiples of the voxel size (and neighbours below)
+    depth[:, ::2] = torch.nextafter(depth[:, ::2], torch.zeros(()))
+    depth[:, 1::4] = torch.nextafter(depth[:, 1::4], torch.full((), 1e9))
+    d = depth.unsqueeze(0).contiguous()
+    vs, pcr = [0.075, 0.075, 0.2], [-54.0, -54.0, -5.0, 54.0, 54.0, 3.0]
+    mod = rd3_b200.DepthToVoxels(vs, pcr, 10, 20000, max_depth=100.0).to(DEV)
+    r = mod(d.to(DEV), K_.unsqueeze(0).to(DEV), M_.unsqueeze(0).to(DEV))
+    pts = oracle.unproject(depth.numpy(), K_.numpy(), M_.numpy(), max_depth=100.0)
+    ov, oc, on = oracle.hard_voxelize(pts, vs, pcr, 10, 20000)
+    m = int(r["voxel_num"][0])
+    assert m == len(oc) and m > 500
+    assert np.array_equal(r["coors"][0, :m].cpu().numpy(), oc)
+    assert np.array_equal(r["num_points"][0, :m].cpu().numpy(), on)
+    assert np.array_equal(bits(r["voxels"][0, :m].cpu().numpy()), bits(ov))
+
+
+def test_hard_simple_vfe_backward():
+    g = torch.Generator().manual_seed(2)
+    M, K, C = 50, 6, 5
+    n = torch.randint(1, K + 1, (M,), generator=g, dtype=torch.int32)
+    x = torch.rand(M, K, C, generator=g)
+    a = x.clone().to(DEV).requires_grad_()
+    out = rd3_b200.HardSimpleVFE(4)(a, n.to(DEV), None)
+    w = torch.rand(M, 4, generator=g)
+    (out * w.to(DEV)).sum().backward()
+    xr = x.clone().requires_grad_()
+    (tr.hard_simple_vfe(xr, n, 4) * w).sum().backward()
+    assert torch.allclose(a.grad.cpu(), xr.grad, rtol=1e-6, atol=1e-7)
+
+
+def test_cuda_graph_capture_of_fused_path():
+    """The whole kernel sequence (incl. the internal stream lanes) is capturable: no host sync,
+    no allocation inside DepthToVoxels.forward in steady state."""
+    c = synthetic.CONFIGS["C1"]
+    H, W = 56, 96
+    b = synthetic.make_batch([0, 1, 2], H, W)
+    d = {k: v.to(DEV) for k, v in b.items()}
+    mod = rd3_b200.DepthToVoxels(c["voxel_size"], c["pcr"], c["max_points"], 3000, max_depth=synthetic.MAX_DEPTH).to(DEV)
+    k_, m_ = d["intrinsics"].contiguous(), d["cam2lidar"].contiguous()
+    ref = {k: v.clone() for k, v in mod(d["depth"], k_, m_).items()}        # warm-up allocates buffers
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        mod(d["depth"], k_, m_)                                               # workspace for stream s
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        out = mod(d["depth"], k_, m_)
+    for _ in range(3):
+        out["voxel_num"].zero_()
+        graph.replay()
+    torch.cuda.synchronize()
+    vn = ref["voxel_num"].tolist()
+    assert out["voxel_num"].tolist() == vn
+    for i, m in enumerate(vn):
+        assert torch.equal(out["coors"][i, :m], ref["coors"][i, :m])
+        assert torch.equal(out["voxels"][i, :m], ref["voxels"][i, :m])
