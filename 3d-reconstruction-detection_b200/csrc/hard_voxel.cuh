@@ -38,12 +38,8 @@
 namespace rd3 {
 
 constexpr int kInsThreads = 256;
-constexpr int kTilePoints = 128;      // points per warp tile (4 per lane)
-#ifndef RD3_TILES_PER_WARP
-#define RD3_TILES_PER_WARP 1
-#endif
-constexpr int kTilesPerWarp = RD3_TILES_PER_WARP;   // tiles a warp walks: amortises the CTA prologue
-constexpr int kInsPoints = (kInsThreads / 32) * kTilePoints * kTilesPerWarp;   // points per insert CTA
+constexpr int kInsPoints = 1024;      // points per insert CTA (4 per thread)
+constexpr int kTilePoints = 128;      // points per warp tile
 constexpr int kTileShift = 7;
 constexpr int kMaxRounds = 64;
 
@@ -279,8 +275,8 @@ template <class Src>
 __global__ void __launch_bounds__(kInsThreads)
     hv_insert_kernel(Src src, VoxelGrid g, HvWork w, int64_t begin, int64_t end, int round) {
   __shared__ float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 1];
-  __shared__ uint32_t s_keyb[(kInsThreads / 32) * kTilePoints];
-  __shared__ uint8_t s_l2b[(kInsThreads / 32) * kTilePoints], s_undb[(kInsThreads / 32) * kTilePoints];
+  __shared__ uint32_t s_keyb[kInsPoints];
+  __shared__ uint8_t s_l2b[kInsPoints], s_undb[kInsPoints];
   __shared__ int s_prev;
 
   const int b = blockIdx.y + w.b0;
@@ -299,15 +295,10 @@ __global__ void __launch_bounds__(kInsThreads)
   __syncthreads();
   const bool lookup_only = s_prev >= w.max_voxels;
 
+  const int64_t base = block_base + wv * kTilePoints;     // this warp's tile
+  if (base >= end) return;
   uint32_t *s_key = s_keyb + wv * kTilePoints;
   uint8_t *s_l2 = s_l2b + wv * kTilePoints, *s_und = s_undb + wv * kTilePoints;
-  unsigned long long *table = w.table + (int64_t)b * w.cap;
-  int claims = 0;
-#pragma unroll 1
-  for (int tw = 0; tw < kTilesPerWarp; ++tw) {
-  // consecutive warps take consecutive tiles (coalesced depth reads across the CTA)
-  const int64_t base = block_base + (int64_t)(tw * (kInsThreads / 32) + wv) * kTilePoints;
-  if (base >= end) break;
 
   // ---- stage AB ---------------------------------------------------------------------
   const int64_t i0 = base + 4 * lane;
@@ -358,8 +349,9 @@ __global__ void __launch_bounds__(kInsThreads)
   __syncwarp();
 
   // ---- stage C ----------------------------------------------------------------------
+  unsigned long long *table = w.table + (int64_t)b * w.cap;
   uint2 *cand = w.cand + (int64_t)b * w.N + base;
-  int nc = 0;
+  int nc = 0, claims = 0;
 #pragma unroll 1
   for (int j0 = 0; j0 < n2; j0 += 32) {
     const int j = j0 + lane;
@@ -379,8 +371,6 @@ __global__ void __launch_bounds__(kInsThreads)
     nc += __popc(bal);
   }
   if (lane == 0) w.cand_cnt[(int64_t)b * w.ntiles + (base >> kTileShift)] = (uint8_t)nc;
-  __syncwarp();
-  }   // tiles of this warp
   if (!lookup_only) {
     for (int d = 16; d > 0; d >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, d);
     if (lane == 0 && claims) atomicAdd(w.round_claims + b * kMaxRounds + round, claims);
@@ -558,54 +548,57 @@ static __global__ void __launch_bounds__(256) hv_slots_kernel(HvWork w, int32_t 
 }
 
 // K4 ------------------------------------------------------------------------
-// A CTA owns V consecutive voxels.  dynamic smem: tile[V*K*C] floats + idx[V*K] + list[V*K] u16.
+// A CTA owns V consecutive voxels (~1024 slot items).  dynamic smem: tile[V*K*C] floats
+// (padded to 16 B) + idx[V*K] u32 + list[V*K] u16.
+//   1. zero the tile (16-byte stores); every warp loads its share of the slot indices and
+//      ballot-compacts the non-empty ones into its own list segment (no atomics, no barrier)
+//   2. each warp gathers / re-unprojects (exact reference arithmetic) its listed items
+//   3. voxels are copied out with 16-byte stores; one thread per voxel writes coors (from the
+//      first point), the count and the HardSimpleVFE mean (slot order, one __fdiv_rn)
 template <class Src>
 __global__ void __launch_bounds__(256) hv_emit_kernel(Src src, VoxelGrid g, HvWork w, HvOut o, int V) {
   extern __shared__ float s_dyn[];
   __shared__ float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 1];
-  __shared__ int s_count;
   const int b = blockIdx.y + w.b0;
   const int vn = o.voxel_num[b];
   const int r0 = blockIdx.x * V;
   if (r0 >= vn) return;
-  src.prepare(s_cal, b);
   const int C = src.num_feats();
   const int K = w.K;
   const int nvox = min(V, vn - r0);
   const int items = nvox * K;
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float *tile = s_dyn;
   uint32_t *s_idx = reinterpret_cast<uint32_t *>(s_dyn + (((size_t)V * K * C + 3) & ~(size_t)3));
+  uint16_t *s_list = reinterpret_cast<uint16_t *>(s_idx + (size_t)V * K);
   const uint32_t *S = w.slots + ((int64_t)b * w.max_voxels + r0) * K;
 
-  // pass 1: slot indices; zero the tile; compact the non-empty items so that the
-  // (expensive) gather / re-unprojection below runs on dense lanes
-  uint16_t *s_list = reinterpret_cast<uint16_t *>(s_idx + (size_t)V * K);
-  if (threadIdx.x == 0) s_count = 0;
+  src.stage(s_cal, b);
   {
-    // zero the whole tile with 16-byte stores; the gather below overwrites the non-empty items
     float4 *t4 = reinterpret_cast<float4 *>(tile);
-    const int n4 = (items * C + 3) >> 2;      // the tile is allocated for V*K*C >= items*C, padded below
-    for (int e = threadIdx.x; e < n4; e += blockDim.x) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int n4 = (items * C + 3) >> 2;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = threadIdx.x; e < n4; e += 256) t4[e] = z4;
   }
-  __syncthreads();
-  for (int it0 = 0; it0 < items; it0 += blockDim.x) {
-    const int it = it0 + threadIdx.x;
+  // warp wv owns items [wv*per, wv*per+per): its list segment starts at the same offset
+  const int per = ((items + nw - 1) / nw + 31) & ~31;
+  const int lo = wv * per, hi = min(items, lo + per);
+  int nmine = 0;
+  for (int it0 = lo; it0 < hi; it0 += 32) {
+    const int it = it0 + lane;
     uint32_t idx = kEmpty32;
-    if (it < items) {
+    if (it < hi) {
       idx = __ldg(S + it);
       s_idx[it] = idx;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, idx != kEmpty32);
-    int wbase = 0;
-    if ((threadIdx.x & 31) == 0 && bal) wbase = atomicAdd(&s_count, __popc(bal));
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    if (idx != kEmpty32) s_list[wbase + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = (uint16_t)it;
+    if (idx != kEmpty32) s_list[lo + nmine + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)it;
+    nmine += __popc(bal);
   }
-  __syncthreads();
-  const int nfull = s_count;
-  for (int j = threadIdx.x; j < nfull; j += blockDim.x) {
-    const int it = s_list[j];
-    src.gather(b, s_idx[it], s_cal, tile + (size_t)it * C);
+  __syncthreads();                       // tile zeroed, calibration staged
+  for (int j = lane; j < nmine; j += 32) {
+    const int it = s_list[lo + j];
+    src.gather(b, s_idx[it], s_cal, tile + it * C);
   }
   __syncthreads();
 
@@ -615,19 +608,23 @@ __global__ void __launch_bounds__(256) hv_emit_kernel(Src src, VoxelGrid g, HvWo
   if ((reinterpret_cast<uintptr_t>(vout) & 15) == 0) {
     const float4 *t4 = reinterpret_cast<const float4 *>(tile);
     float4 *v4 = reinterpret_cast<float4 *>(vout);
-    for (int e = threadIdx.x; e < (nfl >> 2); e += blockDim.x) v4[e] = t4[e];
-    for (int e = (nfl & ~3) + threadIdx.x; e < nfl; e += blockDim.x) vout[e] = tile[e];
+    const int n4 = nfl >> 2;
+    for (int e = threadIdx.x; e < n4; e += 256) v4[e] = t4[e];
+    for (int e = (nfl & ~3) + threadIdx.x; e < nfl; e += 256) vout[e] = tile[e];
   } else {
-    for (int e = threadIdx.x; e < nfl; e += blockDim.x) vout[e] = tile[e];
+    for (int e = threadIdx.x; e < nfl; e += 256) vout[e] = tile[e];
   }
 
-  // per-voxel meta: coords from the first point, count
-  int *s_cnt = reinterpret_cast<int *>(s_list + (((size_t)V * K + 7) & ~(size_t)7));
-  for (int v = threadIdx.x; v < nvox; v += blockDim.x) {
+  // one thread per voxel: count, coors from the first point, HardSimpleVFE mean
+  // (voxel_encoder.py:45-46: sum over ALL K slots in slot order, then one division; the
+  // slots beyond the count are zeros, so the running sum stops changing at the count --
+  // except that (-0.0) + 0.0 = +0.0, which one extra "+ 0.0f" reproduces)
+  const int F = o.F;
+  for (int v = threadIdx.x; v < nvox; v += 256) {
+    const uint32_t *si = s_idx + v * K;
     int cnt = 0;
-    while (cnt < K && s_idx[v * K + cnt] != kEmpty32) ++cnt;
-    s_cnt[v] = cnt;
-    const float *p0 = tile + (size_t)v * K * C;
+    while (cnt < K && si[cnt] != kEmpty32) ++cnt;
+    const float *p0 = tile + v * K * C;
     int cx = 0, cy = 0, cz = 0;
     if (voxel_coor_fast(p0[0], p0[1], p0[2], 0.0f, g, cx, cy, cz) == 2)
       voxel_coor(p0[0], p0[1], p0[2], g, cx, cy, cz);
@@ -636,17 +633,30 @@ __global__ void __launch_bounds__(256) hv_emit_kernel(Src src, VoxelGrid g, HvWo
     o.coors[vr * 3 + 1] = cy;
     o.coors[vr * 3 + 2] = cx;
     o.num[vr] = cnt;
-  }
-  // HardSimpleVFE (voxel_encoder.py:45-46): sum over ALL slots in slot order, one division
-  if (o.mean) {
-    __syncthreads();
-    const int F = o.F;
-    for (int t = threadIdx.x; t < nvox * F; t += blockDim.x) {
-      const int v = t / F, f = t - v * F;
-      const float *p = tile + (size_t)v * K * C + f;
-      float s = 0.0f;
-      for (int k = 0; k < K; ++k) s = __fadd_rn(s, p[(size_t)k * C]);
-      o.mean[((int64_t)b * w.max_voxels + r0 + v) * F + f] = __fdiv_rn(s, (float)s_cnt[v]);
+    if (o.mean) {
+      const float n = (float)cnt;
+      float *mo = o.mean + vr * F;
+      if (F == 3) {
+        float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+        const float *p = p0;
+        for (int k = 0; k < cnt; ++k, p += C) {
+          sx = __fadd_rn(sx, p[0]);
+          sy = __fadd_rn(sy, p[1]);
+          sz = __fadd_rn(sz, p[2]);
+        }
+        if (cnt < K) { sx = __fadd_rn(sx, 0.0f); sy = __fadd_rn(sy, 0.0f); sz = __fadd_rn(sz, 0.0f); }
+        mo[0] = __fdiv_rn(sx, n);
+        mo[1] = __fdiv_rn(sy, n);
+        mo[2] = __fdiv_rn(sz, n);
+      } else {
+        for (int f = 0; f < F; ++f) {
+          float sacc = 0.0f;
+          const float *p = p0 + f;
+          for (int k = 0; k < cnt; ++k, p += C) sacc = __fadd_rn(sacc, *p);
+          if (cnt < K) sacc = __fadd_rn(sacc, 0.0f);
+          mo[f] = __fdiv_rn(sacc, n);
+        }
+      }
     }
   }
 }
