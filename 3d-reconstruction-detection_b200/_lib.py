@@ -10,7 +10,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librd3_b200.so")
+# RD3_LIB_PATH lets A/B experiments load an alternative build of the same C ABI
+LIB_PATH = os.environ.get("RD3_LIB_PATH") or os.path.join(_HERE, "librd3_b200.so")
 
 _c = ctypes
 _vp, _i32, _i64, _sz, _f32 = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_size_t, _c.c_float
