@@ -272,7 +272,7 @@ __device__ __forceinline__ uint32_t table_find(const unsigned long long *table, 
 //   C  dense lanes: table insert (or lookup once max_voxels voxels exist);
 //      hits go to the tile's own region of the candidate list (no global counter)
 template <class Src>
-__global__ void __launch_bounds__(kInsThreads)
+__global__ void __launch_bounds__(kInsThreads, 8)
     hv_insert_kernel(Src src, VoxelGrid g, HvWork w, int64_t begin, int64_t end, int round) {
   __shared__ float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 1];
   __shared__ uint32_t s_keyb[kInsPoints];
