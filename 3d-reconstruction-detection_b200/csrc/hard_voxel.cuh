@@ -504,11 +504,12 @@ __device__ __forceinline__ void slot_insert_tail(uint32_t *S, int K, uint32_t id
 }
 
 // K3 ------------------------------------------------------------------------
-// grid (ceil(ntiles/8), frames), 256 threads: one warp per 128-point tile region.
+// grid (ceil(ntiles/4), frames), 128 threads: one warp per 128-point tile region (small CTAs:
+// warps finish at very different times and a CTA's slot is only recycled when all have).
 // Neighbouring pixels often share a voxel: lanes holding the same table slot form a
 // group (__match_any_sync); only the group leader walks table -> rank -> last slot and
 // broadcasts the result, and a whole group leaves after one load when the voxel is full.
-static __global__ void __launch_bounds__(256) hv_slots_kernel(HvWork w, int32_t *point2voxel) {
+static __global__ void __launch_bounds__(128) hv_slots_kernel(HvWork w, int32_t *point2voxel) {
   const int b = blockIdx.y + w.b0;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= w.ntiles) return;
@@ -797,7 +798,7 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
     scan_chunks_kernel<<<nb, 1024, 0, st>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels, b0);
     prof_mark(st, 4);
     if (p.N > 0)
-      hv_slots_kernel<<<dim3((unsigned)ceil_div(p.ntiles, 8), nb), 256, 0, st>>>(w, out.point2voxel);
+      hv_slots_kernel<<<dim3((unsigned)ceil_div(p.ntiles, 4), nb), 128, 0, st>>>(w, out.point2voxel);
     prof_mark(st, 5);
     hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, V), nb), 256, smem, st>>>(src, g, w, out, V);
     prof_mark(st, 6);
