@@ -137,8 +137,9 @@ struct DepthSource {
     uint32_t cam, v, u;    // of the first pixel
     uint32_t pix0;
     bool wraps;            // the 4 pixels cross a row boundary (only when W % 4 != 0)
+    float tx, ty, tz;      // row part of the direct cell map (valid when !wraps)
   };
-  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *) const {
+  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *s_cal) const {
     Cursor c;
     const int64_t gi = (int64_t)b * p.npix + i0;
     const int64_t left = end - i0;
@@ -156,6 +157,7 @@ struct DepthSource {
     c.pix0 = (uint32_t)i0;
     pixel_cvu(c.pix0, c.cam, c.v, c.u);
     c.wraps = c.u + 3 >= (uint32_t)p.W;
+    pixel_cell_row((float)c.v, s_cal + c.cam * kCalibFloats, c.tx, c.ty, c.tz);
     return c;
   }
   // cell of the lane's Q-th pixel: 1 inside / 0 outside or masked / 2 undecided.
@@ -167,8 +169,12 @@ struct DepthSource {
     if (!((c.valid >> Q) & 1u)) return 0;
     if (!g.fast_ok) return 2;
     uint32_t cam = c.cam, v = c.v, u = c.u + Q;
-    if (c.wraps) pixel_cvu(c.pix0 + Q, cam, v, u);
-    return pixel_cell_fast(c.z[Q], (float)u, (float)v, s_cal + cam * kCalibFloats, g, rg, cx, cy, cz);
+    float tx = c.tx, ty = c.ty, tz = c.tz;
+    if (c.wraps) {                      // rare: recompute the pixel's own row
+      pixel_cvu(c.pix0 + Q, cam, v, u);
+      pixel_cell_row((float)v, s_cal + cam * kCalibFloats, tx, ty, tz);
+    }
+    return pixel_cell_fast(c.z[Q], (float)u, tx, ty, tz, s_cal + cam * kCalibFloats, g, rg, cx, cy, cz);
   }
   // pixel index -> exact ego-frame point (reference arithmetic); false if the range filter drops it
   __device__ __forceinline__ bool point(int b, int64_t i, const float *s_cal, float &x, float &y,

@@ -266,13 +266,22 @@ struct CellRange {          // inclusive range filter expressed in cell units, p
   int32_t on;
 };
 
-__device__ __forceinline__ int pixel_cell_fast(float z, float uf, float vf, const float *cal,
-                                               const VoxelGrid &g, const CellRange &rg, int &cx,
-                                               int &cy, int &cz) {
+// row part of the map, shared by the pixels of one image row: t_a = fma(B_a, v, C_a)
+__device__ __forceinline__ void pixel_cell_row(float vf, const float *cal, float &tx, float &ty,
+                                               float &tz) {
   const float *k = cal + kCalDirect;
-  const float fx = __fmaf_rn(z, __fmaf_rn(k[0], uf, __fmaf_rn(k[1], vf, k[2])), k[3]);
-  const float fy = __fmaf_rn(z, __fmaf_rn(k[4], uf, __fmaf_rn(k[5], vf, k[6])), k[7]);
-  const float fz = __fmaf_rn(z, __fmaf_rn(k[8], uf, __fmaf_rn(k[9], vf, k[10])), k[11]);
+  tx = __fmaf_rn(k[1], vf, k[2]);
+  ty = __fmaf_rn(k[5], vf, k[6]);
+  tz = __fmaf_rn(k[9], vf, k[10]);
+}
+
+__device__ __forceinline__ int pixel_cell_fast(float z, float uf, float rtx, float rty, float rtz,
+                                               const float *cal, const VoxelGrid &g,
+                                               const CellRange &rg, int &cx, int &cy, int &cz) {
+  const float *k = cal + kCalDirect;
+  const float fx = __fmaf_rn(z, __fmaf_rn(k[0], uf, rtx), k[3]);
+  const float fy = __fmaf_rn(z, __fmaf_rn(k[4], uf, rty), k[7]);
+  const float fz = __fmaf_rn(z, __fmaf_rn(k[8], uf, rtz), k[11]);
   const float tol = __fmaf_rn(1.1920929e-7f, __fmaf_rn(z, k[12], k[13]), 1e-30f);
   const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
   const float tx = fminf(fx - flx, (flx + 1.0f) - fx);
