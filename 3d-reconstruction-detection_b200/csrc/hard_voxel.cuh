@@ -151,12 +151,19 @@ struct DepthSource {
 #pragma unroll
       for (int q = 0; q < 4; ++q) c.z[q] = (q < npx) ? __ldg(depth + gi + q) : 0.0f;
     }
+    // z > 0 & isfinite(z) [& z <= max_depth] (:338-340); p.zmax = min(max_depth, FLT_MAX)
     c.valid = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) c.valid |= (q < npx && depth_ok(c.z[q], gi + q)) ? (1u << q) : 0u;
-    c.pix0 = (uint32_t)i0;
+    for (int q = 0; q < 4; ++q) c.valid |= ((c.z[q] > 0.0f) & (c.z[q] <= p.zmax)) ? (1u << q) : 0u;
+    c.valid &= (1u << npx) - 1u;
+    if (p.use_masks) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (((c.valid >> q) & 1u) && !depth_ok(c.z[q], gi + q)) c.valid &= ~(1u << q);
+    }
+    c.pix0 = npx ? (uint32_t)i0 : 0u;          // lanes past the end compute on pixel 0 (masked)
     pixel_cvu(c.pix0, c.cam, c.v, c.u);
-    c.wraps = c.u + 3 >= (uint32_t)p.W;
+    c.wraps = npx && c.u + 3 >= (uint32_t)p.W;
     pixel_cell_row((float)c.v, s_cal + c.cam * kCalibFloats, c.tx, c.ty, c.tz);
     return c;
   }
@@ -166,15 +173,16 @@ struct DepthSource {
   template <int Q>
   __device__ __forceinline__ int cell_q(const Cursor &c, const float *s_cal, const VoxelGrid &g, int &cx,
                                         int &cy, int &cz) const {
-    if (!((c.valid >> Q) & 1u)) return 0;
-    if (!g.fast_ok) return 2;
     uint32_t cam = c.cam, v = c.v, u = c.u + Q;
     float tx = c.tx, ty = c.ty, tz = c.tz;
     if (c.wraps) {                      // rare: recompute the pixel's own row
       pixel_cvu(c.pix0 + Q, cam, v, u);
       pixel_cell_row((float)v, s_cal + cam * kCalibFloats, tx, ty, tz);
     }
-    return pixel_cell_fast(c.z[Q], (float)u, tx, ty, tz, s_cal + cam * kCalibFloats, g, rg, cx, cy, cz);
+    // computed for every pixel (masked ones yield garbage that is discarded): no divergence
+    int r = pixel_cell_fast(c.z[Q], (float)u, tx, ty, tz, s_cal + cam * kCalibFloats, g, rg, cx, cy, cz);
+    r = g.fast_ok ? r : 2;
+    return ((c.valid >> Q) & 1u) ? r : 0;
   }
   // pixel index -> exact ego-frame point (reference arithmetic); false if the range filter drops it
   __device__ __forceinline__ bool point(int b, int64_t i, const float *s_cal, float &x, float &y,

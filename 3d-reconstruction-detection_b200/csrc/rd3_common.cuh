@@ -289,22 +289,20 @@ __device__ __forceinline__ int pixel_cell_fast(float z, float uf, float rtx, flo
   const float tz = fminf(fz - flz, (flz + 1.0f) - fz);
   const float t = fminf(tx, fminf(ty, tz));
   const float sum = (fx + fy) + fz;
-  if (!(t >= tol) || !(sum == sum)) return 2;          // near a boundary, NaN, or huge
-  const int ix = (int)flx, iy = (int)fly, iz = (int)flz;
-  if ((unsigned)ix >= (unsigned)g.grid[0] || (unsigned)iy >= (unsigned)g.grid[1] ||
-      (unsigned)iz >= (unsigned)g.grid[2])
-    return 0;
-  if (rg.on) {
+  // branch-free verdict: near a boundary / NaN / huge -> 2, else inside (1) or outside (0)
+  const bool undecided = !(t >= tol) | !(sum == sum);
+  cx = (int)flx; cy = (int)fly; cz = (int)flz;
+  const bool inside = ((unsigned)cx < (unsigned)g.grid[0]) & ((unsigned)cy < (unsigned)g.grid[1]) &
+                      ((unsigned)cz < (unsigned)g.grid[2]);
+  int r = undecided ? 2 : (inside ? 1 : 0);
+  if (rg.on && r == 1) {
     const bool in_sure = fx - rg.lo[0] >= tol && rg.hi[0] - fx >= tol && fy - rg.lo[1] >= tol &&
                          rg.hi[1] - fy >= tol && fz - rg.lo[2] >= tol && rg.hi[2] - fz >= tol;
-    if (!in_sure) {
-      const bool out_sure = rg.lo[0] - fx > tol || fx - rg.hi[0] > tol || rg.lo[1] - fy > tol ||
-                            fy - rg.hi[1] > tol || rg.lo[2] - fz > tol || fz - rg.hi[2] > tol;
-      return out_sure ? 0 : 2;
-    }
+    const bool out_sure = rg.lo[0] - fx > tol || fx - rg.hi[0] > tol || rg.lo[1] - fy > tol ||
+                          fy - rg.hi[1] > tol || rg.lo[2] - fz > tol || fz - rg.hi[2] > tol;
+    r = in_sure ? 1 : (out_sure ? 0 : 2);
   }
-  cx = ix; cy = iy; cz = iz;
-  return 1;
+  return r;
 }
 
 // ---------------------------------------------------------------------------
