@@ -173,15 +173,11 @@ struct DepthSource {
   template <int Q>
   __device__ __forceinline__ int cell_q(const Cursor &c, const float *s_cal, const VoxelGrid &g, int &cx,
                                         int &cy, int &cz) const {
-    uint32_t cam = c.cam, v = c.v, u = c.u + Q;
-    float tx = c.tx, ty = c.ty, tz = c.tz;
-    if (c.wraps) {                      // rare: recompute the pixel's own row
-      pixel_cvu(c.pix0 + Q, cam, v, u);
-      pixel_cell_row((float)v, s_cal + cam * kCalibFloats, tx, ty, tz);
-    }
-    // computed for every pixel (masked ones yield garbage that is discarded): no divergence
-    int r = pixel_cell_fast(c.z[Q], (float)u, tx, ty, tz, s_cal + cam * kCalibFloats, g, rg, cx, cy, cz);
-    r = g.fast_ok ? r : 2;
+    // computed for every pixel (masked ones yield garbage that is discarded): no divergence.
+    // Lanes whose 4 pixels cross a row boundary (only when W % 4 != 0) leave it to cell_exact.
+    int r = pixel_cell_fast(c.z[Q], (float)(c.u + Q), c.tx, c.ty, c.tz, s_cal + c.cam * kCalibFloats, g, rg, cx,
+                            cy, cz);
+    r = (g.fast_ok && !c.wraps) ? r : 2;
     return ((c.valid >> Q) & 1u) ? r : 0;
   }
   // pixel index -> exact ego-frame point (reference arithmetic); false if the range filter drops it

@@ -134,13 +134,12 @@ __device__ __forceinline__ int voxel_coor_fast(float px, float py, float pz, flo
   // fminf drops NaNs, so test them through the sum (NaN + x = NaN fails the comparison)
   const float t = fminf(tx, fminf(ty, tz));
   const float tol = fmaf(abs_err, g.rvs_max, g.tolc);
-  if (!(t >= tol) || !((fx + fy) + fz == (fx + fy) + fz)) return 2;
-  const int ix = (int)flx, iy = (int)fly, iz = (int)flz;
-  if ((unsigned)ix >= (unsigned)g.grid[0] || (unsigned)iy >= (unsigned)g.grid[1] ||
-      (unsigned)iz >= (unsigned)g.grid[2])
-    return 0;
-  cx = ix; cy = iy; cz = iz;
-  return 1;
+  const float sum = (fx + fy) + fz;
+  const bool undecided = !(t >= tol) | !(sum == sum);
+  cx = (int)flx; cy = (int)fly; cz = (int)flz;
+  const bool inside = ((unsigned)cx < (unsigned)g.grid[0]) & ((unsigned)cy < (unsigned)g.grid[1]) &
+                      ((unsigned)cz < (unsigned)g.grid[2]);
+  return undecided ? 2 : (inside ? 1 : 0);
 }
 
 // linear voxel id in (z,y,x) order == lexicographic order of the output coors
