@@ -772,14 +772,19 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
     }
   }
   if (nl > 1) RD3_CUDA_TRY(cudaEventRecord(lanes->fork, stream));
+  // Inside a lane the frames are processed in groups of G (RD3_GROUP, default: the whole lane).
+  int G = p.B;
+  if (const char *e = getenv("RD3_GROUP")) G = atoi(e);
+  if (G < 1) G = 1;
   for (int l = 0; l < nl; ++l) {
-    const int b0 = (int)((int64_t)p.B * l / nl), b1 = (int)((int64_t)p.B * (l + 1) / nl);
-    const int nb = b1 - b0;
+    const int lb0 = (int)((int64_t)p.B * l / nl), lb1 = (int)((int64_t)p.B * (l + 1) / nl);
     cudaStream_t st = stream;
     if (l > 0) {
       st = lanes->s[l - 1];
       RD3_CUDA_TRY(cudaStreamWaitEvent(st, lanes->fork, 0));
     }
+    for (int b0 = lb0; b0 < lb1; b0 += G) {
+    const int nb = (lb1 - b0 < G) ? lb1 - b0 : G;
     w.b0 = b0;
     prof_mark(st, 0);
     RD3_CUDA_TRY(cudaMemsetAsync(w.table + (size_t)b0 * p.cap, 0xFF, (size_t)nb * p.cap * 8, st));
@@ -813,6 +818,7 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
     hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, V), nb), 256, smem, st>>>(src, g, w, out, V);
     prof_mark(st, 6);
     prof_mark(st, 7);
+    }   // groups of this lane
     if (l > 0) {
       RD3_CUDA_TRY(cudaEventRecord(lanes->join[l - 1], st));
       RD3_CUDA_TRY(cudaStreamWaitEvent(stream, lanes->join[l - 1], 0));
