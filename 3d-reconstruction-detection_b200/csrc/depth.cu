@@ -14,7 +14,7 @@ namespace rd3 {
 
 // calibration table: (B, ncam, kCalibFloats), one block per frame.  With a voxel grid
 // (has_grid) it also holds the direct pixel->cell map and its error-bound constants
-// (rd3_common.cuh: pixel_cell_fast), derived in fp64 and rounded once.
+// (rd3_common.cuh: pixel_key_fast), derived in fp64 and rounded once.
 __global__ void calib_kernel(const float *intr, const float *c2l, int ncam, int H, int W,
                              VoxelGrid g, int has_grid, CellRange rg, float *table) {
   __shared__ float s_cal[kMaxCams * kCalibFloats];
@@ -36,18 +36,21 @@ __global__ void calib_kernel(const float *intr, const float *c2l, int ncam, int 
       const double r0 = M[a * 4 + 0], r1 = M[a * 4 + 1], r2 = M[a * 4 + 2], t = M[12 + a];
       const float A = (float)(r0 / fx * rv), Bc = (float)(r1 / fy * rv);
       const float C = (float)((r2 - r0 * cx / fx - r1 * cy / fy) * rv);
-      const float T = (float)((t - (double)g.lo[a]) * rv);
+      const float T = (float)((t - (double)g.lo[a]) * rv - 0.5);      // h = f' - 0.5 (pixel_key_fast)
       k[a * 4 + 0] = A; k[a * 4 + 1] = Bc; k[a * 4 + 2] = C; k[a * 4 + 3] = T;
       const double D = fabs((double)A) * (W - 1) + fabs((double)Bc) * (H - 1) + fabs((double)C);
       const double Q = (fabs(r0) * ex + fabs(r1) * ey + fabs(r2)) * rv;
       const double P1 = fabs(t) * rv;
-      double P = fabs((double)T) + 10.0 * P1 + 3.0 * fabs((double)g.lo[a]) * rv;
-      if (rg.on) P += fabs((double)rg.lo[a]) + fabs((double)rg.hi[a]);
+      double P = fabs((double)T) + 2.0 + 10.0 * P1 + 3.0 * fabs((double)g.lo[a]) * rv;
+      if (rg.on) P += fabs((double)rg.lo[a]) + fabs((double)rg.hi[a]) + 1.0;
       Qc = fmax(Qc, 3.0 * D + 10.0 * Q);
       Pc = fmax(Pc, P);
     }
-    k[12] = (float)(Qc * 1.000001);
-    k[13] = (float)(Pc * 1.000001);
+    // thr = fma(z, Qn, Pn) <= 0.5 - 2^-23 (z Qc + Pc): constants rounded towards -inf, 2^-20 covers
+    // the rounding of the fma itself.  Non-finite inputs give NaN / -inf: nothing is decided.
+    const double eps2 = 1.1920928955078125e-7;   // 2^-23
+    k[12] = __double2float_rd(-(Qc * 1.000001) * eps2);
+    k[13] = __double2float_rd(0.5 - (Pc * 1.000001) * eps2 - 9.5367431640625e-7);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < ncam * kCalibFloats; i += blockDim.x)
@@ -220,11 +223,11 @@ int rd3_depth_to_voxels(const float *depth, const float *intrinsics, const float
   const size_t cal_bytes = align_up((size_t)p->B * p->ncam * kCalibFloats * 4);
   if (workspace_bytes < plan.total + cal_bytes) return RD3_ERR_WORKSPACE;
   float *cal_table = (float *)((char *)workspace + plan.total);
-  // inclusive range filter in cell units (pixel_cell_fast)
+  // inclusive range filter in cell units minus 0.5 (pixel_key_fast works on h = f' - 0.5)
   src.rg.on = p->use_range;
   for (int a = 0; a < 3; ++a) {
-    src.rg.lo[a] = (float)(((double)p->range[a] - (double)g.lo[a]) / (double)g.vs[a]);
-    src.rg.hi[a] = (float)(((double)p->range[3 + a] - (double)g.lo[a]) / (double)g.vs[a]);
+    src.rg.lo[a] = (float)(((double)p->range[a] - (double)g.lo[a]) / (double)g.vs[a] - 0.5);
+    src.rg.hi[a] = (float)(((double)p->range[3 + a] - (double)g.lo[a]) / (double)g.vs[a] - 0.5);
   }
   calib_kernel<<<p->B, 128, 0, (cudaStream_t)stream>>>(intrinsics, cam2lidar, p->ncam, p->H, p->W, g, 1,
                                                        src.rg, cal_table);

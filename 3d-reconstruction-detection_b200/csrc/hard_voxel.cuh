@@ -38,14 +38,28 @@
 namespace rd3 {
 
 constexpr int kInsThreads = 256;
-constexpr int kInsPoints = 1024;      // points per insert CTA (4 per thread)
+#ifndef RD3_INS_MINB
+#define RD3_INS_MINB 8                // resident insert CTAs per SM the register budget is sized for
+#endif
+#ifndef RD3_INS_SUBTILES
+#define RD3_INS_SUBTILES 1            // tiles every warp of an insert CTA walks (amortises the CTA prologue)
+#endif
+constexpr int kSubTiles = RD3_INS_SUBTILES;
 constexpr int kTilePoints = 128;      // points per warp tile
+constexpr int kInsSpan = 1024;        // points the CTA's warps cover side by side (4 per thread)
+constexpr int kInsPoints = kInsSpan * kSubTiles;   // points per insert CTA
 constexpr int kTileShift = 7;
 constexpr int kMaxRounds = 64;
 
 // ---------------------------------------------------------------------------
 // point sources
 // ---------------------------------------------------------------------------
+// stage-AB result of one lane (4 consecutive points)
+struct Quad {
+  uint32_t key[4];
+  unsigned in, und;
+};
+
 struct PointsSource {
   const float *pts;   // (B, N, C)
   int64_t N;
@@ -64,15 +78,20 @@ struct PointsSource {
     c.p = pts + ((int64_t)b * N + i0) * C;
     const int64_t left = end - i0;
     c.npx = left >= 4 ? 4 : (left > 0 ? (int)left : 0);
+    if (c.npx == 0) c.p = pts;                      // lanes past the end read point 0 (masked)
     return c;
   }
-  // cell of the lane's Q-th point: 1 inside / 0 outside / 2 undecided (-> cell_exact)
-  template <int Q>
-  __device__ __forceinline__ int cell_q(const Cursor &c, const float *, const VoxelGrid &g, int &cx, int &cy,
-                                        int &cz) const {
-    if (Q >= c.npx) return 0;
-    const float *q = c.p + Q * C;
-    return voxel_coor_fast(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.0f, g, cx, cy, cz);
+  // the lane's 4 points: keys of the points surely inside (bit q of `in`), undecided ones in `und`
+  __device__ __forceinline__ void classify(const Cursor &c, const float *, const VoxelGrid &g, Quad &qd) const {
+    qd.in = 0; qd.und = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float *pq = c.p + (q < c.npx ? q : 0) * C;
+      const int r = voxel_key_fast(__ldg(pq), __ldg(pq + 1), __ldg(pq + 2), g, qd.key[q]);
+      const unsigned live = q < c.npx ? 1u : 0u;
+      qd.in |= (r == 1 ? live : 0u) << q;
+      qd.und |= (r == 2 ? live : 0u) << q;
+    }
   }
   __device__ __forceinline__ bool cell_exact(int b, int64_t i, const float *, const VoxelGrid &g,
                                              int &cx, int &cy, int &cz) const {
@@ -134,8 +153,8 @@ struct DepthSource {
   struct Cursor {
     float z[4];
     unsigned valid;        // depth/conf/sky mask of the 4 pixels
-    uint32_t cam, v, u;    // of the first pixel
-    uint32_t pix0;
+    uint32_t cam;
+    float uf;              // column of the first pixel
     bool wraps;            // the 4 pixels cross a row boundary (only when W % 4 != 0)
     float tx, ty, tz;      // row part of the direct cell map (valid when !wraps)
   };
@@ -161,24 +180,29 @@ struct DepthSource {
       for (int q = 0; q < 4; ++q)
         if (((c.valid >> q) & 1u) && !depth_ok(c.z[q], gi + q)) c.valid &= ~(1u << q);
     }
-    c.pix0 = npx ? (uint32_t)i0 : 0u;          // lanes past the end compute on pixel 0 (masked)
-    pixel_cvu(c.pix0, c.cam, c.v, c.u);
-    c.wraps = npx && c.u + 3 >= (uint32_t)p.W;
-    pixel_cell_row((float)c.v, s_cal + c.cam * kCalibFloats, c.tx, c.ty, c.tz);
+    uint32_t v, u;
+    pixel_cvu(npx ? (uint32_t)i0 : 0u, c.cam, v, u);   // lanes past the end compute on pixel 0 (masked)
+    c.uf = (float)u;
+    c.wraps = npx && u + 3 >= (uint32_t)p.W;
+    pixel_cell_row((float)v, s_cal + c.cam * kCalibFloats, c.tx, c.ty, c.tz);
     return c;
   }
-  // cell of the lane's Q-th pixel: 1 inside / 0 outside or masked / 2 undecided.
-  // The direct pixel->cell map (pixel_cell_fast) decides all but the pixels within its error
-  // bound of a cell / range-filter boundary; those are redone by cell_exact.
-  template <int Q>
-  __device__ __forceinline__ int cell_q(const Cursor &c, const float *s_cal, const VoxelGrid &g, int &cx,
-                                        int &cy, int &cz) const {
-    // computed for every pixel (masked ones yield garbage that is discarded): no divergence.
-    // Lanes whose 4 pixels cross a row boundary (only when W % 4 != 0) leave it to cell_exact.
-    int r = pixel_cell_fast(c.z[Q], (float)(c.u + Q), c.tx, c.ty, c.tz, s_cal + c.cam * kCalibFloats, g, rg, cx,
-                            cy, cz);
-    r = (g.fast_ok && !c.wraps) ? r : 2;
-    return ((c.valid >> Q) & 1u) ? r : 0;
+  // The direct pixel->cell map (pixel_key_fast) decides all but the pixels within its error bound
+  // of a cell / range-filter boundary; those (bit q of `und`) are redone by cell_exact.  Computed
+  // for every pixel (masked ones yield garbage that is discarded): no divergence.  Lanes whose 4
+  // pixels cross a row boundary (only when W % 4 != 0) leave all of them to cell_exact.
+  __device__ __forceinline__ void classify(const Cursor &c, const float *s_cal, const VoxelGrid &g, Quad &qd) const {
+    const float *cal = s_cal + c.cam * kCalibFloats;
+    unsigned in = 0, und = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = pixel_key_fast(c.z[q], __fadd_rn(c.uf, (float)q), c.tx, c.ty, c.tz, cal, g, rg, qd.key[q]);
+      in |= (r == 1 ? 1u : 0u) << q;
+      und |= (r == 2 ? 1u : 0u) << q;
+    }
+    const bool fast = g.fast_ok && !c.wraps;
+    qd.in = fast ? (in & c.valid) : 0u;
+    qd.und = fast ? (und & c.valid) : c.valid;
   }
   // pixel index -> exact ego-frame point (reference arithmetic); false if the range filter drops it
   __device__ __forceinline__ bool point(int b, int64_t i, const float *s_cal, float &x, float &y,
@@ -234,8 +258,21 @@ struct HvOut {
   int F;
 };
 
-__device__ __forceinline__ uint32_t hash_key(uint32_t key, int log2cap) {
-  return (key * 2654435769u) >> (32 - log2cap);
+// The table is probed linearly from the start of the key's bucket of 4 entries (= one 32-byte
+// sector).  Every probe sequence enters a bucket at its entry 0 and entries are never released, so
+// a bucket fills in order and "entry 3 is empty" <=> the bucket never overflowed <=> a key that
+// hashes here and is not in it is absent: a lookup is one 256-bit load (one L1 request, one DRAM
+// sector) however it ends, and only moves on when the bucket is full without a match.
+__device__ __forceinline__ uint32_t hash_bucket_slot(uint32_t key, int log2cap) {
+  return ((key * 2654435769u) >> (34 - log2cap)) << 2;
+}
+
+__device__ __forceinline__ void load_bucket(const unsigned long long *p, unsigned long long &e0,
+                                            unsigned long long &e1, unsigned long long &e2,
+                                            unsigned long long &e3) {
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(e0), "=l"(e1), "=l"(e2), "=l"(e3)
+               : "l"(p));
 }
 
 // Insert (key, idx).  Slot ownership is permanent (CAS from empty); the payload
@@ -243,11 +280,32 @@ __device__ __forceinline__ uint32_t hash_key(uint32_t key, int log2cap) {
 // atomic, never a wrong skip.  *claimed = 1 iff this call created the entry.
 __device__ __forceinline__ uint32_t table_insert(unsigned long long *table, const HvWork &w,
                                                  uint32_t key, uint32_t idx, int *claimed) {
-  uint32_t slot = w.direct ? key : hash_key(key, w.log2cap);
   const unsigned long long mine = ((unsigned long long)key << 32) | idx;
   *claimed = 0;
-  while (true) {
-    unsigned long long e = __ldcg(table + slot);
+  uint32_t slot;
+  unsigned long long e;
+  if (w.direct) {
+    slot = key;
+    e = __ldcg(table + slot);
+  } else {
+    // one 256-bit load finds the first entry of the bucket that holds the key or is empty
+    uint32_t s0 = hash_bucket_slot(key, w.log2cap);
+    while (true) {
+      unsigned long long e0, e1, e2, e3;
+      load_bucket(table + s0, e0, e1, e2, e3);
+      const uint32_t k0 = (uint32_t)(e0 >> 32), k1 = (uint32_t)(e1 >> 32), k2 = (uint32_t)(e2 >> 32),
+                     k3 = (uint32_t)(e3 >> 32);
+      int q = 4;
+      if (k3 == key || k3 == kEmpty32) { q = 3; e = e3; }
+      if (k2 == key || k2 == kEmpty32) { q = 2; e = e2; }
+      if (k1 == key || k1 == kEmpty32) { q = 1; e = e1; }
+      if (k0 == key || k0 == kEmpty32) { q = 0; e = e0; }
+      slot = s0 + q;
+      if (q < 4) break;
+      s0 = (s0 + 4) & w.cap_mask;
+    }
+  }
+  while (true) {                       // `e` may be stale: the atomics decide
     if (e == kEmpty64) {
       const unsigned long long old = atomicCAS(table + slot, kEmpty64, mine);
       if (old == kEmpty64) { *claimed = 1; return slot; }
@@ -257,43 +315,52 @@ __device__ __forceinline__ uint32_t table_insert(unsigned long long *table, cons
       if ((uint32_t)e > idx) atomicMin(table + slot, mine);
       return slot;
     }
-    slot = (slot + 1) & w.cap_mask;
+    slot = (slot + 1) & w.cap_mask;    // lost the entry to another key: plain linear probing from here
+    e = __ldcg(table + slot);
   }
 }
 
-// Lookup only; returns kEmpty32 when the key is absent.
+// Lookup only (the table is not written while lookups run); kEmpty32 when the key is absent.
 __device__ __forceinline__ uint32_t table_find(const unsigned long long *table, const HvWork &w,
                                                uint32_t key) {
-  uint32_t slot = w.direct ? key : hash_key(key, w.log2cap);
+  if (w.direct) return __ldcg(table + key) == kEmpty64 ? kEmpty32 : key;
+  uint32_t s0 = hash_bucket_slot(key, w.log2cap);
   while (true) {
-    const unsigned long long e = __ldcg(table + slot);
-    if (e == kEmpty64) return kEmpty32;
-    if ((uint32_t)(e >> 32) == key) return slot;
-    slot = (slot + 1) & w.cap_mask;
+    unsigned long long e0, e1, e2, e3;
+    load_bucket(table + s0, e0, e1, e2, e3);
+    int q = 4;
+    q = (uint32_t)(e3 >> 32) == key ? 3 : q;
+    q = (uint32_t)(e2 >> 32) == key ? 2 : q;
+    q = (uint32_t)(e1 >> 32) == key ? 1 : q;
+    q = (uint32_t)(e0 >> 32) == key ? 0 : q;
+    if (q < 4) return s0 + q;
+    if ((uint32_t)(e3 >> 32) == kEmpty32) return kEmpty32;    // no valid key is ~0
+    s0 = (s0 + 4) & w.cap_mask;
   }
 }
 
 // K1 ------------------------------------------------------------------------
-// grid (ceil((end-begin)/1024), frames), 256 threads; every WARP owns a tile of 128
-// consecutive points and runs its stages without block barriers:
+// grid (ceil((end-begin)/kInsPoints), frames), 256 threads; every WARP owns kSubTiles tiles of 128
+// consecutive points (the CTA's 8 warps side by side) and runs their stages without block barriers:
 //   AB each lane walks its 4 consecutive points (one 16-byte load): validity, voxel cell
 //      by the conservative fast path; in-range keys and the few undecided points are
 //      ballot-compacted; the undecided ones are redone with exact IEEE arithmetic
 //   C  dense lanes: table insert (or lookup once max_voxels voxels exist);
 //      hits go to the tile's own region of the candidate list (no global counter)
 template <class Src>
-__global__ void __launch_bounds__(kInsThreads, 8)
+__global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
     hv_insert_kernel(Src src, VoxelGrid g, HvWork w, int64_t begin, int64_t end, int round) {
   __shared__ float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 1];
-  __shared__ uint32_t s_keyb[kInsPoints];
-  __shared__ uint8_t s_l2b[kInsPoints], s_undb[kInsPoints];
-  __shared__ int s_prev;
+  __shared__ uint2 s_itemb[kInsSpan];            // (key, local point id) of the in-range points
+  __shared__ uint8_t s_undb[kInsSpan];           // local ids of the undecided points
+  __shared__ int s_prev, s_claims, s_done;
 
   const int b = blockIdx.y + w.b0;
   const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const int64_t block_base = begin + (int64_t)blockIdx.x * kInsPoints;
   if (block_base >= end) return;
+  if (tid == 0) { s_claims = 0; s_done = 0; }
   if (wv == 0) {
     // voxels claimed by the previous rounds: insert vs lookup-only for the whole round
     int c = 0;
@@ -305,38 +372,45 @@ __global__ void __launch_bounds__(kInsThreads, 8)
   __syncthreads();
   const bool lookup_only = s_prev >= w.max_voxels;
 
-  const int64_t base = block_base + wv * kTilePoints;     // this warp's tile
-  if (base >= end) return;
-  uint32_t *s_key = s_keyb + wv * kTilePoints;
-  uint8_t *s_l2 = s_l2b + wv * kTilePoints, *s_und = s_undb + wv * kTilePoints;
+  if (block_base + wv * kTilePoints >= end) return;
+  uint2 *s_item = s_itemb + wv * kTilePoints;
+  uint8_t *s_und = s_undb + wv * kTilePoints;
+  unsigned long long *table = w.table + (int64_t)b * w.cap;
+  int claims = 0;
+#pragma unroll 1
+  for (int sub = 0; sub < kSubTiles; ++sub) {
+  const int64_t base = block_base + (sub * (kInsThreads / 32) + wv) * kTilePoints;     // this warp's tile
+  if (base >= end) break;
 
   // ---- stage AB ---------------------------------------------------------------------
-  const int64_t i0 = base + 4 * lane;
-  typename Src::Cursor cur = src.cursor(b, i0, end, s_cal);
-  int n2 = 0, nu = 0;
-  auto put = [&](int r, int q, int cx, int cy, int cz) {
-    const unsigned b1 = __ballot_sync(0xffffffffu, r == 1);
-    const unsigned b2 = __ballot_sync(0xffffffffu, r == 2);
-    if (r == 1) {
-      const int at = n2 + __popc(b1 & lt);
-      s_l2[at] = (uint8_t)(4 * lane + q);
-      s_key[at] = voxel_key(cx, cy, cz, g);
-    } else if (r == 2) {
-      s_und[nu + __popc(b2 & lt)] = (uint8_t)(4 * lane + q);
-    }
-    n2 += __popc(b1);
-    nu += __popc(b2);
-  };
+  int n2, nu;
   {
-    int cx = 0, cy = 0, cz = 0;
-    int r = src.template cell_q<0>(cur, s_cal, g, cx, cy, cz);
-    put(r, 0, cx, cy, cz);
-    r = src.template cell_q<1>(cur, s_cal, g, cx, cy, cz);
-    put(r, 1, cx, cy, cz);
-    r = src.template cell_q<2>(cur, s_cal, g, cx, cy, cz);
-    put(r, 2, cx, cy, cz);
-    r = src.template cell_q<3>(cur, s_cal, g, cx, cy, cz);
-    put(r, 3, cx, cy, cz);
+    typename Src::Cursor cur = src.cursor(b, base + 4 * lane, end, s_cal);
+    Quad qd;
+    src.classify(cur, s_cal, g, qd);
+    // exclusive prefix of the per-lane counts (0..4) from three ballots of the count's bit planes
+    const unsigned cin = __popc(qd.in);
+    const unsigned p0 = __ballot_sync(0xffffffffu, cin & 1u), p1 = __ballot_sync(0xffffffffu, cin & 2u),
+                   p2 = __ballot_sync(0xffffffffu, cin & 4u);
+    n2 = __popc(p0) + 2 * __popc(p1) + 4 * __popc(p2);
+    uint2 *it = s_item + (__popc(p0 & lt) + 2 * __popc(p1 & lt) + 4 * __popc(p2 & lt));
+    const unsigned in = qd.in;
+    // the order inside the list is irrelevant: point q of the lane goes to the lane's slot #(set bits below q)
+    if (in & 1u) it[0] = make_uint2(qd.key[0], (uint32_t)(4 * lane));
+    if (in & 2u) it[in & 1u] = make_uint2(qd.key[1], (uint32_t)(4 * lane + 1));
+    if (in & 4u) it[__popc(in & 3u)] = make_uint2(qd.key[2], (uint32_t)(4 * lane + 2));
+    if (in & 8u) it[__popc(in & 7u)] = make_uint2(qd.key[3], (uint32_t)(4 * lane + 3));
+    nu = 0;
+    if (__any_sync(0xffffffffu, qd.und != 0u)) {
+      const unsigned cun = __popc(qd.und);
+      const unsigned u0 = __ballot_sync(0xffffffffu, cun & 1u), u1 = __ballot_sync(0xffffffffu, cun & 2u),
+                     u2 = __ballot_sync(0xffffffffu, cun & 4u);
+      nu = __popc(u0) + 2 * __popc(u1) + 4 * __popc(u2);
+      int ua = __popc(u0 & lt) + 2 * __popc(u1 & lt) + 4 * __popc(u2 & lt);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if ((qd.und >> q) & 1u) s_und[ua++] = (uint8_t)(4 * lane + q);
+    }
   }
   __syncwarp();
 #pragma unroll 1
@@ -349,30 +423,26 @@ __global__ void __launch_bounds__(kInsThreads, 8)
       in = src.cell_exact(b, base + lid, s_cal, g, cx, cy, cz);
     }
     const unsigned b1 = __ballot_sync(0xffffffffu, in);
-    if (in) {
-      const int at = n2 + __popc(b1 & lt);
-      s_l2[at] = (uint8_t)lid;
-      s_key[at] = voxel_key(cx, cy, cz, g);
-    }
+    if (in) s_item[n2 + __popc(b1 & lt)] = make_uint2(voxel_key(cx, cy, cz, g), (uint32_t)lid);
     n2 += __popc(b1);
   }
   __syncwarp();
 
   // ---- stage C ----------------------------------------------------------------------
-  unsigned long long *table = w.table + (int64_t)b * w.cap;
   uint2 *cand = w.cand + (int64_t)b * w.N + base;
-  int nc = 0, claims = 0;
+  int nc = 0;
 #pragma unroll 1
   for (int j0 = 0; j0 < n2; j0 += 32) {
     const int j = j0 + lane;
     uint32_t slot = kEmpty32, idx = 0;
     if (j < n2) {
-      idx = (uint32_t)(base + s_l2[j]);
+      const uint2 it = s_item[j];
+      idx = (uint32_t)base + it.y;
       if (lookup_only) {
-        slot = table_find(table, w, s_key[j]);
+        slot = table_find(table, w, it.x);
       } else {
         int c;
-        slot = table_insert(table, w, s_key[j], idx, &c);
+        slot = table_insert(table, w, it.x, idx, &c);
         claims += c;
       }
     }
@@ -381,9 +451,21 @@ __global__ void __launch_bounds__(kInsThreads, 8)
     nc += __popc(bal);
   }
   if (lane == 0) w.cand_cnt[(int64_t)b * w.ntiles + (base >> kTileShift)] = (uint8_t)nc;
+  __syncwarp();
+  }   // tiles of this warp
   if (!lookup_only) {
+    // one global atomic per CTA: the last warp to finish adds the CTA's claims to the round's counter
     for (int d = 16; d > 0; d >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, d);
-    if (lane == 0 && claims) atomicAdd(w.round_claims + b * kMaxRounds + round, claims);
+    if (lane == 0) {
+      const int64_t left = end - block_base;
+      const int nwarps = left >= kInsSpan ? kInsThreads / 32 : (int)((left + kTilePoints - 1) >> kTileShift);
+      if (claims) atomicAdd(&s_claims, claims);
+      __threadfence_block();
+      if (atomicAdd(&s_done, 1) == nwarps - 1) {
+        const int c = atomicAdd(&s_claims, 0);
+        if (c) atomicAdd(w.round_claims + b * kMaxRounds + round, c);
+      }
+    }
   }
 }
 
@@ -680,7 +762,7 @@ struct HvPlan {
   int B;
   int K;
   int max_voxels;
-  int64_t S;          // points per insert round (multiple of kInsPoints)
+  int64_t S;          // points per insert round (multiple of kInsSpan)
   int rounds;
   int64_t cap;
   int log2cap;
@@ -695,8 +777,8 @@ inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels) {
   const int64_t n1 = N > 0 ? N : 1;
   // round length: at most 8 rounds, but a round should keep the whole GPU busy
   // (>= ~1.2 M points over all frames), so small batches use fewer, longer rounds
-  int64_t S = ceil_div(ceil_div(n1, 8), kInsPoints) * kInsPoints;
-  const int64_t fill = ceil_div(ceil_div((int64_t)148 * 8 * kInsPoints, B > 0 ? B : 1), kInsPoints) * kInsPoints;
+  int64_t S = ceil_div(ceil_div(n1, 8), kInsSpan) * kInsSpan;
+  const int64_t fill = ceil_div(ceil_div((int64_t)148 * 8 * kInsSpan, B > 0 ? B : 1), kInsSpan) * kInsSpan;
   if (S < fill) S = fill;
   if (S < 65536) S = 65536;
   p.S = S;

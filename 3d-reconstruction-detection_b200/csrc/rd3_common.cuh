@@ -59,6 +59,7 @@ struct VoxelGrid {
   float rvs[3];      // RN(1 / vs): only used by the conservative fast path
   float rvs_max;     // max rvs[i]
   float tolc;        // 2^-21 * (max grid + 2) + 1e-30: rounding slack of the fast path, in cells
+  float thrc;        // 0.5 - tolc - 2^-20 (<= 0 disables the fast path): |h - rne(h)| must stay below
   int32_t fast_ok;   // max grid + 2 < 2^20 (else the fast path is disabled)
   int32_t grid[3];
 };
@@ -142,6 +143,43 @@ __device__ __forceinline__ int voxel_coor_fast(float px, float py, float pz, flo
   return undecided ? 2 : (inside ? 1 : 0);
 }
 
+// Round-to-nearest by adding 1.5 * 2^23: for |h| < 2^22, RN(h + kMagic) = kMagic + rne(h) exactly,
+// so the integer sits in the low mantissa bits and rne(h) = (h + kMagic) - kMagic costs two FADDs
+// (no FRND / F2I, which run on the quarter-rate conversion pipe).
+constexpr float kMagic = 12582912.0f;
+constexpr int kMagicBits = 0x4B400000;
+
+// One axis of the cell decision on h = f' - 0.5 (f' = the conservative cell coordinate):
+// i = rne(h) as an int (garbage >= 2^22 or negative when |h| >= 2^22), d = h - rne(h).
+// If |d| < 0.5 - tol then f_ref (within tol of f') lies strictly inside (i, i + 1), so
+// floor(f_ref) == i; and when i falls outside [0, grid) so does floor(f_ref).
+__device__ __forceinline__ void magic_cell(float h, int &i, float &d) {
+  const float m = __fadd_rn(h, kMagic);
+  i = __float_as_int(m) - kMagicBits;
+  d = __fsub_rn(h, __fsub_rn(m, kMagic));
+}
+
+// Same predicate as voxel_coor_fast (abs_err = 0) in the magic-rounding form:
+// h = fma(p - lo, RN(1/vs), -0.5).  Returns 1 inside (key valid), 0 outside, 2 undecided.
+__device__ __forceinline__ int voxel_key_fast(float px, float py, float pz, const VoxelGrid &g,
+                                              uint32_t &key) {
+  const float hx = __fmaf_rn(__fsub_rn(px, g.lo[0]), g.rvs[0], -0.5f);
+  const float hy = __fmaf_rn(__fsub_rn(py, g.lo[1]), g.rvs[1], -0.5f);
+  const float hz = __fmaf_rn(__fsub_rn(pz, g.lo[2]), g.rvs[2], -0.5f);
+  int ix, iy, iz;
+  float dx, dy, dz;
+  magic_cell(hx, ix, dx);
+  magic_cell(hy, iy, dy);
+  magic_cell(hz, iz, dz);
+  const float dmax = fmaxf(fabsf(dx), fmaxf(fabsf(dy), fabsf(dz)));
+  const float sum = (hx + hy) + hz;                      // fmaxf drops NaNs
+  const bool decided = (dmax < g.thrc) & (sum == sum);
+  const bool inside = ((unsigned)ix < (unsigned)g.grid[0]) & ((unsigned)iy < (unsigned)g.grid[1]) &
+                      ((unsigned)iz < (unsigned)g.grid[2]);
+  key = ((uint32_t)iz * (uint32_t)g.grid[1] + (uint32_t)iy) * (uint32_t)g.grid[0] + (uint32_t)ix;
+  return decided ? (inside ? 1 : 0) : 2;
+}
+
 // linear voxel id in (z,y,x) order == lexicographic order of the output coors
 __device__ __forceinline__ uint32_t voxel_key(int cx, int cy, int cz, const VoxelGrid &g) {
   return ((uint32_t)cz * (uint32_t)g.grid[1] + (uint32_t)cy) * (uint32_t)g.grid[0] + (uint32_t)cx;
@@ -159,7 +197,7 @@ __device__ __forceinline__ void key_to_zyx(uint32_t key, const VoxelGrid &g, int
 //   [0]=fx [1]=fy [2]=cx [3]=cy  [4..12]=R row-major (M[:3,:3])  [13..15]=t (M[3,:3])
 // ---------------------------------------------------------------------------
 constexpr int kCalibFloats = 36;   // +[16]=RN(1/fx) [17]=RN(1/fy) [18]=max|R| [19]=max|t|
-                                   // +[20..31] direct cell map A,B,C,T per axis  [32]=Qc [33]=Pc
+                                   // +[20..31] direct cell map A,B,C,T-0.5 per axis  [32]=Qn [33]=Pn
 constexpr int kCalDirect = 20;
 constexpr int kMaxCams = 16;
 
@@ -256,11 +294,11 @@ __device__ __forceinline__ void unproject_point_approx(float z, int u, int v, co
 //   |f'   - f*| <= eps (3 z D + |T| + |f'|),   D = |A|(W-1) + |B|(H-1) + |C|
 // with eps = 2^-24 and S*/vs <= z Q + P1 (Q = (|R0| ex + |R1| ey + |R2|)/vs, ex/ey = ray
 // extents, P1 = |t|/vs).  Hence |f' - f_ref| <= eps (z (3D + 10Q) + |T| + 10 P1 + 3 |lo|/vs)
-// and   tol = 2^-23 (z Qc + Pc) + 1e-30   (2x slack; Qc, Pc = maxima over the three axes,
-// Pc also covers the rounding of the range-filter limits).  If every f'_a is at least tol
-// away from the nearest integer then floor(f'_a) == floor(f_ref_a): the cell and the
+// and   tol = 2^-23 (z Qc + Pc)   (2x slack; Qc, Pc = maxima over the three axes, Pc also
+// covers the rounding of the range-filter limits and of Th = T - 0.5).  If every f'_a is at
+// least tol away from the nearest integer then floor(f'_a) == floor(f_ref_a): the cell and the
 // in/out verdict are the reference's.  Everything else is redone exactly.
-struct CellRange {          // inclusive range filter expressed in cell units, per axis
+struct CellRange {          // inclusive range filter in cell units minus 0.5 (h units), per axis
   float lo[3], hi[3];
   int32_t on;
 };
@@ -274,31 +312,40 @@ __device__ __forceinline__ void pixel_cell_row(float vf, const float *cal, float
   tz = __fmaf_rn(k[9], vf, k[10]);
 }
 
-__device__ __forceinline__ int pixel_cell_fast(float z, float uf, float rtx, float rty, float rtz,
-                                               const float *cal, const VoxelGrid &g,
-                                               const CellRange &rg, int &cx, int &cy, int &cz) {
+// One pixel of the direct map in the magic-rounding form.  k[a*4+3] holds Th_a = RN(T_a - 0.5), so
+// h_a = fma(z, fma(A_a, u, row_a), Th_a) = f'_a - 0.5 (the extra rounding of Th is covered by Pc);
+// thr = fma(z, Qn, Pn) <= 0.5 - tol with Qn = -2^-23 Qc, Pn = 0.5 - 2^-23 Pc - 2^-20 (both rounded
+// down).  The pixel is decided iff max_a |h_a - rne(h_a)| < thr (NaN compares false); then the cell
+// is rne(h_a) and the in/out verdict is the reference's (magic_cell).  Returns 1 inside (key valid),
+// 0 outside, 2 undecided.  With the range filter on, a pixel inside the grid must also be surely
+// inside / outside the filter box (limits in h units), else it is undecided.
+__device__ __forceinline__ int pixel_key_fast(float z, float uf, float rtx, float rty, float rtz,
+                                              const float *cal, const VoxelGrid &g,
+                                              const CellRange &rg, uint32_t &key) {
   const float *k = cal + kCalDirect;
-  const float fx = __fmaf_rn(z, __fmaf_rn(k[0], uf, rtx), k[3]);
-  const float fy = __fmaf_rn(z, __fmaf_rn(k[4], uf, rty), k[7]);
-  const float fz = __fmaf_rn(z, __fmaf_rn(k[8], uf, rtz), k[11]);
-  const float tol = __fmaf_rn(1.1920929e-7f, __fmaf_rn(z, k[12], k[13]), 1e-30f);
-  const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
-  const float tx = fminf(fx - flx, (flx + 1.0f) - fx);
-  const float ty = fminf(fy - fly, (fly + 1.0f) - fy);
-  const float tz = fminf(fz - flz, (flz + 1.0f) - fz);
-  const float t = fminf(tx, fminf(ty, tz));
-  const float sum = (fx + fy) + fz;
-  // branch-free verdict: near a boundary / NaN / huge -> 2, else inside (1) or outside (0)
-  const bool undecided = !(t >= tol) | !(sum == sum);
-  cx = (int)flx; cy = (int)fly; cz = (int)flz;
-  const bool inside = ((unsigned)cx < (unsigned)g.grid[0]) & ((unsigned)cy < (unsigned)g.grid[1]) &
-                      ((unsigned)cz < (unsigned)g.grid[2]);
-  int r = undecided ? 2 : (inside ? 1 : 0);
+  const float hx = __fmaf_rn(z, __fmaf_rn(k[0], uf, rtx), k[3]);
+  const float hy = __fmaf_rn(z, __fmaf_rn(k[4], uf, rty), k[7]);
+  const float hz = __fmaf_rn(z, __fmaf_rn(k[8], uf, rtz), k[11]);
+  const float thr = __fmaf_rn(z, k[12], k[13]);
+  int ix, iy, iz;
+  float dx, dy, dz;
+  magic_cell(hx, ix, dx);
+  magic_cell(hy, iy, dy);
+  magic_cell(hz, iz, dz);
+  // z is finite here (validity mask) and non-finite constants make thr NaN / -inf: a NaN d_a can
+  // only come from an infinite h_a, whose garbage cell index is outside the grid like the point
+  const float dmax = fmaxf(fabsf(dx), fmaxf(fabsf(dy), fabsf(dz)));
+  const bool decided = dmax < thr;
+  const bool inside = ((unsigned)ix < (unsigned)g.grid[0]) & ((unsigned)iy < (unsigned)g.grid[1]) &
+                      ((unsigned)iz < (unsigned)g.grid[2]);
+  key = ((uint32_t)iz * (uint32_t)g.grid[1] + (uint32_t)iy) * (uint32_t)g.grid[0] + (uint32_t)ix;
+  int r = decided ? (inside ? 1 : 0) : 2;
   if (rg.on && r == 1) {
-    const bool in_sure = fx - rg.lo[0] >= tol && rg.hi[0] - fx >= tol && fy - rg.lo[1] >= tol &&
-                         rg.hi[1] - fy >= tol && fz - rg.lo[2] >= tol && rg.hi[2] - fz >= tol;
-    const bool out_sure = rg.lo[0] - fx > tol || fx - rg.hi[0] > tol || rg.lo[1] - fy > tol ||
-                          fy - rg.hi[1] > tol || rg.lo[2] - fz > tol || fz - rg.hi[2] > tol;
+    const float tol = 0.5f - thr;
+    const bool in_sure = hx - rg.lo[0] >= tol && rg.hi[0] - hx >= tol && hy - rg.lo[1] >= tol &&
+                         rg.hi[1] - hy >= tol && hz - rg.lo[2] >= tol && rg.hi[2] - hz >= tol;
+    const bool out_sure = rg.lo[0] - hx > tol || hx - rg.hi[0] > tol || rg.lo[1] - hy > tol ||
+                          hy - rg.hi[1] > tol || rg.lo[2] - hz > tol || hz - rg.hi[2] > tol;
     r = in_sure ? 1 : (out_sure ? 0 : 2);
   }
   return r;

@@ -97,6 +97,7 @@ int make_grid(const float voxel_size[3], const float coors_range[6], VoxelGrid *
     if (g->grid[2] > gmax) gmax = g->grid[2];
     g->fast_ok = (gmax < (1 << 20) - 2) ? 1 : 0;
     g->tolc = 4.76837158e-7f * (float)(gmax + 2) + 1e-30f;
+    g->thrc = g->fast_ok ? 0.5f - g->tolc - 9.5367431640625e-7f : -1.0f;
   }
   uint64_t vol = 1;
   for (int i = 0; i < 3; ++i) {

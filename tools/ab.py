@@ -1,0 +1,28 @@
+"""Quick same-box A/B: run bench.py (device-resident leg only) for each library build and scene.
+
+    python tools/ab.py name1=path/to/lib1.so name2=path/to/lib2.so   (default: the in-tree build)
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+libs = [a.split("=", 1) for a in sys.argv[1:] if "=" in a] or [["tree", ""]]
+scenes = [a for a in sys.argv[1:] if a in ("mixture", "ground")] or ["mixture", "ground"]
+for name, path in libs:
+    for scene in scenes:
+        env = dict(os.environ)
+        if path:
+            env["RD3_LIB_PATH"] = os.path.join(ROOT, path)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "30", "--warmup", "5",
+                            "--no-cpu-baseline", "--no-e2e", "--scene", scene],
+                           capture_output=True, text=True, env=env)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if not line:
+            print(name, scene, "FAILED", r.stderr[-400:])
+            continue
+        j = json.loads(line[-1])
+        st = j["path_roofline"]["stage_ms_per_step_single_stream"]
+        print(name, scene, round(j["ms_per_step"], 3), int(j["frames_per_sec"]),
+              " ".join(f"{k} {v:.3f}" for k, v in st.items()), flush=True)
