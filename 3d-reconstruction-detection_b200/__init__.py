@@ -9,6 +9,7 @@ names mirror the reference's operator API for this path:
     HardSimpleVFE                         mmdet3d/models/voxel_encoders/voxel_encoder.py
     backproject_depth_to_points           plugin ReconstructionBackbone._backproject_depth_to_points
     DepthToVoxels                         the fused, batched path (no reference equivalent)
+    pack_sparse_inputs                    batched SparseEncoder inputs (sparse_refinement.py:393-402)
 
 All compute runs in librd3_b200.so (hand-written sm_100a CUDA, C ABI in
 include/rd3_b200.h).  There is no CPU or PyTorch fallback.
@@ -21,7 +22,7 @@ from .scatter_points import DynamicScatter, dynamic_scatter  # noqa: F401
 from .voxel_encoder import HardSimpleVFE, hard_simple_vfe  # noqa: F401
 from .backproject import (DepthToPointsMixin, backproject_depth_to_points,  # noqa: F401
                           unproject_padded)
-from .fused import DepthToVoxels  # noqa: F401
+from .fused import DepthToVoxels, pack_sparse_inputs  # noqa: F401
 from .parallel import gather_voxel_outputs, shard_range, shard_sizes  # noqa: F401
 from .patch import patch_mmdet3d  # noqa: F401
 from .pipelines import FilterPointByRange, VoxelDownsample  # noqa: F401

@@ -40,6 +40,8 @@ SIGNATURES = {
     "rd3_hard_voxelize": (_i32, [_vp, _i64, _i32, _F3, _F6, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
                                  _i32, _vp, _vp, _sz, _vp]),
     "rd3_hard_simple_vfe": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "rd3_pack_sparse_inputs": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
+                                      _vp]),
     "rd3_unproject_workspace_bytes": (_sz, [_c.POINTER(DepthParams)]),
     "rd3_unproject": (_i32, [_vp, _vp, _vp, _vp, _vp, _c.POINTER(DepthParams), _vp, _vp, _vp, _vp,
                              _sz, _vp]),

@@ -212,9 +212,10 @@ int rd3_depth_to_voxels(const float *depth, const float *intrinsics, const float
   DepthSource src;
   int st = make_depth_source(depth, intrinsics, cam2lidar, conf, sky, p, &src);
   if (st != RD3_OK) return st;
-  if (max_points <= 0 || max_voxels <= 0 || !voxel_size || !coors_range || !voxels || !coors ||
+  if (max_points <= 0 || max_voxels <= 0 || !voxel_size || !coors_range || !coors ||
       !num_points_per_voxel || !d_voxel_num || !workspace)
     return RD3_ERR_INVALID_ARGUMENT;
+  if (!voxels && !voxel_mean) return RD3_ERR_INVALID_ARGUMENT;   // voxels may be skipped only for the mean
   VoxelGrid g;
   uint64_t vol;
   st = make_grid(voxel_size, coors_range, &g, &vol);

@@ -695,9 +695,9 @@ __global__ void __launch_bounds__(256) hv_emit_kernel(Src src, VoxelGrid g, HvWo
   }
   __syncthreads();
 
-  // voxels: contiguous nvox*K*C floats
+  // voxels: contiguous nvox*K*C floats (skipped when the caller only wants coors / num / mean)
   float *vout = o.voxels + ((int64_t)b * w.max_voxels + r0) * K * C;
-  const int nfl = items * C;
+  const int nfl = o.voxels ? items * C : 0;
   if ((reinterpret_cast<uintptr_t>(vout) & 15) == 0) {
     const float4 *t4 = reinterpret_cast<const float4 *>(tile);
     float4 *v4 = reinterpret_cast<float4 *>(vout);

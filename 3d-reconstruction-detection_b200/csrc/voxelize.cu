@@ -154,6 +154,50 @@ __global__ void __launch_bounds__(256) hard_simple_vfe_kernel(const float *__res
   out[t] = __fdiv_rn(s, (float)__ldg(num + m));
 }
 
+// ---------------------------------------------------------------------------
+// Batched sparse-encoder inputs: rows [0, voxel_num[b]) of every sample, packed in sample order,
+// coors widened to (batch, z, y, x).  grid (ceil(max_voxels / 256), B).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_sparse_kernel(const float *__restrict__ feats,
+                                                          const int32_t *__restrict__ coors,
+                                                          const int32_t *__restrict__ num,
+                                                          const int32_t *__restrict__ voxel_num, int B,
+                                                          int max_voxels, int F, int batch_offset,
+                                                          float *__restrict__ out_feats,
+                                                          int32_t *__restrict__ out_coors,
+                                                          int32_t *__restrict__ out_num,
+                                                          int32_t *__restrict__ offsets) {
+  __shared__ int s_warp[8];
+  __shared__ int s_off;
+  const int b = blockIdx.y;
+  // exclusive prefix of the clamped per-sample counts (every CTA of sample b recomputes it)
+  int acc = 0;
+  for (int i = threadIdx.x; i < b; i += 256) acc += min(max(__ldg(voxel_num + i), 0), max_voxels);
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < 8; ++k) t += s_warp[k];
+    s_off = t;
+  }
+  __syncthreads();
+  const int off = s_off;
+  const int m = min(max(__ldg(voxel_num + b), 0), max_voxels);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    offsets[b] = off;
+    if (b == B - 1) offsets[B] = off + m;
+  }
+  const int v = blockIdx.x * 256 + threadIdx.x;
+  if (v >= m) return;
+  const int64_t src = (int64_t)b * max_voxels + v, dst = (int64_t)off + v;
+  for (int f = 0; f < F; ++f) out_feats[dst * F + f] = __ldg(feats + src * F + f);
+  const int4 c = make_int4(batch_offset + b, __ldg(coors + src * 3), __ldg(coors + src * 3 + 1),
+                           __ldg(coors + src * 3 + 2));
+  reinterpret_cast<int4 *>(out_coors)[dst] = c;
+  if (out_num) out_num[dst] = __ldg(num + src);
+}
+
 }  // namespace rd3
 
 using namespace rd3;
@@ -262,6 +306,21 @@ int rd3_hard_voxelize(const float *points, int64_t N, int C, const float voxel_s
   HvOut out{voxels, coors, num_points_per_voxel, voxel_mean, d_voxel_num, point2voxel,
             voxel_mean ? F : 0};
   return hv_run(src, g, vol, plan, workspace, out, (cudaStream_t)stream);
+}
+
+int rd3_pack_sparse_inputs(const float *voxel_feats, const int32_t *coors, const int32_t *num_points,
+                           const int32_t *d_voxel_num, int B, int max_voxels, int F, int batch_offset,
+                           float *out_feats, int32_t *out_coors, int32_t *out_num_points,
+                           int32_t *d_offsets, rd3_stream_t stream) {
+  if (B <= 0 || B > 65535 || max_voxels <= 0 || F <= 0) return RD3_ERR_INVALID_ARGUMENT;
+  if (!voxel_feats || !coors || !d_voxel_num || !out_feats || !out_coors || !d_offsets)
+    return RD3_ERR_INVALID_ARGUMENT;
+  if (out_num_points && !num_points) return RD3_ERR_INVALID_ARGUMENT;
+  if (reinterpret_cast<uintptr_t>(out_coors) & 15) return RD3_ERR_INVALID_ARGUMENT;
+  pack_sparse_kernel<<<dim3((unsigned)ceil_div(max_voxels, 256), B), 256, 0, (cudaStream_t)stream>>>(
+      voxel_feats, coors, num_points, d_voxel_num, B, max_voxels, F, batch_offset, out_feats, out_coors,
+      out_num_points, d_offsets);
+  return check_launch();
 }
 
 int rd3_hard_simple_vfe(const float *voxels, const int32_t *num_points, int64_t M, int max_points,

@@ -19,8 +19,13 @@ class DepthToVoxels(nn.Module):
     not synchronise with the host."""
 
     def __init__(self, voxel_size, point_cloud_range, max_num_points, max_voxels,
-                 max_depth=None, range_filter=None, with_mean=True):
+                 max_depth=None, range_filter=None, with_mean=True, with_voxels=True):
+        """``with_voxels=False`` skips the padded (B, max_voxels, max_points, 3) tensor -- 85 % of
+        the output bytes -- for callers that only feed the sparse encoder (mean + coors + num)."""
         super().__init__()
+        if not with_voxels and not with_mean:
+            raise ValueError("with_voxels=False needs with_mean=True")
+        self.with_voxels = with_voxels
         self.voxel_size = list(voxel_size)
         self.point_cloud_range = list(point_cloud_range)
         self.max_num_points = int(max_num_points)
@@ -35,7 +40,8 @@ class DepthToVoxels(nn.Module):
         if key not in self._out_cache:
             K = self.max_num_points
             self._out_cache[key] = dict(
-                voxels=torch.empty((B, max_voxels, K, 3), dtype=torch.float32, device=dev),
+                voxels=(torch.empty((B, max_voxels, K, 3), dtype=torch.float32, device=dev)
+                        if self.with_voxels else None),
                 coors=torch.empty((B, max_voxels, 3), dtype=torch.int32, device=dev),
                 num=torch.empty((B, max_voxels), dtype=torch.int32, device=dev),
                 mean=torch.empty((B, max_voxels, 3), dtype=torch.float32, device=dev) if self.with_mean else None,
@@ -69,13 +75,49 @@ class DepthToVoxels(nn.Module):
                     voxel_mean=out["mean"], voxel_num=out["voxel_num"])
 
     @staticmethod
-    def to_sparse_encoder_inputs(result):
+    def to_sparse_encoder_inputs(result, batch_offset=0, with_num_points=False):
         """(voxel_features (sum M, 3), coors (sum M, 4) [b,z,y,x], batch_size): what
-        SparseEncoder.forward consumes (sparse_encoder.py:96-128); mirrors the cat + F.pad
-        of sparse_refinement.py:393-402.  One D2H read of the per-sample voxel counts."""
-        n = result["voxel_num"].tolist()
-        feats, coors = [], []
-        for b, m in enumerate(n):
-            feats.append(result["voxel_mean"][b, :m])
-            coors.append(nn.functional.pad(result["coors"][b, :m], (1, 0), mode="constant", value=b))
-        return torch.cat(feats, dim=0), torch.cat(coors, dim=0), len(n)
+        SparseEncoder.forward consumes (sparse_encoder.py:96-128)."""
+        return pack_sparse_inputs(result, batch_offset=batch_offset, with_num_points=with_num_points)
+
+
+_pack_cache = {}
+
+
+def pack_sparse_inputs(result, batch_offset=0, with_num_points=False, sync=True):
+    """One launch instead of the per-sample slice + F.pad + torch.cat tail of
+    ``_voxelize_and_encode`` (sparse_refinement.py:393-402).
+
+    ``result``: output dict of :class:`DepthToVoxels` (voxel_mean, coors, num_points, voxel_num).
+    Returns ``(voxel_features (sum M, F), coors (sum M, 4) [b,z,y,x], batch_size)`` -- plus
+    ``num_points (sum M)`` after the coors when ``with_num_points`` -- like the reference's
+    ``(voxel_features, num_points, coors)``.  ``sync=True`` reads sum M back (the one D2H read
+    the reference's ``hard_voxelize`` return value forces per sample); ``sync=False`` returns the
+    worst-case-sized buffers and a device tensor ``offsets (B+1)`` instead of the batch size.
+    The returned tensors are views of buffers reused by the next call with the same shape."""
+    feats, coors, num, vnum = result["voxel_mean"], result["coors"], result["num_points"], result["voxel_num"]
+    if feats is None:
+        raise RuntimeError("pack_sparse_inputs needs voxel_mean (DepthToVoxels(with_mean=True))")
+    for t, n, d in ((feats, "voxel_mean", torch.float32), (coors, "coors", torch.int32),
+                    (num, "num_points", torch.int32), (vnum, "voxel_num", torch.int32)):
+        _lib.require_cuda(t, n, d)
+    B, MV, F = feats.shape
+    dev = feats.device
+    key = (B, MV, F, dev, with_num_points)
+    if key not in _pack_cache:
+        _pack_cache[key] = (torch.empty((B * MV, F), dtype=torch.float32, device=dev),
+                            torch.empty((B * MV, 4), dtype=torch.int32, device=dev),
+                            torch.empty((B * MV,), dtype=torch.int32, device=dev) if with_num_points else None,
+                            torch.empty((B + 1,), dtype=torch.int32, device=dev))
+    of, oc, on, offs = _pack_cache[key]
+    with torch.cuda.device_of(feats):
+        st = _lib.lib().rd3_pack_sparse_inputs(_lib.ptr(feats), _lib.ptr(coors), _lib.ptr(num), _lib.ptr(vnum),
+                                               B, MV, F, int(batch_offset), _lib.ptr(of), _lib.ptr(oc),
+                                               _lib.ptr(on), _lib.ptr(offs), _lib.stream_of(feats))
+        _lib.check(st, "pack_sparse_inputs")
+    if not sync:
+        return (of, oc, on, offs) if with_num_points else (of, oc, offs)
+    total = int(offs[B].item())
+    if with_num_points:
+        return of[:total], oc[:total], on[:total], B
+    return of[:total], oc[:total], B

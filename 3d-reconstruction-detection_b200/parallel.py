@@ -6,7 +6,6 @@ gather the fixed-size padded outputs.
 """
 import torch
 import torch.distributed as dist
-from torch import nn
 
 
 def shard_range(num_frames, world_size, rank):
@@ -63,12 +62,9 @@ def gather_voxel_outputs(result, num_frames_total=None, group=None):
     return out
 
 
-def to_sparse_encoder_inputs(result):
+def to_sparse_encoder_inputs(result, batch_offset=0):
     """(voxel_features (sum M, F), coors (sum M, 4) [b,z,y,x], batch_size) of a (gathered)
-    result: the cat + F.pad(coor, (1,0), value=i) of sparse_refinement.py:393-402."""
-    n = result["voxel_num"].tolist()
-    feats, coors = [], []
-    for b, m in enumerate(n):
-        feats.append(result["voxel_mean"][b, :m])
-        coors.append(nn.functional.pad(result["coors"][b, :m], (1, 0), mode="constant", value=b))
-    return torch.cat(feats, dim=0), torch.cat(coors, dim=0), len(n)
+    result: the cat + F.pad(coor, (1,0), value=i) of sparse_refinement.py:393-402 as one kernel
+    (``rd3_pack_sparse_inputs``).  CUDA tensors only -- there is no CPU path."""
+    from .fused import pack_sparse_inputs
+    return pack_sparse_inputs(result, batch_offset=batch_offset)

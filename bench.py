@@ -434,6 +434,34 @@ def main():
                       "voxels+coors+num+mean+count) through rd3_b200.DepthToVoxels" % (chunk, nstreams)}
         assert torch.equal(h_out["voxel_num"], r["voxel_num"].cpu())
 
+    # ---- the same path without the padded voxel tensor: SparseEncoder inputs only ---
+    enc = None
+    if not args.profile_only:
+        lite = rd3_b200.DepthToVoxels(cfg["voxel_size"], cfg["pcr"], K, cfg["max_voxels"],
+                                      max_depth=synthetic.MAX_DEPTH, with_voxels=False).to(dev).train()
+
+        def enc_step():
+            return rd3_b200.pack_sparse_inputs(lite(depth, intr, c2l), batch_offset=rank * B, sync=False)
+
+        for _ in range(3):
+            enc_step()
+        barrier()
+        n_enc = max(3, min(args.steps, 20))
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(n_enc):
+            enc_step()
+        g1.record()
+        barrier()
+        te = torch.tensor([g0.elapsed_time(g1) / n_enc], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        enc_bytes = B * npix * 4 + M_total * (12 + 4 + 4 * F) + M_total * (16 + 4 * F)
+        enc = {"ms_per_step": float(te.item()), "frames_per_sec": world * B / (float(te.item()) * 1e-3),
+               "algorithmic_bytes_per_step": enc_bytes,
+               "what": "DepthToVoxels(with_voxels=False) + pack_sparse_inputs: (sum M,3) features and "
+                       "(sum M,4) [b,z,y,x] coors for the whole batch, inputs resident in HBM"}
+
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) --------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile_only:
@@ -465,6 +493,8 @@ def main():
         }
         if gather_ms is not None:
             line["gather_ms"] = gather_ms
+        if enc is not None:
+            line["encoder_inputs"] = enc
         _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -156,7 +156,10 @@ RD3_API int rd3_unproject(const float *depth, const float *intrinsics,
  * to rd3_unproject(b) followed by rd3_hard_voxelize + rd3_hard_simple_vfe.
  *   voxels (B, max_voxels, max_points, 3), coors (B, max_voxels, 3),
  *   num_points_per_voxel (B, max_voxels), voxel_mean (B, max_voxels, 3) or
- *   NULL, d_voxel_num device int32[B]. */
+ *   NULL, d_voxel_num device int32[B].
+ *   voxels may be NULL when voxel_mean is given: a caller that feeds the sparse
+ *   encoder (HardSimpleVFE features + coors, sparse_refinement.py:382-402) never
+ *   reads the padded voxel tensor, and 85 % of the output bytes are not written. */
 RD3_API size_t rd3_depth_to_voxels_workspace_bytes(const rd3_depth_params *p,
                                            int max_points, int max_voxels);
 
@@ -169,6 +172,28 @@ RD3_API int rd3_depth_to_voxels(const float *depth, const float *intrinsics,
                         float *voxel_mean, int32_t *d_voxel_num,
                         void *workspace, size_t workspace_bytes,
                         rd3_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Batched sparse-encoder inputs.  Replaces the Python tail of
+ * SparseRefinement._voxelize_and_encode
+ * (projects/mmdet3d_plugin/models/backbone/sparse_refinement.py:393-402:
+ * torch.cat of the per-sample slices + F.pad(coor, (1, 0), value=i)) and of
+ * MVXTwoStageDetector.voxelize (mmdet3d/models/detectors/mvx_two_stage.py:211-236)
+ * with one launch and no host synchronisation:
+ *   voxel_feats (B, max_voxels, F), coors (B, max_voxels, 3) zyx, num_points
+ *   (B, max_voxels) or NULL, d_voxel_num device int32[B]  ->  rows
+ *   [0, voxel_num[b]) of every sample packed in sample order:
+ *   out_feats (sum M, F), out_coors (sum M, 4) = (batch_offset + b, z, y, x),
+ *   out_num_points (sum M) or NULL; d_offsets device int32[B + 1] = exclusive
+ *   prefix of the counts, d_offsets[B] = sum M.  Outputs must hold B * max_voxels
+ *   rows (worst case); out_coors 16-byte aligned.  B <= 65535.
+ * ------------------------------------------------------------------------- */
+RD3_API int rd3_pack_sparse_inputs(const float *voxel_feats, const int32_t *coors,
+                           const int32_t *num_points, const int32_t *d_voxel_num,
+                           int B, int max_voxels, int F, int batch_offset,
+                           float *out_feats, int32_t *out_coors,
+                           int32_t *out_num_points, int32_t *d_offsets,
+                           rd3_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * dynamic_point_to_voxel_forward

@@ -303,9 +303,28 @@ def check_fused(cfg, frames, scene, masks, training):
         assert np.array_equal(bits(r["voxels"][i, :m].cpu().numpy()), bits(ov))
         om = oracle.hard_simple_vfe(ov, on, 3)
         assert np.array_equal(bits(r["voxel_mean"][i, :m].cpu().numpy()), bits(om))
-    feats, coors4, bs = mod.to_sparse_encoder_inputs(r)
-    assert bs == len(frames) and coors4.shape[1] == 4 and feats.shape[0] == coors4.shape[0] == vn.sum()
-    assert coors4[-1, 0].item() == len(frames) - 1
+    # batched sparse-encoder inputs == the slice + F.pad + cat tail of sparse_refinement.py:393-402
+    feats, coors4, num, bs = mod.to_sparse_encoder_inputs(r, with_num_points=True)
+    ef = torch.cat([r["voxel_mean"][i, :int(vn[i])] for i in range(len(frames))])
+    ec = torch.cat([torch.nn.functional.pad(r["coors"][i, :int(vn[i])], (1, 0), value=i) for i in range(len(frames))])
+    en = torch.cat([r["num_points"][i, :int(vn[i])] for i in range(len(frames))])
+    assert bs == len(frames) and torch.equal(feats, ef) and torch.equal(coors4, ec) and torch.equal(num, en)
+    f2, c2, offs = rd3_b200.pack_sparse_inputs(r, batch_offset=5, sync=False)
+    assert offs.cpu().tolist() == [0] + np.cumsum(vn).tolist()
+    assert torch.equal(c2[:len(ec), 0], ec[:, 0] + 5) and torch.equal(c2[:len(ec), 1:], ec[:, 1:])
+    # the same call without the padded voxel tensor: coors / num / mean / counts identical
+    keep = {k: v.clone() for k, v in r.items() if v is not None}
+    lite = rd3_b200.DepthToVoxels(c["voxel_size"], c["pcr"], c["max_points"], c["max_voxels"],
+                                  max_depth=synthetic.MAX_DEPTH, range_filter=rf, with_voxels=False).to(DEV)
+    lite.train(training)
+    r2 = lite(d["depth"], d["intrinsics"], d["cam2lidar"], confs=d["conf"] if masks else None,
+              conf_thresh=thr, sky_masks=d["sky"] if masks else None)
+    assert r2["voxels"] is None and torch.equal(r2["voxel_num"], keep["voxel_num"])
+    for i in range(len(frames)):
+        m = int(vn[i])
+        assert torch.equal(r2["coors"][i, :m], keep["coors"][i, :m])
+        assert torch.equal(r2["num_points"][i, :m], keep["num_points"][i, :m])
+        assert np.array_equal(bits(r2["voxel_mean"][i, :m].cpu().numpy()), bits(keep["voxel_mean"][i, :m].cpu().numpy()))
     return vn
 
 
