@@ -38,6 +38,14 @@
 namespace rd3 {
 
 constexpr int kInsThreads = 256;
+#ifndef RD3_SLOT_TILES
+#define RD3_SLOT_TILES 4              // tiles whose candidate regions one warp of the slots kernel merges
+#endif
+constexpr int kSlotTiles = RD3_SLOT_TILES;   // power of two, <= 32
+#ifndef RD3_EMIT_THREADS
+#define RD3_EMIT_THREADS 256
+#endif
+constexpr int kEmitThreads = RD3_EMIT_THREADS;
 #ifndef RD3_INS_MINB
 #define RD3_INS_MINB 8                // resident insert CTAs per SM the register budget is sized for
 #endif
@@ -596,24 +604,38 @@ __device__ __forceinline__ void slot_insert_tail(uint32_t *S, int K, uint32_t id
 }
 
 // K3 ------------------------------------------------------------------------
-// grid (ceil(ntiles/4), frames), 128 threads: one warp per 128-point tile region (small CTAs:
-// warps finish at very different times and a CTA's slot is only recycled when all have).
+// grid (ceil(ntiles/(4*kSlotTiles)), frames), 128 threads (small CTAs: warps finish at very different times
+// and a CTA's slot is only recycled when all have).  A warp works off the candidate regions of kSlotTiles
+// consecutive tiles as ONE list: a warp scan of the counts gives each tile's offset, lane j of
+// a pass finds its (tile, k) by a log2(kSlotTiles)-step search over those offsets, so the lanes stay dense however
+// few candidates a tile has (the lookup-only rounds leave ~5 per tile).
 // Neighbouring pixels often share a voxel: lanes holding the same table slot form a
 // group (__match_any_sync); only the group leader walks table -> rank -> last slot and
 // broadcasts the result, and a whole group leaves after one load when the voxel is full.
 static __global__ void __launch_bounds__(128) hv_slots_kernel(HvWork w, int32_t *point2voxel) {
   const int b = blockIdx.y + w.b0;
-  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (t >= w.ntiles) return;
-  const int n = w.cand_cnt[(int64_t)b * w.ntiles + t];
-  if (n == 0) return;
   const int lane = threadIdx.x & 31;
-  const uint2 *cand = w.cand + (int64_t)b * w.N + ((int64_t)t << kTileShift);
+  const int t0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kSlotTiles;
+  if (t0 >= w.ntiles) return;
+  const int mine = (lane < kSlotTiles && t0 + lane < w.ntiles) ? w.cand_cnt[(int64_t)b * w.ntiles + t0 + lane] : 0;
+  const int inc = warp_inclusive_scan(mine);
+  const int excl = inc - mine;
+  const int n = __shfl_sync(0xffffffffu, inc, 31);
+  const uint2 *cand = w.cand + (int64_t)b * w.N + ((int64_t)t0 << kTileShift);
   const unsigned long long *table = w.table + (int64_t)b * w.cap;
   for (int j0 = 0; j0 < n; j0 += 32) {
     const int j = j0 + lane;
     const bool on = j < n;
-    const uint2 c = on ? __ldg(cand + j) : make_uint2(0u, kEmpty32 - lane);   // distinct dummies
+    // tile of list position j: the largest lane t with excl[t] <= j (empty tiles share their
+    // offset with the next non-empty one, which the "largest" picks)
+    int t = 0;
+#pragma unroll
+    for (int step = kSlotTiles / 2; step > 0; step >>= 1) {
+      const int e = __shfl_sync(0xffffffffu, excl, t + step);
+      if (e <= j) t += step;
+    }
+    const int k = j - __shfl_sync(0xffffffffu, excl, t);
+    const uint2 c = on ? __ldg(cand + (t << kTileShift) + k) : make_uint2(0u, kEmpty32 - lane);   // distinct dummies
     const unsigned grp = __match_any_sync(0xffffffffu, c.y);
     const int leader = __ffs(grp) - 1;
     uint32_t first_idx = 0, last = 0;
@@ -649,7 +671,7 @@ static __global__ void __launch_bounds__(128) hv_slots_kernel(HvWork w, int32_t 
 //   3. voxels are copied out with 16-byte stores; one thread per voxel writes coors (from the
 //      first point), the count and the HardSimpleVFE mean (slot order, one __fdiv_rn)
 template <class Src>
-__global__ void __launch_bounds__(256) hv_emit_kernel(Src src, VoxelGrid g, HvWork w, HvOut o, int V) {
+__global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGrid g, HvWork w, HvOut o, int V) {
   extern __shared__ float s_dyn[];
   __shared__ float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 1];
   const int b = blockIdx.y + w.b0;
@@ -660,7 +682,8 @@ __global__ void __launch_bounds__(256) hv_emit_kernel(Src src, VoxelGrid g, HvWo
   const int K = w.K;
   const int nvox = min(V, vn - r0);
   const int items = nvox * K;
-  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  constexpr int nw = kEmitThreads / 32;
   float *tile = s_dyn;
   uint32_t *s_idx = reinterpret_cast<uint32_t *>(s_dyn + (((size_t)V * K * C + 3) & ~(size_t)3));
   uint16_t *s_list = reinterpret_cast<uint16_t *>(s_idx + (size_t)V * K);
@@ -671,7 +694,7 @@ __global__ void __launch_bounds__(256) hv_emit_kernel(Src src, VoxelGrid g, HvWo
     float4 *t4 = reinterpret_cast<float4 *>(tile);
     const int n4 = (items * C + 3) >> 2;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e = threadIdx.x; e < n4; e += 256) t4[e] = z4;
+    for (int e = threadIdx.x; e < n4; e += kEmitThreads) t4[e] = z4;
   }
   // warp wv owns items [wv*per, wv*per+per): its list segment starts at the same offset
   const int per = ((items + nw - 1) / nw + 31) & ~31;
@@ -702,10 +725,10 @@ __global__ void __launch_bounds__(256) hv_emit_kernel(Src src, VoxelGrid g, HvWo
     const float4 *t4 = reinterpret_cast<const float4 *>(tile);
     float4 *v4 = reinterpret_cast<float4 *>(vout);
     const int n4 = nfl >> 2;
-    for (int e = threadIdx.x; e < n4; e += 256) v4[e] = t4[e];
-    for (int e = (nfl & ~3) + threadIdx.x; e < nfl; e += 256) vout[e] = tile[e];
+    for (int e = threadIdx.x; e < n4; e += kEmitThreads) v4[e] = t4[e];
+    for (int e = (nfl & ~3) + threadIdx.x; e < nfl; e += kEmitThreads) vout[e] = tile[e];
   } else {
-    for (int e = threadIdx.x; e < nfl; e += 256) vout[e] = tile[e];
+    for (int e = threadIdx.x; e < nfl; e += kEmitThreads) vout[e] = tile[e];
   }
 
   // one thread per voxel: count, coors from the first point, HardSimpleVFE mean
@@ -713,7 +736,7 @@ __global__ void __launch_bounds__(256) hv_emit_kernel(Src src, VoxelGrid g, HvWo
   // slots beyond the count are zeros, so the running sum stops changing at the count --
   // except that (-0.0) + 0.0 = +0.0, which one extra "+ 0.0f" reproduces)
   const int F = o.F;
-  for (int v = threadIdx.x; v < nvox; v += 256) {
+  for (int v = threadIdx.x; v < nvox; v += kEmitThreads) {
     const uint32_t *si = s_idx + v * K;
     int cnt = 0;
     while (cnt < K && si[cnt] != kEmpty32) ++cnt;
@@ -826,7 +849,7 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   w.nwords = p.nwords; w.nchunks = p.nchunks; w.K = p.K; w.max_voxels = p.max_voxels;
 
   const int C = src.host_num_feats();
-  int V = 1024 / p.K;            // ~1024 slot items per CTA: amortises the calibration staging
+  int V = 4 * kEmitThreads / p.K;   // ~4 slot items per thread: amortises the calibration staging
   if (V < 1) V = 1;
   if (V > 128) V = 128;
   while (V > 1 && (size_t)V * p.K * (C + 1) * 4 > 40 * 1024) V /= 2;
@@ -895,9 +918,9 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
     scan_chunks_kernel<<<nb, 1024, 0, st>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels, b0);
     prof_mark(st, 4);
     if (p.N > 0)
-      hv_slots_kernel<<<dim3((unsigned)ceil_div(p.ntiles, 4), nb), 128, 0, st>>>(w, out.point2voxel);
+      hv_slots_kernel<<<dim3((unsigned)ceil_div(p.ntiles, 4 * kSlotTiles), nb), 128, 0, st>>>(w, out.point2voxel);
     prof_mark(st, 5);
-    hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, V), nb), 256, smem, st>>>(src, g, w, out, V);
+    hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, V), nb), kEmitThreads, smem, st>>>(src, g, w, out, V);
     prof_mark(st, 6);
     prof_mark(st, 7);
     }   // groups of this lane
