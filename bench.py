@@ -240,6 +240,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--scene", default="mixture", choices=["mixture", "ground"],
                     help="synthetic depth: SURVEY 8(d) per-pixel mixture (default) or a structured ground+walls scene")
+    ap.add_argument("--e2e-chunk", type=int, default=8, help="frames per H2D -> kernels -> D2H chunk of the e2e leg")
+    ap.add_argument("--e2e-streams", type=int, default=3)
     ap.add_argument("--gather", action="store_true", help="also time the NCCL all_gather of the outputs")
     ap.add_argument("--profile-only", action="store_true",
                     help="few steps, no e2e / cpu baseline (the command profiled under ncu)")
@@ -388,9 +390,9 @@ def main():
     # ---- e2e: public API from pinned host buffers, copies inside the timed region ------
     e2e = None
     if not args.no_e2e and not args.profile_only:
-        chunk = 8 if B % 8 == 0 else B
+        chunk = args.e2e_chunk if B % args.e2e_chunk == 0 else B
         nchunks = B // chunk
-        nstreams = min(3, nchunks)
+        nstreams = min(args.e2e_streams, nchunks)
         streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
         mods = [rd3_b200.DepthToVoxels(cfg["voxel_size"], cfg["pcr"], K, cfg["max_voxels"],
                                        max_depth=synthetic.MAX_DEPTH).to(dev).train() for _ in range(nstreams)]
