@@ -594,11 +594,23 @@ __device__ __forceinline__ int voxel_rank(const HvWork &w, int b, uint32_t first
 // slot K-1: if it is already smaller than idx, K smaller indices exist.
 __device__ __forceinline__ void slot_insert_tail(uint32_t *S, int K, uint32_t idx) {
   uint32_t cur = idx;
-  for (int k = 1; k < K; ++k) {
-    const uint32_t s = __ldcg(S + k);
-    if (s < cur) continue;               // stale reads are larger: conservative
+  int k = 1;
+  // Skip the prefix of smaller indices with 8 independent loads at a time instead of one
+  // dependent load per slot (a voxel that already holds 7 points would cost 7 round trips).
+  // A slot read as smaller than cur can only have decreased since: it stays smaller.
+  while (k < K) {
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (k + i < K) ? __ldcg(S + k + i) : kEmpty32;
+    int i = 8;
+#pragma unroll
+    for (int q = 7; q >= 0; --q) i = (v[q] < cur) ? i : q;      // first slot not smaller than cur
+    k += i;
+    if (i < 8) break;
+  }
+  for (; k < K; ++k) {
     const uint32_t old = atomicMin(S + k, cur);
-    if (old == kEmpty32) return;
+    if (old == kEmpty32 || old == cur) return;
     if (old > cur) cur = old;            // displaced a larger index: carry it on
   }
 }
