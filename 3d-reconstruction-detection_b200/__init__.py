@@ -10,6 +10,7 @@ names mirror the reference's operator API for this path:
     backproject_depth_to_points           plugin ReconstructionBackbone._backproject_depth_to_points
     DepthToVoxels                         the fused, batched path (no reference equivalent)
     pack_sparse_inputs                    batched SparseEncoder inputs (sparse_refinement.py:393-402)
+    PillarDecorator, PointPillarsScatter  mmdet3d/models/voxel_encoders/pillar_encoder.py, middle_encoders/pillar_scatter.py
 
 All compute runs in librd3_b200.so (hand-written sm_100a CUDA, C ABI in
 include/rd3_b200.h).  There is no CPU or PyTorch fallback.
@@ -26,3 +27,4 @@ from .fused import DepthToVoxels, pack_sparse_inputs  # noqa: F401
 from .parallel import gather_voxel_outputs, shard_range, shard_sizes  # noqa: F401
 from .patch import patch_mmdet3d  # noqa: F401
 from .pipelines import FilterPointByRange, VoxelDownsample  # noqa: F401
+from .pillar import PillarDecorator, PointPillarsScatter, pillar_decorate  # noqa: F401

@@ -48,6 +48,9 @@ SIGNATURES = {
     "rd3_depth_to_voxels_workspace_bytes": (_sz, [_c.POINTER(DepthParams), _i32, _i32]),
     "rd3_depth_to_voxels": (_i32, [_vp, _vp, _vp, _vp, _vp, _c.POINTER(DepthParams), _F3, _F6, _i32,
                                    _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rd3_pillar_decorate": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32,
+                                   _f32, _f32, _vp, _vp]),
+    "rd3_pillars_scatter": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "rd3_coors_extent": (_i32, [_vp, _i64, _vp, _vp]),
     "rd3_dynamic_scatter_workspace_bytes": (_sz, [_i64, _i32, _I3]),
     "rd3_dynamic_scatter_forward": (_i32, [_vp, _vp, _i64, _i32, _I3, _i32, _vp, _vp, _vp, _vp, _vp,

@@ -878,6 +878,7 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   // whole kernel sequence on their own streams (forked from / joined to the caller's stream),
   // so that the issue-bound insert kernel of one sub-batch overlaps the latency-bound
   // first/slots kernels and memsets of another.  With the stage profiler on, one lane is used.
+  LaneLock lane_lock;              // the lanes' events are shared by all callers on this device
   StreamLanes *lanes = nullptr;
   int nl = 1;
   if (!prof_enabled() && p.B >= 2) {

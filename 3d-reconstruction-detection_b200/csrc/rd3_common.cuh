@@ -36,6 +36,12 @@ struct StreamLanes {
   cudaEvent_t fork, join[kMaxLanes - 1];
 };
 StreamLanes *get_stream_lanes();   // nullptr if creation failed
+// The lanes (streams + events) of a device are shared by every call on it: host threads that
+// enqueue concurrently take this lock for the duration of their enqueue (no device wait inside).
+struct LaneLock {
+  LaneLock();
+  ~LaneLock();
+};
 int stream_lane_count();           // RD3_STREAMS (1..kMaxLanes), default 3
 
 #define RD3_CUDA_TRY(expr)                       \

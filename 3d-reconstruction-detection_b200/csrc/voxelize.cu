@@ -1,6 +1,7 @@
 // voxelize.cu -- C-ABI entry points for dynamic / hard voxelization of a point
 // array and the standalone HardSimpleVFE, plus library-wide helpers.
 #include <math.h>
+#include <mutex>
 #include <stdlib.h>
 #include <string.h>
 
@@ -52,7 +53,11 @@ struct LaneSet {
   StreamLanes lanes;
 };
 LaneSet g_lanes[64];
+std::mutex g_lane_mutex;
 }  // namespace
+
+LaneLock::LaneLock() { g_lane_mutex.lock(); }
+LaneLock::~LaneLock() { g_lane_mutex.unlock(); }
 
 StreamLanes *get_stream_lanes() {
   int dev = 0;

@@ -233,6 +233,37 @@ RD3_API int rd3_dynamic_scatter_backward(float *grad_feats, const float *grad_vo
                                  int C, int reduce_type, void *workspace,
                                  size_t workspace_bytes, rd3_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Pillar encoders, gather side (what follows hard voxelization in the pillar configs,
+ * configs/_base_/models/centerpoint_02pillar_second_secfpn_nus.py:1-16).
+ *
+ * rd3_pillar_decorate: the feature decorations of PillarFeatureNet.forward
+ *   (mmdetection3d/mmdet3d/models/voxel_encoders/pillar_encoder.py:104-146), i.e. everything
+ *   in front of the PFN layers, in one launch:
+ *   voxels (M, max_points, C>=3), num_points (M), coors (M, coors_cols) with the
+ *   last two columns (y, x) [coors_cols 4: (b,z,y,x), 3: (z,y,x)]  ->
+ *   out (M, max_points, C + 3*with_cluster_center + 2*with_voxel_center + with_distance)
+ *   = cat(features, xyz - mean_xyz, (x,y) - pillar centre, |xyz|) * padding mask.
+ *   x_offset = vx/2 + pcr[0], y_offset = vy/2 + pcr[1] (:87-88), narrowed to fp32 by the caller.
+ *   legacy != 0 reproduces the default legacy=True aliasing (:127-133): the raw x, y columns are
+ *   replaced by the centre offsets and the distance is taken from them.
+ *
+ * rd3_pillars_scatter: PointPillarsScatter.forward_batch / forward_single
+ *   (mmdetection3d/mmdet3d/models/middle_encoders/pillar_scatter.py:39-102):
+ *   voxel_features (M, C), coors (M, coors_cols) -> canvas (batch_size, C, ny, nx), zero where
+ *   no pillar.  canvas is fully written (zero fill included).  Rows whose (b, y, x) fall
+ *   outside the canvas are skipped (the reference's indexed assignment would raise).
+ * ------------------------------------------------------------------------- */
+RD3_API int rd3_pillar_decorate(const float *voxels, const int32_t *num_points,
+                        const int32_t *coors, int64_t M, int max_points, int C,
+                        int coors_cols, int with_cluster_center, int with_voxel_center,
+                        int with_distance, int legacy, float vx, float vy,
+                        float x_offset, float y_offset, float *out, rd3_stream_t stream);
+
+RD3_API int rd3_pillars_scatter(const float *voxel_features, const int32_t *coors, int64_t M,
+                        int C, int coors_cols, int batch_size, int ny, int nx,
+                        float *canvas, rd3_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -199,3 +199,66 @@ def voxel_downsample(ref_layer, points, voxel_size, point_cloud_range, colors=No
         idx = torch.argmin(torch.cdist(centers, points, compute_mode='donot_use_mm_for_euclid_dist'), dim=1)
         vcol = colors[idx]
     return centers, vcol, idx
+
+
+def get_paddings_indicator(actual_num, max_num, axis=0):
+    """mmdet3d/models/voxel_encoders/utils.py:9-29."""
+    actual_num = torch.unsqueeze(actual_num, axis + 1)
+    max_num_shape = [1] * len(actual_num.shape)
+    max_num_shape[axis + 1] = -1
+    max_num = torch.arange(max_num, dtype=torch.int, device=actual_num.device).view(max_num_shape)
+    return actual_num.int() > max_num
+
+
+def pillar_feature_decorations(features, num_points, coors, voxel_size=(0.2, 0.2, 4),
+                               point_cloud_range=(0, -40, -3, 70.4, 40, 1), with_cluster_center=True,
+                               with_voxel_center=True, with_distance=False, legacy=True):
+    """PillarFeatureNet.__init__/forward up to the PFN layers, pillar_encoder.py:84-143,
+    statement for statement (the legacy branch aliases ``features`` exactly like the reference)."""
+    vx, vy = voxel_size[0], voxel_size[1]
+    x_offset = vx / 2 + point_cloud_range[0]                            # :87-88
+    y_offset = vy / 2 + point_cloud_range[1]
+    features = features.clone()
+    features_ls = [features]
+    if with_cluster_center:                                             # :108-113
+        points_mean = features[:, :, :3].sum(dim=1, keepdim=True) / num_points.type_as(features).view(-1, 1, 1)
+        f_cluster = features[:, :, :3] - points_mean
+        features_ls.append(f_cluster)
+    dtype = features.dtype
+    if with_voxel_center:                                               # :117-134
+        if not legacy:
+            f_center = torch.zeros_like(features[:, :, :2])
+            f_center[:, :, 0] = features[:, :, 0] - (coors[:, 3].to(dtype).unsqueeze(1) * vx + x_offset)
+            f_center[:, :, 1] = features[:, :, 1] - (coors[:, 2].to(dtype).unsqueeze(1) * vy + y_offset)
+        else:
+            f_center = features[:, :, :2]
+            f_center[:, :, 0] = f_center[:, :, 0] - (coors[:, 3].type_as(features).unsqueeze(1) * vx + x_offset)
+            f_center[:, :, 1] = f_center[:, :, 1] - (coors[:, 2].type_as(features).unsqueeze(1) * vy + y_offset)
+        features_ls.append(f_center)
+    if with_distance:                                                   # :136-138
+        points_dist = torch.norm(features[:, :, :3], 2, 2, keepdim=True)
+        features_ls.append(points_dist)
+    features = torch.cat(features_ls, dim=-1)                           # :141
+    voxel_count = features.shape[1]
+    mask = get_paddings_indicator(num_points, voxel_count, axis=0)      # :146-148
+    mask = torch.unsqueeze(mask, -1).type_as(features)
+    features *= mask
+    return features
+
+
+def point_pillars_scatter(voxel_features, coors, in_channels, ny, nx, batch_size=None):
+    """PointPillarsScatter.forward, pillar_scatter.py:27-102."""
+    if batch_size is None:                                              # forward_single :39-60
+        canvas = torch.zeros(in_channels, nx * ny, dtype=voxel_features.dtype)
+        indices = (coors[:, 1] * nx + coors[:, 2]).long()
+        canvas[:, indices] = voxel_features.t()
+        return [canvas.view(1, in_channels, ny, nx)]
+    batch_canvas = []                                                   # forward_batch :62-102
+    for batch_itt in range(batch_size):
+        canvas = torch.zeros(in_channels, nx * ny, dtype=voxel_features.dtype)
+        batch_mask = coors[:, 0] == batch_itt
+        this_coors = coors[batch_mask, :]
+        indices = (this_coors[:, 2] * nx + this_coors[:, 3]).type(torch.long)
+        canvas[:, indices] = voxel_features[batch_mask, :].t()
+        batch_canvas.append(canvas)
+    return torch.stack(batch_canvas, 0).view(batch_size, in_channels, ny, nx)

@@ -585,3 +585,64 @@ def test_cuda_graph_capture_of_fused_path():
     for i, m in enumerate(vn):
         assert torch.equal(out["coors"][i, :m], ref["coors"][i, :m])
         assert torch.equal(out["voxels"][i, :m], ref["voxels"][i, :m])
+
+
+# ----------------------------------------------------------------------------------------------
+# pillar encoders, gather side
+# ----------------------------------------------------------------------------------------------
+def _pillar_inputs(seed, C=5, frames=(0, 1)):
+    """C4 pillars of real voxelization output (+ random extra features), batched coors (b,z,y,x)."""
+    c = synthetic.CONFIGS["C4"]
+    g = torch.Generator().manual_seed(seed)
+    vox, coors, num = [], [], []
+    for bi, fid in enumerate(frames):
+        f = synthetic.make_frame(fid, 60, 104, scene="ground")
+        pts = oracle.unproject(f["depth"].numpy(), f["intrinsics"].numpy(), f["cam2lidar"].numpy(),
+                               max_depth=synthetic.MAX_DEPTH)
+        pts = np.concatenate([pts, torch.rand(len(pts), C - 3, generator=g).numpy()], axis=1).astype(np.float32)
+        v, co, n = gpu_hard(pts, list(c["voxel_size"]), list(c["pcr"]), c["max_points"], 3000)
+        vox.append(torch.from_numpy(v)); num.append(torch.from_numpy(n))
+        coors.append(torch.nn.functional.pad(torch.from_numpy(co), (1, 0), value=bi))
+    return torch.cat(vox), torch.cat(num), torch.cat(coors), c
+
+
+@pytest.mark.parametrize("legacy,dist,cluster,center", [(False, False, True, True), (True, True, True, True),
+                                                        (False, True, False, True), (True, False, True, False)])
+def test_pillar_decorations(legacy, dist, cluster, center):
+    vox, num, coors, c = _pillar_inputs(3)
+    assert vox.shape[0] > 500 and int(num.max()) == c["max_points"] and int(num.min()) >= 1
+    kw = dict(voxel_size=c["voxel_size"], point_cloud_range=c["pcr"], with_cluster_center=cluster,
+              with_voxel_center=center, with_distance=dist, legacy=legacy)
+    exp = tr.pillar_feature_decorations(vox, num, coors, **kw)
+    mod = rd3_b200.PillarDecorator(in_channels=vox.shape[2], with_distance=dist, with_cluster_center=cluster,
+                                   with_voxel_center=center, voxel_size=c["voxel_size"],
+                                   point_cloud_range=c["pcr"], legacy=legacy)
+    got = mod(vox.to(DEV), num.to(DEV), coors.to(DEV)).cpu()
+    assert got.shape == exp.shape == (vox.shape[0], vox.shape[1], mod.out_channels)
+    C = vox.shape[2]
+    # raw / centre-offset columns: the same separately rounded fp32 operations -> same bits
+    exact = list(range(C)) + ([C + 3 * cluster, C + 3 * cluster + 1] if center else [])
+    assert np.array_equal(bits(got[:, :, exact].numpy()), bits(exp[:, :, exact].numpy()))
+    # cluster offsets (sum order of the mean) and the norm: 1e-6 relative to the coordinate magnitude
+    scale = float(vox[:, :, :3].abs().max())
+    assert torch.allclose(got, exp, rtol=1e-6, atol=1e-6 * scale)
+    # padded slots are exactly zero (sign included) wherever the reference's are
+    pad = ~tr.get_paddings_indicator(num, vox.shape[1])
+    assert np.array_equal(bits(got[pad].numpy()), bits(exp[pad].numpy()))
+
+
+def test_point_pillars_scatter():
+    vox, num, coors, c = _pillar_inputs(4)
+    g = torch.Generator().manual_seed(9)
+    feats = torch.randn(vox.shape[0], 64, generator=g)
+    ny, nx = 512, 512
+    mod = rd3_b200.PointPillarsScatter(64, (ny, nx))
+    got = mod(feats.to(DEV), coors.to(DEV), batch_size=2).cpu()
+    exp = tr.point_pillars_scatter(feats, coors.long(), 64, ny, nx, batch_size=2)
+    assert got.shape == (2, 64, ny, nx) and np.array_equal(bits(got.numpy()), bits(exp.numpy()))
+    one = coors[:, 0] == 1
+    got1 = mod(feats[one].to(DEV), coors[one][:, 1:].contiguous().to(DEV))[0].cpu()      # forward_single, (z,y,x)
+    exp1 = tr.point_pillars_scatter(feats[one], coors[one][:, 1:].long(), 64, ny, nx)[0]
+    assert np.array_equal(bits(got1.numpy()), bits(exp1.numpy()))
+    with pytest.raises(RuntimeError):
+        mod(feats, coors, batch_size=2)                                                   # CPU tensors: no CPU path
