@@ -137,6 +137,37 @@ def main():
         add("fused depth->voxels (%s)" % name, "8 frames, M=%d" % M, B * npix, "pixel", B * npix * 4 + M * (K * 12 + 28),
             timeit(lambda: mod(d["depth"], d["intrinsics"], d["cam2lidar"]), args.iters, flush))
 
+    # f2 packed sparse-encoder inputs (8 frames of the C2 result) and the voxel-free fused variant
+    c2mod = rd3_b200.DepthToVoxels(c2["voxel_size"], c2["pcr"], c2["max_points"], c2["max_voxels"],
+                                   max_depth=synthetic.MAX_DEPTH, with_voxels=False).to(dev).train()
+    r = c2mod(d["depth"], d["intrinsics"], d["cam2lidar"])
+    M = int(r["voxel_num"].sum())
+    add("f2 pack_sparse_inputs", "8 frames, sum M=%d" % M, M, "voxel", M * (12 + 12 + 12 + 16),
+        timeit(lambda: rd3_b200.pack_sparse_inputs(r, sync=False), args.iters, flush))
+    add("f2 fused depth->encoder inputs (C2)", "8 frames, no voxel tensor", B * npix, "pixel",
+        B * npix * 4 + M * 28 + M * 28,
+        timeit(lambda: rd3_b200.pack_sparse_inputs(c2mod(d["depth"], d["intrinsics"], d["cam2lidar"]), sync=False),
+               args.iters, flush))
+
+    # f3 pillar decorations + scatter on the C4 pillars of one frame
+    c4 = synthetic.CONFIGS["C4"]
+    K4, mv4 = c4["max_points"], c4["max_voxels"][0]
+    cloud5 = torch.cat([cloud, torch.rand(N, 2, device=dev)], dim=1).contiguous()
+    v4 = torch.empty((mv4, K4, 5), device=dev)
+    co4 = torch.empty((mv4, 3), dtype=torch.int32, device=dev)
+    nu4 = torch.empty((mv4,), dtype=torch.int32, device=dev)
+    M4 = voxel_layer.hard_voxelize(cloud5, v4, co4, nu4, list(c4["voxel_size"]), list(c4["pcr"]), K4, mv4)
+    v4, nu4 = v4[:M4].contiguous(), nu4[:M4].contiguous()
+    co4 = torch.nn.functional.pad(co4[:M4], (1, 0), value=0).contiguous()
+    deco = rd3_b200.PillarDecorator(in_channels=5, voxel_size=c4["voxel_size"], point_cloud_range=c4["pcr"],
+                                    legacy=False)
+    add("f3 PillarFeatureNet decorations", "M=%d, K=%d, C 5->10" % (M4, K4), M4, "pillar",
+        M4 * (K4 * 20 + 4 + 16 + K4 * 40), timeit(lambda: deco(v4, nu4, co4), args.iters, flush))
+    pf = torch.randn(M4, 64, device=dev)
+    sc = rd3_b200.PointPillarsScatter(64, (512, 512))
+    add("f3 PointPillarsScatter", "M=%d, 64 ch -> 1x64x512x512" % M4, M4, "pillar",
+        M4 * (256 + 16) + 64 * 512 * 512 * 4, timeit(lambda: sc(pf, co4, batch_size=1), args.iters, flush))
+
     print("%-38s %-40s %10s %9s %9s %8s %10s" % ("row", "config", "alg MB", "ms(med)", "GB/s", "of HBM", "Munit/s"))
     for r in rows:
         print("%-38s %-40s %10.1f %9.3f %9.1f %7.1f%% %10.1f" % (r["row"], r["config"][:40], r["alg_MB"], r["ms_median"],
