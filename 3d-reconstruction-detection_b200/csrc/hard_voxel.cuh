@@ -821,7 +821,10 @@ inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels) {
   // the table never holds more than max_voxels + S keys (see header), nor more than N
   int64_t keys = (int64_t)max_voxels + S;
   if (keys > n1) keys = n1;
-  int64_t want = 2 * keys;
+#ifndef RD3_TABLE_LOAD_PCT
+#define RD3_TABLE_LOAD_PCT 50         // worst-case load factor of the table in percent
+#endif
+  int64_t want = keys * 100 / RD3_TABLE_LOAD_PCT;
   int lg = 10;
   while (((int64_t)1 << lg) < want) ++lg;
   p.log2cap = lg;
