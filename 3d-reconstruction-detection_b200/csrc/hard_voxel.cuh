@@ -49,13 +49,8 @@ constexpr int kEmitThreads = RD3_EMIT_THREADS;
 #ifndef RD3_INS_MINB
 #define RD3_INS_MINB 8                // resident insert CTAs per SM the register budget is sized for
 #endif
-#ifndef RD3_INS_SUBTILES
-#define RD3_INS_SUBTILES 1            // tiles every warp of an insert CTA walks (amortises the CTA prologue)
-#endif
-constexpr int kSubTiles = RD3_INS_SUBTILES;
 constexpr int kTilePoints = 128;      // points per warp tile
-constexpr int kInsSpan = 1024;        // points the CTA's warps cover side by side (4 per thread)
-constexpr int kInsPoints = kInsSpan * kSubTiles;   // points per insert CTA
+constexpr int kInsSpan = 1024;        // points per insert CTA (4 per thread)
 constexpr int kTileShift = 7;
 constexpr int kMaxRounds = 64;
 
@@ -80,8 +75,10 @@ struct PointsSource {
   __device__ __forceinline__ int num_feats() const { return C; }
 
   // stage AB: a lane owns 4 consecutive points
+  struct Pre {};
+  __device__ __forceinline__ Pre preload(int, int64_t, int64_t) const { return Pre(); }
   struct Cursor { const float *p; int npx; };
-  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *) const {
+  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *, const Pre &) const {
     Cursor c;
     c.p = pts + ((int64_t)b * N + i0) * C;
     const int64_t left = end - i0;
@@ -166,18 +163,30 @@ struct DepthSource {
     bool wraps;            // the 4 pixels cross a row boundary (only when W % 4 != 0)
     float tx, ty, tz;      // row part of the direct cell map (valid when !wraps)
   };
-  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *s_cal) const {
-    Cursor c;
+  // The depth load does not depend on the calibration: it is issued before the CTA's prologue
+  // barrier so that its DRAM latency overlaps the claims / calibration loads.
+  struct Pre { float z[4]; };
+  __device__ __forceinline__ Pre preload(int b, int64_t i0, int64_t end) const {
+    Pre r;
     const int64_t gi = (int64_t)b * p.npix + i0;
     const int64_t left = end - i0;
     const int npx = left >= 4 ? 4 : (left > 0 ? (int)left : 0);
     if (vec_ok && npx == 4) {
       const float4 t = __ldg(reinterpret_cast<const float4 *>(depth + gi));
-      c.z[0] = t.x; c.z[1] = t.y; c.z[2] = t.z; c.z[3] = t.w;
+      r.z[0] = t.x; r.z[1] = t.y; r.z[2] = t.z; r.z[3] = t.w;
     } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) c.z[q] = (q < npx) ? __ldg(depth + gi + q) : 0.0f;
+      for (int q = 0; q < 4; ++q) r.z[q] = (q < npx) ? __ldg(depth + gi + q) : 0.0f;
     }
+    return r;
+  }
+  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *s_cal, const Pre &pre) const {
+    Cursor c;
+    const int64_t gi = (int64_t)b * p.npix + i0;
+    const int64_t left = end - i0;
+    const int npx = left >= 4 ? 4 : (left > 0 ? (int)left : 0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c.z[q] = pre.z[q];
     // z > 0 & isfinite(z) [& z <= max_depth] (:338-340); p.zmax = min(max_depth, FLT_MAX)
     c.valid = 0;
 #pragma unroll
@@ -348,8 +357,8 @@ __device__ __forceinline__ uint32_t table_find(const unsigned long long *table, 
 }
 
 // K1 ------------------------------------------------------------------------
-// grid (ceil((end-begin)/kInsPoints), frames), 256 threads; every WARP owns kSubTiles tiles of 128
-// consecutive points (the CTA's 8 warps side by side) and runs their stages without block barriers:
+// grid (ceil((end-begin)/1024), frames), 256 threads; every WARP owns a tile of 128
+// consecutive points and runs its stages without block barriers:
 //   AB each lane walks its 4 consecutive points (one 16-byte load): validity, voxel cell
 //      by the conservative fast path; in-range keys and the few undecided points are
 //      ballot-compacted; the undecided ones are redone with exact IEEE arithmetic
@@ -366,9 +375,10 @@ __global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
   const int b = blockIdx.y + w.b0;
   const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  const int64_t block_base = begin + (int64_t)blockIdx.x * kInsPoints;
+  const int64_t block_base = begin + (int64_t)blockIdx.x * kInsSpan;
   if (block_base >= end) return;
   if (tid == 0) { s_claims = 0; s_done = 0; }
+  const typename Src::Pre pre = src.preload(b, block_base + wv * kTilePoints + 4 * lane, end);
   if (wv == 0) {
     // voxels claimed by the previous rounds: insert vs lookup-only for the whole round
     int c = 0;
@@ -385,15 +395,12 @@ __global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
   uint8_t *s_und = s_undb + wv * kTilePoints;
   unsigned long long *table = w.table + (int64_t)b * w.cap;
   int claims = 0;
-#pragma unroll 1
-  for (int sub = 0; sub < kSubTiles; ++sub) {
-  const int64_t base = block_base + (sub * (kInsThreads / 32) + wv) * kTilePoints;     // this warp's tile
-  if (base >= end) break;
+  const int64_t base = block_base + wv * kTilePoints;     // this warp's tile
 
   // ---- stage AB ---------------------------------------------------------------------
   int n2, nu;
   {
-    typename Src::Cursor cur = src.cursor(b, base + 4 * lane, end, s_cal);
+    typename Src::Cursor cur = src.cursor(b, base + 4 * lane, end, s_cal, pre);
     Quad qd;
     src.classify(cur, s_cal, g, qd);
     // exclusive prefix of the per-lane counts (0..4) from three ballots of the count's bit planes
@@ -459,8 +466,6 @@ __global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
     nc += __popc(bal);
   }
   if (lane == 0) w.cand_cnt[(int64_t)b * w.ntiles + (base >> kTileShift)] = (uint8_t)nc;
-  __syncwarp();
-  }   // tiles of this warp
   if (!lookup_only) {
     // one global atomic per CTA: the last warp to finish adds the CTA's claims to the round's counter
     for (int d = 16; d > 0; d >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, d);
@@ -918,7 +923,7 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
     for (int r = 0; r < p.rounds && p.N > 0; ++r) {
       const int64_t begin = (int64_t)r * p.S;
       const int64_t end = begin + p.S < p.N ? begin + p.S : p.N;
-      dim3 grid((unsigned)ceil_div(end - begin, kInsPoints), nb);
+      dim3 grid((unsigned)ceil_div(end - begin, kInsSpan), nb);
       hv_insert_kernel<Src><<<grid, kInsThreads, 0, st>>>(src, g, w, begin, end, r);
     }
     prof_mark(st, 2);
