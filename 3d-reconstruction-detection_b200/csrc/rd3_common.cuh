@@ -271,24 +271,6 @@ __device__ __forceinline__ bool unproject_point(float z, int u, int v, const flo
   return true;
 }
 
-// Reciprocal-based unprojection used ONLY to decide the voxel cell: identical to
-// unproject_point() except that the two divisions become multiplications by
-// RN(1/fx), RN(1/fy).  |x' - x| <= 2^-22 |x'| (same for y); pushing that and the
-// (at most 4) differing roundings through the 3x3 product gives
-//   |o' - o| <= 3 * 2^-22 * S,  S = (|x'| + |y'| + |z|) * max|R| + max|t|;
-// err = 2^-19 * S is returned (2.7x slack).
-__device__ __forceinline__ void unproject_point_approx(float z, int u, int v, const float *cal,
-                                                       float &ox, float &oy, float &oz,
-                                                       float &err) {
-  const float x = __fmul_rn(__fmul_rn(__fsub_rn((float)u, cal[2]), z), cal[16]);
-  const float y = __fmul_rn(__fmul_rn(__fsub_rn((float)v, cal[3]), z), cal[17]);
-  ox = __fadd_rn(__fmaf_rn(z, cal[6], __fmaf_rn(y, cal[5], __fmul_rn(x, cal[4]))), cal[13]);
-  oy = __fadd_rn(__fmaf_rn(z, cal[9], __fmaf_rn(y, cal[8], __fmul_rn(x, cal[7]))), cal[14]);
-  oz = __fadd_rn(__fmaf_rn(z, cal[12], __fmaf_rn(y, cal[11], __fmul_rn(x, cal[10]))), cal[15]);
-  // analysis gives 3 * 2^-22 * S; 2^-19 * S (+ a floor for denormal products) is used
-  err = fmaf(1.90734863e-6f, fmaf(fabsf(x) + fabsf(y) + fabsf(z), cal[18], cal[19]), 1e-30f);
-}
-
 // Direct pixel -> cell map used ONLY to decide the voxel cell (fused path).
 // With per-camera, per-axis constants (fp64-derived, rounded once to fp32)
 //   A = R[a][0] / (fx vs_a)      B = R[a][1] / (fy vs_a)

@@ -10,6 +10,10 @@ Sources of truth:
   hard/dynamic voxelization : oracle/_ref = the reference's voxelization_cpu.cpp compiled unmodified
   unprojection              : torch-CPU ops of reconstruction_backbone.py:305-386 (oracle/torch_restatement.py)
   DynamicScatter            : torch-CPU ops of scatter_points_cuda.cu:183-239 (ibid.)
+  pillar decorations/scatter: the reference's hard_voxelize (oracle/_ref) + torch-CPU ops of
+                              pillar_encoder.py:104-146 and pillar_scatter.py:39-102 (ibid.)
+
+    python tests/golden/make_golden.py pillar      # only (re)generate pillar.npz
 """
 import os
 import sys
@@ -29,9 +33,39 @@ from test_oracle import _adversarial_points, kat_points  # noqa: E402
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
+def pillar(ref):
+    """5. pillar encoders, gather side: 0.2 m pillars of a small two-sample cloud (5 features)"""
+    vs, pcr, K = [0.2, 0.2, 8.0], [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], 20
+    g = torch.Generator().manual_seed(7)
+    vox, num, coors = [], [], []
+    for bi in range(2):
+        f = synthetic.make_frame(200 + bi, 20, 36, scene="ground")
+        pts = tr.backproject_depth_to_points(f["depth"][None], f["intrinsics"][None], f["cam2lidar"][None],
+                                             max_depth=synthetic.MAX_DEPTH)[0]
+        pts = torch.cat([pts, torch.rand(len(pts), 2, generator=g)], dim=1).contiguous()
+        v, c, n = tr.voxelization_forward(ref, pts, vs, pcr, K, 400)
+        vox.append(v); num.append(n)
+        coors.append(torch.nn.functional.pad(c, (1, 0), value=bi))
+    vox, num, coors = torch.cat(vox), torch.cat(num), torch.cat(coors)
+    d = dict(voxels=vox.numpy(), num=num.numpy(), coors=coors.numpy(), voxel_size=vs, pcr=pcr)
+    for legacy in (False, True):
+        for dist in (False, True):
+            d["deco_legacy%d_dist%d" % (legacy, dist)] = tr.pillar_feature_decorations(
+                vox, num, coors, voxel_size=vs, point_cloud_range=pcr, with_distance=dist, legacy=legacy).numpy()
+    feats = torch.randn(vox.shape[0], 8, generator=g)
+    d["scatter_feats"] = feats.numpy()
+    d["canvas"] = tr.point_pillars_scatter(feats, coors.long(), 8, 512, 512, batch_size=2).to_sparse().indices().numpy()
+    d["canvas_values"] = tr.point_pillars_scatter(feats, coors.long(), 8, 512, 512, batch_size=2).to_sparse().values().numpy()
+    np.savez_compressed(os.path.join(OUT, "pillar.npz"), **d)
+
+
 def main():
     ref = oracle.ref_voxel_layer()
     assert ref is not None, "build oracle/_ref first (python oracle/build_ref.py)"
+    if sys.argv[1:] == ["pillar"]:
+        pillar(ref)
+        print("pillar.npz", os.path.getsize(os.path.join(OUT, "pillar.npz")))
+        return
 
     # 1. the reference's known-answer input through the reference's own op
     pts = torch.from_numpy(kat_points())
@@ -71,6 +105,7 @@ def main():
         d[red + "_feats"] = rf.numpy()
         d["voxel_coors"], d["map"], d["count"] = rc.numpy(), rm.numpy(), rn.numpy()
     np.savez_compressed(os.path.join(OUT, "dynamic_scatter.npz"), **d)
+    pillar(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

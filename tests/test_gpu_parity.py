@@ -646,3 +646,19 @@ def test_point_pillars_scatter():
     assert np.array_equal(bits(got1.numpy()), bits(exp1.numpy()))
     with pytest.raises(RuntimeError):
         mod(feats, coors, batch_size=2)                                                   # CPU tensors: no CPU path
+
+
+def test_pillar_golden():
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pillar.npz"))
+    vox, num, coors = (torch.from_numpy(d[k]).to(DEV) for k in ("voxels", "num", "coors"))
+    vs, pcr = d["voxel_size"].tolist(), d["pcr"].tolist()
+    scale = float(np.abs(d["voxels"][:, :, :3]).max())
+    for legacy in (0, 1):
+        for dist in (0, 1):
+            got = rd3_b200.pillar_decorate(vox, num, coors, vs, pcr, True, True, bool(dist), bool(legacy)).cpu().numpy()
+            exp = d["deco_legacy%d_dist%d" % (legacy, dist)]
+            assert np.array_equal(bits(got[:, :, [0, 1, 2, 3, 4, 8, 9]]), bits(exp[:, :, [0, 1, 2, 3, 4, 8, 9]]))
+            assert np.allclose(got, exp, rtol=1e-6, atol=1e-6 * scale)
+    canvas = rd3_b200.PointPillarsScatter(8, (512, 512))(torch.from_numpy(d["scatter_feats"]).to(DEV), coors, 2)
+    sp = canvas.cpu().to_sparse()
+    assert np.array_equal(sp.indices().numpy(), d["canvas"]) and np.array_equal(sp.values().numpy(), d["canvas_values"])

@@ -2,6 +2,8 @@
 
 CPU only.  These tests are what allows tests/test_*_gpu.py to trust ``oracle``.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -190,3 +192,23 @@ def test_dynamic_scatter_c_vs_torch(reduce_type):
     u = coors.unique(dim=0, sorted=True)
     u = u[u.min(dim=-1).values >= 0]
     assert np.array_equal(oc, u.numpy())
+
+
+def test_pillar_restatement_matches_golden():
+    """oracle/torch_restatement.py pillar functions vs tests/golden/pillar.npz (generated from the
+    reference's own hard_voxelize output, tests/golden/make_golden.py)."""
+    from oracle import torch_restatement as tr
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pillar.npz"))
+    vox, num, coors = torch.from_numpy(d["voxels"]), torch.from_numpy(d["num"]), torch.from_numpy(d["coors"])
+    vs, pcr = d["voxel_size"].tolist(), d["pcr"].tolist()
+    for legacy in (0, 1):
+        for dist in (0, 1):
+            got = tr.pillar_feature_decorations(vox, num, coors, voxel_size=vs, point_cloud_range=pcr,
+                                                with_distance=bool(dist), legacy=bool(legacy))
+            assert np.array_equal(got.numpy().view(np.uint32), d["deco_legacy%d_dist%d" % (legacy, dist)].view(np.uint32))
+    canvas = tr.point_pillars_scatter(torch.from_numpy(d["scatter_feats"]), coors.long(), 8, 512, 512, batch_size=2)
+    sp = canvas.to_sparse()
+    assert np.array_equal(sp.indices().numpy(), d["canvas"]) and np.array_equal(sp.values().numpy(), d["canvas_values"])
+    # legacy=True really aliases: the raw x column equals the centre-offset column
+    leg = d["deco_legacy1_dist0"]
+    assert np.array_equal(leg[:, :, 0], leg[:, :, 8]) and not np.array_equal(d["deco_legacy0_dist0"][:, :, 0], leg[:, :, 0])
