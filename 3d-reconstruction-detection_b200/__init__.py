@@ -27,4 +27,5 @@ from .fused import DepthToVoxels, pack_sparse_inputs  # noqa: F401
 from .parallel import gather_voxel_outputs, shard_range, shard_sizes  # noqa: F401
 from .patch import patch_mmdet3d  # noqa: F401
 from .pipelines import FilterPointByRange, VoxelDownsample  # noqa: F401
-from .pillar import PillarDecorator, PointPillarsScatter, pillar_decorate  # noqa: F401
+from .pillar import (PillarDecorator, PointPillarsScatter, map_voxel_center_to_point,  # noqa: F401
+                     pillar_decorate)

@@ -98,6 +98,67 @@ __global__ void __launch_bounds__(256) pillars_scatter_kernel(const float *__res
   for (int ch = lane; ch < C; ch += 32) dst[(int64_t)ch * ny * nx] = __ldg(feats + m * C + ch);
 }
 
+// ---------------------------------------------------------------------------
+// DynamicVFE.map_voxel_center_to_point (voxel_encoder.py:179-219): per point, the feature row of
+// the voxel with the same (b,z,y,x).  The reference scatters voxel indices into a dense int64
+// canvas of z*y*x*batch cells (5.3 GB per sample on the nuScenes grid); here the voxel rows go
+// into an open-addressing table of 2M..4M int32 indices keyed by the 4 coordinates.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash_row(int4 c, uint32_t mask) {
+  uint32_t h = (uint32_t)c.x * 0x9E3779B1u;
+  h = (h ^ (uint32_t)c.y) * 0x85EBCA77u;
+  h = (h ^ (uint32_t)c.z) * 0xC2B2AE3Du;
+  h = (h ^ (uint32_t)c.w) * 0x27D4EB2Fu;
+  return (h ^ (h >> 15)) & mask;
+}
+
+__global__ void __launch_bounds__(256) v2p_build_kernel(const int4 *__restrict__ voxel_coors, int64_t M,
+                                                        int32_t *table, uint32_t mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int4 c = __ldg(voxel_coors + i);
+  uint32_t s = hash_row(c, mask);
+  while (true) {
+    const int32_t old = atomicCAS(table + s, -1, (int32_t)i);
+    if (old == -1) return;
+    const int4 o = __ldg(voxel_coors + old);
+    if (o.x == c.x && o.y == c.y && o.z == c.z && o.w == c.w) {   // duplicate row: the highest index wins
+      atomicMax(table + s, (int32_t)i);
+      return;
+    }
+    s = (s + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(256) v2p_lookup_kernel(const int4 *__restrict__ pts_coors, int64_t N,
+                                                         const int4 *__restrict__ voxel_coors,
+                                                         const float *__restrict__ voxel_feats, int C,
+                                                         const int32_t *__restrict__ table, uint32_t mask,
+                                                         float *__restrict__ out, int32_t *__restrict__ out_index) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int4 c = __ldg(pts_coors + i);
+  uint32_t s = hash_row(c, mask);
+  int32_t idx = 0;                         // the reference's canvas is zero-initialised: unknown -> voxel 0
+  while (true) {
+    const int32_t t = __ldg(table + s);
+    if (t < 0) break;
+    const int4 o = __ldg(voxel_coors + t);
+    if (o.x == c.x && o.y == c.y && o.z == c.z && o.w == c.w) { idx = t; break; }
+    s = (s + 1) & mask;
+  }
+  if (out_index) out_index[i] = idx;
+  const float *src = voxel_feats + (int64_t)idx * C;
+  float *dst = out + i * C;
+  for (int f = 0; f < C; ++f) dst[f] = __ldg(src + f);
+}
+
+static int v2p_log2cap(int64_t M) {
+  int lg = 10;
+  while (((int64_t)1 << lg) < 2 * M) ++lg;
+  return lg;
+}
+
 }  // namespace rd3
 
 using namespace rd3;
@@ -133,6 +194,33 @@ int rd3_pillars_scatter(const float *voxel_features, const int32_t *coors, int64
   if (!voxel_features || !coors) return RD3_ERR_INVALID_ARGUMENT;
   pillars_scatter_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(
       voxel_features, coors, M, C, coors_cols, batch_size, ny, nx, canvas);
+  return check_launch();
+}
+
+size_t rd3_map_voxel_to_point_workspace_bytes(int64_t M) {
+  if (M <= 0) return 256;
+  return align_up(((size_t)1 << v2p_log2cap(M)) * 4);
+}
+
+int rd3_map_voxel_to_point(const int32_t *pts_coors, int64_t N, const int32_t *voxel_coors,
+                           const float *voxel_feats, int64_t M, int C, float *out, int32_t *out_index,
+                           void *workspace, size_t workspace_bytes, rd3_stream_t stream) {
+  if (N < 0 || M < 0 || C <= 0 || M >= ((int64_t)1 << 30)) return RD3_ERR_INVALID_ARGUMENT;
+  if (N == 0) return RD3_OK;
+  if (M == 0 || !pts_coors || !voxel_coors || !voxel_feats || !out || !workspace) return RD3_ERR_INVALID_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(pts_coors) & 15) || (reinterpret_cast<uintptr_t>(voxel_coors) & 15))
+    return RD3_ERR_INVALID_ARGUMENT;
+  const int lg = v2p_log2cap(M);
+  const size_t cap = (size_t)1 << lg;
+  if (workspace_bytes < cap * 4) return RD3_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t *table = (int32_t *)workspace;
+  RD3_CUDA_TRY(cudaMemsetAsync(table, 0xFF, cap * 4, s));
+  v2p_build_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, s>>>((const int4 *)voxel_coors, M, table,
+                                                              (uint32_t)(cap - 1));
+  v2p_lookup_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, s>>>((const int4 *)pts_coors, N,
+                                                               (const int4 *)voxel_coors, voxel_feats, C, table,
+                                                               (uint32_t)(cap - 1), out, out_index);
   return check_launch();
 }
 

@@ -106,3 +106,31 @@ class PointPillarsScatter(nn.Module):
 
     def forward_batch(self, voxel_features, coors, batch_size):
         return self._scatter(voxel_features, coors, batch_size, False)
+
+
+def map_voxel_center_to_point(pts_coors, voxel_mean, voxel_coors, return_index=False):
+    """DynamicVFE.map_voxel_center_to_point (voxel_encoder.py:179-219; same code in HardVFE's
+    dynamic branch and pillar_encoder.py:235-275): the feature row of each point's voxel.
+
+    pts_coors (N,4) and voxel_coors (M,4) [b,z,y,x]; voxel_mean (M,C) -> (N,C).  No dense
+    z*y*x*batch canvas is built; a point whose voxel is missing gets row 0 like the reference."""
+    pts_coors = pts_coors.to(torch.int32).contiguous()
+    voxel_coors = voxel_coors.to(torch.int32).contiguous()
+    voxel_mean = voxel_mean.float().contiguous()
+    for t, n in ((pts_coors, "pts_coors"), (voxel_coors, "voxel_coors"), (voxel_mean, "voxel_mean")):
+        _lib.require_cuda(t, n)
+    if pts_coors.dim() != 2 or pts_coors.shape[1] != 4 or voxel_coors.dim() != 2 or voxel_coors.shape[1] != 4:
+        raise RuntimeError("pts_coors / voxel_coors must be (N,4) / (M,4) [b,z,y,x]")
+    N, M, C = pts_coors.shape[0], voxel_coors.shape[0], voxel_mean.shape[1]
+    if voxel_mean.shape[0] != M or (M == 0 and N > 0):
+        raise RuntimeError("voxel_mean must be (M,C) with M = voxel_coors rows > 0")
+    out = torch.empty((N, C), dtype=torch.float32, device=voxel_mean.device)
+    index = torch.empty((N,), dtype=torch.int32, device=voxel_mean.device) if return_index else None
+    L = _lib.lib()
+    with torch.cuda.device_of(voxel_mean):
+        ws = _lib.workspace(voxel_mean.device, L.rd3_map_voxel_to_point_workspace_bytes(M))
+        st = L.rd3_map_voxel_to_point(_lib.ptr(pts_coors), N, _lib.ptr(voxel_coors), _lib.ptr(voxel_mean), M, C,
+                                      _lib.ptr(out), _lib.ptr(index), _lib.ptr(ws), ws.numel(),
+                                      _lib.stream_of(voxel_mean))
+        _lib.check(st, "map_voxel_to_point")
+    return (out, index) if return_index else out

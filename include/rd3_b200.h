@@ -264,6 +264,20 @@ RD3_API int rd3_pillars_scatter(const float *voxel_features, const int32_t *coor
                         int C, int coors_cols, int batch_size, int ny, int nx,
                         float *canvas, rd3_stream_t stream);
 
+/* DynamicVFE.map_voxel_center_to_point / HardVFE's and DynamicPillarFeatureNet's copies of it
+ *   (mmdetection3d/mmdet3d/models/voxel_encoders/voxel_encoder.py:179-219,
+ *    pillar_encoder.py:235-275): out[i] = voxel_feats[j] where voxel_coors[j] == pts_coors[i]
+ *   (all four columns b,z,y,x); a point whose voxel is not listed gets row 0, like the reference's
+ *   zero-initialised canvas.  pts_coors (N,4), voxel_coors (M,4) int32, 16-byte aligned, any row
+ *   order; voxel_feats (M,C); out (N,C); out_index (N) int32 or NULL (the voxel row used).
+ *   The reference's dense z*y*x*batch int64 canvas is replaced by a table of 2M..4M int32. */
+RD3_API size_t rd3_map_voxel_to_point_workspace_bytes(int64_t M);
+
+RD3_API int rd3_map_voxel_to_point(const int32_t *pts_coors, int64_t N, const int32_t *voxel_coors,
+                           const float *voxel_feats, int64_t M, int C, float *out,
+                           int32_t *out_index, void *workspace, size_t workspace_bytes,
+                           rd3_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -262,3 +262,21 @@ def point_pillars_scatter(voxel_features, coors, in_channels, ny, nx, batch_size
         canvas[:, indices] = voxel_features[batch_mask, :].t()
         batch_canvas.append(canvas)
     return torch.stack(batch_canvas, 0).view(batch_size, in_channels, ny, nx)
+
+
+def map_voxel_center_to_point(pts_coors, voxel_mean, voxel_coors, voxel_size, point_cloud_range):
+    """DynamicVFE.map_voxel_center_to_point, voxel_encoder.py:179-219 (dense canvas and all)."""
+    vx, vy, vz = voxel_size
+    canvas_z = int((point_cloud_range[5] - point_cloud_range[2]) / vz)          # :192-197
+    canvas_y = int((point_cloud_range[4] - point_cloud_range[1]) / vy)
+    canvas_x = int((point_cloud_range[3] - point_cloud_range[0]) / vx)
+    batch_size = pts_coors[-1, 0] + 1
+    canvas_len = canvas_z * canvas_y * canvas_x * batch_size
+    canvas = voxel_mean.new_zeros(canvas_len, dtype=torch.long)
+    indices = (voxel_coors[:, 0] * canvas_z * canvas_y * canvas_x + voxel_coors[:, 1] * canvas_y * canvas_x +
+               voxel_coors[:, 2] * canvas_x + voxel_coors[:, 3])
+    canvas[indices.long()] = torch.arange(start=0, end=voxel_mean.size(0))
+    voxel_index = (pts_coors[:, 0] * canvas_z * canvas_y * canvas_x + pts_coors[:, 1] * canvas_y * canvas_x +
+                   pts_coors[:, 2] * canvas_x + pts_coors[:, 3])
+    voxel_inds = canvas[voxel_index.long()]
+    return voxel_mean[voxel_inds, ...]

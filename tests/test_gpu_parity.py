@@ -662,3 +662,33 @@ def test_pillar_golden():
     canvas = rd3_b200.PointPillarsScatter(8, (512, 512))(torch.from_numpy(d["scatter_feats"]).to(DEV), coors, 2)
     sp = canvas.cpu().to_sparse()
     assert np.array_equal(sp.indices().numpy(), d["canvas"]) and np.array_equal(sp.values().numpy(), d["canvas_values"])
+
+
+def test_map_voxel_center_to_point():
+    """DynamicVFE's cluster-centre step: dynamic voxelize -> batched DynamicScatter mean -> per-point
+    gather of the voxel mean, against the reference's dense-canvas formulation."""
+    vs, pcr = [0.5, 0.5, 0.5], [-54.0, -54.0, -5.0, 54.0, 54.0, 3.0]
+    pts, coors = [], []
+    for bi in range(2):
+        f = synthetic.make_frame(300 + bi, 40, 72, scene="ground")
+        p = oracle.unproject(f["depth"].numpy(), f["intrinsics"].numpy(), f["cam2lidar"].numpy(),
+                             max_depth=synthetic.MAX_DEPTH)
+        c = oracle.dynamic_voxelize(p, vs, pcr)
+        keep = c[:, 0] >= 0                                    # DynamicVFE sees in-range points only
+        pts.append(torch.from_numpy(p[keep]))
+        coors.append(torch.nn.functional.pad(torch.from_numpy(c[keep]), (1, 0), value=bi))
+    pts, coors = torch.cat(pts).to(DEV), torch.cat(coors).to(DEV)
+    vmean, vcoors = rd3_b200.DynamicScatter(vs, pcr, True)(pts, coors)
+    assert vcoors.shape[1] == 4 and 1000 < vmean.shape[0] < pts.shape[0]
+    got, idx = rd3_b200.map_voxel_center_to_point(coors, vmean, vcoors, return_index=True)
+    exp = tr.map_voxel_center_to_point(coors.cpu().long(), vmean.cpu(), vcoors.cpu().long(), vs, pcr)
+    assert np.array_equal(bits(got.cpu().numpy()), bits(exp.numpy()))
+    assert torch.equal(vcoors[idx.long()], coors)              # every point found its own voxel
+    # voxel rows in any order, duplicates and unknown voxels (-> row 0, the reference's zero canvas)
+    perm = torch.randperm(vmean.shape[0], generator=torch.Generator().manual_seed(1)).to(DEV)
+    got2 = rd3_b200.map_voxel_center_to_point(coors, vmean[perm].contiguous(), vcoors[perm].contiguous())
+    assert torch.equal(got2, got)
+    half = vmean.shape[0] // 2
+    got3 = rd3_b200.map_voxel_center_to_point(coors, vmean[:half].contiguous(), vcoors[:half].contiguous())
+    exp3 = tr.map_voxel_center_to_point(coors.cpu().long(), vmean[:half].cpu(), vcoors[:half].cpu().long(), vs, pcr)
+    assert np.array_equal(bits(got3.cpu().numpy()), bits(exp3.numpy()))
