@@ -22,7 +22,7 @@ from .voxelize import Voxelization, voxelization  # noqa: F401
 from .scatter_points import DynamicScatter, dynamic_scatter  # noqa: F401
 from .voxel_encoder import HardSimpleVFE, hard_simple_vfe  # noqa: F401
 from .backproject import (DepthToPointsMixin, backproject_depth_to_points,  # noqa: F401
-                          unproject_padded)
+                          conf_threshold, unproject_padded)
 from .fused import DepthToVoxels, pack_sparse_inputs  # noqa: F401
 from .parallel import gather_voxel_outputs, shard_range, shard_sizes  # noqa: F401
 from .patch import patch_mmdet3d  # noqa: F401

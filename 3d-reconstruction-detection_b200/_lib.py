@@ -23,7 +23,7 @@ class DepthParams(ctypes.Structure):
     _fields_ = [("B", _c.c_int32), ("ncam", _c.c_int32), ("H", _c.c_int32), ("W", _c.c_int32),
                 ("use_max_depth", _c.c_int32), ("max_depth", _c.c_float),
                 ("conf_thresh", _c.c_float), ("use_range", _c.c_int32),
-                ("range", _c.c_float * 6)]
+                ("range", _c.c_float * 6), ("conf_thresh_dev", _c.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/rd3_b200.h declares
@@ -53,6 +53,8 @@ SIGNATURES = {
     "rd3_pillars_scatter": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "rd3_map_voxel_to_point_workspace_bytes": (_sz, [_i64]),
     "rd3_map_voxel_to_point": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "rd3_conf_percentile_workspace_bytes": (_sz, [_i32]),
+    "rd3_conf_percentile": (_i32, [_vp, _vp, _i32, _i64, _c.c_double, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rd3_coors_extent": (_i32, [_vp, _i64, _vp, _vp]),
     "rd3_dynamic_scatter_workspace_bytes": (_sz, [_i64, _i32, _I3]),
     "rd3_dynamic_scatter_forward": (_i32, [_vp, _vp, _i64, _i32, _I3, _i32, _vp, _vp, _vp, _vp, _vp,

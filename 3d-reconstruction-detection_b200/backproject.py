@@ -35,7 +35,17 @@ def make_params(B, N, H, W, max_depth=None, conf_thresh=None, range_filter=None)
     p.B, p.ncam, p.H, p.W = int(B), int(N), int(H), int(W)
     p.use_max_depth = int(max_depth is not None)
     p.max_depth = float(max_depth) if max_depth is not None else 0.0
-    p.conf_thresh = f32_ceil(conf_thresh) if conf_thresh is not None else 0.0
+    if torch.is_tensor(conf_thresh):
+        # per-sample thresholds that already live on the device (conf_threshold() below): no host read
+        if not conf_thresh.is_cuda or conf_thresh.dtype != torch.float32 or conf_thresh.numel() != int(B) \
+                or not conf_thresh.is_contiguous():
+            raise RuntimeError("a tensor conf_thresh must be a contiguous CUDA fp32 tensor with one value per sample")
+        p.conf_thresh = 0.0
+        p.conf_thresh_dev = conf_thresh.data_ptr()
+        p._keepalive = conf_thresh
+    else:
+        p.conf_thresh = f32_ceil(conf_thresh) if conf_thresh is not None else 0.0
+        p.conf_thresh_dev = None
     p.use_range = int(range_filter is not None)
     for i in range(6):
         p.range[i] = float(range_filter[i]) if range_filter is not None else 0.0
@@ -144,3 +154,34 @@ class DepthToPointsMixin:
         return backproject_depth_to_points(multi_batch_depths, multi_batch_intrinsics,
                                            multi_batch_ori_imgs, multi_batch_cam2lidar_rts,
                                            max_depth=getattr(self, "max_depth", None))
+
+
+def conf_threshold(confs, sky_masks=None, percentile=30.0, numpy2=True, return_float64=False):
+    """Per-sample ``np.percentile(conf[~sky] if (~sky).sum() > 10 else conf.flatten(), percentile)``
+    (tools/inference_nuscenes.py:351-361) computed on the device by an exact radix select.
+
+    confs (B, N, H, W) fp32 CUDA, sky_masks (B, N, H, W) bool/uint8 or None.  Returns a (B,) fp32
+    CUDA tensor that can be passed as ``conf_thresh`` to ``unproject_padded`` / ``DepthToVoxels`` /
+    ``backproject_depth_to_points`` without a host round trip.  ``numpy2``: follow NumPy >= 2's
+    fp32 index arithmetic for fp32 data (what ``np.percentile`` of the installed numpy returns);
+    False: the fp64 arithmetic of NumPy < 2 (the reference's pin), rounded to fp32 like its
+    ``conf >= thresh`` comparison does.  ``return_float64``: also return the unrounded values."""
+    _lib.require_cuda(confs, "confs", torch.float32)
+    B = confs.shape[0]
+    npix = confs[0].numel()
+    sky = None
+    if sky_masks is not None:
+        sky = sky_masks.to(device=confs.device).contiguous()
+        sky = sky.view(torch.uint8) if sky.dtype == torch.bool else sky.to(torch.uint8)
+        if sky.numel() != confs.numel():
+            raise RuntimeError("sky_masks must have the shape of confs")
+    t64 = torch.empty((B,), dtype=torch.float64, device=confs.device)
+    t32 = torch.empty((B,), dtype=torch.float32, device=confs.device)
+    L = _lib.lib()
+    with torch.cuda.device_of(confs):
+        ws = _lib.workspace(confs.device, L.rd3_conf_percentile_workspace_bytes(B))
+        st = L.rd3_conf_percentile(_lib.ptr(confs), _lib.ptr(sky), B, npix, float(percentile), int(bool(numpy2)),
+                                   _lib.ptr(t64), _lib.ptr(t32), None, _lib.ptr(ws), ws.numel(),
+                                   _lib.stream_of(confs))
+        _lib.check(st, "conf_percentile")
+    return (t32, t64) if return_float64 else t32

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librd3_b200.so")
-SOURCES = ["voxelize.cu", "depth.cu", "scatter.cu", "pillar.cu"]
+SOURCES = ["voxelize.cu", "depth.cu", "scatter.cu", "pillar.cu", "select.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--fmad=true", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
               "-Xptxas", "-v"]

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kScanThreads)
     if (i < src.p.npix) {
       const int64_t gi = (int64_t)b * src.p.npix + i;
       const float d = __ldg(src.depth + gi);
-      if (src.depth_ok(d, gi)) {
+      if (src.depth_ok(d, gi, b)) {
         float x, y, z;
         valid = !src.p.use_range || src.point(b, i, s_cal, x, y, z);
       }
@@ -149,6 +149,7 @@ static int make_depth_source(const float *depth, const float *intrinsics, const 
   d.ncam = p->ncam; d.H = p->H; d.W = p->W; d.HW = p->H * p->W; d.npix = (int32_t)npix;
   d.use_max_depth = p->use_max_depth; d.max_depth = p->max_depth;
   d.use_conf = conf != nullptr; d.conf_thresh = p->conf_thresh;
+  d.conf_thresh_dev = p->conf_thresh_dev;
   d.use_sky = sky != nullptr;
   d.use_masks = d.use_conf || d.use_sky;
   d.zmax = 3.402823466e+38f;

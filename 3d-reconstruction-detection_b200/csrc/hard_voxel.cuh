@@ -138,11 +138,12 @@ struct DepthSource {
   int host_num_feats() const { return 3; }
   __device__ __forceinline__ int num_feats() const { return 3; }
 
-  __device__ __forceinline__ bool depth_ok(float z, int64_t gidx) const {
+  __device__ __forceinline__ bool depth_ok(float z, int64_t gidx, int b) const {
     // z > 0 & isfinite(z) [& z <= max_depth] (:338-340); p.zmax = min(max_depth, FLT_MAX)
     bool ok = (z > 0.0f) && (z <= p.zmax);
     if (p.use_masks) {
-      if (ok && p.use_conf) ok = __ldg(conf + gidx) >= p.conf_thresh;
+      if (ok && p.use_conf)
+        ok = __ldg(conf + gidx) >= (p.conf_thresh_dev ? __ldg(p.conf_thresh_dev + b) : p.conf_thresh);
       if (ok && p.use_sky) ok = __ldg(sky + gidx) == 0;
     }
     return ok;
@@ -195,7 +196,7 @@ struct DepthSource {
     if (p.use_masks) {
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (((c.valid >> q) & 1u) && !depth_ok(c.z[q], gi + q)) c.valid &= ~(1u << q);
+        if (((c.valid >> q) & 1u) && !depth_ok(c.z[q], gi + q, b)) c.valid &= ~(1u << q);
     }
     uint32_t v, u;
     pixel_cvu(npx ? (uint32_t)i0 : 0u, c.cam, v, u);   // lanes past the end compute on pixel 0 (masked)

@@ -217,6 +217,7 @@ struct DepthParams {
   int32_t use_masks;     // use_conf || use_sky
   int32_t use_conf;
   float conf_thresh;
+  const float *conf_thresh_dev;   // per-frame thresholds on the device (overrides conf_thresh) or null
   int32_t use_sky;
   int32_t use_range;
   float range[6];

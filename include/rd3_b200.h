@@ -137,6 +137,9 @@ typedef struct rd3_depth_params {
   float conf_thresh;      /* used when conf != NULL */
   int32_t use_range;      /* 0/1: inclusive filter on the transformed point */
   float range[6];         /* x0 y0 z0 x1 y1 z1 */
+  const float *conf_thresh_dev; /* optional DEVICE float[B]: per-sample thresholds (e.g. the
+                                   d_thresh32 output of rd3_conf_percentile, no host round trip);
+                                   overrides conf_thresh when not NULL */
 } rd3_depth_params;
 
 /* Order-preserving compaction (cameras in index order, pixels row-major).
@@ -277,6 +280,30 @@ RD3_API int rd3_map_voxel_to_point(const int32_t *pts_coors, int64_t N, const in
                            const float *voxel_feats, int64_t M, int C, float *out,
                            int32_t *out_index, void *workspace, size_t workspace_bytes,
                            rd3_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Confidence threshold of the depth -> points hand-off, per sample, on the device:
+ *   conf_thresh = np.percentile(conf[~sky] if (~sky).sum() > 10 else conf.flatten(), p)
+ *   (tools/inference_nuscenes.py:351-361; the GLB export does the same,
+ *    depth_anything_3/utils/export/glb.py:227-229) -- a partition of 2.7 M values per
+ *   sample on one CPU core in the reference.
+ *   conf (B, npix) fp32, sky (B, npix) uint8/bool or NULL, percentile in [0, 100] (host).
+ *   Exact: a 3-pass radix select finds the two order statistics that numpy's "linear"
+ *   method interpolates between; index, weight and interpolation follow numpy's
+ *   arithmetic (numpy/lib/_function_base_impl.py: (n-1)*q, _get_indexes, _lerp):
+ *   numpy2_fp32_index != 0 -> fp32 index / weight / result, what NumPy >= 2 computes for
+ *   fp32 data and a Python-float percentile; 0 -> fp64 index and interpolation (NumPy < 2,
+ *   the reference's pin, requirements.txt:8).
+ *   d_thresh device double[B]; d_thresh32 device float[B] or NULL (the value rounded to
+ *   fp32); d_count device int32[B] or NULL (number of values selected).  NaN when a sample
+ *   has no pixel.  NaNs in conf sort last, as in np.partition.
+ * ------------------------------------------------------------------------- */
+RD3_API size_t rd3_conf_percentile_workspace_bytes(int B);
+
+RD3_API int rd3_conf_percentile(const float *conf, const uint8_t *sky, int B, int64_t npix,
+                        double percentile, int numpy2_fp32_index, double *d_thresh,
+                        float *d_thresh32, int32_t *d_count, void *workspace,
+                        size_t workspace_bytes, rd3_stream_t stream);
 
 #ifdef __cplusplus
 }

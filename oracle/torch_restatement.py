@@ -280,3 +280,35 @@ def map_voxel_center_to_point(pts_coors, voxel_mean, voxel_coors, voxel_size, po
                    pts_coors[:, 2] * canvas_x + pts_coors[:, 3])
     voxel_inds = canvas[voxel_index.long()]
     return voxel_mean[voxel_inds, ...]
+
+
+def conf_threshold_numpy1(conf, sky, percentile):
+    """The same selection as :func:`conf_threshold` with the arithmetic NumPy < 2 (the reference's
+    pin, requirements.txt:8) performs inside ``np.percentile`` (numpy/lib/function_base.py,
+    method 'linear'): q/100 and the virtual index (n-1)*q in fp64, the difference of the two
+    fp32 order statistics in fp32, the interpolation in fp64.  Pinned by source only: the
+    installed numpy is 2.x, whose result :func:`conf_threshold` returns."""
+    import numpy as np
+    c = conf.numpy() if torch.is_tensor(conf) else np.asarray(conf)
+    if sky is not None:
+        s = sky.numpy() if torch.is_tensor(sky) else np.asarray(sky)
+        px = c[~s] if (~s).sum() > 10 else c.flatten()
+    else:
+        px = c.flatten()
+    n = px.size
+    if n == 0:
+        return float("nan")
+    vidx = np.float64(n - 1) * (np.float64(percentile) / np.float64(100))
+    prev, nxt = np.floor(vidx), np.floor(vidx) + 1
+    gamma = vidx - prev
+    if vidx >= n - 1:
+        prev = nxt = n - 1
+    if vidx < 0:
+        prev = nxt = 0
+    srt = np.sort(px.astype(np.float32))
+    a, b = srt[int(prev)], srt[int(nxt)]
+    d = np.float64(np.float32(b) - np.float32(a))
+    r = np.float64(a) + d * gamma
+    if gamma >= 0.5:
+        r = np.float64(b) - d * (1 - gamma)
+    return float(r)

@@ -692,3 +692,64 @@ def test_map_voxel_center_to_point():
     got3 = rd3_b200.map_voxel_center_to_point(coors, vmean[:half].contiguous(), vcoors[:half].contiguous())
     exp3 = tr.map_voxel_center_to_point(coors.cpu().long(), vmean[:half].cpu(), vcoors[:half].cpu().long(), vs, pcr)
     assert np.array_equal(bits(got3.cpu().numpy()), bits(exp3.numpy()))
+
+
+# ----------------------------------------------------------------------------------------------
+# the confidence-percentile threshold on the device
+# ----------------------------------------------------------------------------------------------
+def _conf_cases():
+    g = torch.Generator().manual_seed(11)
+    b = synthetic.make_batch([400, 401, 402], 70, 126)                    # 1 + Exp(1), 10 % sky
+    yield "synthetic", b["conf"], b["sky"]
+    q = (torch.rand(3, 6, 40, 64, generator=g) * 37).floor() / 8 + 1     # heavy ties
+    yield "ties", q, torch.rand(3, 6, 40, 64, generator=g) < 0.5
+    few = torch.ones(3, 6, 16, 24, dtype=torch.bool)
+    few[0, 0, 0, :11] = False                                            # 11 non-sky pixels: still non-sky only
+    few[1, 0, 0, :10] = False                                            # 10: falls back to every pixel
+    yield "few", torch.randn(3, 6, 16, 24, generator=g) * 3, few         # negative values too
+    yield "nosky", torch.rand(2, 1, 1, 7, generator=g), None
+
+
+@pytest.mark.parametrize("pct", [30.0, 0.0, 100.0, 50.0, 99.9])
+def test_conf_percentile_matches_numpy(pct):
+    for name, conf, sky in _conf_cases():
+        t32, t64 = rd3_b200.conf_threshold(conf.to(DEV), sky.to(DEV) if sky is not None else None, pct,
+                                           numpy2=True, return_float64=True)
+        o32, o64 = rd3_b200.conf_threshold(conf.to(DEV), sky.to(DEV) if sky is not None else None, pct,
+                                           numpy2=False, return_float64=True)
+        for i in range(conf.shape[0]):
+            c, s = conf[i].numpy(), (sky[i].numpy() if sky is not None else None)
+            px = c[~s] if (s is not None and (~s).sum() > 10) else c.flatten()
+            exp = np.percentile(px, pct)                                  # the installed numpy (2.x): fp32 result
+            assert exp.dtype == np.float32
+            assert bits(np.float32(t32[i].item())) == bits(exp), (name, i, pct, t32[i].item(), exp)
+            assert t64[i].item() == float(exp)
+            e1 = tr.conf_threshold_numpy1(conf[i], sky[i] if sky is not None else None, pct)
+            assert o64[i].item() == e1, (name, i, pct, o64[i].item(), e1)
+            assert bits(np.float32(o32[i].item())) == bits(np.float32(e1))
+
+
+def test_conf_threshold_tensor_feeds_the_masks():
+    """thresholds computed on the device and passed as a tensor == the host-float path per sample"""
+    b = synthetic.make_batch([410, 411], 56, 96)
+    d = {k: v.to(DEV) for k, v in b.items()}
+    thr = rd3_b200.conf_threshold(d["conf"], d["sky"], synthetic.CONF_PERCENTILE)
+    pts, cnt = rd3_b200.unproject_padded(d["depth"], d["intrinsics"], d["cam2lidar"], max_depth=synthetic.MAX_DEPTH,
+                                         confs=d["conf"], conf_thresh=thr, sky_masks=d["sky"])
+    mod = rd3_b200.DepthToVoxels([0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3], 10, 5000,
+                                 max_depth=synthetic.MAX_DEPTH).to(DEV)
+    r = mod(d["depth"], d["intrinsics"], d["cam2lidar"], confs=d["conf"], conf_thresh=thr, sky_masks=d["sky"])
+    vnum = r["voxel_num"].clone()
+    coors = r["coors"].clone()
+    for i in range(2):
+        t = tr.conf_threshold(b["conf"][i], b["sky"][i], synthetic.CONF_PERCENTILE)
+        assert np.float32(t) == np.float32(thr[i].item())
+        p1, c1 = rd3_b200.unproject_padded(d["depth"][i:i + 1], d["intrinsics"][i:i + 1], d["cam2lidar"][i:i + 1],
+                                           max_depth=synthetic.MAX_DEPTH, confs=d["conf"][i:i + 1], conf_thresh=t,
+                                           sky_masks=d["sky"][i:i + 1])
+        n = int(c1[0])
+        assert n == int(cnt[i]) and n > 1000 and torch.equal(p1[0, :n], pts[i, :n])
+        r1 = mod(d["depth"][i:i + 1], d["intrinsics"][i:i + 1], d["cam2lidar"][i:i + 1], confs=d["conf"][i:i + 1],
+                 conf_thresh=t, sky_masks=d["sky"][i:i + 1])
+        m = int(r1["voxel_num"][0])
+        assert m == int(vnum[i]) and torch.equal(r1["coors"][0, :m], coors[i, :m])

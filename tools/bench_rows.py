@@ -168,6 +168,10 @@ def main():
     add("f3 PointPillarsScatter", "M=%d, 64 ch -> 1x64x512x512" % M4, M4, "pillar",
         M4 * (256 + 16) + 64 * 512 * 512 * 4, timeit(lambda: sc(pf, co4, batch_size=1), args.iters, flush))
 
+    # f4 confidence-percentile threshold (exact 3-pass radix select), 8 samples of 6x504x896
+    add("f4 conf percentile (p=30, non-sky)", "8 x 6x504x896 conf + sky", B * npix, "pixel", B * npix * 5,
+        timeit(lambda: rd3_b200.conf_threshold(d["conf"], d["sky"], 30.0), args.iters, flush))
+
     print("%-38s %-40s %10s %9s %9s %8s %10s" % ("row", "config", "alg MB", "ms(med)", "GB/s", "of HBM", "Munit/s"))
     for r in rows:
         print("%-38s %-40s %10.1f %9.3f %9.1f %7.1f%% %10.1f" % (r["row"], r["config"][:40], r["alg_MB"], r["ms_median"],
