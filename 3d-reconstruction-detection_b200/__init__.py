@@ -20,7 +20,8 @@ __version__ = "0.1.0"
 from . import voxel_layer  # noqa: F401
 from .voxelize import Voxelization, voxelization  # noqa: F401
 from .scatter_points import DynamicScatter, dynamic_scatter  # noqa: F401
-from .voxel_encoder import HardSimpleVFE, hard_simple_vfe  # noqa: F401
+from .voxel_encoder import (HardSimpleVFE, HardVoxelOccupancyVFE, SoftVoxelOccupancyVFE,  # noqa: F401
+                            hard_simple_vfe, voxel_occupancy)
 from .backproject import (DepthToPointsMixin, backproject_depth_to_points,  # noqa: F401
                           conf_threshold, unproject_padded)
 from .fused import DepthToVoxels, pack_sparse_inputs  # noqa: F401

@@ -55,6 +55,8 @@ SIGNATURES = {
     "rd3_map_voxel_to_point": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "rd3_conf_percentile_workspace_bytes": (_sz, [_i32]),
     "rd3_conf_percentile": (_i32, [_vp, _vp, _i32, _i64, _c.c_double, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rd3_voxel_occupancy": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp, _i32, _i32, _i32,
+                                   _i32, _i32, _vp, _vp]),
     "rd3_coors_extent": (_i32, [_vp, _i64, _vp, _vp]),
     "rd3_dynamic_scatter_workspace_bytes": (_sz, [_i64, _i32, _I3]),
     "rd3_dynamic_scatter_forward": (_i32, [_vp, _vp, _i64, _i32, _I3, _i32, _vp, _vp, _vp, _vp, _vp,

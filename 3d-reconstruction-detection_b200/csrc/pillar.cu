@@ -153,6 +153,62 @@ __global__ void __launch_bounds__(256) v2p_lookup_kernel(const int4 *__restrict_
   for (int f = 0; f < C; ++f) dst[f] = __ldg(src + f);
 }
 
+// ---------------------------------------------------------------------------
+// GT-side occupancy of the sparse refinement:
+//   SoftVoxelOccupancyVFE.forward  projects/mmdet3d_plugin/models/backbone/voxel_occupancy_encoder.py:60-99
+//     p_occ = 1 - exp(-lambda * n - gamma * var),  var = mean_xyz( sum_k mask (p - mean)^2 / (n + eps) )
+//   dense scatter                  projects/mmdet3d_plugin/models/backbone/sparse_refinement.py:572-587
+//     map[b, z, y, x] = p_occ
+// One thread per voxel; sums in slot order (torch leaves the order open: 1e-6).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) soft_occupancy_kernel(const float *__restrict__ voxels,
+                                                             const int32_t *__restrict__ num, int64_t M, int K,
+                                                             int C, float lambda_n, float gamma_var, float eps,
+                                                             int hard, float *__restrict__ occ,
+                                                             const int32_t *__restrict__ coors, int coors_cols,
+                                                             int B, int Z, int Y, int X, float *__restrict__ map) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int n = __ldg(num + m);
+  float p;
+  if (hard) {
+    p = n > 0 ? 1.0f : 0.0f;                               // HardVoxelOccupancyVFE (:35)
+  } else {
+    const float *v = voxels + m * K * C;
+    const int live = n < K ? (n > 0 ? n : 0) : K;          // mask = arange(M) < num_points (:77-79)
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    for (int k = 0; k < live; ++k) {
+      sx = __fadd_rn(sx, __ldg(v + k * C));
+      sy = __fadd_rn(sy, __ldg(v + k * C + 1));
+      sz = __fadd_rn(sz, __ldg(v + k * C + 2));
+    }
+    const float denom = __fadd_rn((float)n, eps);          // num_points.float() + eps (:83)
+    const float mx = __fdiv_rn(sx, denom), my = __fdiv_rn(sy, denom), mz = __fdiv_rn(sz, denom);
+    float vx = 0.0f, vy = 0.0f, vz = 0.0f;
+    for (int k = 0; k < live; ++k) {
+      const float dx = __fsub_rn(__ldg(v + k * C), mx), dy = __fsub_rn(__ldg(v + k * C + 1), my),
+                  dz = __fsub_rn(__ldg(v + k * C + 2), mz);
+      vx = __fadd_rn(vx, __fmul_rn(dx, dx));
+      vy = __fadd_rn(vy, __fmul_rn(dy, dy));
+      vz = __fadd_rn(vz, __fmul_rn(dz, dz));
+    }
+    // (diff.pow(2).sum(dim=1) / denom).mean(dim=1)  (:88)
+    const float var = __fdiv_rn(__fadd_rn(__fadd_rn(__fdiv_rn(vx, denom), __fdiv_rn(vy, denom)), __fdiv_rn(vz, denom)),
+                                3.0f);
+    // 1 - exp(-lambda * n - gamma * var)  (:92-94)
+    const float a = __fsub_rn(__fmul_rn(-lambda_n, (float)n), __fmul_rn(gamma_var, var));
+    p = __fsub_rn(1.0f, expf(a));
+  }
+  if (occ) occ[m] = p;
+  if (map) {
+    const int32_t *c = coors + m * coors_cols;
+    const int b = coors_cols == 4 ? __ldg(c) : 0;
+    const int z = __ldg(c + coors_cols - 3), y = __ldg(c + coors_cols - 2), x = __ldg(c + coors_cols - 1);
+    if (b >= 0 && b < B && z >= 0 && z < Z && y >= 0 && y < Y && x >= 0 && x < X)
+      map[(((int64_t)b * Z + z) * Y + y) * X + x] = p;
+  }
+}
+
 static int v2p_log2cap(int64_t M) {
   int lg = 10;
   while (((int64_t)1 << lg) < 2 * M) ++lg;
@@ -194,6 +250,24 @@ int rd3_pillars_scatter(const float *voxel_features, const int32_t *coors, int64
   if (!voxel_features || !coors) return RD3_ERR_INVALID_ARGUMENT;
   pillars_scatter_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(
       voxel_features, coors, M, C, coors_cols, batch_size, ny, nx, canvas);
+  return check_launch();
+}
+
+int rd3_voxel_occupancy(const float *voxels, const int32_t *num_points, int64_t M, int max_points, int C,
+                        int hard, float lambda_n, float gamma_var, float eps, float *occupancy,
+                        const int32_t *coors, int coors_cols, int batch_size, int Z, int Y, int X,
+                        float *dense_map, rd3_stream_t stream) {
+  if (M < 0 || max_points <= 0 || C < 3) return RD3_ERR_INVALID_ARGUMENT;
+  if (!occupancy && !dense_map) return RD3_ERR_INVALID_ARGUMENT;
+  if (dense_map && (batch_size <= 0 || Z <= 0 || Y <= 0 || X <= 0 || (coors_cols != 3 && coors_cols != 4)))
+    return RD3_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dense_map) RD3_CUDA_TRY(cudaMemsetAsync(dense_map, 0, (size_t)batch_size * Z * Y * X * 4, s));
+  if (M == 0) return RD3_OK;
+  if (!num_points || (!hard && !voxels) || (dense_map && !coors)) return RD3_ERR_INVALID_ARGUMENT;
+  soft_occupancy_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, s>>>(voxels, num_points, M, max_points, C, lambda_n,
+                                                                   gamma_var, eps, hard, occupancy, coors,
+                                                                   coors_cols, batch_size, Z, Y, X, dense_map);
   return check_launch();
 }
 

@@ -59,3 +59,55 @@ class HardSimpleVFE(nn.Module):
         else:
             out = hard_simple_vfe(feats, num_points.contiguous(), self.num_features)
         return out.half() if out_half else out
+
+
+def voxel_occupancy(features, num_points, coors=None, hard=False, lambda_n=0.3, gamma_var=5.0, eps=1e-6,
+                    dense_shape=None, batch_size=None):
+    """Occupancy value per voxel (M, 1) and, with ``dense_shape=(Z, Y, X)``, the dense map
+    (batch_size, Z, Y, X) of sparse_refinement.py:572-587 in the same launch."""
+    _lib.require_cuda(features, "features", torch.float32)
+    num_points = num_points.to(torch.int32).contiguous()
+    _lib.require_cuda(num_points, "num_points", torch.int32)
+    M, K, C = features.shape
+    occ = torch.empty((M, 1), dtype=torch.float32, device=features.device)
+    dense, cc, cols, B, Z, Y, X = None, None, 4, 1, 1, 1, 1
+    if dense_shape is not None:
+        cc = coors.to(torch.int32).contiguous()
+        _lib.require_cuda(cc, "coors", torch.int32)
+        cols = cc.shape[1]
+        Z, Y, X = (int(v) for v in dense_shape)
+        B = int(batch_size) if batch_size is not None else 1
+        dense = torch.empty((B, Z, Y, X), dtype=torch.float32, device=features.device)
+    with torch.cuda.device_of(features):
+        st = _lib.lib().rd3_voxel_occupancy(_lib.ptr(features), _lib.ptr(num_points), M, K, C, int(bool(hard)),
+                                            float(lambda_n), float(gamma_var), float(eps), _lib.ptr(occ),
+                                            _lib.ptr(cc), cols, B, Z, Y, X, _lib.ptr(dense),
+                                            _lib.stream_of(features))
+        _lib.check(st, "voxel_occupancy")
+    return occ if dense is None else (occ, dense)
+
+
+class HardVoxelOccupancyVFE(nn.Module):
+    """voxel_occupancy_encoder.py:12-37: 1 for a non-empty voxel."""
+
+    def __init__(self):
+        super().__init__()
+        self.fp16_enabled = False
+
+    def forward(self, features, num_points, coors):
+        return voxel_occupancy(features, num_points, hard=True)
+
+
+class SoftVoxelOccupancyVFE(nn.Module):
+    """voxel_occupancy_encoder.py:40-99: p_occ = 1 - exp(-lambda*n - gamma*var)."""
+
+    def __init__(self, lambda_n=0.3, gamma_var=5.0, eps=1e-6):
+        super().__init__()
+        self.lambda_n = lambda_n
+        self.gamma_var = gamma_var
+        self.eps = eps
+        self.fp16_enabled = False
+
+    def forward(self, features, num_points, coors):
+        return voxel_occupancy(features, num_points, lambda_n=self.lambda_n, gamma_var=self.gamma_var,
+                               eps=self.eps)

@@ -267,6 +267,21 @@ RD3_API int rd3_pillars_scatter(const float *voxel_features, const int32_t *coor
                         int C, int coors_cols, int batch_size, int ny, int nx,
                         float *canvas, rd3_stream_t stream);
 
+/* GT-side occupancy of the sparse refinement:
+ *   SoftVoxelOccupancyVFE / HardVoxelOccupancyVFE.forward
+ *     (projects/mmdet3d_plugin/models/backbone/voxel_occupancy_encoder.py:22-37,60-99):
+ *     soft: p = 1 - exp(-lambda_n * n - gamma_var * var), var = mean over xyz of the masked
+ *     variance around the masked mean (denominator n + eps);  hard != 0: p = (n > 0).
+ *   and the dense scatter of sparse_refinement.py:572-587: dense_map[b, z, y, x] = p.
+ *   voxels (M, max_points, C>=3), num_points (M); occupancy (M) or NULL; dense_map
+ *   (batch_size, Z, Y, X) or NULL -- fully written (zero fill included) -- with coors
+ *   (M, coors_cols) = (b,z,y,x) or (z,y,x). */
+RD3_API int rd3_voxel_occupancy(const float *voxels, const int32_t *num_points, int64_t M,
+                        int max_points, int C, int hard, float lambda_n, float gamma_var,
+                        float eps, float *occupancy, const int32_t *coors, int coors_cols,
+                        int batch_size, int Z, int Y, int X, float *dense_map,
+                        rd3_stream_t stream);
+
 /* DynamicVFE.map_voxel_center_to_point / HardVFE's and DynamicPillarFeatureNet's copies of it
  *   (mmdetection3d/mmdet3d/models/voxel_encoders/voxel_encoder.py:179-219,
  *    pillar_encoder.py:235-275): out[i] = voxel_feats[j] where voxel_coors[j] == pts_coors[i]

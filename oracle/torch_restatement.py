@@ -312,3 +312,29 @@ def conf_threshold_numpy1(conf, sky, percentile):
     if gamma >= 0.5:
         r = np.float64(b) - d * (1 - gamma)
     return float(r)
+
+
+def soft_voxel_occupancy(features, num_points, lambda_n=0.3, gamma_var=5.0, eps=1e-6):
+    """SoftVoxelOccupancyVFE.forward, voxel_occupancy_encoder.py:60-99."""
+    N, M, C = features.shape
+    xyz = features[:, :, :3]
+    mask = (torch.arange(M).unsqueeze(0) < num_points.unsqueeze(1))
+    mask_exp = mask.unsqueeze(-1).float()
+    xyz_sum = (xyz * mask_exp).sum(dim=1)
+    denom = num_points.unsqueeze(1).float() + eps
+    xyz_mean = xyz_sum / denom
+    diff = (xyz - xyz_mean.unsqueeze(1)) * mask_exp
+    var = (diff.pow(2).sum(dim=1) / denom).mean(dim=1)
+    n = num_points.float()
+    occupancy = 1.0 - torch.exp(-lambda_n * n - gamma_var * var)
+    return occupancy.view(-1, 1).contiguous()
+
+
+def occupancy_feature_map(voxel_occupancy, coors_list, B, Z, Y, X):
+    """sparse_refinement.py:566-587: dense (B, Z, Y, X) map from per-sample (z,y,x) coors."""
+    per_batch = torch.split(voxel_occupancy, [c.shape[0] for c in coors_list], dim=0)
+    out = torch.zeros(B, Z, Y, X)
+    for b_idx in range(B):
+        c = coors_list[b_idx]
+        out[b_idx, c[:, 0].long(), c[:, 1].long(), c[:, 2].long()] = per_batch[b_idx].squeeze(-1)
+    return out

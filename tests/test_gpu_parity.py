@@ -753,3 +753,29 @@ def test_conf_threshold_tensor_feeds_the_masks():
                  conf_thresh=t, sky_masks=d["sky"][i:i + 1])
         m = int(r1["voxel_num"][0])
         assert m == int(vnum[i]) and torch.equal(r1["coors"][0, :m], coors[i, :m])
+
+
+def test_voxel_occupancy_and_dense_map():
+    """GT-side occupancy: hard voxelization -> SoftVoxelOccupancyVFE -> dense (B, Z, Y, X) map."""
+    vs, pcr, K = [0.6, 0.6, 0.8], [-54.0, -54.0, -5.0, 54.0, 54.0, 3.0], 10      # occ grid 180 x 180 x 10
+    Z, Y, X = 10, 180, 180
+    vox, num, coors_list = [], [], []
+    for bi in range(2):
+        f = synthetic.make_frame(500 + bi, 48, 84, scene="ground")
+        p = oracle.unproject(f["depth"].numpy(), f["intrinsics"].numpy(), f["cam2lidar"].numpy(),
+                             max_depth=synthetic.MAX_DEPTH)
+        v, c, n = gpu_hard(p, vs, pcr, K, 20000)
+        vox.append(torch.from_numpy(v)); num.append(torch.from_numpy(n)); coors_list.append(torch.from_numpy(c))
+    voxels, nums = torch.cat(vox), torch.cat(num)
+    coors = torch.cat([torch.nn.functional.pad(c, (1, 0), value=i) for i, c in enumerate(coors_list)])
+    assert voxels.shape[0] > 2000 and int(nums.max()) == K
+    exp = tr.soft_voxel_occupancy(voxels, nums)
+    got = rd3_b200.SoftVoxelOccupancyVFE()(voxels.to(DEV), nums.to(DEV), coors.to(DEV)).cpu()
+    assert got.shape == exp.shape and torch.allclose(got, exp, rtol=1e-6, atol=1e-7)
+    hard = rd3_b200.HardVoxelOccupancyVFE()(voxels.to(DEV), nums.to(DEV), coors.to(DEV)).cpu()
+    assert torch.equal(hard, (nums > 0).float().view(-1, 1))
+    occ, dense = rd3_b200.voxel_occupancy(voxels.to(DEV), nums.to(DEV), coors.to(DEV), dense_shape=(Z, Y, X),
+                                          batch_size=2)
+    exp_map = tr.occupancy_feature_map(occ.cpu(), coors_list, 2, Z, Y, X)
+    assert torch.equal(dense.cpu(), exp_map) and torch.equal(occ.cpu(), got)
+    assert int((dense != 0).sum()) == voxels.shape[0]
