@@ -37,7 +37,10 @@
 
 namespace rd3 {
 
-constexpr int kInsThreads = 256;
+#ifndef RD3_INS_THREADS
+#define RD3_INS_THREADS 256
+#endif
+constexpr int kInsThreads = RD3_INS_THREADS;
 #ifndef RD3_SLOT_TILES
 #define RD3_SLOT_TILES 4              // tiles whose candidate regions one warp of the slots kernel merges
 #endif
@@ -50,7 +53,7 @@ constexpr int kEmitThreads = RD3_EMIT_THREADS;
 #define RD3_INS_MINB 8                // resident insert CTAs per SM the register budget is sized for
 #endif
 constexpr int kTilePoints = 128;      // points per warp tile
-constexpr int kInsSpan = 1024;        // points per insert CTA (4 per thread)
+constexpr int kInsSpan = 4 * kInsThreads;   // points per insert CTA (4 per thread)
 constexpr int kTileShift = 7;
 constexpr int kMaxRounds = 64;
 
@@ -803,7 +806,7 @@ struct HvPlan {
   int B;
   int K;
   int max_voxels;
-  int64_t S;          // points per insert round (multiple of kInsSpan)
+  int64_t S;          // points per insert round (multiple of 1024)
   int rounds;
   int64_t cap;
   int log2cap;
@@ -818,8 +821,8 @@ inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels) {
   const int64_t n1 = N > 0 ? N : 1;
   // round length: at most 8 rounds, but a round should keep the whole GPU busy
   // (>= ~1.2 M points over all frames), so small batches use fewer, longer rounds
-  int64_t S = ceil_div(ceil_div(n1, 8), kInsSpan) * kInsSpan;
-  const int64_t fill = ceil_div(ceil_div((int64_t)148 * 8 * kInsSpan, B > 0 ? B : 1), kInsSpan) * kInsSpan;
+  int64_t S = ceil_div(ceil_div(n1, 8), 1024) * 1024;
+  const int64_t fill = ceil_div(ceil_div((int64_t)148 * 8 * 1024, B > 0 ? B : 1), 1024) * 1024;
   if (S < fill) S = fill;
   if (S < 65536) S = 65536;
   p.S = S;
