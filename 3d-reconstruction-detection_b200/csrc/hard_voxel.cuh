@@ -873,10 +873,13 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   w.nwords = p.nwords; w.nchunks = p.nchunks; w.K = p.K; w.max_voxels = p.max_voxels;
 
   const int C = src.host_num_feats();
-  int V = 4 * kEmitThreads / p.K;   // ~4 slot items per thread: amortises the calibration staging
+#ifndef RD3_EMIT_ITEMS
+#define RD3_EMIT_ITEMS 4             // slot items per thread of an emit CTA: amortises the CTA prologue
+#endif
+  int V = RD3_EMIT_ITEMS * kEmitThreads / p.K;
   if (V < 1) V = 1;
-  if (V > 128) V = 128;
-  while (V > 1 && (size_t)V * p.K * (C + 1) * 4 > 40 * 1024) V /= 2;
+  if (V > 32 * RD3_EMIT_ITEMS) V = 32 * RD3_EMIT_ITEMS;
+  while (V > 1 && (size_t)V * p.K * (C + 1) * 4 > 10 * 1024 * RD3_EMIT_ITEMS) V /= 2;
   const size_t smem = align_up((size_t)V * p.K * C * 4, 16) + (size_t)V * p.K * 4 +
                       align_up((size_t)V * p.K * 2, 16) + (size_t)V * 4;
   if (smem > 200 * 1024) return RD3_ERR_UNSUPPORTED;
