@@ -10,20 +10,22 @@
 // from explicit point indices, so the result does not depend on scheduling.
 //
 //   K1 insert (R rounds over consecutive index ranges of S points):
-//        block = 1024 points; three in-block compactions keep lanes dense:
-//        valid pixels -> unproject + voxel key -> in-range keys -> table op.
-//        Table entry {key:32 | min point index:32}; 64-bit CAS claims a slot,
-//        64-bit atomicMin lowers the index.  A round only INSERTS while fewer
-//        than max_voxels voxels were claimed by the previous rounds; later
-//        rounds only look keys up.  Voxels first seen after that point have
+//        a warp owns a tile of 128 points (4 per lane, one 16-byte load): validity, voxel cell by a
+//        conservative fast path (magic-number rounding, proven error bound) with an exact IEEE
+//        redo for the few points near a cell boundary, in-range keys compacted into a per-warp
+//        list, then table operations with dense lanes.
+//        Table entry {key:32 | min point index:32} in buckets of 4 (one 32-byte sector, one
+//        256-bit load per probe); 64-bit CAS claims an entry, 64-bit atomicMin lowers the index.
+//        A round only INSERTS while fewer than max_voxels voxels were claimed by the previous
+//        rounds; later rounds only look keys up.  Voxels first seen after that point have
 //        rank >= max_voxels and are dropped by the reference anyway, so the
 //        table never holds more than max_voxels + S keys, whatever N is.
-//        Points whose voxel is in the table are appended to a candidate list.
+//        Points whose voxel is in the table are appended to their tile's candidate region.
 //   K2a first : every table entry marks bit[min index] in a per-frame bitmask
 //   K2b scan  : per-chunk exclusive popcount prefix; K2s chunk totals -> voxel_num
-//   K3 slots  : per candidate: rank r = #first-points before its voxel's first
-//        point; if r < max_voxels insert its index into S[r][0..K) with a cascade
-//        of atomicMin that keeps the K smallest indices, sorted.
+//   K3 slots  : a warp merges the candidate regions of 4 tiles into one dense list; per candidate:
+//        rank r = #first-points before its voxel's first point; if r < max_voxels insert its
+//        index into S[r][0..K) with a cascade of atomicMin that keeps the K smallest indices, sorted.
 //   K4 emit   : a CTA owns V voxels; gathers (or re-unprojects) the slot points
 //        into a shared-memory tile, then writes voxels (coalesced), coors, count
 //        and the HardSimpleVFE mean from the tile.

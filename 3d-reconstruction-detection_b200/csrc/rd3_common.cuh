@@ -202,7 +202,7 @@ __device__ __forceinline__ void key_to_zyx(uint32_t key, const VoxelGrid &g, int
 // Per-camera calibration staged in shared memory (16 floats per camera).
 //   [0]=fx [1]=fy [2]=cx [3]=cy  [4..12]=R row-major (M[:3,:3])  [13..15]=t (M[3,:3])
 // ---------------------------------------------------------------------------
-constexpr int kCalibFloats = 36;   // +[16]=RN(1/fx) [17]=RN(1/fy) [18]=max|R| [19]=max|t|
+constexpr int kCalibFloats = 36;   // +[16..19] spare
                                    // +[20..31] direct cell map A,B,C,T-0.5 per axis  [32]=Qn [33]=Pn
 constexpr int kCalDirect = 20;
 constexpr int kMaxCams = 16;
@@ -237,17 +237,7 @@ __device__ __forceinline__ void stage_calibration(float *s_cal, const float *int
     else if (j == 3) v = K[5];
     else if (j < 13) { int r = (j - 4) / 3, c = (j - 4) % 3; v = M[r * 4 + c]; }
     else if (j < 16) v = M[12 + (j - 13)];
-    else if (j == 16) v = __frcp_rn(K[0]);
-    else if (j == 17) v = __frcp_rn(K[4]);
-    else if (j == 18) {
-      v = 0.0f;
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) v = fmaxf(v, fabsf(M[r * 4 + c]));
-    } else if (j == 19) {
-      v = fmaxf(fabsf(M[12]), fmaxf(fabsf(M[13]), fabsf(M[14])));
-    } else {
-      v = 0.0f;        // direct cell map: filled by calib_kernel when a voxel grid is known
-    }
+    else v = 0.0f;     // [16..19] spare; [20..33] direct cell map: filled by calib_kernel when a voxel grid is known
     s_cal[i] = v;
   }
 }
