@@ -149,3 +149,27 @@ def test_product_never_touches_the_oracle():
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
                 assert "librd3_oracle" not in src and "ref_voxel_layer" not in src, f
                 assert "/root/reference" not in src, f
+
+
+def test_committed_bench_line_keeps_the_contract():
+    """profiles/r1_bench_default.json is a line bench.py printed on a B200: every key the bench
+    contract names is there with a sane type (guards bench.py edits that cannot be run here)."""
+    import json
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles",
+                        "r1_bench_default.json")
+    j = json.load(open(path))
+    for k, t in (("metric", str), ("value", float), ("unit", str), ("n_gpus", int), ("steps", int),
+                 ("warmup", int), ("ms_per_step", float), ("higher_is_better", bool), ("scaling", str),
+                 ("dtype", str), ("data", str), ("config", dict), ("clocks", dict), ("gpu_launches", int),
+                 ("roofline", dict), ("e2e", dict), ("cpu_baseline", dict)):
+        assert isinstance(j[k], t), k
+    assert j["vs_baseline"] is None and j["scaling"] == "weak" and j["warmup"] >= 3 and j["gpu_launches"] > 0
+    assert "workload" in j["config"] and "model" not in j["config"]
+    r = j["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] is None or r["traffic"] > 0
+    e = j["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < j["value"]
+    c = j["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    assert set(j["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
