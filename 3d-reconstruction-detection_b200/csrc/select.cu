@@ -24,6 +24,7 @@ struct SelState {                 // per sample
 
 __device__ __forceinline__ uint32_t sel_key(float v) {       // monotone: a < b  <=>  key(a) < key(b); NaN last
   const uint32_t u = __float_as_uint(v);
+  if (v != v) return 0xFFFFFFFFu;                            // any NaN sorts last (np.partition)
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __device__ __forceinline__ float sel_unkey(uint32_t k) {
@@ -36,7 +37,8 @@ template <int PASS>
 __global__ void __launch_bounds__(kSelThreads) sel_hist_kernel(const float *__restrict__ conf,
                                                                const uint8_t *__restrict__ sky, int64_t npix,
                                                                const SelState *__restrict__ state,
-                                                               uint32_t *__restrict__ hist) {
+                                                               uint32_t *__restrict__ hist,
+                                                               uint32_t *__restrict__ nanflag) {
   __shared__ uint32_t s_h[2][kSelBins];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < 2 * kSelBins; i += kSelThreads) (&s_h[0][0])[i] = 0;
@@ -56,6 +58,10 @@ __global__ void __launch_bounds__(kSelThreads) sel_hist_kernel(const float *__re
     if (PASS == 0) {
       if (ns) atomicAdd(&s_h[0][k >> 21], 1u);
       atomicAdd(&s_h[1][k >> 21], 1u);
+      if (k == 0xFFFFFFFFu) {                               // np.percentile of data with a NaN is NaN
+        if (ns) nanflag[2 * b] = 1u;
+        nanflag[2 * b + 1] = 1u;
+      }
     } else if (ns || use_all) {
       if (PASS == 1) {
         if ((k >> 21) == (p0 >> 21)) atomicAdd(&s_h[0][(k >> 10) & 2047u], 1u);
@@ -108,7 +114,7 @@ __device__ __forceinline__ void sel_find(const uint32_t *h, int64_t r, int lane,
 template <int PASS>
 __global__ void __launch_bounds__(32) sel_pick_kernel(uint32_t *hist, SelState *state, double q64, float q32,
                                                       int f32_index, double *out_thr, float *out_thr32,
-                                                      int32_t *out_n) {
+                                                      int32_t *out_n, const uint32_t *nanflag) {
   const int b = blockIdx.x, lane = threadIdx.x;
   uint32_t *h = hist + (int64_t)b * 2 * kSelBins;
   SelState st;
@@ -156,8 +162,8 @@ __global__ void __launch_bounds__(32) sel_pick_kernel(uint32_t *hist, SelState *
     if (PASS == 2) {
       const float a = sel_unkey(st.prefix[0]), bb = sel_unkey(st.prefix[1]);
       double thr;
-      if (st.n <= 0) {
-        thr = __longlong_as_double(0x7FF8000000000000ll);            // np.percentile of nothing: nan
+      if (st.n <= 0 || nanflag[2 * b + (st.use_all ? 1 : 0)]) {
+        thr = __longlong_as_double(0x7FF8000000000000ll);            // np.percentile of nothing / of NaNs: nan
       } else if (f32_index) {                                        // _lerp, everything fp32
         const float t = (float)st.gamma, d = __fsub_rn(bb, a);
         float r = __fadd_rn(a, __fmul_rn(d, t));
@@ -183,7 +189,7 @@ extern "C" {
 
 size_t rd3_conf_percentile_workspace_bytes(int B) {
   if (B <= 0) return 0;
-  return align_up((size_t)B * 2 * kSelBins * 4) + align_up((size_t)B * sizeof(SelState));
+  return align_up((size_t)B * (2 * kSelBins + 2) * 4) + align_up((size_t)B * sizeof(SelState));
 }
 
 int rd3_conf_percentile(const float *conf, const uint8_t *sky, int B, int64_t npix, double percentile,
@@ -194,19 +200,23 @@ int rd3_conf_percentile(const float *conf, const uint8_t *sky, int B, int64_t np
   if (!(percentile >= 0.0 && percentile <= 100.0)) return RD3_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < rd3_conf_percentile_workspace_bytes(B)) return RD3_ERR_WORKSPACE;
   uint32_t *hist = (uint32_t *)workspace;
-  SelState *state = (SelState *)((char *)workspace + align_up((size_t)B * 2 * kSelBins * 4));
+  uint32_t *nanflag = hist + (size_t)B * 2 * kSelBins;
+  SelState *state = (SelState *)((char *)workspace + align_up((size_t)B * (2 * kSelBins + 2) * 4));
   cudaStream_t s = (cudaStream_t)stream;
   // np.true_divide(q, a.dtype.type(100)) with a Python-float q: fp32 / fp32 (NumPy >= 2); q / 100 in fp64 before
   const float q32 = (float)percentile / 100.0f;
   const double q64 = percentile / 100.0;
-  RD3_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)B * 2 * kSelBins * 4, s));
+  RD3_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)B * (2 * kSelBins + 2) * 4, s));
   const dim3 grid((unsigned)ceil_div(npix, kSelChunk), B);
-  sel_hist_kernel<0><<<grid, kSelThreads, 0, s>>>(conf, sky, npix, state, hist);
-  sel_pick_kernel<0><<<B, 32, 0, s>>>(hist, state, q64, q32, numpy2_fp32_index, d_thresh, d_thresh32, d_count);
-  sel_hist_kernel<1><<<grid, kSelThreads, 0, s>>>(conf, sky, npix, state, hist);
-  sel_pick_kernel<1><<<B, 32, 0, s>>>(hist, state, q64, q32, numpy2_fp32_index, d_thresh, d_thresh32, d_count);
-  sel_hist_kernel<2><<<grid, kSelThreads, 0, s>>>(conf, sky, npix, state, hist);
-  sel_pick_kernel<2><<<B, 32, 0, s>>>(hist, state, q64, q32, numpy2_fp32_index, d_thresh, d_thresh32, d_count);
+  sel_hist_kernel<0><<<grid, kSelThreads, 0, s>>>(conf, sky, npix, state, hist, nanflag);
+  sel_pick_kernel<0><<<B, 32, 0, s>>>(hist, state, q64, q32, numpy2_fp32_index, d_thresh, d_thresh32, d_count,
+                                      nanflag);
+  sel_hist_kernel<1><<<grid, kSelThreads, 0, s>>>(conf, sky, npix, state, hist, nanflag);
+  sel_pick_kernel<1><<<B, 32, 0, s>>>(hist, state, q64, q32, numpy2_fp32_index, d_thresh, d_thresh32, d_count,
+                                      nanflag);
+  sel_hist_kernel<2><<<grid, kSelThreads, 0, s>>>(conf, sky, npix, state, hist, nanflag);
+  sel_pick_kernel<2><<<B, 32, 0, s>>>(hist, state, q64, q32, numpy2_fp32_index, d_thresh, d_thresh32, d_count,
+                                      nanflag);
   return check_launch();
 }
 

@@ -311,7 +311,7 @@ RD3_API int rd3_map_voxel_to_point(const int32_t *pts_coors, int64_t N, const in
  *   the reference's pin, requirements.txt:8).
  *   d_thresh device double[B]; d_thresh32 device float[B] or NULL (the value rounded to
  *   fp32); d_count device int32[B] or NULL (number of values selected).  NaN when a sample
- *   has no pixel.  NaNs in conf sort last, as in np.partition.
+ *   has no pixel or when a selected value is NaN (like np.percentile).
  * ------------------------------------------------------------------------- */
 RD3_API size_t rd3_conf_percentile_workspace_bytes(int B);
 

@@ -708,6 +708,9 @@ def _conf_cases():
     few[1, 0, 0, :10] = False                                            # 10: falls back to every pixel
     yield "few", torch.randn(3, 6, 16, 24, generator=g) * 3, few         # negative values too
     yield "nosky", torch.rand(2, 1, 1, 7, generator=g), None
+    withnan = torch.rand(2, 2, 8, 16, generator=g) + 1
+    withnan[0, 1, 3, 5] = float("nan")                                   # np.percentile of data with a NaN: nan
+    yield "nan", withnan, None
 
 
 @pytest.mark.parametrize("pct", [30.0, 0.0, 100.0, 50.0, 99.9])
@@ -722,6 +725,9 @@ def test_conf_percentile_matches_numpy(pct):
             px = c[~s] if (s is not None and (~s).sum() > 10) else c.flatten()
             exp = np.percentile(px, pct)                                  # the installed numpy (2.x): fp32 result
             assert exp.dtype == np.float32
+            if np.isnan(exp):
+                assert np.isnan(t32[i].item()) and np.isnan(t64[i].item()) and np.isnan(o64[i].item())
+                continue
             assert bits(np.float32(t32[i].item())) == bits(exp), (name, i, pct, t32[i].item(), exp)
             assert t64[i].item() == float(exp)
             e1 = tr.conf_threshold_numpy1(conf[i], sky[i] if sky is not None else None, pct)
