@@ -217,6 +217,7 @@ int rd3_depth_to_voxels(const float *depth, const float *intrinsics, const float
       !num_points_per_voxel || !d_voxel_num || !workspace)
     return RD3_ERR_INVALID_ARGUMENT;
   if (!voxels && !voxel_mean) return RD3_ERR_INVALID_ARGUMENT;   // voxels may be skipped only for the mean
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return RD3_ERR_INVALID_ARGUMENT;   // 256-bit loads, TMA
   VoxelGrid g;
   uint64_t vol;
   st = make_grid(voxel_size, coors_range, &g, &vol);

@@ -75,6 +75,7 @@ struct PointsSource {
   static constexpr bool kIsDepth = false;
 
   __device__ __forceinline__ void stage(float *, int) const {}
+  __device__ __forceinline__ bool stage_async(float *, uint64_t *, int) const { return false; }
   __device__ __forceinline__ void prepare(float *, int) const {}
   int host_num_feats() const { return C; }
   __device__ __forceinline__ int num_feats() const { return C; }
@@ -135,6 +136,17 @@ struct DepthSource {
     } else {
       stage_calibration(s_cal, intr + (int64_t)b * p.ncam * 9, c2l + (int64_t)b * p.ncam * 16, p.ncam);
     }
+  }
+  // the same copy as one TMA bulk transfer issued by thread 0 (true: wait with tma_wait after the
+  // CTA's next barrier); falls back to the load / store loop when there is no precomputed table
+  __device__ __forceinline__ bool stage_async(float *s_cal, uint64_t *s_bar, int b) const {
+    if (!cal_table) {
+      stage(s_cal, b);
+      return false;
+    }
+    if (threadIdx.x == 0)
+      tma_load_1d(s_cal, cal_table + (int64_t)b * p.ncam * kCalibFloats, (uint32_t)(p.ncam * kCalibFloats * 4), s_bar);
+    return true;
   }
   __device__ __forceinline__ void prepare(float *s_cal, int b) const {
     stage(s_cal, b);
@@ -373,7 +385,8 @@ __device__ __forceinline__ uint32_t table_find(const unsigned long long *table, 
 template <class Src>
 __global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
     hv_insert_kernel(Src src, VoxelGrid g, HvWork w, int64_t begin, int64_t end, int round) {
-  __shared__ float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 1];
+  __shared__ __align__(16) float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 4];
+  __shared__ __align__(8) uint64_t s_bar;        // completion of the calibration's TMA copy
   __shared__ uint2 s_itemb[kInsSpan];            // (key, local point id) of the in-range points
   __shared__ uint8_t s_undb[kInsSpan];           // local ids of the undecided points
   __shared__ int s_prev, s_claims, s_done;
@@ -392,8 +405,9 @@ __global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
     if (lane == 0) s_prev = c;
   }
-  src.stage(s_cal, b);
+  const bool cal_async = src.stage_async(s_cal, &s_bar, b);
   __syncthreads();
+  if (cal_async) tma_wait(&s_bar);
   const bool lookup_only = s_prev >= w.max_voxels;
 
   if (block_base + wv * kTilePoints >= end) return;

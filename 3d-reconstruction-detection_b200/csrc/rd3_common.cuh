@@ -331,6 +331,33 @@ __device__ __forceinline__ int pixel_key_fast(float z, float uf, float rtx, floa
 }
 
 // ---------------------------------------------------------------------------
+// TMA bulk copy global -> shared (cp.async.bulk, 1-D) completing on an mbarrier: one thread issues
+// it, nobody executes a load / store loop.  dst, src 16-byte aligned, bytes a multiple of 16.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                            uint64_t *smem_bar) {
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem_bar);
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(gmem_src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// every consumer thread, after a __syncthreads() that follows tma_load_1d (phase 0 of a fresh barrier)
+__device__ __forceinline__ void tma_wait(uint64_t *smem_bar) {
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem_bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(bar)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
 // warp / block scan helpers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int warp_inclusive_scan(int v) {

@@ -301,6 +301,7 @@ int rd3_hard_voxelize(const float *points, int64_t N, int C, const float voxel_s
   if (N > 0 && !points) return RD3_ERR_INVALID_ARGUMENT;
   if (voxel_mean && (F < 1 || F > C)) return RD3_ERR_INVALID_ARGUMENT;
   if (N >= ((int64_t)1 << 30)) return RD3_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return RD3_ERR_INVALID_ARGUMENT;   // 256-bit table loads
   VoxelGrid g;
   uint64_t vol;
   int st = make_grid(voxel_size, coors_range, &g, &vol);

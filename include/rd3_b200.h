@@ -92,6 +92,7 @@ RD3_API int rd3_dynamic_voxelize(const float *points, int64_t N, int C,
  *   (unused slots = 0); rows beyond are left untouched (the reference's caller
  *   pre-zeroes them, voxelize.py:57-61).
  *   d_voxel_num: device int32[1], the value the reference returns as `int`.
+ *   workspace: 256-byte aligned, rd3_hard_voxelize_workspace_bytes() bytes.
  *   Optional outputs (may be NULL):
  *     voxel_mean (max_voxels, F): HardSimpleVFE fused (sum of slots / count).
  *     point2voxel (N): voxel id of each point, -1 if out of range / dropped.
