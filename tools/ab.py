@@ -1,6 +1,7 @@
 """Quick same-box A/B: run bench.py (device-resident leg only) for each library build and scene.
 
-    python tools/ab.py name1=path/to/lib1.so name2=path/to/lib2.so   (default: the in-tree build)
+    python tools/ab.py name1=path/to/lib1.so name2=path/to/lib2.so,RD3_GROUP:8   (default: the in-tree build;
+    ,KEY:VALUE pairs are environment variables of that run)
 """
 import json
 import os
@@ -13,6 +14,9 @@ scenes = [a for a in sys.argv[1:] if a in ("mixture", "ground")] or ["mixture", 
 for name, path in libs:
     for scene in scenes:
         env = dict(os.environ)
+        path, *kv = path.split(",")                      # name=lib.so,RD3_X=1,RD3_Y=2
+        for a in kv:
+            env[a.split(":", 1)[0]] = a.split(":", 1)[1]
         if path:
             env["RD3_LIB_PATH"] = os.path.join(ROOT, path)
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "30", "--warmup", "5",
