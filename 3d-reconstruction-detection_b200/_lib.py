@@ -23,7 +23,8 @@ class DepthParams(ctypes.Structure):
     _fields_ = [("B", _c.c_int32), ("ncam", _c.c_int32), ("H", _c.c_int32), ("W", _c.c_int32),
                 ("use_max_depth", _c.c_int32), ("max_depth", _c.c_float),
                 ("conf_thresh", _c.c_float), ("use_range", _c.c_int32),
-                ("range", _c.c_float * 6), ("conf_thresh_dev", _c.c_void_p)]
+                ("range", _c.c_float * 6), ("conf_thresh_dev", _c.c_void_p),
+                ("sky_prob", _c.c_void_p), ("sky_prob_thresh", _c.c_float)]
 
 
 # name -> (restype, argtypes); must list every symbol include/rd3_b200.h declares
@@ -55,6 +56,8 @@ SIGNATURES = {
     "rd3_map_voxel_to_point": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "rd3_conf_percentile_workspace_bytes": (_sz, [_i32]),
     "rd3_conf_percentile": (_i32, [_vp, _vp, _i32, _i64, _c.c_double, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rd3_conf_percentile_skyprob": (_i32, [_vp, _vp, _f32, _i32, _i64, _c.c_double, _i32, _vp, _vp, _vp, _vp, _sz,
+                                           _vp]),
     "rd3_voxel_occupancy": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp, _i32, _i32, _i32,
                                    _i32, _i32, _vp, _vp]),
     "rd3_coors_extent": (_i32, [_vp, _i64, _vp, _vp]),

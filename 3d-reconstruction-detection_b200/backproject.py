@@ -30,8 +30,34 @@ def f32_ceil(x):
     return struct.unpack("f", struct.pack("I", bits))[0]
 
 
-def make_params(B, N, H, W, max_depth=None, conf_thresh=None, range_filter=None):
+def squeeze_head(t):
+    """DA3's heads emit (B, N, H, W, 1) (output_processor.py:79-168 squeezes them): accept both, as a view."""
+    if t is not None and torch.is_tensor(t) and t.dim() == 5 and t.shape[-1] == 1:
+        return t.squeeze(-1)
+    return t
+
+
+def sky_arg(sky_masks, dev):
+    """(uint8 mask | None, fp32 probability | None).  A boolean / integer tensor is a mask; a floating-point
+    tensor is DA3's raw sky output, thresholded inside the kernels (sky iff >= 0.5, output_processor.py:165-167)
+    so that the boolean tensor is never written."""
+    if sky_masks is None:
+        return None, None
+    sky = squeeze_head(sky_masks).to(device=dev)
+    if sky.is_floating_point():
+        return None, sky.to(torch.float32).contiguous()
+    sky = sky.contiguous()
+    return (sky.view(torch.uint8) if sky.dtype == torch.bool else sky.to(torch.uint8)), None
+
+
+SKY_PROB_THRESH = 0.5
+
+
+def make_params(B, N, H, W, max_depth=None, conf_thresh=None, range_filter=None, sky_prob=None):
     p = _lib.DepthParams()
+    p.sky_prob = sky_prob.data_ptr() if sky_prob is not None else None
+    p.sky_prob_thresh = SKY_PROB_THRESH
+    p._keepalive_sky = sky_prob
     p.B, p.ncam, p.H, p.W = int(B), int(N), int(H), int(W)
     p.use_max_depth = int(max_depth is not None)
     p.max_depth = float(max_depth) if max_depth is not None else 0.0
@@ -62,13 +88,16 @@ def _prep(depths, intrinsics, cam2lidar, confs, sky_masks, conf_thresh):
     B, N = depths.shape[:2]
     if tuple(K.shape) != (B, N, 3, 3) or tuple(M.shape) != (B, N, 4, 4):
         raise RuntimeError("intrinsics must be (B,N,3,3) and cam2lidar_rts (B,N,4,4)")
-    conf = sky = None
+    conf = None
     if confs is not None and conf_thresh is not None:
-        conf = confs.to(device=dev, dtype=torch.float32).contiguous()
-    if sky_masks is not None:
-        sky = sky_masks.to(device=dev).contiguous()
-        sky = sky.view(torch.uint8) if sky.dtype == torch.bool else sky.to(torch.uint8)
-    return K, M, conf, sky
+        conf = squeeze_head(confs).to(device=dev, dtype=torch.float32).contiguous()
+        if conf.numel() != depths.numel():
+            raise RuntimeError("confs must have the shape of the depths")
+    sky, sky_prob = sky_arg(sky_masks, dev)
+    for t in (sky, sky_prob):
+        if t is not None and t.numel() != depths.numel():
+            raise RuntimeError("sky_masks must have the shape of the depths")
+    return K, M, conf, sky, sky_prob
 
 
 def unproject_padded(depths, intrinsics, cam2lidar_rts, max_depth=None, confs=None,
@@ -80,10 +109,11 @@ def unproject_padded(depths, intrinsics, cam2lidar_rts, max_depth=None, confs=No
     and pixels row-major -- exactly the order of the reference's concatenation.
     No host synchronisation.
     """
-    K, M, conf, sky = _prep(depths, intrinsics, cam2lidar_rts, confs, sky_masks, conf_thresh)
+    depths = squeeze_head(depths)
+    K, M, conf, sky, sky_prob = _prep(depths, intrinsics, cam2lidar_rts, confs, sky_masks, conf_thresh)
     B, N, H, W = depths.shape
     dev = depths.device
-    p = make_params(B, N, H, W, max_depth, conf_thresh if conf is not None else None, range_filter)
+    p = make_params(B, N, H, W, max_depth, conf_thresh if conf is not None else None, range_filter, sky_prob)
     L = _lib.lib()
     with torch.cuda.device_of(depths):
         pts = torch.empty((B, N * H * W, 3), dtype=torch.float32, device=dev)
@@ -110,7 +140,7 @@ def backproject_depth_to_points(multi_batch_depths, multi_batch_intrinsics,
     """
     if multi_batch_cam2lidar_rts is None:
         raise RuntimeError("multi_batch_cam2lidar_rts is required (the reference indexes it unconditionally)")
-    depths = multi_batch_depths.contiguous()
+    depths = squeeze_head(multi_batch_depths).contiguous()
     want_cols = multi_batch_ori_imgs is not None
     out = unproject_padded(depths, multi_batch_intrinsics, multi_batch_cam2lidar_rts, max_depth,
                            multi_batch_confs, conf_thresh, multi_batch_sky_masks, range_filter,
@@ -160,28 +190,33 @@ def conf_threshold(confs, sky_masks=None, percentile=30.0, numpy2=True, return_f
     """Per-sample ``np.percentile(conf[~sky] if (~sky).sum() > 10 else conf.flatten(), percentile)``
     (tools/inference_nuscenes.py:351-361) computed on the device by an exact radix select.
 
-    confs (B, N, H, W) fp32 CUDA, sky_masks (B, N, H, W) bool/uint8 or None.  Returns a (B,) fp32
+    confs (B, N, H, W[, 1]) fp32 CUDA, sky_masks (B, N, H, W[, 1]) bool/uint8, DA3's raw fp32 sky output
+    (sky iff >= 0.5) or None.  Returns a (B,) fp32
     CUDA tensor that can be passed as ``conf_thresh`` to ``unproject_padded`` / ``DepthToVoxels`` /
     ``backproject_depth_to_points`` without a host round trip.  ``numpy2``: follow NumPy >= 2's
     fp32 index arithmetic for fp32 data (what ``np.percentile`` of the installed numpy returns);
     False: the fp64 arithmetic of NumPy < 2 (the reference's pin), rounded to fp32 like its
     ``conf >= thresh`` comparison does.  ``return_float64``: also return the unrounded values."""
+    confs = squeeze_head(confs)
     _lib.require_cuda(confs, "confs", torch.float32)
     B = confs.shape[0]
     npix = confs[0].numel()
-    sky = None
-    if sky_masks is not None:
-        sky = sky_masks.to(device=confs.device).contiguous()
-        sky = sky.view(torch.uint8) if sky.dtype == torch.bool else sky.to(torch.uint8)
-        if sky.numel() != confs.numel():
+    sky, sky_prob = sky_arg(sky_masks, confs.device)
+    for t in (sky, sky_prob):
+        if t is not None and t.numel() != confs.numel():
             raise RuntimeError("sky_masks must have the shape of confs")
     t64 = torch.empty((B,), dtype=torch.float64, device=confs.device)
     t32 = torch.empty((B,), dtype=torch.float32, device=confs.device)
     L = _lib.lib()
     with torch.cuda.device_of(confs):
         ws = _lib.workspace(confs.device, L.rd3_conf_percentile_workspace_bytes(B))
-        st = L.rd3_conf_percentile(_lib.ptr(confs), _lib.ptr(sky), B, npix, float(percentile), int(bool(numpy2)),
-                                   _lib.ptr(t64), _lib.ptr(t32), None, _lib.ptr(ws), ws.numel(),
-                                   _lib.stream_of(confs))
+        if sky_prob is not None:
+            st = L.rd3_conf_percentile_skyprob(_lib.ptr(confs), _lib.ptr(sky_prob), SKY_PROB_THRESH, B, npix,
+                                               float(percentile), int(bool(numpy2)), _lib.ptr(t64), _lib.ptr(t32),
+                                               None, _lib.ptr(ws), ws.numel(), _lib.stream_of(confs))
+        else:
+            st = L.rd3_conf_percentile(_lib.ptr(confs), _lib.ptr(sky), B, npix, float(percentile),
+                                       int(bool(numpy2)), _lib.ptr(t64), _lib.ptr(t32), None, _lib.ptr(ws),
+                                       ws.numel(), _lib.stream_of(confs))
         _lib.check(st, "conf_percentile")
     return (t32, t64) if return_float64 else t32

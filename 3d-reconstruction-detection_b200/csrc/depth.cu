@@ -141,6 +141,8 @@ static int make_depth_source(const float *depth, const float *intrinsics, const 
   src->depth = depth;
   src->conf = conf;
   src->sky = sky;
+  src->sky_prob = sky ? nullptr : p->sky_prob;
+  src->sky_thr = p->sky_prob_thresh;
   src->intr = intrinsics;
   src->c2l = cam2lidar;
   src->cal_table = nullptr;
@@ -150,7 +152,7 @@ static int make_depth_source(const float *depth, const float *intrinsics, const 
   d.use_max_depth = p->use_max_depth; d.max_depth = p->max_depth;
   d.use_conf = conf != nullptr; d.conf_thresh = p->conf_thresh;
   d.conf_thresh_dev = p->conf_thresh_dev;
-  d.use_sky = sky != nullptr;
+  d.use_sky = sky != nullptr || src->sky_prob != nullptr;
   d.use_masks = d.use_conf || d.use_sky;
   d.zmax = 3.402823466e+38f;
   if (p->use_max_depth && p->max_depth < d.zmax) d.zmax = p->max_depth;   // NaN max_depth: comparison false

@@ -120,6 +120,8 @@ struct DepthSource {
   const float *depth;      // (B, npix)
   const float *conf;       // (B, npix) or null
   const uint8_t *sky;      // (B, npix) or null
+  const float *sky_prob;   // (B, npix) or null: raw sky probability, sky iff >= sky_thr (used when sky is null)
+  float sky_thr;
   const float *intr;       // (B, ncam, 9)
   const float *c2l;        // (B, ncam, 16)
   const float *cal_table;  // (B, ncam, kCalibFloats) precomputed by calib_kernel, or null
@@ -161,7 +163,7 @@ struct DepthSource {
     if (p.use_masks) {
       if (ok && p.use_conf)
         ok = __ldg(conf + gidx) >= (p.conf_thresh_dev ? __ldg(p.conf_thresh_dev + b) : p.conf_thresh);
-      if (ok && p.use_sky) ok = __ldg(sky + gidx) == 0;
+      if (ok && p.use_sky) ok = sky ? __ldg(sky + gidx) == 0 : !(__ldg(sky_prob + gidx) >= sky_thr);
     }
     return ok;
   }

@@ -35,8 +35,9 @@ __device__ __forceinline__ float sel_unkey(uint32_t k) {
 // their 11-bit prefixes;  2: key & 1023 inside their 21-bit prefixes.  hist: [B][2][kSelBins].
 template <int PASS>
 __global__ void __launch_bounds__(kSelThreads) sel_hist_kernel(const float *__restrict__ conf,
-                                                               const uint8_t *__restrict__ sky, int64_t npix,
-                                                               const SelState *__restrict__ state,
+                                                               const uint8_t *__restrict__ sky,
+                                                               const float *__restrict__ sky_prob, float sky_thr,
+                                                               int64_t npix, const SelState *__restrict__ state,
                                                                uint32_t *__restrict__ hist,
                                                                uint32_t *__restrict__ nanflag) {
   __shared__ uint32_t s_h[2][kSelBins];
@@ -54,7 +55,8 @@ __global__ void __launch_bounds__(kSelThreads) sel_hist_kernel(const float *__re
   const int64_t hi = lo + kSelChunk < npix ? lo + kSelChunk : npix;
   for (int64_t i = lo + threadIdx.x; i < hi; i += kSelThreads) {
     const uint32_t k = sel_key(__ldg(conf + (int64_t)b * npix + i));
-    const bool ns = sky ? __ldg(sky + (int64_t)b * npix + i) == 0 : true;
+    const bool ns = sky ? __ldg(sky + (int64_t)b * npix + i) == 0
+                        : (sky_prob ? !(__ldg(sky_prob + (int64_t)b * npix + i) >= sky_thr) : true);
     if (PASS == 0) {
       if (ns) atomicAdd(&s_h[0][k >> 21], 1u);
       atomicAdd(&s_h[1][k >> 21], 1u);
@@ -192,9 +194,10 @@ size_t rd3_conf_percentile_workspace_bytes(int B) {
   return align_up((size_t)B * (2 * kSelBins + 2) * 4) + align_up((size_t)B * sizeof(SelState));
 }
 
-int rd3_conf_percentile(const float *conf, const uint8_t *sky, int B, int64_t npix, double percentile,
-                        int numpy2_fp32_index, double *d_thresh, float *d_thresh32, int32_t *d_count,
-                        void *workspace, size_t workspace_bytes, rd3_stream_t stream) {
+static int conf_percentile_impl(const float *conf, const uint8_t *sky, const float *sky_prob, float sky_thr, int B,
+                                int64_t npix, double percentile, int numpy2_fp32_index, double *d_thresh,
+                                float *d_thresh32, int32_t *d_count, void *workspace, size_t workspace_bytes,
+                                rd3_stream_t stream) {
   if (B <= 0 || B > 65535 || npix <= 0 || npix >= ((int64_t)1 << 31) || !conf || !d_thresh || !workspace)
     return RD3_ERR_INVALID_ARGUMENT;
   if (!(percentile >= 0.0 && percentile <= 100.0)) return RD3_ERR_INVALID_ARGUMENT;
@@ -208,16 +211,31 @@ int rd3_conf_percentile(const float *conf, const uint8_t *sky, int B, int64_t np
   const double q64 = percentile / 100.0;
   RD3_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)B * (2 * kSelBins + 2) * 4, s));
   const dim3 grid((unsigned)ceil_div(npix, kSelChunk), B);
-  sel_hist_kernel<0><<<grid, kSelThreads, 0, s>>>(conf, sky, npix, state, hist, nanflag);
+  sel_hist_kernel<0><<<grid, kSelThreads, 0, s>>>(conf, sky, sky_prob, sky_thr, npix, state, hist, nanflag);
   sel_pick_kernel<0><<<B, 32, 0, s>>>(hist, state, q64, q32, numpy2_fp32_index, d_thresh, d_thresh32, d_count,
                                       nanflag);
-  sel_hist_kernel<1><<<grid, kSelThreads, 0, s>>>(conf, sky, npix, state, hist, nanflag);
+  sel_hist_kernel<1><<<grid, kSelThreads, 0, s>>>(conf, sky, sky_prob, sky_thr, npix, state, hist, nanflag);
   sel_pick_kernel<1><<<B, 32, 0, s>>>(hist, state, q64, q32, numpy2_fp32_index, d_thresh, d_thresh32, d_count,
                                       nanflag);
-  sel_hist_kernel<2><<<grid, kSelThreads, 0, s>>>(conf, sky, npix, state, hist, nanflag);
+  sel_hist_kernel<2><<<grid, kSelThreads, 0, s>>>(conf, sky, sky_prob, sky_thr, npix, state, hist, nanflag);
   sel_pick_kernel<2><<<B, 32, 0, s>>>(hist, state, q64, q32, numpy2_fp32_index, d_thresh, d_thresh32, d_count,
                                       nanflag);
   return check_launch();
+}
+
+int rd3_conf_percentile(const float *conf, const uint8_t *sky, int B, int64_t npix, double percentile,
+                        int numpy2_fp32_index, double *d_thresh, float *d_thresh32, int32_t *d_count,
+                        void *workspace, size_t workspace_bytes, rd3_stream_t stream) {
+  return conf_percentile_impl(conf, sky, nullptr, 0.0f, B, npix, percentile, numpy2_fp32_index, d_thresh,
+                              d_thresh32, d_count, workspace, workspace_bytes, stream);
+}
+
+int rd3_conf_percentile_skyprob(const float *conf, const float *sky_prob, float sky_prob_thresh, int B,
+                                int64_t npix, double percentile, int numpy2_fp32_index, double *d_thresh,
+                                float *d_thresh32, int32_t *d_count, void *workspace, size_t workspace_bytes,
+                                rd3_stream_t stream) {
+  return conf_percentile_impl(conf, nullptr, sky_prob, sky_prob_thresh, B, npix, percentile, numpy2_fp32_index,
+                              d_thresh, d_thresh32, d_count, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

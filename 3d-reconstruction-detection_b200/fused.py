@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .backproject import _prep, make_params
+from .backproject import _prep, make_params, squeeze_head
 
 
 class DepthToVoxels(nn.Module):
@@ -49,15 +49,16 @@ class DepthToVoxels(nn.Module):
         return self._out_cache[key]
 
     def forward(self, depths, intrinsics, cam2lidar_rts, confs=None, conf_thresh=None, sky_masks=None):
-        """depths (B,N,H,W) -> dict(voxels (B,MV,K,3), coors (B,MV,3), num_points (B,MV),
+        """depths (B,N,H,W[,1]); confs / sky_masks of the same shape -- sky_masks either a bool / uint8 mask or DA3's
+        raw fp32 sky output (sky iff >= 0.5, thresholded inside the kernels) -> dict(voxels (B,MV,K,3), coors (B,MV,3), num_points (B,MV),
         voxel_mean (B,MV,3) | None, voxel_num (B,)): rows [0, voxel_num[b]) of sample b
         are valid and equal to the reference's outputs; the rest is undefined."""
-        depths = depths.contiguous()
-        K, M, conf, sky = _prep(depths, intrinsics, cam2lidar_rts, confs, sky_masks, conf_thresh)
+        depths = squeeze_head(depths).contiguous()
+        K, M, conf, sky, sky_prob = _prep(depths, intrinsics, cam2lidar_rts, confs, sky_masks, conf_thresh)
         B, N, H, W = depths.shape
         max_voxels = self.max_voxels[0] if self.training else self.max_voxels[1]
         p = make_params(B, N, H, W, self.max_depth, conf_thresh if conf is not None else None,
-                        self.range_filter)
+                        self.range_filter, sky_prob)
         out = self._get_buffers(B, depths.device, max_voxels)
         L = _lib.lib()
         with torch.cuda.device_of(depths):

@@ -141,6 +141,11 @@ typedef struct rd3_depth_params {
   const float *conf_thresh_dev; /* optional DEVICE float[B]: per-sample thresholds (e.g. the
                                    d_thresh32 output of rd3_conf_percentile, no host round trip);
                                    overrides conf_thresh when not NULL */
+  const float *sky_prob;  /* optional DEVICE fp32 (B, ncam, H, W): DA3's raw sky head output; a pixel is sky
+                             iff sky_prob >= sky_prob_thresh (output_processor.py:152-168 uses 0.5).  Read
+                             only when the `sky` argument of the call is NULL, so the boolean mask is never
+                             materialised. */
+  float sky_prob_thresh;
 } rd3_depth_params;
 
 /* Order-preserving compaction (cameras in index order, pixels row-major).
@@ -319,6 +324,14 @@ RD3_API size_t rd3_conf_percentile_workspace_bytes(int B);
 RD3_API int rd3_conf_percentile(const float *conf, const uint8_t *sky, int B, int64_t npix,
                         double percentile, int numpy2_fp32_index, double *d_thresh,
                         float *d_thresh32, int32_t *d_count, void *workspace,
+                        size_t workspace_bytes, rd3_stream_t stream);
+
+/* The same with DA3's raw sky head output instead of a boolean mask: a pixel is sky iff
+ * sky_prob >= sky_prob_thresh (depth_anything_3/utils/io/output_processor.py:152-168: 0.5), so the
+ * `(sky >= 0.5)` tensor between the network and the threshold is never written.  sky_prob may be NULL. */
+RD3_API int rd3_conf_percentile_skyprob(const float *conf, const float *sky_prob, float sky_prob_thresh,
+                        int B, int64_t npix, double percentile, int numpy2_fp32_index,
+                        double *d_thresh, float *d_thresh32, int32_t *d_count, void *workspace,
                         size_t workspace_bytes, rd3_stream_t stream);
 
 #ifdef __cplusplus

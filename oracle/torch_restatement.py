@@ -63,6 +63,15 @@ def filter_point_by_range(points, point_cloud_range):
     return points[m], torch.nonzero(m, as_tuple=False).squeeze(1)
 
 
+def extract_head_outputs(depth, conf=None, sky=None):
+    """depth_anything_3/utils/io/output_processor.py:79-101,152-168: the heads emit (B, N, H, W, 1);
+    depth / conf are squeezed, the sky probability becomes the boolean mask ``sky >= 0.5``."""
+    d = depth.squeeze(-1)
+    c = conf.squeeze(-1) if conf is not None else None
+    s = (sky.squeeze(-1) >= 0.5) if sky is not None else None
+    return d, c, s
+
+
 def conf_threshold(conf, sky, percentile):
     """tools/inference_nuscenes.py:351-361 (numpy percentile, linear interp).
 

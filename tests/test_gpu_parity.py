@@ -761,6 +761,55 @@ def test_conf_threshold_tensor_feeds_the_masks():
         assert m == int(vnum[i]) and torch.equal(r1["coors"][0, :m], coors[i, :m])
 
 
+def test_raw_head_outputs_without_the_boolean_sky_tensor():
+    """DA3's raw (B, N, H, W, 1) depth / conf / sky-probability outputs go straight into the
+    kernels (sky iff prob >= 0.5, output_processor.py:152-168) == the restated squeeze + boolean mask path."""
+    b = synthetic.make_batch([420, 421], 56, 96)
+    g = torch.Generator().manual_seed(77)
+    prob = torch.rand(b["sky"].shape, generator=g) * 0.5             # non-sky: [0, 0.5)
+    prob = torch.where(b["sky"], 0.5 + prob, prob)                    # sky: [0.5, 1)
+    flat = prob.view(-1)
+    flat[5] = 0.5                                                     # exactly the threshold: sky
+    flat[6] = float("nan")                                            # NaN >= 0.5 is False: not sky
+    flat[7] = float(np.nextafter(np.float32(0.5), np.float32(0)))     # just below: not sky
+    raw = dict(depth=b["depth"].unsqueeze(-1), conf=b["conf"].unsqueeze(-1), sky=prob.unsqueeze(-1))
+    dep, conf, mask = tr.extract_head_outputs(raw["depth"], raw["conf"], raw["sky"])
+    assert mask.view(-1)[5] and not mask.view(-1)[6] and not mask.view(-1)[7]
+    d = {k: v.to(DEV) for k, v in b.items()}
+    rawd = {k: v.to(DEV) for k, v in raw.items()}
+    maskd = mask.to(DEV)
+    # confidence threshold: raw probability == boolean mask == numpy on the restated mask
+    t_raw = rd3_b200.conf_threshold(rawd["conf"], rawd["sky"], synthetic.CONF_PERCENTILE)
+    t_msk = rd3_b200.conf_threshold(d["conf"], maskd, synthetic.CONF_PERCENTILE)
+    assert torch.equal(t_raw, t_msk)
+    for i in range(2):
+        assert np.float32(tr.conf_threshold(conf[i], mask[i], synthetic.CONF_PERCENTILE)) == np.float32(t_raw[i].item())
+    # unprojection and the fused path
+    p_raw, c_raw = rd3_b200.unproject_padded(rawd["depth"], d["intrinsics"], d["cam2lidar"], max_depth=synthetic.MAX_DEPTH,
+                                             confs=rawd["conf"], conf_thresh=t_raw, sky_masks=rawd["sky"])
+    p_msk, c_msk = rd3_b200.unproject_padded(d["depth"], d["intrinsics"], d["cam2lidar"], max_depth=synthetic.MAX_DEPTH,
+                                             confs=d["conf"], conf_thresh=t_msk, sky_masks=maskd)
+    assert torch.equal(c_raw, c_msk)
+    for i in range(2):
+        n = int(c_raw[i])
+        assert n > 1000 and torch.equal(p_raw[i, :n], p_msk[i, :n])
+        o = oracle.unproject(dep[i].numpy(), b["intrinsics"][i].numpy(), b["cam2lidar"][i].numpy(),
+                             max_depth=synthetic.MAX_DEPTH, conf=conf[i].numpy(),
+                             conf_thresh=float(t_raw[i].item()), sky=mask[i].numpy())
+        assert o.shape[0] == n and np.array_equal(bits(o), bits(p_raw[i, :n].cpu().numpy()))
+    mod = rd3_b200.DepthToVoxels([0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3], 10, 5000,
+                                 max_depth=synthetic.MAX_DEPTH).to(DEV)
+    r = mod(rawd["depth"], d["intrinsics"], d["cam2lidar"], confs=rawd["conf"], conf_thresh=t_raw, sky_masks=rawd["sky"])
+    r = {k: (v.clone() if v is not None else None) for k, v in r.items()}
+    q = mod(d["depth"], d["intrinsics"], d["cam2lidar"], confs=d["conf"], conf_thresh=t_msk, sky_masks=maskd)
+    assert torch.equal(r["voxel_num"], q["voxel_num"])
+    for i in range(2):
+        m = int(r["voxel_num"][i])
+        assert m > 500
+        for k in ("voxels", "coors", "num_points", "voxel_mean"):
+            assert torch.equal(r[k][i, :m], q[k][i, :m]), k
+
+
 def test_voxel_occupancy_and_dense_map():
     """GT-side occupancy: hard voxelization -> SoftVoxelOccupancyVFE -> dense (B, Z, Y, X) map."""
     vs, pcr, K = [0.6, 0.6, 0.8], [-54.0, -54.0, -5.0, 54.0, 54.0, 3.0], 10      # occ grid 180 x 180 x 10
