@@ -173,3 +173,27 @@ def test_committed_bench_line_keeps_the_contract():
     c = j["cpu_baseline"]
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
     assert set(j["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_raw_head_output_arguments():
+    """DA3's raw outputs (output_processor.py:79-168): trailing singleton squeezed as a view, a floating-point
+    sky tensor is a probability (thresholded in the kernels), bool / integer tensors are masks."""
+    from rd3_b200.backproject import SKY_PROB_THRESH, make_params, sky_arg, squeeze_head
+    d = torch.rand(2, 6, 4, 8, 1)
+    v = squeeze_head(d)
+    assert v.shape == (2, 6, 4, 8) and v.data_ptr() == d.data_ptr() and v.is_contiguous()
+    assert squeeze_head(v) is v and squeeze_head(None) is None
+    assert squeeze_head(torch.rand(2, 6, 4, 8, 3)).dim() == 5            # only a trailing 1 is a head dim
+    prob = torch.rand(2, 6, 4, 8, 1)
+    m, p = sky_arg(prob, "cpu")
+    assert m is None and p.dtype == torch.float32 and p.shape == (2, 6, 4, 8) and p.data_ptr() == prob.data_ptr()
+    m, p = sky_arg(prob.double(), "cpu")
+    assert m is None and p.dtype == torch.float32
+    for mask in (prob.squeeze(-1) >= 0.5, (prob.squeeze(-1) >= 0.5).to(torch.int32)):
+        m, p = sky_arg(mask, "cpu")
+        assert p is None and m.dtype == torch.uint8 and torch.equal(m.bool(), prob.squeeze(-1) >= 0.5)
+    assert sky_arg(None, "cpu") == (None, None)
+    assert SKY_PROB_THRESH == 0.5
+    prm = make_params(2, 6, 4, 8, max_depth=100.0, sky_prob=p if p is not None else prob.squeeze(-1))
+    assert prm.sky_prob == prob.data_ptr() and prm.sky_prob_thresh == 0.5
+    assert make_params(2, 6, 4, 8).sky_prob is None
