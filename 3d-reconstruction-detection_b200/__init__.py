@@ -6,7 +6,7 @@ names mirror the reference's operator API for this path:
     Voxelization, voxelization            mmdet3d/ops/voxel/voxelize.py
     DynamicScatter, dynamic_scatter       mmdet3d/ops/voxel/scatter_points.py
     voxel_layer (4 functions)             mmdet3d/ops/voxel/src/voxelization.cpp
-    HardSimpleVFE                         mmdet3d/models/voxel_encoders/voxel_encoder.py
+    HardSimpleVFE, DynamicSimpleVFE       mmdet3d/models/voxel_encoders/voxel_encoder.py
     backproject_depth_to_points           plugin ReconstructionBackbone._backproject_depth_to_points
     DepthToVoxels                         the fused, batched path (no reference equivalent)
     pack_sparse_inputs                    batched SparseEncoder inputs (sparse_refinement.py:393-402)
@@ -20,7 +20,7 @@ __version__ = "0.1.0"
 from . import voxel_layer  # noqa: F401
 from .voxelize import Voxelization, voxelization  # noqa: F401
 from .scatter_points import DynamicScatter, dynamic_scatter  # noqa: F401
-from .voxel_encoder import (HardSimpleVFE, HardVoxelOccupancyVFE, SoftVoxelOccupancyVFE,  # noqa: F401
+from .voxel_encoder import (DynamicSimpleVFE, HardSimpleVFE, HardVoxelOccupancyVFE, SoftVoxelOccupancyVFE,  # noqa: F401
                             hard_simple_vfe, voxel_occupancy)
 from .backproject import (DepthToPointsMixin, backproject_depth_to_points,  # noqa: F401
                           conf_threshold, unproject_padded)

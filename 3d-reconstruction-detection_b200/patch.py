@@ -7,6 +7,8 @@ call site of the reference goes through:
     mmdet3d.ops.voxel.scatter_points:  dynamic_point_to_voxel_forward/backward, DynamicScatter, dynamic_scatter
     mmdet3d.ops (and mmdet3d.ops.voxel): Voxelization, voxelization, DynamicScatter, dynamic_scatter
     mmdet3d.models.voxel_encoders.voxel_encoder.HardSimpleVFE.forward
+    every already imported mmdet3d.* / projects.* module that holds the old Voxelization / DynamicScatter through a
+    ``from mmdet3d.ops import ...`` (DynamicSimpleVFE, DynamicVFE, the pillar encoders, SparseRefinement, VoxelDownsample)
     ReconstructionBackbone._backproject_depth_to_points   (the plugin, when it is importable)
 
 so existing configs (``pts_voxel_layer=dict(max_num_points=..., voxel_size=..., ...)``) run
@@ -35,6 +37,18 @@ def patch_mmdet3d(verbose=False):
             setattr(mod, attr, value)
             done.append("%s.%s" % (mod.__name__, attr))
 
+    # the objects call sites may already hold through ``from mmdet3d.ops import Voxelization, DynamicScatter``
+    # (voxel_encoder.py, pillar_encoder.py, sparse_refinement.py:15, respoint_post_processing.py:15, mvx_two_stage.py)
+    stale = {}
+    for name, attrs, new_mod in (("mmdet3d.ops.voxel.voxelize", ("Voxelization", "voxelization"), voxelize),
+                                 ("mmdet3d.ops.voxel.scatter_points", ("DynamicScatter", "dynamic_scatter"),
+                                  scatter_points)):
+        m = _try_import(name)
+        for a in attrs:
+            old = getattr(m, a, None) if m is not None else None
+            if old is not None and old is not getattr(new_mod, a):
+                stale[a] = (old, getattr(new_mod, a))
+
     m = _try_import("mmdet3d.ops.voxel.voxelize")
     for a in ("hard_voxelize", "dynamic_voxelize"):
         rebind(m, a, getattr(voxel_layer, a))
@@ -51,6 +65,13 @@ def patch_mmdet3d(verbose=False):
             rebind(m, a, getattr(voxelize, a))
         for a in ("DynamicScatter", "dynamic_scatter"):
             rebind(m, a, getattr(scatter_points, a))
+    for mname, m in list(sys.modules.items()):
+        if m is None or not (mname.startswith("mmdet3d") or mname.startswith("projects.")):
+            continue
+        for a, (old, new) in stale.items():
+            if getattr(m, a, None) is old:
+                setattr(m, a, new)
+                done.append("%s.%s" % (mname, a))
     m = _try_import("mmdet3d.models.voxel_encoders.voxel_encoder")
     if m is not None and hasattr(m, "HardSimpleVFE"):
         def forward(self, features, num_points, coors=None):

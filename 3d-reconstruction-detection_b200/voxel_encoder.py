@@ -61,6 +61,24 @@ class HardSimpleVFE(nn.Module):
         return out.half() if out_half else out
 
 
+class DynamicSimpleVFE(nn.Module):
+    """mmdet3d/models/voxel_encoders/voxel_encoder.py:50-90: the mean of the points of every (dynamic) voxel,
+    i.e. ``DynamicScatter(voxel_size, point_cloud_range, True)`` under ``torch.no_grad`` and ``force_fp32``.
+    ``forward(features (N, C), coors (N, 3|4)) -> (voxel_features (M, C), voxel_coors (M, 3|4))``."""
+
+    def __init__(self, voxel_size=(0.2, 0.2, 4), point_cloud_range=(0, -40, -3, 70.4, 40, 1)):
+        super(DynamicSimpleVFE, self).__init__()
+        from .scatter_points import DynamicScatter
+        self.scatter = DynamicScatter(voxel_size, point_cloud_range, True)
+        self.fp16_enabled = False
+
+    @torch.no_grad()
+    def forward(self, features, coors):
+        out_half = features.dtype == torch.half
+        feats, feats_coors = self.scatter(features.float().contiguous(), coors)
+        return (feats.half() if out_half else feats), feats_coors
+
+
 def voxel_occupancy(features, num_points, coors=None, hard=False, lambda_n=0.3, gamma_var=5.0, eps=1e-6,
                     dense_shape=None, batch_size=None):
     """Occupancy value per voxel (M, 1) and, with ``dense_shape=(Z, Y, X)``, the dense map

@@ -414,6 +414,28 @@ def test_dynamic_scatter_c3_full_size(red):
     assert len(oc) > 100000
 
 
+def test_dynamic_simple_vfe():
+    """DynamicSimpleVFE (voxel_encoder.py:50-90) = no-grad DynamicScatter mean, single sample and batched (N, 4) coors."""
+    g = torch.Generator().manual_seed(9)
+    N = 20000
+    feats = torch.rand(N, 4, generator=g) * 100 - 50
+    coors = torch.randint(-1, 12, (N, 3), generator=g, dtype=torch.int32)
+    vfe = rd3_b200.DynamicSimpleVFE([0.2, 0.2, 4], [0, -40, -3, 70.4, 40, 1]).to(DEV)
+    f = feats.to(DEV).requires_grad_()
+    vf, vc = vfe(f, coors.to(DEV))
+    assert not vf.requires_grad                                   # @torch.no_grad() in the reference
+    of, oc, _, _ = oracle.dynamic_scatter(feats.numpy(), coors.numpy(), "mean")
+    assert np.array_equal(vc.cpu().numpy(), oc)
+    assert np.allclose(vf.cpu().numpy(), of, rtol=1e-6, atol=5e-5)
+    batch = torch.sort(torch.randint(0, 3, (N,), generator=g, dtype=torch.int32)).values
+    coors4 = torch.cat([batch.view(-1, 1), coors], dim=1)
+    vf4, vc4 = vfe(feats.to(DEV), coors4.to(DEV))
+    rf, rc = tr.dynamic_scatter_batched(feats, coors4, "mean")
+    assert torch.equal(vc4.cpu(), rc) and torch.allclose(vf4.cpu(), rf, rtol=1e-6, atol=5e-5)
+    h, _ = vfe(feats.to(DEV).half(), coors.to(DEV))               # force_fp32(out_fp16=True)
+    assert h.dtype == torch.half and torch.allclose(h.float().cpu(), torch.from_numpy(of).half().float(), atol=0.1)
+
+
 def test_dynamic_scatter_batched_and_backward():
     g = torch.Generator().manual_seed(3)
     N = 30000

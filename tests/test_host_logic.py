@@ -129,6 +129,16 @@ def test_patch_mmdet3d_rebinds_standin_modules(monkeypatch):
     for a in ("Voxelization", "voxelization", "DynamicScatter", "dynamic_scatter"):
         setattr(mods["mmdet3d.ops"], a, None)
 
+    class OldVoxelization:
+        pass
+
+    class OldDynamicScatter:
+        pass
+    vz.Voxelization, sp.DynamicScatter = OldVoxelization, OldDynamicScatter
+    # a call site that did ``from mmdet3d.ops import DynamicScatter, Voxelization`` before the patch
+    enc = mods["mmdet3d.models.voxel_encoders.voxel_encoder"]
+    enc.DynamicScatter, enc.Voxelization = OldDynamicScatter, OldVoxelization
+
     class HardSimpleVFE:
         num_features = 4
     mods["mmdet3d.models.voxel_encoders.voxel_encoder"].HardSimpleVFE = HardSimpleVFE
@@ -137,6 +147,8 @@ def test_patch_mmdet3d_rebinds_standin_modules(monkeypatch):
     assert sp.DynamicScatter is rd3_b200.DynamicScatter
     assert mods["mmdet3d.ops"].Voxelization is rd3_b200.Voxelization
     assert "mmdet3d.models.voxel_encoders.voxel_encoder.HardSimpleVFE.forward" in done
+    assert enc.DynamicScatter is rd3_b200.DynamicScatter and enc.Voxelization is rd3_b200.Voxelization
+    assert "mmdet3d.models.voxel_encoders.voxel_encoder.DynamicScatter" in done
 
 
 def test_product_never_touches_the_oracle():
