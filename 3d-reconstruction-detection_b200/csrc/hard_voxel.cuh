@@ -58,9 +58,6 @@ constexpr int kTilePoints = 128;      // points per warp tile
 constexpr int kInsSpan = 4 * kInsThreads;   // points per insert CTA (4 per thread)
 constexpr int kTileShift = 7;
 constexpr int kMaxRounds = 64;
-#ifndef RD3_TABLE_SOA
-#define RD3_TABLE_SOA 0               // EXPERIMENT (see profiles/r1_analysis.md, not yet run on a GPU): buckets as
-#endif                                // {k0 k1 k2 k3 | i0 i1 i2 i3}, 16-byte key probes, two probes in flight per lane
 
 // ---------------------------------------------------------------------------
 // point sources
@@ -379,81 +376,6 @@ __device__ __forceinline__ uint32_t table_find(const unsigned long long *table, 
   }
 }
 
-#if RD3_TABLE_SOA
-// ---- SoA buckets (hashed tables only; a direct-mapped table keeps the {key | idx} entries) -------------
-// The 32-byte bucket of slots s0 .. s0+3 holds its four key words first, then its four index words:
-// key word of slot s = 8 (s >> 2) + (s & 3), index word = key word + 4 (in 32-bit words from the table base).
-// All words start at ~0 (one 0xFF memset): a key word is claimed with a 32-bit CAS, the index word is only
-// ever lowered with atomicMin, so the two need not be updated together.
-__device__ __forceinline__ uint32_t soa_key_word(uint32_t slot) { return ((slot >> 2) << 3) + (slot & 3u); }
-
-__device__ __forceinline__ uint4 soa_load_keys(const uint32_t *t32, uint32_t s0) {
-  uint4 k;
-  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(k.x), "=r"(k.y), "=r"(k.z), "=r"(k.w) : "l"(t32 + (s0 << 1)));
-  return k;
-}
-
-// lookup whose first bucket is already loaded
-__device__ __forceinline__ uint32_t soa_find_loaded(const uint32_t *t32, const HvWork &w, uint32_t key, uint32_t s0,
-                                                    uint4 k) {
-  while (true) {
-    int q = 4;
-    q = k.w == key ? 3 : q;
-    q = k.z == key ? 2 : q;
-    q = k.y == key ? 1 : q;
-    q = k.x == key ? 0 : q;
-    if (q < 4) return s0 + q;
-    if (k.w == kEmpty32) return kEmpty32;
-    s0 = (s0 + 4) & w.cap_mask;
-    k = soa_load_keys(t32, s0);
-  }
-}
-
-__device__ __forceinline__ uint32_t soa_insert(uint32_t *t32, const HvWork &w, uint32_t key, uint32_t idx,
-                                               int *claimed) {
-  *claimed = 0;
-  uint32_t s0 = hash_bucket_slot(key, w.log2cap);
-  uint32_t slot, kq;
-  while (true) {                       // first entry of the bucket chain that holds the key or is empty
-    const uint4 k = soa_load_keys(t32, s0);
-    int q = 4;
-    if (k.w == key || k.w == kEmpty32) { q = 3; kq = k.w; }
-    if (k.z == key || k.z == kEmpty32) { q = 2; kq = k.z; }
-    if (k.y == key || k.y == kEmpty32) { q = 1; kq = k.y; }
-    if (k.x == key || k.x == kEmpty32) { q = 0; kq = k.x; }
-    slot = s0 + q;
-    if (q < 4) break;
-    s0 = (s0 + 4) & w.cap_mask;
-  }
-  while (true) {                       // `kq` may be stale: the atomics decide
-    uint32_t *kw = t32 + soa_key_word(slot);
-    if (kq == kEmpty32) {
-      const uint32_t old = atomicCAS(kw, kEmpty32, key);
-      if (old == kEmpty32) {
-        *claimed = 1;
-        atomicMin(kw + 4, idx);
-        return slot;
-      }
-      kq = old;
-    }
-    if (kq == key) {
-      if (__ldcg(kw + 4) > idx) atomicMin(kw + 4, idx);    // a stale (larger) read only costs a redundant atomic
-      return slot;
-    }
-    slot = (slot + 1) & w.cap_mask;    // lost the entry to another key: plain linear probing from here
-    kq = __ldcg(t32 + soa_key_word(slot));
-  }
-}
-#endif
-
-// first point of the voxel in table slot `slot` (after the last insert round)
-__device__ __forceinline__ uint32_t table_first_idx(const unsigned long long *table, const HvWork &w, uint32_t slot) {
-#if RD3_TABLE_SOA
-  if (!w.direct) return __ldg(reinterpret_cast<const uint32_t *>(table) + soa_key_word(slot) + 4);
-#endif
-  return (uint32_t)__ldg(table + slot);
-}
-
 // K1 ------------------------------------------------------------------------
 // grid (ceil((end-begin)/1024), frames), 256 threads; every WARP owns a tile of 128
 // consecutive points and runs its stages without block barriers:
@@ -546,33 +468,6 @@ __global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
   // ---- stage C ----------------------------------------------------------------------
   uint2 *cand = w.cand + (int64_t)b * w.N + base;
   int nc = 0;
-#if RD3_TABLE_SOA
-  if (lookup_only && !w.direct) {
-    // a tile has ~46 in-range keys: the 16-byte key loads of items j and j + 32 are requested back to back,
-    // so that the two DRAM round trips of the one-probe loop below overlap
-    const uint32_t *t32 = reinterpret_cast<const uint32_t *>(table);
-#pragma unroll 1
-    for (int j0 = 0; j0 < n2; j0 += 64) {
-      const int ja = j0 + lane, jb = j0 + 32 + lane;
-      const bool ona = ja < n2, onb = jb < n2;
-      const uint2 ia = ona ? s_item[ja] : make_uint2(0u, 0u);
-      const uint2 ib = onb ? s_item[jb] : make_uint2(0u, 0u);
-      const uint32_t sa = ona ? hash_bucket_slot(ia.x, w.log2cap) : 0u;      // idle lanes read bucket 0
-      const uint32_t sb = onb ? hash_bucket_slot(ib.x, w.log2cap) : 0u;
-      const uint4 ka = soa_load_keys(t32, sa);
-      const uint4 kb = soa_load_keys(t32, sb);
-      const uint32_t slota = ona ? soa_find_loaded(t32, w, ia.x, sa, ka) : kEmpty32;
-      const uint32_t slotb = onb ? soa_find_loaded(t32, w, ib.x, sb, kb) : kEmpty32;
-      const unsigned bala = __ballot_sync(0xffffffffu, slota != kEmpty32);
-      if (slota != kEmpty32) cand[nc + __popc(bala & lt)] = make_uint2((uint32_t)base + ia.y, slota);
-      nc += __popc(bala);
-      const unsigned balb = __ballot_sync(0xffffffffu, slotb != kEmpty32);
-      if (slotb != kEmpty32) cand[nc + __popc(balb & lt)] = make_uint2((uint32_t)base + ib.y, slotb);
-      nc += __popc(balb);
-    }
-    n2 = 0;                                   // nothing left for the loop below
-  }
-#endif
 #pragma unroll 1
   for (int j0 = 0; j0 < n2; j0 += 32) {
     const int j = j0 + lane;
@@ -584,12 +479,7 @@ __global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
         slot = table_find(table, w, it.x);
       } else {
         int c;
-#if RD3_TABLE_SOA
-        slot = w.direct ? table_insert(table, w, it.x, idx, &c)
-                        : soa_insert(reinterpret_cast<uint32_t *>(table), w, it.x, idx, &c);
-#else
         slot = table_insert(table, w, it.x, idx, &c);
-#endif
         claims += c;
       }
     }
@@ -621,19 +511,6 @@ static __global__ void __launch_bounds__(256) hv_first_kernel(HvWork w) {
   const int b = blockIdx.y + w.b0;
   const unsigned long long *table = w.table + (int64_t)b * w.cap;
   uint32_t *flags = w.flags + (int64_t)b * w.nwords;
-#if RD3_TABLE_SOA
-  if (!w.direct) {                     // key word s of a bucket sits 4 words in front of its index word
-    const uint32_t *t32 = reinterpret_cast<const uint32_t *>(table);
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < w.cap;
-         s += (int64_t)gridDim.x * blockDim.x) {
-      const uint32_t kw = soa_key_word((uint32_t)s);
-      if (__ldg(t32 + kw) == kEmpty32) continue;
-      const uint32_t first = __ldg(t32 + kw + 4);
-      atomicOr(flags + (first >> 5), 1u << (first & 31));
-    }
-    return;
-  }
-#endif
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < w.cap;
        s += (int64_t)gridDim.x * blockDim.x) {
     const unsigned long long e = __ldg(table + s);
@@ -803,7 +680,7 @@ static __global__ void __launch_bounds__(128) hv_slots_kernel(HvWork w, int32_t 
     uint32_t first_idx = 0, last = 0;
     int r = w.max_voxels;
     if (on && lane == leader) {
-      first_idx = table_first_idx(table, w, c.y);
+      first_idx = (uint32_t)__ldg(table + c.y);
       r = voxel_rank(w, b, first_idx);
     }
     first_idx = __shfl_sync(0xffffffffu, first_idx, leader);
