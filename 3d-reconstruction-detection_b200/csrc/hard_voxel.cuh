@@ -58,6 +58,9 @@ constexpr int kTilePoints = 128;      // points per warp tile
 constexpr int kInsSpan = 4 * kInsThreads;   // points per insert CTA (4 per thread)
 constexpr int kTileShift = 7;
 constexpr int kMaxRounds = 64;
+#ifndef RD3_KNOCK
+#define RD3_KNOCK 0                   // DIAGNOSTIC builds only (wrong results): lookup-only rounds skip 1: the exact
+#endif                                // redo, 2: + the probes, 3: everything after the prologue (tools/knockout.sh)
 
 // ---------------------------------------------------------------------------
 // point sources
@@ -413,6 +416,12 @@ __global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
   const bool lookup_only = s_prev >= w.max_voxels;
 
   if (block_base + wv * kTilePoints >= end) return;
+#if RD3_KNOCK >= 3
+  if (lookup_only) {                                        // timing only: prologue + depth load
+    if (lane == 0 && sizeof(pre) == 16 && reinterpret_cast<const float *>(&pre)[0] == 123.456f) w.cand_cnt[0] = 1;
+    return;
+  }
+#endif
   uint2 *s_item = s_itemb + wv * kTilePoints;
   uint8_t *s_und = s_undb + wv * kTilePoints;
   unsigned long long *table = w.table + (int64_t)b * w.cap;
@@ -450,6 +459,15 @@ __global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
     }
   }
   __syncwarp();
+#if RD3_KNOCK >= 1
+  if (lookup_only) nu = 0;                                  // timing only: no exact redo of undecided points
+#endif
+#if RD3_KNOCK >= 2
+  if (lookup_only) {                                        // timing only: no table probes
+    if (lane == 0) w.cand_cnt[(int64_t)b * w.ntiles + (base >> kTileShift)] = (uint8_t)(n2 == 77777);
+    return;
+  }
+#endif
 #pragma unroll 1
   for (int j0 = 0; j0 < nu; j0 += 32) {       // within the error bound of a boundary: exact arithmetic
     const int j = j0 + lane;
