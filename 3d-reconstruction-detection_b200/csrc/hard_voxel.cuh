@@ -58,6 +58,12 @@ constexpr int kTilePoints = 128;      // points per warp tile
 constexpr int kInsSpan = 4 * kInsThreads;   // points per insert CTA (4 per thread)
 constexpr int kTileShift = 7;
 constexpr int kMaxRounds = 64;
+#ifndef RD3_EMIT_TMA
+#define RD3_EMIT_TMA 0                // EXPERIMENT (not yet run on a GPU): emit stages the calibration with the TMA bulk
+#endif                                // copy of the insert kernel (its load / store loop holds 7 % of emit's stall samples)
+#ifndef RD3_LATE_CLAIMS
+#define RD3_LATE_CLAIMS 0             // EXPERIMENT (profiles/r1_analysis.md, not yet run on a GPU): the claims sum is
+#endif                                // loaded after the prologue barrier and waited for (mbarrier) only at stage C
 #ifndef RD3_KNOCK
 #define RD3_KNOCK 0                   // DIAGNOSTIC builds only (wrong results): lookup-only rounds skip 1: the exact
 #endif                                // redo, 2: + the probes, 3: everything after the prologue (tools/knockout.sh)
@@ -401,6 +407,30 @@ __global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
   const unsigned lt = (1u << lane) - 1u;
   const int64_t block_base = begin + (int64_t)blockIdx.x * kInsSpan;
   if (block_base >= end) return;
+#if RD3_LATE_CLAIMS
+#if RD3_KNOCK
+#error "the RD3_KNOCK builds need the claims before the prologue barrier"
+#endif
+  // The source-level profile puts 14 % of all warp time on the prologue barrier: seven warps wait there for
+  // warp 0's load of the round claims, a value that is first needed at stage C.  Here the barrier only covers
+  // the mbarrier inits + the calibration copy; warp 0 loads the claims after it and publishes them through a
+  // one-shot mbarrier that the other warps look at when they reach stage C (by then it has long completed).
+  __shared__ __align__(8) uint64_t s_bar2;
+  if (tid == 0) { s_claims = 0; s_done = 0; mbar_init(&s_bar2, 1); }
+  const typename Src::Pre pre = src.preload(b, block_base + wv * kTilePoints + 4 * lane, end);
+  const bool cal_async = src.stage_async(s_cal, &s_bar, b);
+  __syncthreads();
+  if (wv == 0) {
+    int c = 0;
+    for (int r = lane; r < round; r += 32) c += __ldcg(w.round_claims + b * kMaxRounds + r);
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (lane == 0) {
+      s_prev = c;
+      mbar_arrive(&s_bar2);               // release: s_prev is visible to whoever sees the phase complete
+    }
+  }
+  if (cal_async) tma_wait(&s_bar);
+#else
   if (tid == 0) { s_claims = 0; s_done = 0; }
   const typename Src::Pre pre = src.preload(b, block_base + wv * kTilePoints + 4 * lane, end);
   if (wv == 0) {
@@ -414,6 +444,7 @@ __global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
   __syncthreads();
   if (cal_async) tma_wait(&s_bar);
   const bool lookup_only = s_prev >= w.max_voxels;
+#endif
 
   if (block_base + wv * kTilePoints >= end) return;
 #if RD3_KNOCK >= 3
@@ -484,6 +515,10 @@ __global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
   __syncwarp();
 
   // ---- stage C ----------------------------------------------------------------------
+#if RD3_LATE_CLAIMS
+  tma_wait(&s_bar2);
+  const bool lookup_only = s_prev >= w.max_voxels;
+#endif
   uint2 *cand = w.cand + (int64_t)b * w.N + base;
   int nc = 0;
 #pragma unroll 1
@@ -730,7 +765,12 @@ static __global__ void __launch_bounds__(128) hv_slots_kernel(HvWork w, int32_t 
 template <class Src>
 __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGrid g, HvWork w, HvOut o, int V) {
   extern __shared__ float s_dyn[];
+#if RD3_EMIT_TMA
+  __shared__ __align__(16) float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 4];
+  __shared__ __align__(8) uint64_t s_bar;
+#else
   __shared__ float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 1];
+#endif
   const int b = blockIdx.y + w.b0;
   const int vn = o.voxel_num[b];
   const int r0 = blockIdx.x * V;
@@ -758,7 +798,11 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
     const int it = lo + 32 * q + lane;
     pre[q] = it < hi ? __ldg(S + it) : kEmpty32;
   }
+#if RD3_EMIT_TMA
+  const bool cal_async = src.stage_async(s_cal, &s_bar, b);     // one bulk copy instead of a load / store loop
+#else
   src.stage(s_cal, b);
+#endif
   {
     float4 *t4 = reinterpret_cast<float4 *>(tile);
     const int n4 = (items * C + 3) >> 2;
@@ -787,6 +831,9 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
     nmine += __popc(bal);
   }
   __syncthreads();                       // tile zeroed, calibration staged
+#if RD3_EMIT_TMA
+  if (cal_async) tma_wait(&s_bar);
+#endif
   for (int j = lane; j < nmine; j += 32) {
     const int it = s_list[lo + j];
     src.gather(b, s_idx[it], s_cal, tile + it * C);

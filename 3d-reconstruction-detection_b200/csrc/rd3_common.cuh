@@ -345,6 +345,17 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
                "l"(gmem_src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// a plain mbarrier used as a one-shot flag inside a CTA: init by one thread (then a __syncthreads()), one arrive
+// (release) by the producer after its shared-memory stores, tma_wait (acquire, phase 0) by the consumers
+__device__ __forceinline__ void mbar_init(uint64_t *smem_bar, uint32_t count) {
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem_bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *smem_bar) {
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem_bar);
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // every consumer thread, after a __syncthreads() that follows tma_load_1d (phase 0 of a fresh barrier)
 __device__ __forceinline__ void tma_wait(uint64_t *smem_bar) {
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem_bar);
