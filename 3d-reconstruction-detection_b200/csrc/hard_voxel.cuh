@@ -58,6 +58,9 @@ constexpr int kTilePoints = 128;      // points per warp tile
 constexpr int kInsSpan = 4 * kInsThreads;   // points per insert CTA (4 per thread)
 constexpr int kTileShift = 7;
 constexpr int kMaxRounds = 64;
+#ifndef RD3_PREFETCH
+#define RD3_PREFETCH 0                // EXPERIMENT (not yet run on a GPU): the table sector of every in-range key is
+#endif                                // prefetched into L2 right after the cell decision, ~150 instructions before its probe
 #ifndef RD3_EMIT_TMA
 #define RD3_EMIT_TMA 0                // EXPERIMENT (not yet run on a GPU): emit stages the calibration with the TMA bulk
 #endif                                // copy of the insert kernel (its load / store loop holds 7 % of emit's stall samples)
@@ -465,6 +468,17 @@ __global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
     typename Src::Cursor cur = src.cursor(b, base + 4 * lane, end, s_cal, pre);
     Quad qd;
     src.classify(cur, s_cal, g, qd);
+#if RD3_PREFETCH
+    // 23 % of the kernel's stall samples are the long-scoreboard wait for the probed bucket.  The key is known
+    // here, the probe only happens after the compaction: a prefetch (no register, no dependency) starts the
+    // DRAM access now, so that the probe finds its sector in L2.
+    if (!w.direct) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if ((qd.in >> q) & 1u)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(table + hash_bucket_slot(qd.key[q], w.log2cap)));
+    }
+#endif
     // exclusive prefix of the per-lane counts (0..4) from three ballots of the count's bit planes
     const unsigned cin = __popc(qd.in);
     const unsigned p0 = __ballot_sync(0xffffffffu, cin & 1u), p1 = __ballot_sync(0xffffffffu, cin & 2u),
