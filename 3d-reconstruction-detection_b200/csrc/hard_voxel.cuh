@@ -58,6 +58,9 @@ constexpr int kTilePoints = 128;      // points per warp tile
 constexpr int kInsSpan = 4 * kInsThreads;   // points per insert CTA (4 per thread)
 constexpr int kTileShift = 7;
 constexpr int kMaxRounds = 64;
+#ifndef RD3_RANK_PACKED
+#define RD3_RANK_PACKED 0             // EXPERIMENT (not yet run on a GPU): first-point flag word and its popcount prefix
+#endif                                // interleaved as {flags, prefix} pairs: one random sector per rank lookup, not two
 #ifndef RD3_PREFETCH
 #define RD3_PREFETCH 0                // EXPERIMENT (not yet run on a GPU): the table sector of every in-range key is
 #endif                                // prefetched into L2 right after the cell decision, ~150 instructions before its probe
@@ -577,13 +580,13 @@ __global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
 static __global__ void __launch_bounds__(256) hv_first_kernel(HvWork w) {
   const int b = blockIdx.y + w.b0;
   const unsigned long long *table = w.table + (int64_t)b * w.cap;
-  uint32_t *flags = w.flags + (int64_t)b * w.nwords;
+  uint32_t *flags = w.flags + (int64_t)b * w.nwords * (RD3_RANK_PACKED ? 2 : 1);
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < w.cap;
        s += (int64_t)gridDim.x * blockDim.x) {
     const unsigned long long e = __ldg(table + s);
     if (e == kEmpty64) continue;
     const uint32_t first = (uint32_t)e;
-    atomicOr(flags + (first >> 5), 1u << (first & 31));
+    atomicOr(flags + (first >> 5) * (RD3_RANK_PACKED ? 2 : 1), 1u << (first & 31));
   }
 }
 
@@ -594,7 +597,11 @@ static __global__ void __launch_bounds__(kScanThreads) hv_flagscan_kernel(HvWork
   const int b = blockIdx.y + w.b0;
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
   const int64_t wi = (int64_t)b * w.nwords + (int64_t)blockIdx.x * kChunkWords + threadIdx.x;
+#if RD3_RANK_PACKED
+  const int cnt = __popc(w.flags[2 * wi]);
+#else
   const int cnt = __popc(w.flags[wi]);
+#endif
   const int inc = warp_inclusive_scan(cnt);
   if (lane == 31) s_warp[wv] = inc;
   __syncthreads();
@@ -605,7 +612,11 @@ static __global__ void __launch_bounds__(kScanThreads) hv_flagscan_kernel(HvWork
     if (k < wv) base += t;
     total += t;
   }
+#if RD3_RANK_PACKED
+  w.flags[2 * wi + 1] = (uint32_t)(base + inc - cnt);
+#else
   w.wordprefix[wi] = base + inc - cnt;
+#endif
   if (threadIdx.x == 0) w.chunk_base[(int64_t)b * w.nchunks + blockIdx.x] = total;
 }
 
@@ -674,9 +685,15 @@ static __global__ void __launch_bounds__(1024) scan_chunks_kernel(int32_t *chunk
 __device__ __forceinline__ int voxel_rank(const HvWork &w, int b, uint32_t first_idx) {
   const uint32_t word = first_idx >> 5;
   const int64_t wi = (int64_t)b * w.nwords + word;
+#if RD3_RANK_PACKED
+  const uint2 fw = __ldg(reinterpret_cast<const uint2 *>(w.flags) + wi);
+  return __ldg(w.chunk_base + (int64_t)b * w.nchunks + (first_idx >> kChunkShift)) + (int)fw.y +
+         __popc(fw.x & ((1u << (first_idx & 31)) - 1u));
+#else
   const uint32_t bits = __ldg(w.flags + wi) & ((1u << (first_idx & 31)) - 1u);
   return __ldg(w.chunk_base + (int64_t)b * w.nchunks + (first_idx >> kChunkShift)) +
          __ldg(w.wordprefix + wi) + __popc(bits);
+#endif
 }
 
 // Keep the K smallest point indices of a voxel, sorted, with atomicMin only.
@@ -959,7 +976,7 @@ inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels) {
   size_t off = 0;
   p.off_table = off; off += align_up((size_t)B * p.cap * 8);
   p.off_slots = off; off += align_up((size_t)B * max_voxels * K * 4);
-  p.off_flags = off; off += align_up((size_t)B * p.nwords * 4);
+  p.off_flags = off; off += align_up((size_t)B * p.nwords * 4 * (RD3_RANK_PACKED ? 2 : 1));
   p.off_claims = off; off += align_up((size_t)B * kMaxRounds * 4);
   p.off_ccount = off; off += align_up((size_t)B * p.ntiles);
   p.off_prefix = off; off += align_up((size_t)B * p.nwords * 4);
@@ -1038,7 +1055,8 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
     RD3_CUDA_TRY(cudaMemsetAsync(w.table + (size_t)b0 * p.cap, 0xFF, (size_t)nb * p.cap * 8, st));
     RD3_CUDA_TRY(cudaMemsetAsync(w.slots + (size_t)b0 * p.max_voxels * p.K, 0xFF,
                                  (size_t)nb * p.max_voxels * p.K * 4, st));
-    RD3_CUDA_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords, 0, (size_t)nb * p.nwords * 4, st));
+    RD3_CUDA_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords * (RD3_RANK_PACKED ? 2 : 1), 0,
+                                 (size_t)nb * p.nwords * 4 * (RD3_RANK_PACKED ? 2 : 1), st));
     RD3_CUDA_TRY(cudaMemsetAsync(w.round_claims + (size_t)b0 * kMaxRounds, 0, (size_t)nb * kMaxRounds * 4,
                                  st));
     prof_mark(st, 1);
