@@ -168,7 +168,10 @@ RD3_API int rd3_unproject(const float *depth, const float *intrinsics,
  *   NULL, d_voxel_num device int32[B].
  *   voxels may be NULL when voxel_mean is given: a caller that feeds the sparse
  *   encoder (HardSimpleVFE features + coors, sparse_refinement.py:382-402) never
- *   reads the padded voxel tensor, and 85 % of the output bytes are not written. */
+ *   reads the padded voxel tensor, and 85 % of the output bytes are not written.
+ *   workspace: 256-byte aligned (256-bit table loads, TMA bulk copies of the
+ *   calibration table), rd3_depth_to_voxels_workspace_bytes() bytes;
+ *   RD3_ERR_INVALID_ARGUMENT otherwise. */
 RD3_API size_t rd3_depth_to_voxels_workspace_bytes(const rd3_depth_params *p,
                                            int max_points, int max_voxels);
 

@@ -80,6 +80,16 @@ def test_workspace_sizes_and_argument_validation_without_gpu():
     assert st == 1
     st = L.rd3_dynamic_voxelize(null, -5, 3, _lib.f3([1, 1, 1]), _lib.f6([0, 0, 0, 1, 1, 1]), null, null)
     assert st == 1
+    # a workspace that is not 256-byte aligned is an invalid argument (256-bit table loads, TMA bulk copies);
+    # the pointers are never dereferenced on the host and the check comes before the first CUDA call
+    fake = lambda a: ctypes.c_void_p(0x10000 + a)
+    vs, pcr = _lib.f3([0.075, 0.075, 0.2]), _lib.f6([-54, -54, -5, 54, 54, 3])
+    st = L.rd3_depth_to_voxels(fake(0), fake(0), fake(0), null, null, ctypes.byref(p), vs, pcr, 10, 1000, fake(0),
+                               fake(0), fake(0), null, fake(0), fake(64), 1 << 40, null)
+    assert st == 1
+    st = L.rd3_hard_voxelize(fake(0), 10, 3, vs, pcr, 5, 5, fake(0), fake(0), fake(0), fake(0), null, 0, null,
+                             fake(128), 1 << 40, null)
+    assert st == 1
 
 
 def test_no_fallback_without_cuda_tensors():
