@@ -110,7 +110,9 @@ static __global__ void __launch_bounds__(256)
 
 __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
   if (v != v) return;                       // fmaxf(NaN, m) == m  (scatter_points_cuda.cu:22-30)
-  if (v >= 0.0f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+  // branch on the SIGN BIT, not on v >= 0: -0.0 (0x80000000 = INT_MIN as a signed int) must take the
+  // unsigned branch, where it beats the -inf initial value like every other negative number
+  if (__float_as_int(v) >= 0) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
   else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
 }
 

@@ -201,3 +201,53 @@ def dynamic_scatter(feats, coors, reduce_type):
                                   _ptr(oc, _i32p), _ptr(mp, _i32p),
                                   _ptr(ct, _i32p))
     return of[:M].copy(), oc[:M].copy(), mp[:N].copy(), ct[:M].copy()
+
+
+def soft_voxel_occupancy_f64(voxels, num, lambda_n=0.3, gamma_var=5.0, eps=1e-6):
+    """SoftVoxelOccupancyVFE.forward (voxel_occupancy_encoder.py:60-99) evaluated in fp64, plus a
+    per-voxel bound on what ANY fp32 evaluation of the same formula (whatever its summation order) may
+    differ from it.  Returns (p_occ (M,1) float64, tol (M,1) float64).
+
+    Derivation, u = 2^-24 (fp32 unit roundoff), X = max |xyz| of the voxel, D = max |xyz - mean|:
+      mean   n-term sum, any order, then one division:  dm   <= u X (n + 2)
+      diff   one subtraction on top of the mean's error: dd  <= dm + u D
+      var    sum of n squares / denom, mean of 3 axes:   dvar <= 2 D dd + u D^2 (n + 4)
+             (the cancellation |xyz| ~ 50 m against |diff| ~ 0.2 m sits in the 2 D dm term: ~1e-4 relative)
+      a = -lambda n - gamma var:                          da   <= gamma dvar + 3 u |a|
+      p = 1 - exp(a), exp within 2 ulp:                   dp   <= exp(a) (da + 3 u) + u
+    The returned tol is twice that bound.
+    """
+    v = np.asarray(voxels, dtype=np.float64)[:, :, :3]
+    n = np.asarray(num, dtype=np.float64)
+    M, K, _ = v.shape
+    mask = (np.arange(K)[None, :] < n[:, None])[:, :, None].astype(np.float64)
+    denom = n[:, None] + np.float64(np.float32(eps))
+    mean = (v * mask).sum(axis=1) / denom
+    diff = (v - mean[:, None, :]) * mask
+    var = ((diff ** 2).sum(axis=1) / denom).mean(axis=1)
+    a = -np.float64(np.float32(lambda_n)) * n - np.float64(np.float32(gamma_var)) * var
+    p = 1.0 - np.exp(a)
+    u = 2.0 ** -24
+    X = np.abs(v * mask).max(axis=(1, 2))
+    D = np.abs(diff).max(axis=(1, 2))
+    dm = u * X * (n + 2)
+    dd = dm + u * D
+    dvar = 2 * D * dd + u * D * D * (n + 4)
+    da = gamma_var * dvar + 3 * u * np.abs(a)
+    dp = np.exp(a) * (da + 3 * u) + u
+    return p.reshape(-1, 1), (2 * dp).reshape(-1, 1)
+
+
+def masked_mean_f64(voxels, num, num_features=None):
+    """Per-voxel mean of the first num[m] slots in fp64 and the bound 2 (n + 2) 2^-24 max|x| on the
+    difference of any fp32 evaluation (n-term sum in any order + one division).  Returns (mean, tol)."""
+    v = np.asarray(voxels, dtype=np.float64)
+    n = np.asarray(num, dtype=np.float64)
+    M, K, C = v.shape
+    F = C if num_features is None else num_features
+    mask = (np.arange(K)[None, :] < n[:, None])[:, :, None]
+    vm = np.where(mask, v[:, :, :F], 0.0)
+    mean = vm.sum(axis=1) / np.maximum(n, 1.0)[:, None]
+    X = np.abs(vm).max(axis=1)
+    tol = 2 * (n[:, None] + 2) * 2.0 ** -24 * X
+    return mean, tol

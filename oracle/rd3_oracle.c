@@ -289,8 +289,12 @@ int64_t orc_dynamic_scatter(const float *feats, const int32_t *coors,
     for (int f = 0; f < C; ++f) {
       if (reduce_type == 2) {
         float m = -INFINITY;
-        for (int64_t j = s; j < e; ++j)
-          m = fmaxf(feats[rows[j].idx * C + f], m);
+        // reduceMax (scatter_points_cuda.cu:22-30) is a CAS loop around the DEVICE fmaxf: NaN operands are
+        // dropped and +0.0 orders above -0.0 (PTX max.f32); written out because C's fmaxf leaves the zeros open
+        for (int64_t j = s; j < e; ++j) {
+          const float x = feats[rows[j].idx * C + f];
+          if (x > m || (x == m && !signbit(x))) m = x;
+        }
         out_feats[M * C + f] = m;
       } else {
         double a = 0.0;

@@ -212,3 +212,23 @@ def test_pillar_restatement_matches_golden():
     # legacy=True really aliases: the raw x column equals the centre-offset column
     leg = d["deco_legacy1_dist0"]
     assert np.array_equal(leg[:, :, 0], leg[:, :, 8]) and not np.array_equal(d["deco_legacy0_dist0"][:, :, 0], leg[:, :, 0])
+
+
+def test_fp64_anchors_bound_the_torch_restatement():
+    """The float parity tests compare against fp64 anchors with DERIVED bounds (oracle.soft_voxel_occupancy_f64,
+    oracle.masked_mean_f64), not against a torch-CPU reduction whose order depends on the host: the
+    restatement itself has to sit inside those bounds, with room to spare, on this machine too."""
+    import torch
+    from oracle import torch_restatement as tr
+    from rd3_b200 import synthetic
+    f = synthetic.make_frame(500, 48, 84, scene="ground")
+    p = oracle.unproject(f["depth"].numpy(), f["intrinsics"].numpy(), f["cam2lidar"].numpy(), max_depth=synthetic.MAX_DEPTH)
+    v, c, n = oracle.hard_voxelize(p, [0.6, 0.6, 0.8], [-54.0, -54.0, -5.0, 54.0, 54.0, 3.0], 10, 20000)
+    assert len(n) > 2000 and int(n.max()) == 10
+    p64, tol = oracle.soft_voxel_occupancy_f64(v, n)
+    exp = tr.soft_voxel_occupancy(torch.from_numpy(v), torch.from_numpy(n)).numpy()
+    assert (np.abs(exp - p64) <= tol).all() and tol.max() < 5e-4
+    m64, mt = oracle.masked_mean_f64(v, n)
+    ref = tr.hard_simple_vfe(torch.from_numpy(v), torch.from_numpy(n), 3).numpy()
+    assert (np.abs(ref - m64) <= mt).all()
+    assert (np.abs(oracle.hard_simple_vfe(v, n, 3) - m64) <= mt).all()
