@@ -144,7 +144,7 @@ def workspace(device, nbytes):
     return ws
 
 
-PROFILE_STAGES = ("memset", "insert", "flags", "scan", "slots", "emit", "meta")
+PROFILE_STAGES = ("memset", "insert", "flags", "rank", "lookup", "emit", "meta")
 
 
 def profile_enable(on=True):

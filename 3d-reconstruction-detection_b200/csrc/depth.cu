@@ -8,6 +8,8 @@
 // once per pass with exactly the reference's fp32 operation order, and the
 // row-major / camera-major output order is reproduced with a ballot + popcount
 // scan instead of a stream compaction primitive.
+#include <math.h>
+
 #include "hard_voxel.cuh"
 
 namespace rd3 {
@@ -130,6 +132,38 @@ static UpPlan up_plan(int B, int64_t npix) {
   return p;
 }
 
+// fp32 cell coordinate of p on axis a exactly as voxel_coor() computes it on the device: IEEE subtract, TRUE
+// division (volatile: no contraction, no double evaluation on the host)
+static float host_cellf(float p, const VoxelGrid &g, int a) {
+  volatile float d = p - g.lo[a];
+  volatile float q = d / g.vs[a];
+  return q;
+}
+
+// Does "the point is inside the voxel grid" imply "the point passes the inclusive range filter"
+// (respoint_post_processing.py:190-195) on all six planes?  q(p) = RN(RN(p - lo) / vs) is a monotone
+// non-decreasing function of p and the device accepts a point iff 0 <= floor(q) < grid, so
+//   upper plane: every p > hi has q(p) >= q(nextafter(hi)); if that is >= grid, p is outside the grid
+//   lower plane: every p < lo has q(p) <= q(nextbefore(lo)); if that is < 0 (and not -0, whose floor passes
+//                the device's ">= 0" test), p is outside the grid
+// NaN anywhere: not implied.  When this returns true the fast cell decision ignores the filter; the exact path
+// (unproject_point) still applies it literally.
+static bool range_filter_implied(const float range[6], const VoxelGrid &g) {
+  for (int a = 0; a < 3; ++a) {
+    const float lo = range[a], hi = range[3 + a];
+    if (!(lo == lo) || !(hi == hi)) return false;
+    if (hi < 3.0e38f) {
+      const float q = host_cellf(nextafterf(hi, INFINITY), g, a);
+      if (!(q == q) || !((double)q >= (double)g.grid[a])) return false;   // a point above hi can still be in the grid
+    }
+    if (lo > -3.0e38f) {
+      const float q = host_cellf(nextafterf(lo, -INFINITY), g, a);
+      if (!(q == q) || q >= 0.0f) return false;                           // q >= 0 is true for -0.0f as well
+    }
+  }
+  return true;
+}
+
 static int make_depth_source(const float *depth, const float *intrinsics, const float *cam2lidar,
                              const float *conf, const uint8_t *sky, const rd3_depth_params *p,
                              DepthSource *src) {
@@ -162,6 +196,8 @@ static int make_depth_source(const float *depth, const float *intrinsics, const 
   d.div_hw = make_fastdiv((uint32_t)d.HW);
   d.div_w = make_fastdiv((uint32_t)d.W);
   src->vec_ok = ((npix & 3) == 0) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0);
+  src->cbshift = 7;                                  // culling: blocks of >= 128 image columns, at most 32 per row
+  while (((p->W - 1) >> src->cbshift) >= 32) ++src->cbshift;
   return RD3_OK;
 }
 
@@ -228,8 +264,10 @@ int rd3_depth_to_voxels(const float *depth, const float *intrinsics, const float
   const size_t cal_bytes = align_up((size_t)p->B * p->ncam * kCalibFloats * 4);
   if (workspace_bytes < plan.total + cal_bytes) return RD3_ERR_WORKSPACE;
   float *cal_table = (float *)((char *)workspace + plan.total);
-  // inclusive range filter in cell units minus 0.5 (pixel_key_fast works on h = f' - 0.5)
-  src.rg.on = p->use_range;
+  // inclusive range filter in cell units minus 0.5 (pixel_key_fast works on h = f' - 0.5).  When the voxel grid's
+  // own test implies every plane of the filter (the usual case: the filter box contains the grid), the fast
+  // path does not look at it at all; the exact path still applies it literally.
+  src.rg.on = p->use_range && !range_filter_implied(p->range, g);
   for (int a = 0; a < 3; ++a) {
     src.rg.lo[a] = (float)(((double)p->range[a] - (double)g.lo[a]) / (double)g.vs[a] - 0.5);
     src.rg.hi[a] = (float)(((double)p->range[3 + a] - (double)g.lo[a]) / (double)g.vs[a] - 0.5);

@@ -9,26 +9,35 @@
 // voxelization_cuda.cu:105-180) is reused.  Everything order-related is derived
 // from explicit point indices, so the result does not depend on scheduling.
 //
-//   K1 insert (R rounds over consecutive index ranges of S points):
-//        a warp owns a tile of 128 points (4 per lane, one 16-byte load): validity, voxel cell by a
-//        conservative fast path (magic-number rounding, proven error bound) with an exact IEEE
-//        redo for the few points near a cell boundary, in-range keys compacted into a per-warp
-//        list, then table operations with dense lanes.
-//        Table entry {key:32 | min point index:32} in buckets of 4 (one 32-byte sector, one
-//        256-bit load per probe); 64-bit CAS claims an entry, 64-bit atomicMin lowers the index.
-//        A round only INSERTS while fewer than max_voxels voxels were claimed by the previous
-//        rounds; later rounds only look keys up.  Voxels first seen after that point have
-//        rank >= max_voxels and are dropped by the reference anyway, so the
+//   P1 insert  (R launches over consecutive index ranges of S points, `hv_pass_kernel<Src, 0>`):
+//        voxel cell of every point; {key | min point index} into a hash table (64-bit CAS claims an
+//        entry, 64-bit atomicMin lowers the index); the bit "point i is the first of its voxel" is
+//        kept current by XOR toggles (claim: toggle i; lowering j -> i: toggle both), so no pass
+//        over the table is needed to find the first points.  A frame whose earlier rounds already
+//        claimed max_voxels voxels is CLOSED: its CTAs of the later rounds return at once (voxels
+//        first seen after that point have rank >= max_voxels and the reference drops them), so the
 //        table never holds more than max_voxels + S keys, whatever N is.
-//        Points whose voxel is in the table are appended to their tile's candidate region.
-//   K2a first : every table entry marks bit[min index] in a per-frame bitmask
-//   K2b scan  : per-chunk exclusive popcount prefix; K2s chunk totals -> voxel_num
-//   K3 slots  : a warp merges the candidate regions of 4 tiles into one dense list; per candidate:
-//        rank r = #first-points before its voxel's first point; if r < max_voxels insert its
-//        index into S[r][0..K) with a cascade of atomicMin that keeps the K smallest indices, sorted.
-//   K4 emit   : a CTA owns V voxels; gathers (or re-unprojects) the slot points
-//        into a shared-memory tile, then writes voxels (coalesced), coors, count
-//        and the HardSimpleVFE mean from the tile.
+//   P2 rank    flag scan (per-chunk popcount prefix, chunk totals -> voxel_num), then one pass over
+//        the table: entry -> rank r = #first-points before its first point; the entry becomes
+//        {key | r} (or {key | ~0} when r >= max_voxels), slot row r gets its first point, coors[r]
+//        is decoded from the key, and (depth source) the voxel is marked in a 64x64 bird's-eye mask.
+//   P2c cull   (depth source) per camera and block of image columns: can a pixel of this block reach
+//        any marked bird's-eye cell?  Exact plane test of the block's viewing wedge against the cells,
+//        widened by the proven error bound of the pixel->cell map.  Pseudo point clouds are camera-major,
+//        so with max_voxels reached early most cameras cannot contribute any more.
+//   P3 lookup  (`hv_pass_kernel<Src, 1>`, ONE launch over all points, frame-major so that a frame's
+//        table and slot rows stay in L2): tiles whose column blocks are all culled are skipped without
+//        reading their depth; every other point: cell -> table -> rank -> sorted insertion of its index
+//        into S[r][0..K) (atomicMin cascade keeping the K smallest indices; a full row rejects a later
+//        point with one load).
+//   P4 emit    a CTA owns V voxels: gathers (or re-unprojects exactly) the slot points into a
+//        shared-memory tile, writes voxels (coalesced), count and the HardSimpleVFE mean.
+//
+// A warp of the pass kernels owns a STRIP of `iters` consecutive 128-point tiles: the depth of the next
+// tile is in flight while the current one is classified; in-range keys are appended to a per-warp list that
+// is worked off only in full 32-lane passes (the remainder is carried to the next tile), and the few points
+// that need the exact IEEE path are collected over the strip, so that pass runs once per strip with dense
+// lanes instead of once per tile with one or two.
 //
 // Templated on the point source: a (N,C) point array, or DA3 depth maps
 // unprojected on the fly (the point cloud never exists in memory).
@@ -39,48 +48,60 @@
 
 namespace rd3 {
 
-#ifndef RD3_INS_THREADS
-#define RD3_INS_THREADS 256
-#endif
-constexpr int kInsThreads = RD3_INS_THREADS;
-#ifndef RD3_SLOT_TILES
-#define RD3_SLOT_TILES 4              // tiles whose candidate regions one warp of the slots kernel merges
-#endif
-constexpr int kSlotTiles = RD3_SLOT_TILES;   // power of two, <= 32
+constexpr int kPassThreads = 256;
+constexpr int kPassWarps = kPassThreads / 32;
 #ifndef RD3_EMIT_THREADS
 #define RD3_EMIT_THREADS 256
 #endif
 constexpr int kEmitThreads = RD3_EMIT_THREADS;
 #ifndef RD3_INS_MINB
-#define RD3_INS_MINB 8                // resident insert CTAs per SM the register budget is sized for
+#define RD3_INS_MINB 6                // resident CTAs per SM the insert pass is compiled for
 #endif
-constexpr int kTilePoints = 128;      // points per warp tile
-constexpr int kInsSpan = 4 * kInsThreads;   // points per insert CTA (4 per thread)
-constexpr int kTileShift = 7;
+#ifndef RD3_LKP_MINB
+#define RD3_LKP_MINB 6                // ... and the lookup pass
+#endif
+constexpr int kTilePoints = 128;      // points per warp tile (4 per lane)
+constexpr int kListCap = 160;         // per-warp item / undecided lists: 31 carried + 128 new
 constexpr int kMaxRounds = 64;
-#ifndef RD3_RANK_PACKED
-#define RD3_RANK_PACKED 0             // EXPERIMENT (not yet run on a GPU): first-point flag word and its popcount prefix
-#endif                                // interleaved as {flags, prefix} pairs: one random sector per rank lookup, not two
-#ifndef RD3_PREFETCH
-#define RD3_PREFETCH 0                // EXPERIMENT (not yet run on a GPU): the table sector of every in-range key is
-#endif                                // prefetched into L2 right after the cell decision, ~150 instructions before its probe
-#ifndef RD3_EMIT_TMA
-#define RD3_EMIT_TMA 0                // EXPERIMENT (not yet run on a GPU): emit stages the calibration with the TMA bulk
-#endif                                // copy of the insert kernel (its load / store loop holds 7 % of emit's stall samples)
-#ifndef RD3_LATE_CLAIMS
-#define RD3_LATE_CLAIMS 0             // EXPERIMENT (profiles/r1_analysis.md, not yet run on a GPU): the claims sum is
-#endif                                // loaded after the prologue barrier and waited for (mbarrier) only at stage C
-#ifndef RD3_KNOCK
-#define RD3_KNOCK 0                   // DIAGNOSTIC builds only (wrong results): lookup-only rounds skip 1: the exact
-#endif                                // redo, 2: + the probes, 3: everything after the prologue (tools/knockout.sh)
+constexpr int kBevDim = 64;           // bird's-eye mask of the kept voxels: kBevDim x kBevDim bits over the x,y grid
+constexpr int kBevWords = kBevDim * kBevDim / 32;
+
+// ---------------------------------------------------------------------------
+// packed fp32 pairs (FFMA2 / FADD2 on sm_100a: two IEEE-rounded results per issue slot)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mov.b64 rc, {%6,%7};\n"
+      " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0,%1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n add.rn.f32x2 rd, ra, rb;\n"
+      " mov.b64 {%0,%1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n sub.rn.f32x2 rd, ra, rb;\n"
+      " mov.b64 {%0,%1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
 
 // ---------------------------------------------------------------------------
 // point sources
 // ---------------------------------------------------------------------------
-// stage-AB result of one lane (4 consecutive points)
+// classification of one lane's 4 consecutive points
 struct Quad {
   uint32_t key[4];
-  unsigned in, und;
+  unsigned in, und;     // bit q: point q is surely inside (key valid) / needs the exact path
 };
 
 struct PointsSource {
@@ -89,17 +110,18 @@ struct PointsSource {
   int C;
   static constexpr bool kIsDepth = false;
 
-  __device__ __forceinline__ void stage(float *, int) const {}
   __device__ __forceinline__ bool stage_async(float *, uint64_t *, int) const { return false; }
-  __device__ __forceinline__ void prepare(float *, int) const {}
   int host_num_feats() const { return C; }
   __device__ __forceinline__ int num_feats() const { return C; }
 
-  // stage AB: a lane owns 4 consecutive points
+  struct Loc {};
+  __device__ __forceinline__ Loc locate(int64_t) const { return Loc(); }
+  __device__ __forceinline__ bool lane_live(const Loc &, const uint32_t *, int) const { return true; }
   struct Pre {};
   __device__ __forceinline__ Pre preload(int, int64_t, int64_t) const { return Pre(); }
   struct Cursor { const float *p; int npx; };
-  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *, const Pre &) const {
+  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *, const Pre &,
+                                           const Loc &) const {
     Cursor c;
     c.p = pts + ((int64_t)b * N + i0) * C;
     const int64_t left = end - i0;
@@ -141,8 +163,9 @@ struct DepthSource {
   const float *c2l;        // (B, ncam, 16)
   const float *cal_table;  // (B, ncam, kCalibFloats) precomputed by calib_kernel, or null
   DepthParams p;
-  CellRange rg;            // range filter in cell units (fused path)
+  CellRange rg;            // range filter in cell units (fused path); on = 0 when the grid test implies it
   int vec_ok;              // 16-byte aligned float4 loads are legal
+  int cbshift;             // culling: image columns are grouped in blocks of 2^cbshift (>= 128, <= 32 blocks)
   static constexpr bool kIsDepth = true;
 
   // copy this frame's calibration into shared memory (no barrier)
@@ -189,6 +212,19 @@ struct DepthSource {
     v = fast_div(rem, p.div_w);
     u = rem - v * (uint32_t)p.W;
   }
+  struct Loc { uint32_t cam, v, u; };
+  __device__ __forceinline__ Loc locate(int64_t i0) const {
+    Loc l;
+    pixel_cvu(i0 < p.npix ? (uint32_t)i0 : 0u, l.cam, l.v, l.u);    // lanes past the end compute on pixel 0 (masked)
+    return l;
+  }
+  // Can the lane's 4 pixels (columns u..u+3 of one row, or wrapping into the next row) reach a kept voxel?
+  // s_cull[cam] has one bit per block of 2^cbshift image columns (hv_cull_kernel).
+  __device__ __forceinline__ bool lane_live(const Loc &l, const uint32_t *s_cull, int) const {
+    const uint32_t m = s_cull[l.cam];
+    if (l.u + 3 >= (uint32_t)p.W) return true;                       // wraps (or ends the row): not culled
+    return ((m >> (l.u >> cbshift)) | (m >> ((l.u + 3) >> cbshift))) & 1u;
+  }
   // stage AB: a lane owns 4 consecutive pixels
   struct Cursor {
     float z[4];
@@ -198,8 +234,8 @@ struct DepthSource {
     bool wraps;            // the 4 pixels cross a row boundary (only when W % 4 != 0)
     float tx, ty, tz;      // row part of the direct cell map (valid when !wraps)
   };
-  // The depth load does not depend on the calibration: it is issued before the CTA's prologue
-  // barrier so that its DRAM latency overlaps the claims / calibration loads.
+  // The depth load does not depend on the calibration: the load of the NEXT tile is issued before the
+  // current one is classified.
   struct Pre { float z[4]; };
   __device__ __forceinline__ Pre preload(int b, int64_t i0, int64_t end) const {
     Pre r;
@@ -215,7 +251,8 @@ struct DepthSource {
     }
     return r;
   }
-  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *s_cal, const Pre &pre) const {
+  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *s_cal, const Pre &pre,
+                                           const Loc &l) const {
     Cursor c;
     const int64_t gi = (int64_t)b * p.npix + i0;
     const int64_t left = end - i0;
@@ -232,25 +269,57 @@ struct DepthSource {
       for (int q = 0; q < 4; ++q)
         if (((c.valid >> q) & 1u) && !depth_ok(c.z[q], gi + q, b)) c.valid &= ~(1u << q);
     }
-    uint32_t v, u;
-    pixel_cvu(npx ? (uint32_t)i0 : 0u, c.cam, v, u);   // lanes past the end compute on pixel 0 (masked)
-    c.uf = (float)u;
-    c.wraps = npx && u + 3 >= (uint32_t)p.W;
-    pixel_cell_row((float)v, s_cal + c.cam * kCalibFloats, c.tx, c.ty, c.tz);
+    c.cam = l.cam;
+    c.uf = (float)l.u;
+    c.wraps = npx && l.u + 3 >= (uint32_t)p.W;
+    pixel_cell_row((float)l.v, s_cal + c.cam * kCalibFloats, c.tx, c.ty, c.tz);
     return c;
   }
-  // The direct pixel->cell map (pixel_key_fast) decides all but the pixels within its error bound
-  // of a cell / range-filter boundary; those (bit q of `und`) are redone by cell_exact.  Computed
+  // The direct pixel->cell map (rd3_common.cuh: pixel_key_fast) decides all but the pixels within its error
+  // bound of a cell / range-filter boundary; those (bit q of `und`) are redone by cell_exact.  Computed
   // for every pixel (masked ones yield garbage that is discarded): no divergence.  Lanes whose 4
   // pixels cross a row boundary (only when W % 4 != 0) leave all of them to cell_exact.
+  // Same arithmetic as pixel_key_fast, two pixels per instruction (fma.rn.f32x2 / add.rn.f32x2: each
+  // half is the separately rounded IEEE result) and the three |d| of a pixel reduced by one 3-input max.
   __device__ __forceinline__ void classify(const Cursor &c, const float *s_cal, const VoxelGrid &g, Quad &qd) const {
     const float *cal = s_cal + c.cam * kCalibFloats;
     unsigned in = 0, und = 0;
+    if (rg.on) {             // a range-filter plane the grid test does not imply: generic (scalar) form
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int r = pixel_key_fast(c.z[q], __fadd_rn(c.uf, (float)q), c.tx, c.ty, c.tz, cal, g, rg, qd.key[q]);
-      in |= (r == 1 ? 1u : 0u) << q;
-      und |= (r == 2 ? 1u : 0u) << q;
+      for (int q = 0; q < 4; ++q) {
+        const int r = pixel_key_fast(c.z[q], __fadd_rn(c.uf, (float)q), c.tx, c.ty, c.tz, cal, g, rg, qd.key[q]);
+        in |= (r == 1 ? 1u : 0u) << q;
+        und |= (r == 2 ? 1u : 0u) << q;
+      }
+    } else {
+      const float *k = cal + kCalDirect;
+      const float row[3] = {c.tx, c.ty, c.tz};
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {                   // pixels (0,1), then (2,3): half the live registers
+        const float2 z = make_float2(c.z[2 * pr], c.z[2 * pr + 1]);
+        const float2 u = fadd2(splat2(c.uf), make_float2((float)(2 * pr), (float)(2 * pr + 1)));
+        float2 m[3], d[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float2 h = ffma2(z, ffma2(splat2(k[a * 4]), u, splat2(row[a])), splat2(k[a * 4 + 3]));
+          m[a] = fadd2(h, splat2(kMagic));
+          d[a] = fsub2(h, fsub2(m[a], splat2(kMagic)));
+        }
+        const float2 thr = ffma2(z, splat2(k[12]), splat2(k[13]));
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int q = 2 * pr + e;
+          const uint32_t ix = (uint32_t)(__float_as_int(e ? m[0].y : m[0].x) - kMagicBits),
+                         iy = (uint32_t)(__float_as_int(e ? m[1].y : m[1].x) - kMagicBits),
+                         iz = (uint32_t)(__float_as_int(e ? m[2].y : m[2].x) - kMagicBits);
+          const float dmax = fmaxf(fabsf(e ? d[0].y : d[0].x), fmaxf(fabsf(e ? d[1].y : d[1].x), fabsf(e ? d[2].y : d[2].x)));
+          const bool decided = dmax < (e ? thr.y : thr.x);
+          const bool inside = (ix < (uint32_t)g.grid[0]) & (iy < (uint32_t)g.grid[1]) & (iz < (uint32_t)g.grid[2]);
+          qd.key[q] = (iz * (uint32_t)g.grid[1] + iy) * (uint32_t)g.grid[0] + ix;
+          in |= ((decided & inside) ? 1u : 0u) << q;
+          und |= (decided ? 0u : 1u) << q;
+        }
+      }
     }
     const bool fast = g.fast_ok && !c.wraps;
     qd.in = fast ? (in & c.valid) : 0u;
@@ -279,15 +348,14 @@ struct DepthSource {
 // per-call work description (device pointers, all with a leading frame dim)
 // ---------------------------------------------------------------------------
 struct HvWork {
-  unsigned long long *table;  // [B][cap]   {key:32 | min point idx:32}, empty = ~0
+  unsigned long long *table;  // [B][cap]   {key:32 | min point idx:32}, after P2 {key:32 | rank:32}; empty = ~0
   uint32_t *slots;            // [B][max_voxels*K] sorted point indices, empty = ~0
   uint32_t *flags;            // [B][nwords] bit i: point i is the first of a voxel
   int32_t *wordprefix;        // [B][nwords] exclusive popcount prefix inside the chunk
-  int32_t *chunk_base;        // [B][nchunks] totals, then exclusive bases after K2s
+  int32_t *chunk_base;        // [B][nchunks] totals, then exclusive bases after the chunk scan
   int32_t *round_claims;      // [B][kMaxRounds] voxels claimed per insert round
-  uint8_t *cand_cnt;          // [B][ntiles] candidates of each 128-point tile (0..128)
-  uint2 *cand;                // [B][N] (point idx, table slot); tile t owns [t*128, t*128+128)
-  int ntiles;
+  uint32_t *bev;              // [B][kBevWords] bird's-eye mask of the kept voxels, or null
+  uint32_t *cull;             // [B][kMaxCams] live column blocks per camera, or null (nothing culled)
   int64_t N;
   int b0;                     // first frame of the group this launch works on
   int64_t cap;
@@ -313,7 +381,7 @@ struct HvOut {
 // The table is probed linearly from the start of the key's bucket of 4 entries (= one 32-byte
 // sector).  Every probe sequence enters a bucket at its entry 0 and entries are never released, so
 // a bucket fills in order and "entry 3 is empty" <=> the bucket never overflowed <=> a key that
-// hashes here and is not in it is absent: a lookup is one 256-bit load (one L1 request, one DRAM
+// hashes here and is not in it is absent: a lookup is one 256-bit load (one L1 request, one
 // sector) however it ends, and only moves on when the bucket is full without a match.
 __device__ __forceinline__ uint32_t hash_bucket_slot(uint32_t key, int log2cap) {
   return ((key * 2654435769u) >> (34 - log2cap)) << 2;
@@ -327,13 +395,18 @@ __device__ __forceinline__ void load_bucket(const unsigned long long *p, unsigne
                : "l"(p));
 }
 
+// "point idx is / is no longer the first point of its voxel": XOR, so that the owner's toggle and the
+// toggle of whoever displaces it commute (an index that was displaced is toggled exactly twice)
+__device__ __forceinline__ void first_toggle(uint32_t *flags, uint32_t idx) {
+  atomicXor(flags + (idx >> 5), 1u << (idx & 31));
+}
+
 // Insert (key, idx).  Slot ownership is permanent (CAS from empty); the payload
 // only ever decreases (atomicMin), so a stale read can only cause a redundant
-// atomic, never a wrong skip.  *claimed = 1 iff this call created the entry.
-__device__ __forceinline__ uint32_t table_insert(unsigned long long *table, const HvWork &w,
-                                                 uint32_t key, uint32_t idx, int *claimed) {
+// atomic, never a wrong skip.  Returns 1 iff this call created the entry.
+__device__ __forceinline__ int table_insert(unsigned long long *table, uint32_t *flags, const HvWork &w,
+                                            uint32_t key, uint32_t idx) {
   const unsigned long long mine = ((unsigned long long)key << 32) | idx;
-  *claimed = 0;
   uint32_t slot;
   unsigned long long e;
   if (w.direct) {
@@ -360,248 +433,232 @@ __device__ __forceinline__ uint32_t table_insert(unsigned long long *table, cons
   while (true) {                       // `e` may be stale: the atomics decide
     if (e == kEmpty64) {
       const unsigned long long old = atomicCAS(table + slot, kEmpty64, mine);
-      if (old == kEmpty64) { *claimed = 1; return slot; }
+      if (old == kEmpty64) {
+        first_toggle(flags, idx);
+        return 1;
+      }
       e = old;
     }
     if ((uint32_t)(e >> 32) == key) {
-      if ((uint32_t)e > idx) atomicMin(table + slot, mine);
-      return slot;
+      if ((uint32_t)e > idx) {
+        const unsigned long long old = atomicMin(table + slot, mine);
+        if ((uint32_t)old > idx) {     // this point is the voxel's first one now, the previous holder is not
+          first_toggle(flags, idx);
+          first_toggle(flags, (uint32_t)old);
+        }
+      }
+      return 0;
     }
     slot = (slot + 1) & w.cap_mask;    // lost the entry to another key: plain linear probing from here
     e = __ldcg(table + slot);
   }
 }
 
-// Lookup only (the table is not written while lookups run); kEmpty32 when the key is absent.
-__device__ __forceinline__ uint32_t table_find(const unsigned long long *table, const HvWork &w,
-                                               uint32_t key) {
-  if (w.direct) return __ldcg(table + key) == kEmpty64 ? kEmpty32 : key;
+// Lookup after P2 (the table is not written any more): the voxel's rank, kEmpty32 when the key is absent or
+// its voxel was dropped (rank >= max_voxels).
+__device__ __forceinline__ uint32_t table_rank(const unsigned long long *table, const HvWork &w, uint32_t key) {
+  if (w.direct) return (uint32_t)__ldcg(table + key);            // empty entries read ~0 as well
   uint32_t s0 = hash_bucket_slot(key, w.log2cap);
   while (true) {
     unsigned long long e0, e1, e2, e3;
     load_bucket(table + s0, e0, e1, e2, e3);
-    int q = 4;
-    q = (uint32_t)(e3 >> 32) == key ? 3 : q;
-    q = (uint32_t)(e2 >> 32) == key ? 2 : q;
-    q = (uint32_t)(e1 >> 32) == key ? 1 : q;
-    q = (uint32_t)(e0 >> 32) == key ? 0 : q;
-    if (q < 4) return s0 + q;
-    if ((uint32_t)(e3 >> 32) == kEmpty32) return kEmpty32;    // no valid key is ~0
+    uint32_t r = kEmpty32;
+    bool hit = false;
+    if ((uint32_t)(e3 >> 32) == key) { r = (uint32_t)e3; hit = true; }
+    if ((uint32_t)(e2 >> 32) == key) { r = (uint32_t)e2; hit = true; }
+    if ((uint32_t)(e1 >> 32) == key) { r = (uint32_t)e1; hit = true; }
+    if ((uint32_t)(e0 >> 32) == key) { r = (uint32_t)e0; hit = true; }
+    if (hit || (uint32_t)(e3 >> 32) == kEmpty32) return r;       // no valid key is ~0
     s0 = (s0 + 4) & w.cap_mask;
   }
 }
 
-// K1 ------------------------------------------------------------------------
-// grid (ceil((end-begin)/1024), frames), 256 threads; every WARP owns a tile of 128
-// consecutive points and runs its stages without block barriers:
-//   AB each lane walks its 4 consecutive points (one 16-byte load): validity, voxel cell
-//      by the conservative fast path; in-range keys and the few undecided points are
-//      ballot-compacted; the undecided ones are redone with exact IEEE arithmetic
-//   C  dense lanes: table insert (or lookup once max_voxels voxels exist);
-//      hits go to the tile's own region of the candidate list (no global counter)
-template <class Src>
-__global__ void __launch_bounds__(kInsThreads, RD3_INS_MINB)
-    hv_insert_kernel(Src src, VoxelGrid g, HvWork w, int64_t begin, int64_t end, int round) {
+// Keep the K smallest point indices of a voxel, sorted, with atomicMin only.  Slot 0 holds the voxel's first
+// point (the smallest index of all, written by P2).  Every other point cascades through the row: a value
+// reaches slot k only after losing against the slots before it, so the non-empty prefix is strictly
+// increasing at all times and the final content is independent of arrival order.
+__device__ __forceinline__ void slot_insert(uint32_t *S, int K, uint32_t idx) {
+  // a (possibly stale, hence larger) copy of the last slot that is already smaller: K smaller indices exist
+  if (__ldcg(S + K - 1) < idx) return;
+  uint32_t cur = idx;
+  int k = 0;
+  // Skip the prefix of smaller indices with 8 independent loads at a time instead of one
+  // dependent load per slot.  A slot read as smaller than cur can only have decreased since: it stays smaller.
+  while (k < K) {
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (k + i < K) ? __ldcg(S + k + i) : kEmpty32;
+    int i = 8;
+    bool same = false;
+#pragma unroll
+    for (int q = 7; q >= 0; --q) {
+      i = (v[q] < cur) ? i : q;      // first slot not smaller than cur
+      same |= v[q] == cur;
+    }
+    if (same) return;                // already there (the voxel's first point)
+    k += i;
+    if (i < 8) break;
+  }
+  for (; k < K; ++k) {
+    const uint32_t old = atomicMin(S + k, cur);
+    if (old == kEmpty32 || old == cur) return;
+    if (old > cur) cur = old;            // displaced a larger index: carry it on
+  }
+}
+
+// P1 / P3 ---------------------------------------------------------------------
+// grid (ceil((end-begin) / (8 * iters * 128)), frames), 256 threads; every WARP owns a strip of `iters`
+// consecutive 128-point tiles and runs without block barriers after the prologue:
+//   per tile: one 16-byte load per lane (4 consecutive points; the next tile's load is already in
+//        flight), validity, voxel cell by the conservative fast path; in-range keys are appended to the
+//        warp's item list, the few undecided points to its second list
+//   full 32-lane passes over the item list: MODE 0 table insert; MODE 1 table lookup -> rank -> slot row
+//   undecided points: exact IEEE arithmetic, once 32 have collected or at the end of the strip
+template <class Src, int MODE>
+__global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MINB)
+    hv_pass_kernel(Src src, VoxelGrid g, HvWork w, int32_t *point2voxel, int64_t begin, int64_t end, int round,
+                   int iters) {
   __shared__ __align__(16) float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 4];
   __shared__ __align__(8) uint64_t s_bar;        // completion of the calibration's TMA copy
-  __shared__ uint2 s_itemb[kInsSpan];            // (key, local point id) of the in-range points
-  __shared__ uint8_t s_undb[kInsSpan];           // local ids of the undecided points
-  __shared__ int s_prev, s_claims, s_done;
+  __shared__ uint2 s_itemb[kPassWarps * kListCap];     // (key, strip-local point id) of the in-range points
+  __shared__ uint16_t s_undb[kPassWarps * kListCap];   // strip-local ids of the undecided points
+  __shared__ uint32_t s_cull[kMaxCams];
+  __shared__ int s_prev;
 
   const int b = blockIdx.y + w.b0;
   const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  const int64_t block_base = begin + (int64_t)blockIdx.x * kInsSpan;
-  if (block_base >= end) return;
-#if RD3_LATE_CLAIMS
-#if RD3_KNOCK
-#error "the RD3_KNOCK builds need the claims before the prologue barrier"
-#endif
-  // The source-level profile puts 14 % of all warp time on the prologue barrier: seven warps wait there for
-  // warp 0's load of the round claims, a value that is first needed at stage C.  Here the barrier only covers
-  // the mbarrier inits + the calibration copy; warp 0 loads the claims after it and publishes them through a
-  // one-shot mbarrier that the other warps look at when they reach stage C (by then it has long completed).
-  __shared__ __align__(8) uint64_t s_bar2;
-  if (tid == 0) { s_claims = 0; s_done = 0; mbar_init(&s_bar2, 1); }
-  const typename Src::Pre pre = src.preload(b, block_base + wv * kTilePoints + 4 * lane, end);
-  const bool cal_async = src.stage_async(s_cal, &s_bar, b);
-  __syncthreads();
-  if (wv == 0) {
-    int c = 0;
-    for (int r = lane; r < round; r += 32) c += __ldcg(w.round_claims + b * kMaxRounds + r);
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if (lane == 0) {
-      s_prev = c;
-      mbar_arrive(&s_bar2);               // release: s_prev is visible to whoever sees the phase complete
-    }
-  }
-  if (cal_async) tma_wait(&s_bar);
-#else
-  if (tid == 0) { s_claims = 0; s_done = 0; }
-  const typename Src::Pre pre = src.preload(b, block_base + wv * kTilePoints + 4 * lane, end);
-  if (wv == 0) {
-    // voxels claimed by the previous rounds: insert vs lookup-only for the whole round
+  const int64_t strip = (int64_t)iters * kTilePoints;
+  const int64_t cta_base = begin + (int64_t)blockIdx.x * kPassWarps * strip;
+  if (cta_base >= end) return;
+  if (MODE == 0 && wv == 0) {
+    // voxels claimed by the previous rounds: once max_voxels exist the frame is closed
     int c = 0;
     for (int r = lane; r < round; r += 32) c += __ldcg(w.round_claims + b * kMaxRounds + r);
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
     if (lane == 0) s_prev = c;
   }
+  if (MODE == 1 && Src::kIsDepth && tid < kMaxCams) s_cull[tid] = w.cull ? __ldg(w.cull + b * kMaxCams + tid) : 0xFFFFFFFFu;
   const bool cal_async = src.stage_async(s_cal, &s_bar, b);
   __syncthreads();
   if (cal_async) tma_wait(&s_bar);
-  const bool lookup_only = s_prev >= w.max_voxels;
-#endif
+  if (MODE == 0 && s_prev >= w.max_voxels) return;
 
-  if (block_base + wv * kTilePoints >= end) return;
-#if RD3_KNOCK >= 3
-  if (lookup_only) {                                        // timing only: prologue + depth load
-    if (lane == 0 && sizeof(pre) == 16 && reinterpret_cast<const float *>(&pre)[0] == 123.456f) w.cand_cnt[0] = 1;
-    return;
-  }
-#endif
-  uint2 *s_item = s_itemb + wv * kTilePoints;
-  uint8_t *s_und = s_undb + wv * kTilePoints;
+  const int64_t sb = cta_base + wv * strip;                 // this warp's strip [sb, se)
+  if (sb >= end) return;
+  const int64_t se = sb + strip < end ? sb + strip : end;
+  uint2 *s_item = s_itemb + wv * kListCap;
+  uint16_t *s_und = s_undb + wv * kListCap;
   unsigned long long *table = w.table + (int64_t)b * w.cap;
-  int claims = 0;
-  const int64_t base = block_base + wv * kTilePoints;     // this warp's tile
+  uint32_t *flags = w.flags + (int64_t)b * w.nwords;
+  uint32_t *slots = w.slots + (int64_t)b * w.max_voxels * w.K;
+  int cnt = 0, nu = 0, claims = 0;
 
-  // ---- stage AB ---------------------------------------------------------------------
-  int n2, nu;
-  {
-    typename Src::Cursor cur = src.cursor(b, base + 4 * lane, end, s_cal, pre);
+  typename Src::Loc loc = src.locate(sb + 4 * lane);
+  bool live = MODE == 0 || !Src::kIsDepth || __any_sync(0xffffffffu, src.lane_live(loc, s_cull, 0));
+  typename Src::Pre pre = src.preload(b, live ? sb + 4 * lane : se, se);
+  int64_t tb = sb;
+  bool flushing = false;
+  // One loop, one copy of each stage (the kernel has to stay inside the instruction cache): item passes while
+  // 32 items are waiting, exact passes while 32 undecided points are waiting, else the next tile; at the end
+  // of the strip the two lists are flushed with partial passes.  Both lists are consumed from their END.
+#pragma unroll 1
+  while (true) {
+    if (cnt >= 32 || (flushing && nu == 0 && cnt > 0)) {
+      // ---- item pass: MODE 0 table insert, MODE 1 table lookup -> rank -> slot row ----
+      const int n = cnt < 32 ? cnt : 32;
+      if (lane < n) {
+        const uint2 it = s_item[cnt - n + lane];
+        const uint32_t idx = (uint32_t)sb + it.y;
+        if (MODE == 0) {
+          claims += table_insert(table, flags, w, it.x, idx);
+        } else {
+          const uint32_t r = table_rank(table, w, it.x);
+          if (r != kEmpty32) {
+            slot_insert(slots + (int64_t)r * w.K, w.K, idx);
+            if (point2voxel) point2voxel[(int64_t)b * w.N + idx] = (int32_t)r;
+          }
+        }
+      }
+      cnt -= n;
+      __syncwarp();
+      continue;
+    }
+    if (nu >= 32 || (flushing && nu > 0)) {
+      // ---- exact pass: IEEE arithmetic of the reference for up to 32 undecided points; hits join the item list ----
+      const int n = nu < 32 ? nu : 32;
+      bool in = false;
+      int lid = 0, cx, cy, cz;
+      if (lane < n) {
+        lid = s_und[nu - n + lane];
+        in = src.cell_exact(b, sb + lid, s_cal, g, cx, cy, cz);
+      }
+      const unsigned b1 = __ballot_sync(0xffffffffu, in);
+      if (in) s_item[cnt + __popc(b1 & lt)] = make_uint2(voxel_key(cx, cy, cz, g), (uint32_t)lid);
+      cnt += __popc(b1);
+      nu -= n;
+      __syncwarp();
+      continue;
+    }
+    if (tb >= se) {
+      if (flushing) break;
+      flushing = true;
+      continue;
+    }
+    // ---- next tile ----
+    const int64_t i0 = tb + 4 * lane;
+    const typename Src::Loc cloc = loc;
+    const typename Src::Pre cpre = pre;
+    const bool clive = live;
+    const uint32_t l0 = (uint32_t)(tb - sb) + 4 * lane;
+    tb += kTilePoints;
+    if (tb < se) {                                          // the tile after this one: position, liveness, depth load
+      loc = src.locate(i0 + kTilePoints);
+      live = MODE == 0 || !Src::kIsDepth || __any_sync(0xffffffffu, src.lane_live(loc, s_cull, 0));
+      pre = src.preload(b, live ? i0 + kTilePoints : se, se);
+    }
+    if (!clive) continue;                                   // no pixel of this tile can reach a kept voxel
+    typename Src::Cursor cur = src.cursor(b, i0, se, s_cal, cpre, cloc);
     Quad qd;
     src.classify(cur, s_cal, g, qd);
-#if RD3_PREFETCH
-    // 23 % of the kernel's stall samples are the long-scoreboard wait for the probed bucket.  The key is known
-    // here, the probe only happens after the compaction: a prefetch (no register, no dependency) starts the
-    // DRAM access now, so that the probe finds its sector in L2.
-    if (!w.direct) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if ((qd.in >> q) & 1u)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(table + hash_bucket_slot(qd.key[q], w.log2cap)));
-    }
-#endif
     // exclusive prefix of the per-lane counts (0..4) from three ballots of the count's bit planes
-    const unsigned cin = __popc(qd.in);
+    const unsigned in = qd.in;
+    const unsigned cin = __popc(in);
     const unsigned p0 = __ballot_sync(0xffffffffu, cin & 1u), p1 = __ballot_sync(0xffffffffu, cin & 2u),
                    p2 = __ballot_sync(0xffffffffu, cin & 4u);
-    n2 = __popc(p0) + 2 * __popc(p1) + 4 * __popc(p2);
-    uint2 *it = s_item + (__popc(p0 & lt) + 2 * __popc(p1 & lt) + 4 * __popc(p2 & lt));
-    const unsigned in = qd.in;
+    uint2 *it = s_item + cnt + (__popc(p0 & lt) + 2 * __popc(p1 & lt) + 4 * __popc(p2 & lt));
     // the order inside the list is irrelevant: point q of the lane goes to the lane's slot #(set bits below q)
-    if (in & 1u) it[0] = make_uint2(qd.key[0], (uint32_t)(4 * lane));
-    if (in & 2u) it[in & 1u] = make_uint2(qd.key[1], (uint32_t)(4 * lane + 1));
-    if (in & 4u) it[__popc(in & 3u)] = make_uint2(qd.key[2], (uint32_t)(4 * lane + 2));
-    if (in & 8u) it[__popc(in & 7u)] = make_uint2(qd.key[3], (uint32_t)(4 * lane + 3));
-    nu = 0;
+    if (in & 1u) it[0] = make_uint2(qd.key[0], l0);
+    if (in & 2u) it[in & 1u] = make_uint2(qd.key[1], l0 + 1);
+    if (in & 4u) it[__popc(in & 3u)] = make_uint2(qd.key[2], l0 + 2);
+    if (in & 8u) it[__popc(in & 7u)] = make_uint2(qd.key[3], l0 + 3);
+    cnt += __popc(p0) + 2 * __popc(p1) + 4 * __popc(p2);
     if (__any_sync(0xffffffffu, qd.und != 0u)) {
       const unsigned cun = __popc(qd.und);
       const unsigned u0 = __ballot_sync(0xffffffffu, cun & 1u), u1 = __ballot_sync(0xffffffffu, cun & 2u),
                      u2 = __ballot_sync(0xffffffffu, cun & 4u);
-      nu = __popc(u0) + 2 * __popc(u1) + 4 * __popc(u2);
-      int ua = __popc(u0 & lt) + 2 * __popc(u1 & lt) + 4 * __popc(u2 & lt);
+      int ua = nu + __popc(u0 & lt) + 2 * __popc(u1 & lt) + 4 * __popc(u2 & lt);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if ((qd.und >> q) & 1u) s_und[ua++] = (uint8_t)(4 * lane + q);
+        if ((qd.und >> q) & 1u) s_und[ua++] = (uint16_t)(l0 + q);
+      nu += __popc(u0) + 2 * __popc(u1) + 4 * __popc(u2);
     }
+    __syncwarp();
   }
-  __syncwarp();
-#if RD3_KNOCK >= 1
-  if (lookup_only) nu = 0;                                  // timing only: no exact redo of undecided points
-#endif
-#if RD3_KNOCK >= 2
-  if (lookup_only) {                                        // timing only: no table probes
-    if (lane == 0) w.cand_cnt[(int64_t)b * w.ntiles + (base >> kTileShift)] = (uint8_t)(n2 == 77777);
-    return;
-  }
-#endif
-#pragma unroll 1
-  for (int j0 = 0; j0 < nu; j0 += 32) {       // within the error bound of a boundary: exact arithmetic
-    const int j = j0 + lane;
-    bool in = false;
-    int lid = 0, cx, cy, cz;
-    if (j < nu) {
-      lid = s_und[j];
-      in = src.cell_exact(b, base + lid, s_cal, g, cx, cy, cz);
-    }
-    const unsigned b1 = __ballot_sync(0xffffffffu, in);
-    if (in) s_item[n2 + __popc(b1 & lt)] = make_uint2(voxel_key(cx, cy, cz, g), (uint32_t)lid);
-    n2 += __popc(b1);
-  }
-  __syncwarp();
-
-  // ---- stage C ----------------------------------------------------------------------
-#if RD3_LATE_CLAIMS
-  tma_wait(&s_bar2);
-  const bool lookup_only = s_prev >= w.max_voxels;
-#endif
-  uint2 *cand = w.cand + (int64_t)b * w.N + base;
-  int nc = 0;
-#pragma unroll 1
-  for (int j0 = 0; j0 < n2; j0 += 32) {
-    const int j = j0 + lane;
-    uint32_t slot = kEmpty32, idx = 0;
-    if (j < n2) {
-      const uint2 it = s_item[j];
-      idx = (uint32_t)base + it.y;
-      if (lookup_only) {
-        slot = table_find(table, w, it.x);
-      } else {
-        int c;
-        slot = table_insert(table, w, it.x, idx, &c);
-        claims += c;
-      }
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, slot != kEmpty32);
-    if (slot != kEmpty32) cand[nc + __popc(bal & lt)] = make_uint2(idx, slot);
-    nc += __popc(bal);
-  }
-  if (lane == 0) w.cand_cnt[(int64_t)b * w.ntiles + (base >> kTileShift)] = (uint8_t)nc;
-  if (!lookup_only) {
-    // one global atomic per CTA: the last warp to finish adds the CTA's claims to the round's counter
+  if (MODE == 0) {
     for (int d = 16; d > 0; d >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, d);
-    if (lane == 0) {
-      const int64_t left = end - block_base;
-      const int nwarps = left >= kInsSpan ? kInsThreads / 32 : (int)((left + kTilePoints - 1) >> kTileShift);
-      if (claims) atomicAdd(&s_claims, claims);
-      __threadfence_block();
-      if (atomicAdd(&s_done, 1) == nwarps - 1) {
-        const int c = atomicAdd(&s_claims, 0);
-        if (c) atomicAdd(w.round_claims + b * kMaxRounds + round, c);
-      }
-    }
+    if (lane == 0 && claims) atomicAdd(w.round_claims + b * kMaxRounds + round, claims);
   }
 }
 
-// K2a -----------------------------------------------------------------------
-// every table entry marks its voxel's first point.  grid (gx, frames), grid-stride over the
-// table so that the launch has a few thousand fat blocks instead of cap/256 per frame.
-static __global__ void __launch_bounds__(256) hv_first_kernel(HvWork w) {
-  const int b = blockIdx.y + w.b0;
-  const unsigned long long *table = w.table + (int64_t)b * w.cap;
-  uint32_t *flags = w.flags + (int64_t)b * w.nwords * (RD3_RANK_PACKED ? 2 : 1);
-  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < w.cap;
-       s += (int64_t)gridDim.x * blockDim.x) {
-    const unsigned long long e = __ldg(table + s);
-    if (e == kEmpty64) continue;
-    const uint32_t first = (uint32_t)e;
-    atomicOr(flags + (first >> 5) * (RD3_RANK_PACKED ? 2 : 1), 1u << (first & 31));
-  }
-}
-
-// K2b -----------------------------------------------------------------------
+// P2a -----------------------------------------------------------------------
 // grid (nchunks, B), kScanThreads threads, one flag word each.
 static __global__ void __launch_bounds__(kScanThreads) hv_flagscan_kernel(HvWork w) {
   __shared__ int s_warp[kScanThreads / 32];
   const int b = blockIdx.y + w.b0;
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
   const int64_t wi = (int64_t)b * w.nwords + (int64_t)blockIdx.x * kChunkWords + threadIdx.x;
-#if RD3_RANK_PACKED
-  const int cnt = __popc(w.flags[2 * wi]);
-#else
   const int cnt = __popc(w.flags[wi]);
-#endif
   const int inc = warp_inclusive_scan(cnt);
   if (lane == 31) s_warp[wv] = inc;
   __syncthreads();
@@ -612,11 +669,7 @@ static __global__ void __launch_bounds__(kScanThreads) hv_flagscan_kernel(HvWork
     if (k < wv) base += t;
     total += t;
   }
-#if RD3_RANK_PACKED
-  w.flags[2 * wi + 1] = (uint32_t)(base + inc - cnt);
-#else
   w.wordprefix[wi] = base + inc - cnt;
-#endif
   if (threadIdx.x == 0) w.chunk_base[(int64_t)b * w.nchunks + blockIdx.x] = total;
 }
 
@@ -643,7 +696,7 @@ __device__ __forceinline__ void chunk_scan_store(uint32_t my_word, int *s_warp, 
   if (threadIdx.x == 0) chunk_total[blockIdx.x] = total;
 }
 
-// K2s -----------------------------------------------------------------------
+// P2s -----------------------------------------------------------------------
 // one CTA per frame: exclusive scan of the chunk totals in place; the frame's
 // total (clamped) goes to out_total[b].
 static __global__ void __launch_bounds__(1024) scan_chunks_kernel(int32_t *chunk_base, int nchunks,
@@ -685,123 +738,167 @@ static __global__ void __launch_bounds__(1024) scan_chunks_kernel(int32_t *chunk
 __device__ __forceinline__ int voxel_rank(const HvWork &w, int b, uint32_t first_idx) {
   const uint32_t word = first_idx >> 5;
   const int64_t wi = (int64_t)b * w.nwords + word;
-#if RD3_RANK_PACKED
-  const uint2 fw = __ldg(reinterpret_cast<const uint2 *>(w.flags) + wi);
-  return __ldg(w.chunk_base + (int64_t)b * w.nchunks + (first_idx >> kChunkShift)) + (int)fw.y +
-         __popc(fw.x & ((1u << (first_idx & 31)) - 1u));
-#else
   const uint32_t bits = __ldg(w.flags + wi) & ((1u << (first_idx & 31)) - 1u);
   return __ldg(w.chunk_base + (int64_t)b * w.nchunks + (first_idx >> kChunkShift)) +
          __ldg(w.wordprefix + wi) + __popc(bits);
-#endif
 }
 
-// Keep the K smallest point indices of a voxel, sorted, with atomicMin only.
-// Slot 0 is reserved for the voxel's first point (known from the table), which is
-// stored without an atomic; every other point cascades through slots 1..K-1:
-// a value reaches slot k only after losing against the slots before it, so the
-// non-empty prefix is strictly increasing at all times and the final content is
-// independent of arrival order.  `s_last` is a (possibly stale, hence larger) copy of
-// slot K-1: if it is already smaller than idx, K smaller indices exist.
-__device__ __forceinline__ void slot_insert_tail(uint32_t *S, int K, uint32_t idx) {
-  uint32_t cur = idx;
-  int k = 1;
-  // Skip the prefix of smaller indices with 8 independent loads at a time instead of one
-  // dependent load per slot (a voxel that already holds 7 points would cost 7 round trips).
-  // A slot read as smaller than cur can only have decreased since: it stays smaller.
-  while (k < K) {
-    uint32_t v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (k + i < K) ? __ldcg(S + k + i) : kEmpty32;
-    int i = 8;
-#pragma unroll
-    for (int q = 7; q >= 0; --q) i = (v[q] < cur) ? i : q;      // first slot not smaller than cur
-    k += i;
-    if (i < 8) break;
-  }
-  for (; k < K; ++k) {
-    const uint32_t old = atomicMin(S + k, cur);
-    if (old == kEmpty32 || old == cur) return;
-    if (old > cur) cur = old;            // displaced a larger index: carry it on
-  }
-}
-
-// K3 ------------------------------------------------------------------------
-// grid (ceil(ntiles/(4*kSlotTiles)), frames), 128 threads (small CTAs: warps finish at very different times
-// and a CTA's slot is only recycled when all have).  A warp works off the candidate regions of kSlotTiles
-// consecutive tiles as ONE list: a warp scan of the counts gives each tile's offset, lane j of
-// a pass finds its (tile, k) by a log2(kSlotTiles)-step search over those offsets, so the lanes stay dense however
-// few candidates a tile has (the lookup-only rounds leave ~5 per tile).
-// Neighbouring pixels often share a voxel: lanes holding the same table slot form a
-// group (__match_any_sync); only the group leader walks table -> rank -> last slot and
-// broadcasts the result, and a whole group leaves after one load when the voxel is full.
-static __global__ void __launch_bounds__(128) hv_slots_kernel(HvWork w, int32_t *point2voxel) {
+// P2r -----------------------------------------------------------------------
+// One pass over the table, grid (gx, frames), grid-stride.  Entry {key | first point} -> {key | rank}
+// ({key | ~0} for the voxels the reference drops); row r of the slots gets its first point; coors[r] is the
+// key decoded as (z, y, x); the kept voxels are marked in the frame's bird's-eye mask.
+static __global__ void __launch_bounds__(256) hv_rank_kernel(HvWork w, VoxelGrid g, int32_t *coors) {
+  __shared__ uint32_t s_bev[kBevWords];
   const int b = blockIdx.y + w.b0;
-  const int lane = threadIdx.x & 31;
-  const int t0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kSlotTiles;
-  if (t0 >= w.ntiles) return;
-  const int mine = (lane < kSlotTiles && t0 + lane < w.ntiles) ? w.cand_cnt[(int64_t)b * w.ntiles + t0 + lane] : 0;
-  const int inc = warp_inclusive_scan(mine);
-  const int excl = inc - mine;
-  const int n = __shfl_sync(0xffffffffu, inc, 31);
-  const uint2 *cand = w.cand + (int64_t)b * w.N + ((int64_t)t0 << kTileShift);
-  const unsigned long long *table = w.table + (int64_t)b * w.cap;
-  for (int j0 = 0; j0 < n; j0 += 32) {
-    const int j = j0 + lane;
-    const bool on = j < n;
-    // tile of list position j: the largest lane t with excl[t] <= j (empty tiles share their
-    // offset with the next non-empty one, which the "largest" picks)
-    int t = 0;
-#pragma unroll
-    for (int step = kSlotTiles / 2; step > 0; step >>= 1) {
-      const int e = __shfl_sync(0xffffffffu, excl, t + step);
-      if (e <= j) t += step;
+  unsigned long long *table = w.table + (int64_t)b * w.cap;
+  if (w.bev) {
+    for (int i = threadIdx.x; i < kBevWords; i += blockDim.x) s_bev[i] = 0u;
+    __syncthreads();
+  }
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < w.cap;
+       s += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long e = __ldcs(table + s);
+    if (e == kEmpty64) continue;
+    const uint32_t first = (uint32_t)e, key = (uint32_t)(e >> 32);
+    const int r = voxel_rank(w, b, first);
+    if (r >= w.max_voxels) {
+      table[s] = e | 0xFFFFFFFFull;
+      continue;
     }
-    const int k = j - __shfl_sync(0xffffffffu, excl, t);
-    const uint2 c = on ? __ldg(cand + (t << kTileShift) + k) : make_uint2(0u, kEmpty32 - lane);   // distinct dummies
-    const unsigned grp = __match_any_sync(0xffffffffu, c.y);
-    const int leader = __ffs(grp) - 1;
-    uint32_t first_idx = 0, last = 0;
-    int r = w.max_voxels;
-    if (on && lane == leader) {
-      first_idx = (uint32_t)__ldg(table + c.y);
-      r = voxel_rank(w, b, first_idx);
+    table[s] = (e & 0xFFFFFFFF00000000ull) | (uint32_t)r;
+    const int64_t vr = (int64_t)b * w.max_voxels + r;
+    w.slots[vr * w.K] = first;
+    int cz, cy, cx;
+    key_to_zyx(key, g, cz, cy, cx);
+    coors[vr * 3 + 0] = cz;
+    coors[vr * 3 + 1] = cy;
+    coors[vr * 3 + 2] = cx;
+    if (w.bev) {
+      const uint32_t bx = (uint32_t)cx * kBevDim / (uint32_t)g.grid[0], by = (uint32_t)cy * kBevDim / (uint32_t)g.grid[1];
+      const uint32_t bit = by * kBevDim + bx;
+      const uint32_t m = 1u << (bit & 31);
+      if (!(s_bev[bit >> 5] & m)) atomicOr(s_bev + (bit >> 5), m);
     }
-    first_idx = __shfl_sync(0xffffffffu, first_idx, leader);
-    r = __shfl_sync(0xffffffffu, r, leader);
-    // the last slot is only needed by points that are not their voxel's first point
-    const bool tail = on && r < w.max_voxels && w.K > 1 && c.x != first_idx;
-    const unsigned tails = __ballot_sync(0xffffffffu, tail);
-    if (tails & grp) {
-      if (lane == leader) last = __ldcg(w.slots + ((int64_t)b * w.max_voxels + r) * w.K + (w.K - 1));
-      last = __shfl_sync(grp, last, leader);
-    }
-    if (on && r < w.max_voxels) {
-      uint32_t *S = w.slots + ((int64_t)b * w.max_voxels + r) * w.K;
-      if (c.x == first_idx) S[0] = c.x;                       // the voxel's first point
-      else if (w.K > 1 && !(last < c.x)) slot_insert_tail(S, w.K, c.x);
-      if (point2voxel) point2voxel[(int64_t)b * w.N + c.x] = r;
+  }
+  if (w.bev) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kBevWords; i += blockDim.x) {
+      const uint32_t v = s_bev[i];
+      if (v) atomicOr(w.bev + (int64_t)b * kBevWords + i, v);
     }
   }
 }
 
-// K4 ------------------------------------------------------------------------
+// P2c -----------------------------------------------------------------------
+// grid (frames), 256 threads.  For every camera and block of 2^cbshift image columns: is there a kept voxel
+// that a pixel of the block can fall into?  A pixel (u, v, z > 0) lands at the continuous cell coordinate
+//   P = z * Mc (u, v, 1)^T + T,   Mc = [A B C] of the direct cell map (rd3_common.cuh), T = Th + 0.5,
+// and its reference cell is within tol(z) <= tolmax of floor(P) (the proven bound of that map), so with
+// w = Mc^-1 (P - T) = (z u, z v, z) the block's pixels fill the wedge
+//   w3 >= 0,  w1 - u0 w3 >= 0,  u1 w3 - w1 >= 0,  w2 >= 0,  (H-1) w3 - w2 >= 0.
+// A bird's-eye cell (a box over all z, widened by 1 + 2 tolmax cells) that lies entirely on the negative side of
+// one of these five planes cannot receive a pixel of the block; the largest value of a plane function over a
+// box is its value at the centre plus |n| . half-extents.  Everything is evaluated in fp64; a camera whose
+// map is singular / non-finite keeps all its blocks.
+static __global__ void __launch_bounds__(256) hv_cull_kernel(DepthSource src, VoxelGrid g, HvWork w) {
+  __shared__ uint32_t s_bev[kBevWords];
+  __shared__ double s_inv[kMaxCams][9], s_T[kMaxCams][3], s_margin[kMaxCams];
+  __shared__ int s_ok[kMaxCams];
+  __shared__ uint32_t s_mask[kMaxCams];
+  const int b = blockIdx.x + w.b0;
+  const int ncam = src.p.ncam;
+  for (int i = threadIdx.x; i < kBevWords; i += blockDim.x) s_bev[i] = w.bev[(int64_t)b * kBevWords + i];
+  if (threadIdx.x < kMaxCams) s_mask[threadIdx.x] = 0u;
+  if (threadIdx.x < ncam) {
+    const int cam = threadIdx.x;
+    const float *k = src.cal_table + ((int64_t)b * ncam + cam) * kCalibFloats + kCalDirect;
+    double m[9];
+    for (int a = 0; a < 3; ++a) {
+      m[a * 3 + 0] = k[a * 4 + 0]; m[a * 3 + 1] = k[a * 4 + 1]; m[a * 3 + 2] = k[a * 4 + 2];
+      s_T[cam][a] = (double)k[a * 4 + 3] + 0.5;
+    }
+    const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+    const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+    double scale = 0.0;
+    for (int i = 0; i < 9; ++i) scale = fmax(scale, fabs(m[i]));
+    const double id = 1.0 / det;
+    s_inv[cam][0] = c00 * id; s_inv[cam][1] = (m[2] * m[7] - m[1] * m[8]) * id; s_inv[cam][2] = (m[1] * m[5] - m[2] * m[4]) * id;
+    s_inv[cam][3] = c01 * id; s_inv[cam][4] = (m[0] * m[8] - m[2] * m[6]) * id; s_inv[cam][5] = (m[2] * m[3] - m[0] * m[5]) * id;
+    s_inv[cam][6] = c02 * id; s_inv[cam][7] = (m[1] * m[6] - m[0] * m[7]) * id; s_inv[cam][8] = (m[0] * m[4] - m[1] * m[3]) * id;
+    // tol(z) = 0.5 - thr(z) >= the proven bound; largest at the largest valid depth
+    const double tolmax = 0.5 - ((double)src.p.zmax * (double)k[12] + (double)k[13]);
+    s_margin[cam] = 1.0 + 2.0 * tolmax;
+    bool ok = fabs(det) > 1e-12 * scale * scale * scale && isfinite(id) && tolmax >= 0.0 && tolmax < 1e6;
+    for (int i = 0; i < 9; ++i) ok = ok && isfinite(s_inv[cam][i]);
+    for (int a = 0; a < 3; ++a) ok = ok && isfinite(s_T[cam][a]);
+    s_ok[cam] = ok ? 1 : 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const int nblk = ((src.p.W - 1) >> src.cbshift) + 1;
+  const double gx = g.grid[0], gy = g.grid[1], gz = g.grid[2];
+  for (int pair = wv; pair < ncam * nblk; pair += blockDim.x >> 5) {
+    const int cam = pair / nblk, blk = pair - cam * nblk;
+    bool hit = false;
+    if (!s_ok[cam]) {
+      hit = true;
+    } else {
+      const double *iv = s_inv[cam];
+      const double u0 = (double)(blk << src.cbshift);
+      double u1 = (double)(((blk + 1) << src.cbshift) - 1);
+      if (u1 > (double)(src.p.W - 1)) u1 = (double)(src.p.W - 1);
+      const double hm1 = (double)(src.p.H - 1);
+      // plane normals n (rows: w3 | w1 - u0 w3 | u1 w3 - w1 | w2 | (H-1) w3 - w2)
+      double n[5][3];
+      for (int a = 0; a < 3; ++a) {
+        n[0][a] = iv[6 + a];
+        n[1][a] = iv[a] - u0 * iv[6 + a];
+        n[2][a] = u1 * iv[6 + a] - iv[a];
+        n[3][a] = iv[3 + a];
+        n[4][a] = hm1 * iv[6 + a] - iv[3 + a];
+      }
+      const double mg = s_margin[cam];
+      const double hx = 0.5 * gx / kBevDim + 1.0 + mg, hy = 0.5 * gy / kBevDim + 1.0 + mg, hz = 0.5 * gz + mg;
+      double cst[5], slack[5];
+      for (int k = 0; k < 5; ++k) {
+        // z part (the box spans the whole height), -n.T and the half-extent terms are the same for every cell
+        cst[k] = n[k][2] * (0.5 * gz - s_T[cam][2]) - n[k][0] * s_T[cam][0] - n[k][1] * s_T[cam][1] +
+                 fabs(n[k][0]) * hx + fabs(n[k][1]) * hy + fabs(n[k][2]) * hz;
+        slack[k] = 1e-9 * (fabs(n[k][0]) * (gx + fabs(s_T[cam][0]) + hx) + fabs(n[k][1]) * (gy + fabs(s_T[cam][1]) + hy) +
+                           fabs(n[k][2]) * (gz + fabs(s_T[cam][2]) + hz));
+      }
+      for (int wi = lane; wi < kBevWords && !hit; wi += 32) {
+        uint32_t bits = s_bev[wi];
+        while (bits && !hit) {
+          const int bp = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int cell = wi * 32 + bp;
+          const double cxc = ((double)(cell % kBevDim) + 0.5) * gx / kBevDim, cyc = ((double)(cell / kBevDim) + 0.5) * gy / kBevDim;
+          bool out = false;
+          for (int k = 0; k < 5; ++k) out = out || (cst[k] + n[k][0] * cxc + n[k][1] * cyc < -slack[k]);
+          hit = !out;
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, hit) && lane == 0) atomicOr(s_mask + cam, 1u << blk);
+  }
+  __syncthreads();
+  if (threadIdx.x < kMaxCams) w.cull[b * kMaxCams + threadIdx.x] = s_mask[threadIdx.x];
+}
+
+// P4 ------------------------------------------------------------------------
 // A CTA owns V consecutive voxels (~1024 slot items).  dynamic smem: tile[V*K*C] floats
 // (padded to 16 B) + idx[V*K] u32 + list[V*K] u16.
 //   1. zero the tile (16-byte stores); every warp loads its share of the slot indices and
 //      ballot-compacts the non-empty ones into its own list segment (no atomics, no barrier)
 //   2. each warp gathers / re-unprojects (exact reference arithmetic) its listed items
-//   3. voxels are copied out with 16-byte stores; one thread per voxel writes coors (from the
-//      first point), the count and the HardSimpleVFE mean (slot order, one __fdiv_rn)
+//   3. voxels are copied out with 16-byte stores; one thread per voxel writes the count and the
+//      HardSimpleVFE mean (slot order, one __fdiv_rn); coors were written by P2
 template <class Src>
 __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGrid g, HvWork w, HvOut o, int V) {
   extern __shared__ float s_dyn[];
-#if RD3_EMIT_TMA
   __shared__ __align__(16) float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 4];
   __shared__ __align__(8) uint64_t s_bar;
-#else
-  __shared__ float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 1];
-#endif
   const int b = blockIdx.y + w.b0;
   const int vn = o.voxel_num[b];
   const int r0 = blockIdx.x * V;
@@ -821,19 +918,14 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
   const int per = ((items + nw - 1) / nw + 31) & ~31;
   const int lo = wv * per, hi = min(items, lo + per);
   // The first 128 slot indices of the warp's share are requested up front (4 independent loads per
-  // lane): one DRAM round trip instead of four dependent ones (each pass of the compaction loop below
-  // waits for its load), overlapped with the calibration staging and the zero fill (emit 0.362 -> 0.320 ms).
+  // lane): one DRAM round trip instead of four dependent ones, overlapped with the calibration copy and the zero fill.
   uint32_t pre[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int it = lo + 32 * q + lane;
     pre[q] = it < hi ? __ldg(S + it) : kEmpty32;
   }
-#if RD3_EMIT_TMA
-  const bool cal_async = src.stage_async(s_cal, &s_bar, b);     // one bulk copy instead of a load / store loop
-#else
-  src.stage(s_cal, b);
-#endif
+  const bool cal_async = src.stage_async(s_cal, &s_bar, b);     // one TMA bulk copy, no load / store loop
   {
     float4 *t4 = reinterpret_cast<float4 *>(tile);
     const int n4 = (items * C + 3) >> 2;
@@ -861,10 +953,8 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
     if (idx != kEmpty32) s_list[lo + nmine + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)it;
     nmine += __popc(bal);
   }
-  __syncthreads();                       // tile zeroed, calibration staged
-#if RD3_EMIT_TMA
+  __syncthreads();                       // tile zeroed, calibration copy issued
   if (cal_async) tma_wait(&s_bar);
-#endif
   for (int j = lane; j < nmine; j += 32) {
     const int it = s_list[lo + j];
     src.gather(b, s_idx[it], s_cal, tile + it * C);
@@ -878,13 +968,13 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
     const float4 *t4 = reinterpret_cast<const float4 *>(tile);
     float4 *v4 = reinterpret_cast<float4 *>(vout);
     const int n4 = nfl >> 2;
-    for (int e = threadIdx.x; e < n4; e += kEmitThreads) v4[e] = t4[e];
+    for (int e = threadIdx.x; e < n4; e += kEmitThreads) __stcs(v4 + e, t4[e]);
     for (int e = (nfl & ~3) + threadIdx.x; e < nfl; e += kEmitThreads) vout[e] = tile[e];
   } else {
     for (int e = threadIdx.x; e < nfl; e += kEmitThreads) vout[e] = tile[e];
   }
 
-  // one thread per voxel: count, coors from the first point, HardSimpleVFE mean
+  // one thread per voxel: count and HardSimpleVFE mean
   // (voxel_encoder.py:45-46: sum over ALL K slots in slot order, then one division; the
   // slots beyond the count are zeros, so the running sum stops changing at the count --
   // except that (-0.0) + 0.0 = +0.0, which one extra "+ 0.0f" reproduces)
@@ -894,13 +984,7 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
     int cnt = 0;
     while (cnt < K && si[cnt] != kEmpty32) ++cnt;
     const float *p0 = tile + v * K * C;
-    int cx = 0, cy = 0, cz = 0;
-    if (voxel_coor_fast(p0[0], p0[1], p0[2], 0.0f, g, cx, cy, cz) == 2)
-      voxel_coor(p0[0], p0[1], p0[2], g, cx, cy, cz);
     const int64_t vr = (int64_t)b * w.max_voxels + r0 + v;
-    o.coors[vr * 3 + 0] = cz;
-    o.coors[vr * 3 + 1] = cy;
-    o.coors[vr * 3 + 2] = cx;
     o.num[vr] = cnt;
     if (o.mean) {
       const float n = (float)cnt;
@@ -933,6 +1017,15 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
 // ---------------------------------------------------------------------------
 // host side: workspace carving + launch sequence
 // ---------------------------------------------------------------------------
+struct HvTuning {           // read once from the environment (experiments); defaults are the measured best
+  int rounds;               // target number of insert rounds (RD3_ROUNDS)
+  int load_pct;             // worst-case load factor of the table in percent (RD3_TABLE_LOAD_PCT)
+  int ins_iters, lkp_iters; // tiles per warp strip (RD3_INS_ITERS, RD3_LKP_ITERS)
+  int cull;                 // RD3_CULL=0 disables the camera / column-block culling
+  int sm_count;
+};
+const HvTuning &hv_tuning();
+
 struct HvPlan {
   int64_t N;
   int B;
@@ -942,19 +1035,20 @@ struct HvPlan {
   int rounds;
   int64_t cap;
   int log2cap;
-  int nwords, nchunks, ntiles;
-  // [table | slots] are set to 0xFF with one memset, [flags | round_claims] to 0 with another
-  size_t off_table, off_slots, off_flags, off_claims, off_ccount, off_prefix, off_chunk, off_cand, total;
+  int nwords, nchunks;
+  // [table | slots] are set to 0xFF with one memset, [flags | bev | round_claims] to 0 with another
+  size_t off_table, off_slots, off_flags, off_bev, off_claims, off_cull, off_prefix, off_chunk, total;
 };
 
 inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels) {
+  const HvTuning &t = hv_tuning();
   HvPlan p;
   p.N = N; p.B = B; p.K = K; p.max_voxels = max_voxels;
   const int64_t n1 = N > 0 ? N : 1;
-  // round length: at most 8 rounds, but a round should keep the whole GPU busy
+  // round length: at most `rounds` rounds, but a round should keep the whole GPU busy
   // (>= ~1.2 M points over all frames), so small batches use fewer, longer rounds
-  int64_t S = ceil_div(ceil_div(n1, 8), 1024) * 1024;
-  const int64_t fill = ceil_div(ceil_div((int64_t)148 * 8 * 1024, B > 0 ? B : 1), 1024) * 1024;
+  int64_t S = ceil_div(ceil_div(n1, t.rounds), 1024) * 1024;
+  const int64_t fill = ceil_div(ceil_div((int64_t)t.sm_count * 8 * 1024, B > 0 ? B : 1), 1024) * 1024;
   if (S < fill) S = fill;
   if (S < 65536) S = 65536;
   p.S = S;
@@ -962,44 +1056,53 @@ inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels) {
   // the table never holds more than max_voxels + S keys (see header), nor more than N
   int64_t keys = (int64_t)max_voxels + S;
   if (keys > n1) keys = n1;
-#ifndef RD3_TABLE_LOAD_PCT
-#define RD3_TABLE_LOAD_PCT 50         // worst-case load factor of the table in percent
-#endif
-  int64_t want = keys * 100 / RD3_TABLE_LOAD_PCT;
+  int64_t want = keys * 100 / t.load_pct;
   int lg = 10;
   while (((int64_t)1 << lg) < want) ++lg;
   p.log2cap = lg;
   p.cap = (int64_t)1 << lg;
   p.nchunks = (int)ceil_div(n1, kChunkPoints);
   p.nwords = p.nchunks * kChunkWords;
-  p.ntiles = (int)ceil_div(n1, kTilePoints);
   size_t off = 0;
   p.off_table = off; off += align_up((size_t)B * p.cap * 8);
   p.off_slots = off; off += align_up((size_t)B * max_voxels * K * 4);
-  p.off_flags = off; off += align_up((size_t)B * p.nwords * 4 * (RD3_RANK_PACKED ? 2 : 1));
+  p.off_flags = off; off += align_up((size_t)B * p.nwords * 4);
+  p.off_bev = off; off += align_up((size_t)B * kBevWords * 4);
   p.off_claims = off; off += align_up((size_t)B * kMaxRounds * 4);
-  p.off_ccount = off; off += align_up((size_t)B * p.ntiles);
+  p.off_cull = off; off += align_up((size_t)B * kMaxCams * 4);
   p.off_prefix = off; off += align_up((size_t)B * p.nwords * 4);
   p.off_chunk = off; off += align_up((size_t)B * p.nchunks * 4);
-  p.off_cand = off; off += align_up((size_t)B * n1 * 8);
   p.total = off;
   return p;
 }
 
+// culling needs the precomputed calibration table and more than one column block or camera to pay off
+template <class Src> struct CullLaunch {
+  static bool wanted(const Src &) { return false; }
+  static void run(const Src &, const VoxelGrid &, const HvWork &, int, cudaStream_t) {}
+};
+template <> struct CullLaunch<DepthSource> {
+  static bool wanted(const DepthSource &s) { return hv_tuning().cull && s.cal_table != nullptr; }
+  static void run(const DepthSource &s, const VoxelGrid &g, const HvWork &w, int nb, cudaStream_t st) {
+    hv_cull_kernel<<<nb, 256, 0, st>>>(s, g, w);
+  }
+};
+
 template <class Src>
 int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p, void *ws,
            HvOut out, cudaStream_t stream) {
+  const HvTuning &tune = hv_tuning();
   char *base = (char *)ws;
   HvWork w;
   w.table = (unsigned long long *)(base + p.off_table);
   w.slots = (uint32_t *)(base + p.off_slots);
   w.flags = (uint32_t *)(base + p.off_flags);
   w.round_claims = (int32_t *)(base + p.off_claims);
-  w.cand_cnt = (uint8_t *)(base + p.off_ccount);
-  w.ntiles = p.ntiles;
   w.wordprefix = (int32_t *)(base + p.off_prefix);
   w.chunk_base = (int32_t *)(base + p.off_chunk);
-  w.cand = (uint2 *)(base + p.off_cand);
+  const bool cull = CullLaunch<Src>::wanted(src) && g.fast_ok;
+  w.bev = cull ? (uint32_t *)(base + p.off_bev) : nullptr;
+  w.cull = cull ? (uint32_t *)(base + p.off_cull) : nullptr;
   w.N = p.N; w.cap = p.cap; w.cap_mask = (uint32_t)(p.cap - 1); w.log2cap = p.log2cap;
   w.direct = (volume <= (uint64_t)p.cap) ? 1 : 0;
   w.nwords = p.nwords; w.nchunks = p.nchunks; w.K = p.K; w.max_voxels = p.max_voxels;
@@ -1023,8 +1126,8 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
 
   // Frames are independent: the batch is split into up to kMaxLanes sub-batches that run the
   // whole kernel sequence on their own streams (forked from / joined to the caller's stream),
-  // so that the issue-bound insert kernel of one sub-batch overlaps the latency-bound
-  // first/slots kernels and memsets of another.  With the stage profiler on, one lane is used.
+  // so that the latency-bound small kernels of one sub-batch overlap the passes of another.
+  // With the stage profiler on, one lane is used.
   LaneLock lane_lock;              // the lanes' events are shared by all callers on this device
   StreamLanes *lanes = nullptr;
   int nl = 1;
@@ -1036,60 +1139,70 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
       if (!lanes) nl = 1;
     }
   }
-  if (nl > 1) RD3_CUDA_TRY(cudaEventRecord(lanes->fork, stream));
-  // Inside a lane the frames are processed in groups of G (RD3_GROUP, default: the whole lane).
-  int G = p.B;
-  if (const char *e = getenv("RD3_GROUP")) G = atoi(e);
-  if (G < 1) G = 1;
-  for (int l = 0; l < nl; ++l) {
-    const int lb0 = (int)((int64_t)p.B * l / nl), lb1 = (int)((int64_t)p.B * (l + 1) / nl);
+  int status = RD3_OK;
+  int forked = 0;                  // side lanes that wait on the fork event and must be joined, also on an error
+#define RD3_LANE_TRY(expr)                                                            \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) { rd3::set_last_cuda_error(_e); status = RD3_ERR_CUDA; }   \
+  } while (0)
+  if (nl > 1) RD3_LANE_TRY(cudaEventRecord(lanes->fork, stream));
+  if (status != RD3_OK) return status;
+  const int ins_span = kPassWarps * tune.ins_iters * kTilePoints, lkp_span = kPassWarps * tune.lkp_iters * kTilePoints;
+  for (int l = 0; l < nl && status == RD3_OK; ++l) {
+    const int b0 = (int)((int64_t)p.B * l / nl), b1 = (int)((int64_t)p.B * (l + 1) / nl);
+    const int nb = b1 - b0;
     cudaStream_t st = stream;
     if (l > 0) {
       st = lanes->s[l - 1];
-      RD3_CUDA_TRY(cudaStreamWaitEvent(st, lanes->fork, 0));
+      RD3_LANE_TRY(cudaStreamWaitEvent(st, lanes->fork, 0));
+      if (status != RD3_OK) break;
+      forked = l;
     }
-    for (int b0 = lb0; b0 < lb1; b0 += G) {
-    const int nb = (lb1 - b0 < G) ? lb1 - b0 : G;
     w.b0 = b0;
     prof_mark(st, 0);
-    RD3_CUDA_TRY(cudaMemsetAsync(w.table + (size_t)b0 * p.cap, 0xFF, (size_t)nb * p.cap * 8, st));
-    RD3_CUDA_TRY(cudaMemsetAsync(w.slots + (size_t)b0 * p.max_voxels * p.K, 0xFF,
+    RD3_LANE_TRY(cudaMemsetAsync(w.table + (size_t)b0 * p.cap, 0xFF, (size_t)nb * p.cap * 8, st));
+    RD3_LANE_TRY(cudaMemsetAsync(w.slots + (size_t)b0 * p.max_voxels * p.K, 0xFF,
                                  (size_t)nb * p.max_voxels * p.K * 4, st));
-    RD3_CUDA_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords * (RD3_RANK_PACKED ? 2 : 1), 0,
-                                 (size_t)nb * p.nwords * 4 * (RD3_RANK_PACKED ? 2 : 1), st));
-    RD3_CUDA_TRY(cudaMemsetAsync(w.round_claims + (size_t)b0 * kMaxRounds, 0, (size_t)nb * kMaxRounds * 4,
-                                 st));
+    RD3_LANE_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords, 0, (size_t)nb * p.nwords * 4, st));
+    RD3_LANE_TRY(cudaMemsetAsync(w.round_claims + (size_t)b0 * kMaxRounds, 0, (size_t)nb * kMaxRounds * 4, st));
+    if (cull) RD3_LANE_TRY(cudaMemsetAsync(w.bev + (size_t)b0 * kBevWords, 0, (size_t)nb * kBevWords * 4, st));
     prof_mark(st, 1);
     for (int r = 0; r < p.rounds && p.N > 0; ++r) {
       const int64_t begin = (int64_t)r * p.S;
       const int64_t end = begin + p.S < p.N ? begin + p.S : p.N;
-      dim3 grid((unsigned)ceil_div(end - begin, kInsSpan), nb);
-      hv_insert_kernel<Src><<<grid, kInsThreads, 0, st>>>(src, g, w, begin, end, r);
+      dim3 grid((unsigned)ceil_div(end - begin, ins_span), nb);
+      hv_pass_kernel<Src, 0><<<grid, kPassThreads, 0, st>>>(src, g, w, nullptr, begin, end, r, tune.ins_iters);
     }
     prof_mark(st, 2);
+    hv_flagscan_kernel<<<dim3(p.nchunks, nb), kScanThreads, 0, st>>>(w);
+    scan_chunks_kernel<<<nb, 1024, 0, st>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels, b0);
+    prof_mark(st, 3);
     {
       int gx = (int)ceil_div(p.cap, 256 * 8);
-      const int lim = (148 * 16 + nb - 1) / nb;
+      const int lim = (tune.sm_count * 16 + nb - 1) / nb;
       if (gx > lim) gx = lim;
       if (gx < 1) gx = 1;
-      hv_first_kernel<<<dim3(gx, nb), 256, 0, st>>>(w);
+      hv_rank_kernel<<<dim3(gx, nb), 256, 0, st>>>(w, g, out.coors);
     }
-    hv_flagscan_kernel<<<dim3(p.nchunks, nb), kScanThreads, 0, st>>>(w);
-    prof_mark(st, 3);
-    scan_chunks_kernel<<<nb, 1024, 0, st>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels, b0);
+    if (cull) CullLaunch<Src>::run(src, g, w, nb, st);
     prof_mark(st, 4);
     if (p.N > 0)
-      hv_slots_kernel<<<dim3((unsigned)ceil_div(p.ntiles, 4 * kSlotTiles), nb), 128, 0, st>>>(w, out.point2voxel);
+      hv_pass_kernel<Src, 1><<<dim3((unsigned)ceil_div(p.N, lkp_span), nb), kPassThreads, 0, st>>>(
+          src, g, w, out.point2voxel, 0, p.N, 0, tune.lkp_iters);
     prof_mark(st, 5);
     hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, V), nb), kEmitThreads, smem, st>>>(src, g, w, out, V);
     prof_mark(st, 6);
     prof_mark(st, 7);
-    }   // groups of this lane
-    if (l > 0) {
-      RD3_CUDA_TRY(cudaEventRecord(lanes->join[l - 1], st));
-      RD3_CUDA_TRY(cudaStreamWaitEvent(stream, lanes->join[l - 1], 0));
-    }
   }
+  // join every side lane that was forked, also after an error: an un-joined lane would leave a stream capture
+  // of the caller open and the caller's stream unordered against work already enqueued
+  for (int l = 1; l <= forked; ++l) {
+    RD3_LANE_TRY(cudaEventRecord(lanes->join[l - 1], lanes->s[l - 1]));
+    RD3_LANE_TRY(cudaStreamWaitEvent(stream, lanes->join[l - 1], 0));
+  }
+#undef RD3_LANE_TRY
+  if (status != RD3_OK) return status;
   return check_launch();
 }
 

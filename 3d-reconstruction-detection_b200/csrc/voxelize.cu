@@ -75,12 +75,34 @@ StreamLanes *get_stream_lanes() {
   return L.ok ? &L.lanes : nullptr;
 }
 
+static int env_int(const char *name, int dflt, int lo, int hi) {
+  int v = dflt;
+  if (const char *e = getenv(name)) v = atoi(e);
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+
 int stream_lane_count() {
-  int n = 3;
-  if (const char *e = getenv("RD3_STREAMS")) n = atoi(e);
-  if (n < 1) n = 1;
-  if (n > kMaxLanes) n = kMaxLanes;
+  static const int n = env_int("RD3_STREAMS", 3, 1, kMaxLanes);    // read once, not in the launch path
   return n;
+}
+
+const HvTuning &hv_tuning() {
+  static const HvTuning t = [] {
+    HvTuning v;
+    v.rounds = env_int("RD3_ROUNDS", 8, 1, kMaxRounds);
+    v.load_pct = env_int("RD3_TABLE_LOAD_PCT", 50, 10, 90);
+    v.ins_iters = env_int("RD3_INS_ITERS", 4, 1, 64);
+    v.lkp_iters = env_int("RD3_LKP_ITERS", 8, 1, 64);
+    v.cull = env_int("RD3_CULL", 1, 0, 1);
+    v.sm_count = 148;                                              // B200; replaced by the device's own count when one is visible
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+      v.sm_count = sms;
+    (void)cudaGetLastError();
+    return v;
+  }();
+  return t;
 }
 
 int make_grid(const float voxel_size[3], const float coors_range[6], VoxelGrid *g,

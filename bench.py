@@ -355,8 +355,9 @@ def main():
     C = F = 3
     # ALGORITHMIC bytes per launch (DESIGN.md "Kernels"): compulsory reads+writes only
     alg = {
-        "insert": B * npix * 4,                                 # depth read
-        "flags": 0, "scan": 0, "slots": 0, "memset": 0,         # scratch-only stages
+        "insert": B * npix * 4,                                 # depth read (rounds of the still open frames)
+        "lookup": B * npix * 4,                                 # depth read
+        "flags": 0, "rank": 0, "memset": 0,                     # scratch-only stages
         "emit": M_total * K * C * 4,                            # voxels written
         "meta": M_total * (12 + 4 + 4 * F),                     # coors + num + mean written
     }
@@ -370,7 +371,7 @@ def main():
     dom_ms = stage_ms[dom] / dom_launches
     dom_achieved = alg[dom] / dom_launches / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     path_achieved = path_bytes / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "hv_%s_kernel" % dom, "achieved": dom_achieved, "peak": hbm_peak,
+    roofline = {"bound": "hbm", "kernel": {"insert": "hv_pass_kernel<0>", "lookup": "hv_pass_kernel<1>"}.get(dom, "hv_%s_kernel" % dom), "achieved": dom_achieved, "peak": hbm_peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": dom_achieved / hbm_peak, "traffic": None,
                 "ms_per_launch": dom_ms, "launches_per_step": dom_launches,
                 "algorithmic_bytes_per_launch": alg[dom] / dom_launches,
