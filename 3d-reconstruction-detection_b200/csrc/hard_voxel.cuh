@@ -55,10 +55,10 @@ constexpr int kPassWarps = kPassThreads / 32;
 #endif
 constexpr int kEmitThreads = RD3_EMIT_THREADS;
 #ifndef RD3_INS_MINB
-#define RD3_INS_MINB 6                // resident CTAs per SM the insert pass is compiled for
+#define RD3_INS_MINB 5                // resident CTAs per SM the insert pass is compiled for
 #endif
 #ifndef RD3_LKP_MINB
-#define RD3_LKP_MINB 6                // ... and the lookup pass
+#define RD3_LKP_MINB 5                // ... and the lookup pass
 #endif
 constexpr int kTilePoints = 128;      // points per warp tile (4 per lane)
 constexpr int kListCap = 160;         // per-warp item / undecided lists: 31 carried + 128 new
@@ -744,28 +744,28 @@ __device__ __forceinline__ int voxel_rank(const HvWork &w, int b, uint32_t first
 }
 
 // P2r -----------------------------------------------------------------------
-// One pass over the table, grid (gx, frames), grid-stride.  Entry {key | first point} -> {key | rank}
-// ({key | ~0} for the voxels the reference drops); row r of the slots gets its first point; coors[r] is the
-// key decoded as (z, y, x); the kept voxels are marked in the frame's bird's-eye mask.
+// One pass over the table, one thread per pair of entries (a 16-byte load; no loop: the dependent chain
+// entry -> rank words -> stores is hidden by thread-level parallelism).  grid (cap / 512, frames).
+// Entry {key | first point} -> {key | rank} ({key | ~0} for the voxels the reference drops); row r of the
+// slots gets its first point; coors[r] is the key decoded as (z, y, x); the kept voxels are marked in the
+// frame's bird's-eye mask (read first: after the first few hundred voxels nearly every bit is already set).
 static __global__ void __launch_bounds__(256) hv_rank_kernel(HvWork w, VoxelGrid g, int32_t *coors) {
-  __shared__ uint32_t s_bev[kBevWords];
   const int b = blockIdx.y + w.b0;
-  unsigned long long *table = w.table + (int64_t)b * w.cap;
-  if (w.bev) {
-    for (int i = threadIdx.x; i < kBevWords; i += blockDim.x) s_bev[i] = 0u;
-    __syncthreads();
-  }
-  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < w.cap;
-       s += (int64_t)gridDim.x * blockDim.x) {
-    const unsigned long long e = __ldcs(table + s);
+  const int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (s0 >= w.cap) return;
+  unsigned long long *table = w.table + (int64_t)b * w.cap + s0;
+  const ulonglong2 ee = __ldcs(reinterpret_cast<const ulonglong2 *>(table));
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const unsigned long long e = q ? ee.y : ee.x;
     if (e == kEmpty64) continue;
     const uint32_t first = (uint32_t)e, key = (uint32_t)(e >> 32);
     const int r = voxel_rank(w, b, first);
     if (r >= w.max_voxels) {
-      table[s] = e | 0xFFFFFFFFull;
+      table[q] = e | 0xFFFFFFFFull;
       continue;
     }
-    table[s] = (e & 0xFFFFFFFF00000000ull) | (uint32_t)r;
+    table[q] = (e & 0xFFFFFFFF00000000ull) | (uint32_t)r;
     const int64_t vr = (int64_t)b * w.max_voxels + r;
     w.slots[vr * w.K] = first;
     int cz, cy, cx;
@@ -776,15 +776,9 @@ static __global__ void __launch_bounds__(256) hv_rank_kernel(HvWork w, VoxelGrid
     if (w.bev) {
       const uint32_t bx = (uint32_t)cx * kBevDim / (uint32_t)g.grid[0], by = (uint32_t)cy * kBevDim / (uint32_t)g.grid[1];
       const uint32_t bit = by * kBevDim + bx;
+      uint32_t *word = w.bev + (int64_t)b * kBevWords + (bit >> 5);
       const uint32_t m = 1u << (bit & 31);
-      if (!(s_bev[bit >> 5] & m)) atomicOr(s_bev + (bit >> 5), m);
-    }
-  }
-  if (w.bev) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < kBevWords; i += blockDim.x) {
-      const uint32_t v = s_bev[i];
-      if (v) atomicOr(w.bev + (int64_t)b * kBevWords + i, v);
+      if (!(__ldcg(word) & m)) atomicOr(word, m);
     }
   }
 }
@@ -968,7 +962,11 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
     const float4 *t4 = reinterpret_cast<const float4 *>(tile);
     float4 *v4 = reinterpret_cast<float4 *>(vout);
     const int n4 = nfl >> 2;
+#ifdef RD3_EMIT_STCS
     for (int e = threadIdx.x; e < n4; e += kEmitThreads) __stcs(v4 + e, t4[e]);
+#else
+    for (int e = threadIdx.x; e < n4; e += kEmitThreads) v4[e] = t4[e];
+#endif
     for (int e = (nfl & ~3) + threadIdx.x; e < nfl; e += kEmitThreads) vout[e] = tile[e];
   } else {
     for (int e = threadIdx.x; e < nfl; e += kEmitThreads) vout[e] = tile[e];
@@ -1178,13 +1176,7 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
     hv_flagscan_kernel<<<dim3(p.nchunks, nb), kScanThreads, 0, st>>>(w);
     scan_chunks_kernel<<<nb, 1024, 0, st>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels, b0);
     prof_mark(st, 3);
-    {
-      int gx = (int)ceil_div(p.cap, 256 * 8);
-      const int lim = (tune.sm_count * 16 + nb - 1) / nb;
-      if (gx > lim) gx = lim;
-      if (gx < 1) gx = 1;
-      hv_rank_kernel<<<dim3(gx, nb), 256, 0, st>>>(w, g, out.coors);
-    }
+    hv_rank_kernel<<<dim3((unsigned)ceil_div(p.cap, 512), nb), 256, 0, st>>>(w, g, out.coors);
     if (cull) CullLaunch<Src>::run(src, g, w, nb, st);
     prof_mark(st, 4);
     if (p.N > 0)
