@@ -195,7 +195,8 @@ static int make_depth_source(const float *depth, const float *intrinsics, const 
   for (int i = 0; i < 6; ++i) d.range[i] = p->range[i];
   d.div_hw = make_fastdiv((uint32_t)d.HW);
   d.div_w = make_fastdiv((uint32_t)d.W);
-  src->vec_ok = ((npix & 3) == 0) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0);
+  src->vec_ok = ((p->W & 3) == 0) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0);
+  src->div_h = make_fastdiv((uint32_t)p->H);
   src->cbshift = 7;                                  // culling: blocks of >= 128 image columns, at most 32 per row
   while (((p->W - 1) >> src->cbshift) >= 32) ++src->cbshift;
   return RD3_OK;
@@ -238,7 +239,7 @@ int rd3_unproject(const float *depth, const float *intrinsics, const float *cam2
 size_t rd3_depth_to_voxels_workspace_bytes(const rd3_depth_params *p, int max_points,
                                            int max_voxels) {
   if (!p || p->B <= 0 || max_points <= 0 || max_voxels <= 0) return 0;
-  return hv_plan((int64_t)p->ncam * p->H * p->W, p->B, max_points, max_voxels).total +
+  return hv_plan((int64_t)p->ncam * p->H * p->W, p->B, max_points, max_voxels, p->W).total +
          align_up((size_t)p->B * p->ncam * kCalibFloats * 4);
 }
 
@@ -260,7 +261,7 @@ int rd3_depth_to_voxels(const float *depth, const float *intrinsics, const float
   uint64_t vol;
   st = make_grid(voxel_size, coors_range, &g, &vol);
   if (st != RD3_OK) return st;
-  const HvPlan plan = hv_plan(src.p.npix, p->B, max_points, max_voxels);
+  const HvPlan plan = hv_plan(src.p.npix, p->B, max_points, max_voxels, p->W);
   const size_t cal_bytes = align_up((size_t)p->B * p->ncam * kCalibFloats * 4);
   if (workspace_bytes < plan.total + cal_bytes) return RD3_ERR_WORKSPACE;
   float *cal_table = (float *)((char *)workspace + plan.total);

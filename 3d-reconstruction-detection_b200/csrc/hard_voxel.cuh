@@ -65,6 +65,7 @@ constexpr int kListCap = 160;         // per-warp item / undecided lists: 31 car
 constexpr int kMaxRounds = 64;
 constexpr int kBevDim = 64;           // bird's-eye mask of the kept voxels: kBevDim x kBevDim bits over the x,y grid
 constexpr int kBevWords = kBevDim * kBevDim / 32;
+constexpr int kBevCopies = 32;        // privatised copies of the mask (power of two): spreads the marking atomics
 
 // ---------------------------------------------------------------------------
 // packed fp32 pairs (FFMA2 / FADD2 on sm_100a: two IEEE-rounded results per issue slot)
@@ -98,12 +99,24 @@ __device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
 // ---------------------------------------------------------------------------
 // point sources
 // ---------------------------------------------------------------------------
+// culling masks of the lookup pass (depth source): [B][kMaxCams] live column blocks per camera, or null
+struct HvCull {
+  const uint32_t *mask;
+};
+
 // classification of one lane's 4 consecutive points
 struct Quad {
   uint32_t key[4];
   unsigned in, und;     // bit q: point q is surely inside (key valid) / needs the exact path
 };
 
+// Both sources hand the pass kernels their work through a WALKER: a warp visits a sequence of 128-element
+// tiles, lane L owning 4 consecutive elements of each.  Neither pass depends on the order in which the
+// elements of its range are visited (the table keeps minima, the slot rows sort), so the decomposition is free:
+//   points : consecutive tiles of the flat (N, C) array
+//   depth  : a 128-column block of `iters` consecutive image rows -- the lane's column never changes (no
+//            index -> (cam, v, u) division per tile, the row advances by one pointer increment), and a whole
+//            CTA of culled columns leaves before its prologue.
 struct PointsSource {
   const float *pts;   // (B, N, C)
   int64_t N;
@@ -113,20 +126,40 @@ struct PointsSource {
   __device__ __forceinline__ bool stage_async(float *, uint64_t *, int) const { return false; }
   int host_num_feats() const { return C; }
   __device__ __forceinline__ int num_feats() const { return C; }
+  // CTAs that cover the element range [begin, end) with strips of `iters` tiles per warp
+  unsigned host_grid(int64_t begin, int64_t end, int iters) const {
+    return (unsigned)ceil_div(end - begin, (int64_t)kPassWarps * iters * kTilePoints);
+  }
+  int64_t host_round_multiple() const { return 1024; }
 
-  struct Loc {};
-  __device__ __forceinline__ Loc locate(int64_t) const { return Loc(); }
-  __device__ __forceinline__ bool lane_live(const Loc &, const uint32_t *, int) const { return true; }
+  struct Walker {
+    int64_t cur, end;     // first element of the warp's current tile, end of its strip
+    int lane;
+  };
+  __device__ __forceinline__ bool cta_live(const HvCull &, int, int64_t, int64_t, int) const { return true; }
+  __device__ __forceinline__ bool walk_init(Walker &k, int64_t begin, int64_t end, int iters, int wv, int lane) const {
+    const int64_t strip = (int64_t)iters * kTilePoints;
+    k.cur = begin + ((int64_t)blockIdx.x * kPassWarps + wv) * strip;
+    k.end = k.cur + strip < end ? k.cur + strip : end;
+    k.lane = lane;
+    return k.cur < end;
+  }
+  __device__ __forceinline__ bool walk_more(const Walker &k) const { return k.cur < k.end; }
+  __device__ __forceinline__ void walk_next(Walker &k) const { k.cur += kTilePoints; }
+  __device__ __forceinline__ bool walk_live(const Walker &, const uint32_t *) const { return true; }
+  __device__ __forceinline__ uint32_t walk_index(const Walker &k) const { return (uint32_t)k.cur + 4u * k.lane; }
+  __device__ __forceinline__ int walk_npx(const Walker &k) const {
+    const int64_t left = k.end - (k.cur + 4 * k.lane);
+    return left >= 4 ? 4 : (left > 0 ? (int)left : 0);
+  }
+
   struct Pre {};
-  __device__ __forceinline__ Pre preload(int, int64_t, int64_t) const { return Pre(); }
+  __device__ __forceinline__ Pre preload(int, const Walker &, bool) const { return Pre(); }
   struct Cursor { const float *p; int npx; };
-  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *, const Pre &,
-                                           const Loc &) const {
+  __device__ __forceinline__ Cursor cursor(int b, const Walker &k, const float *, const Pre &) const {
     Cursor c;
-    c.p = pts + ((int64_t)b * N + i0) * C;
-    const int64_t left = end - i0;
-    c.npx = left >= 4 ? 4 : (left > 0 ? (int)left : 0);
-    if (c.npx == 0) c.p = pts;                      // lanes past the end read point 0 (masked)
+    c.npx = walk_npx(k);
+    c.p = pts + ((int64_t)b * N + (c.npx ? k.cur + 4 * k.lane : 0)) * C;   // lanes past the end read point 0 (masked)
     return c;
   }
   // the lane's 4 points: keys of the points surely inside (bit q of `in`), undecided ones in `und`
@@ -164,8 +197,9 @@ struct DepthSource {
   const float *cal_table;  // (B, ncam, kCalibFloats) precomputed by calib_kernel, or null
   DepthParams p;
   CellRange rg;            // range filter in cell units (fused path); on = 0 when the grid test implies it
-  int vec_ok;              // 16-byte aligned float4 loads are legal
+  int vec_ok;              // 16-byte aligned float4 loads of 4 pixels of a row are legal (W % 4 == 0, aligned base)
   int cbshift;             // culling: image columns are grouped in blocks of 2^cbshift (>= 128, <= 32 blocks)
+  FastDiv div_h;           // global row -> camera
   static constexpr bool kIsDepth = true;
 
   // copy this frame's calibration into shared memory (no barrier)
@@ -194,6 +228,13 @@ struct DepthSource {
   }
   int host_num_feats() const { return 3; }
   __device__ __forceinline__ int num_feats() const { return 3; }
+  int host_col_tiles() const { return (p.W + kTilePoints - 1) / kTilePoints; }
+  // [begin, end) are multiples of W (whole image rows): a CTA owns 8 * iters rows of one 128-column tile
+  unsigned host_grid(int64_t begin, int64_t end, int iters) const {
+    const int64_t rows = (end - begin) / p.W;
+    return (unsigned)(ceil_div(rows, (int64_t)kPassWarps * iters) * host_col_tiles());
+  }
+  int64_t host_round_multiple() const { return p.W; }
 
   __device__ __forceinline__ bool depth_ok(float z, int64_t gidx, int b) const {
     // z > 0 & isfinite(z) [& z <= max_depth] (:338-340); p.zmax = min(max_depth, FLT_MAX)
@@ -212,73 +253,107 @@ struct DepthSource {
     v = fast_div(rem, p.div_w);
     u = rem - v * (uint32_t)p.W;
   }
-  struct Loc { uint32_t cam, v, u; };
-  __device__ __forceinline__ Loc locate(int64_t i0) const {
-    Loc l;
-    pixel_cvu(i0 < p.npix ? (uint32_t)i0 : 0u, l.cam, l.v, l.u);    // lanes past the end compute on pixel 0 (masked)
-    return l;
+
+  struct Walker {
+    uint32_t gr, gr_end;   // global image row (cam * H + v) of the warp's current tile, end of its rows
+    uint32_t cam, v;       // the same row as (camera, row)
+    uint32_t u;            // the lane's first column (fixed)
+    uint32_t blk;          // culling block of the column tile
+    int npx;               // columns u .. u + npx - 1 exist (0 for lanes right of the image)
+  };
+  // rows [r0, r1) of the CTA blockIdx.x for the element range [begin, end)
+  __device__ __forceinline__ void cta_rows(int64_t begin, int64_t end, int iters, uint32_t &r0, uint32_t &r1,
+                                           uint32_t &ct) const {
+    const uint32_t nct = (uint32_t)((p.W + kTilePoints - 1) / kTilePoints);
+    const uint32_t rg = blockIdx.x / nct;
+    ct = blockIdx.x - rg * nct;
+    const uint32_t first = (uint32_t)(begin / p.W), last = (uint32_t)(end / p.W);
+    r0 = first + rg * (uint32_t)(kPassWarps * iters);
+    r1 = r0 + (uint32_t)(kPassWarps * iters);
+    if (r1 > last) r1 = last;
   }
-  // Can the lane's 4 pixels (columns u..u+3 of one row, or wrapping into the next row) reach a kept voxel?
-  // s_cull[cam] has one bit per block of 2^cbshift image columns (hv_cull_kernel).
-  __device__ __forceinline__ bool lane_live(const Loc &l, const uint32_t *s_cull, int) const {
-    const uint32_t m = s_cull[l.cam];
-    if (l.u + 3 >= (uint32_t)p.W) return true;                       // wraps (or ends the row): not culled
-    return ((m >> (l.u >> cbshift)) | (m >> ((l.u + 3) >> cbshift))) & 1u;
+  // lookup pass: can any row of this CTA's column tile reach a kept voxel?  (before the prologue: one or two loads)
+  __device__ __forceinline__ bool cta_live(const HvCull &c, int b, int64_t begin, int64_t end, int iters) const {
+    if (!c.mask) return true;
+    uint32_t r0, r1, ct;
+    cta_rows(begin, end, iters, r0, r1, ct);
+    if (r0 >= r1) return false;
+    const uint32_t blk = (ct * kTilePoints) >> cbshift;
+    const uint32_t c0 = fast_div(r0, div_h), c1 = fast_div(r1 - 1, div_h);
+    uint32_t m = 0;
+    for (uint32_t cam = c0; cam <= c1; ++cam) m |= __ldg(c.mask + b * kMaxCams + cam);
+    return (m >> blk) & 1u;
   }
-  // stage AB: a lane owns 4 consecutive pixels
+  __device__ __forceinline__ bool walk_init(Walker &k, int64_t begin, int64_t end, int iters, int wv, int lane) const {
+    uint32_t r0, r1, ct;
+    cta_rows(begin, end, iters, r0, r1, ct);
+    k.gr = r0 + (uint32_t)(wv * iters);
+    k.gr_end = k.gr + (uint32_t)iters < r1 ? k.gr + (uint32_t)iters : r1;
+    k.cam = fast_div(k.gr, div_h);
+    k.v = k.gr - k.cam * (uint32_t)p.H;
+    k.u = ct * kTilePoints + 4u * lane;
+    k.blk = (ct * kTilePoints) >> cbshift;
+    const int left = p.W - (int)k.u;
+    k.npx = left >= 4 ? 4 : (left > 0 ? left : 0);
+    return k.gr < r1;
+  }
+  __device__ __forceinline__ bool walk_more(const Walker &k) const { return k.gr < k.gr_end; }
+  __device__ __forceinline__ void walk_next(Walker &k) const {
+    ++k.gr;
+    if (++k.v == (uint32_t)p.H) { k.v = 0; ++k.cam; }
+  }
+  __device__ __forceinline__ bool walk_live(const Walker &k, const uint32_t *s_cull) const {
+    return (s_cull[k.cam] >> k.blk) & 1u;
+  }
+  __device__ __forceinline__ uint32_t walk_index(const Walker &k) const { return k.gr * (uint32_t)p.W + k.u; }
+  __device__ __forceinline__ int walk_npx(const Walker &k) const { return k.npx; }
+
+  // The depth load does not depend on the calibration: the load of the NEXT tile is issued before the
+  // current one is classified.
+  struct Pre { float z[4]; };
+  __device__ __forceinline__ Pre preload(int b, const Walker &k, bool on) const {
+    Pre r;
+    const float *src = depth + (int64_t)b * p.npix + walk_index(k);
+    if (on && vec_ok && k.npx == 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4 *>(src));
+      r.z[0] = t.x; r.z[1] = t.y; r.z[2] = t.z; r.z[3] = t.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r.z[q] = (on && q < k.npx) ? __ldg(src + q) : 0.0f;
+    }
+    return r;
+  }
+  // one lane's 4 consecutive pixels of one image row
   struct Cursor {
     float z[4];
     unsigned valid;        // depth/conf/sky mask of the 4 pixels
     uint32_t cam;
     float uf;              // column of the first pixel
-    bool wraps;            // the 4 pixels cross a row boundary (only when W % 4 != 0)
-    float tx, ty, tz;      // row part of the direct cell map (valid when !wraps)
+    float tx, ty, tz;      // row part of the direct cell map
   };
-  // The depth load does not depend on the calibration: the load of the NEXT tile is issued before the
-  // current one is classified.
-  struct Pre { float z[4]; };
-  __device__ __forceinline__ Pre preload(int b, int64_t i0, int64_t end) const {
-    Pre r;
-    const int64_t gi = (int64_t)b * p.npix + i0;
-    const int64_t left = end - i0;
-    const int npx = left >= 4 ? 4 : (left > 0 ? (int)left : 0);
-    if (vec_ok && npx == 4) {
-      const float4 t = __ldg(reinterpret_cast<const float4 *>(depth + gi));
-      r.z[0] = t.x; r.z[1] = t.y; r.z[2] = t.z; r.z[3] = t.w;
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) r.z[q] = (q < npx) ? __ldg(depth + gi + q) : 0.0f;
-    }
-    return r;
-  }
-  __device__ __forceinline__ Cursor cursor(int b, int64_t i0, int64_t end, const float *s_cal, const Pre &pre,
-                                           const Loc &l) const {
+  __device__ __forceinline__ Cursor cursor(int b, const Walker &k, const float *s_cal, const Pre &pre) const {
     Cursor c;
-    const int64_t gi = (int64_t)b * p.npix + i0;
-    const int64_t left = end - i0;
-    const int npx = left >= 4 ? 4 : (left > 0 ? (int)left : 0);
 #pragma unroll
     for (int q = 0; q < 4; ++q) c.z[q] = pre.z[q];
     // z > 0 & isfinite(z) [& z <= max_depth] (:338-340); p.zmax = min(max_depth, FLT_MAX)
     c.valid = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) c.valid |= ((c.z[q] > 0.0f) & (c.z[q] <= p.zmax)) ? (1u << q) : 0u;
-    c.valid &= (1u << npx) - 1u;
+    c.valid &= (1u << k.npx) - 1u;
     if (p.use_masks) {
+      const int64_t gi = (int64_t)b * p.npix + walk_index(k);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         if (((c.valid >> q) & 1u) && !depth_ok(c.z[q], gi + q, b)) c.valid &= ~(1u << q);
     }
-    c.cam = l.cam;
-    c.uf = (float)l.u;
-    c.wraps = npx && l.u + 3 >= (uint32_t)p.W;
-    pixel_cell_row((float)l.v, s_cal + c.cam * kCalibFloats, c.tx, c.ty, c.tz);
+    c.cam = k.cam;
+    c.uf = (float)k.u;
+    pixel_cell_row((float)k.v, s_cal + c.cam * kCalibFloats, c.tx, c.ty, c.tz);
     return c;
   }
   // The direct pixel->cell map (rd3_common.cuh: pixel_key_fast) decides all but the pixels within its error
   // bound of a cell / range-filter boundary; those (bit q of `und`) are redone by cell_exact.  Computed
-  // for every pixel (masked ones yield garbage that is discarded): no divergence.  Lanes whose 4
-  // pixels cross a row boundary (only when W % 4 != 0) leave all of them to cell_exact.
+  // for every pixel (masked ones yield garbage that is discarded): no divergence.
   // Same arithmetic as pixel_key_fast, two pixels per instruction (fma.rn.f32x2 / add.rn.f32x2: each
   // half is the separately rounded IEEE result) and the three |d| of a pixel reduced by one 3-input max.
   __device__ __forceinline__ void classify(const Cursor &c, const float *s_cal, const VoxelGrid &g, Quad &qd) const {
@@ -321,9 +396,8 @@ struct DepthSource {
         }
       }
     }
-    const bool fast = g.fast_ok && !c.wraps;
-    qd.in = fast ? (in & c.valid) : 0u;
-    qd.und = fast ? (und & c.valid) : c.valid;
+    qd.in = g.fast_ok ? (in & c.valid) : 0u;
+    qd.und = g.fast_ok ? (und & c.valid) : c.valid;
   }
   // pixel index -> exact ego-frame point (reference arithmetic); false if the range filter drops it
   __device__ __forceinline__ bool point(int b, int64_t i, const float *s_cal, float &x, float &y,
@@ -354,8 +428,10 @@ struct HvWork {
   int32_t *wordprefix;        // [B][nwords] exclusive popcount prefix inside the chunk
   int32_t *chunk_base;        // [B][nchunks] totals, then exclusive bases after the chunk scan
   int32_t *round_claims;      // [B][kMaxRounds] voxels claimed per insert round
-  uint32_t *bev;              // [B][kBevWords] bird's-eye mask of the kept voxels, or null
+  uint32_t *bev;              // [B][kBevCopies][kBevWords] bird's-eye masks of the kept voxels (OR of the copies), or null
   uint32_t *cull;             // [B][kMaxCams] live column blocks per camera, or null (nothing culled)
+  FastDiv div_gx, div_gy;     // key -> (x, y) cell
+  uint32_t bev_kx, bev_ky;    // bird's-eye cell of voxel column i: (i * k) >> 20, k = floor(kBevDim 2^20 / grid)
   int64_t N;
   int b0;                     // first frame of the group this launch works on
   int64_t cap;
@@ -473,10 +549,10 @@ __device__ __forceinline__ uint32_t table_rank(const unsigned long long *table, 
   }
 }
 
-// Keep the K smallest point indices of a voxel, sorted, with atomicMin only.  Slot 0 holds the voxel's first
-// point (the smallest index of all, written by P2).  Every other point cascades through the row: a value
-// reaches slot k only after losing against the slots before it, so the non-empty prefix is strictly
-// increasing at all times and the final content is independent of arrival order.
+// Keep the K smallest point indices of a voxel, sorted, with atomicMin only.  Every point cascades through
+// the row: a value reaches slot k only after losing against the slots before it, so the non-empty prefix is
+// strictly increasing at all times and the final content is independent of arrival order (every point is
+// offered exactly once).
 __device__ __forceinline__ void slot_insert(uint32_t *S, int K, uint32_t idx) {
   // a (possibly stale, hence larger) copy of the last slot that is already smaller: K smaller indices exist
   if (__ldcg(S + K - 1) < idx) return;
@@ -489,79 +565,76 @@ __device__ __forceinline__ void slot_insert(uint32_t *S, int K, uint32_t idx) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = (k + i < K) ? __ldcg(S + k + i) : kEmpty32;
     int i = 8;
-    bool same = false;
 #pragma unroll
-    for (int q = 7; q >= 0; --q) {
-      i = (v[q] < cur) ? i : q;      // first slot not smaller than cur
-      same |= v[q] == cur;
-    }
-    if (same) return;                // already there (the voxel's first point)
+    for (int q = 7; q >= 0; --q) i = (v[q] < cur) ? i : q;      // first slot not smaller than cur
     k += i;
     if (i < 8) break;
   }
   for (; k < K; ++k) {
     const uint32_t old = atomicMin(S + k, cur);
-    if (old == kEmpty32 || old == cur) return;
+    if (old == kEmpty32) return;
     if (old > cur) cur = old;            // displaced a larger index: carry it on
   }
 }
 
 // P1 / P3 ---------------------------------------------------------------------
-// grid (ceil((end-begin) / (8 * iters * 128)), frames), 256 threads; every WARP owns a strip of `iters`
-// consecutive 128-point tiles and runs without block barriers after the prologue:
-//   per tile: one 16-byte load per lane (4 consecutive points; the next tile's load is already in
+// 256 threads; every WARP walks its own sequence of 128-element tiles (Src::Walker) and runs without block
+// barriers after the prologue:
+//   per tile: one 16-byte load per lane (4 consecutive elements; the next tile's load is already in
 //        flight), validity, voxel cell by the conservative fast path; in-range keys are appended to the
-//        warp's item list, the few undecided points to its second list
-//   full 32-lane passes over the item list: MODE 0 table insert; MODE 1 table lookup -> rank -> slot row
-//   undecided points: exact IEEE arithmetic, once 32 have collected or at the end of the strip
+//        warp's item list, the few undecided elements to its second list
+//   item passes (32 lanes each) while 32 items are waiting: MODE 0 table insert; MODE 1 table lookup -> rank
+//        -> slot row
+//   undecided elements: exact IEEE arithmetic, once 32 have collected or at the end of the walk
 template <class Src, int MODE>
 __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MINB)
     hv_pass_kernel(Src src, VoxelGrid g, HvWork w, int32_t *point2voxel, int64_t begin, int64_t end, int round,
                    int iters) {
   __shared__ __align__(16) float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 4];
   __shared__ __align__(8) uint64_t s_bar;        // completion of the calibration's TMA copy
-  __shared__ uint2 s_itemb[kPassWarps * kListCap];     // (key, strip-local point id) of the in-range points
-  __shared__ uint16_t s_undb[kPassWarps * kListCap];   // strip-local ids of the undecided points
+  __shared__ uint2 s_itemb[kPassWarps * kListCap];     // (key, element index) of the in-range elements
+  __shared__ uint32_t s_undb[kPassWarps * kListCap];   // indices of the undecided elements
   __shared__ uint32_t s_cull[kMaxCams];
   __shared__ int s_prev;
 
   const int b = blockIdx.y + w.b0;
   const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  const int64_t strip = (int64_t)iters * kTilePoints;
-  const int64_t cta_base = begin + (int64_t)blockIdx.x * kPassWarps * strip;
-  if (cta_base >= end) return;
-  if (MODE == 0 && wv == 0) {
+  if (MODE == 1) {
+    // a column tile no kept voxel can be seen from: nothing to do, nothing to stage
+    HvCull cl{w.cull};
+    if (!src.cta_live(cl, b, begin, end, iters)) return;
+  } else {
     // voxels claimed by the previous rounds: once max_voxels exist the frame is closed
-    int c = 0;
-    for (int r = lane; r < round; r += 32) c += __ldcg(w.round_claims + b * kMaxRounds + r);
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if (lane == 0) s_prev = c;
+    if (wv == 0) {
+      int c = 0;
+      for (int r = lane; r < round; r += 32) c += __ldcg(w.round_claims + b * kMaxRounds + r);
+      for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+      if (lane == 0) s_prev = c;
+    }
+    __syncthreads();
+    if (s_prev >= w.max_voxels) return;
   }
   if (MODE == 1 && Src::kIsDepth && tid < kMaxCams) s_cull[tid] = w.cull ? __ldg(w.cull + b * kMaxCams + tid) : 0xFFFFFFFFu;
   const bool cal_async = src.stage_async(s_cal, &s_bar, b);
   __syncthreads();
   if (cal_async) tma_wait(&s_bar);
-  if (MODE == 0 && s_prev >= w.max_voxels) return;
 
-  const int64_t sb = cta_base + wv * strip;                 // this warp's strip [sb, se)
-  if (sb >= end) return;
-  const int64_t se = sb + strip < end ? sb + strip : end;
+  typename Src::Walker wk;
+  if (!src.walk_init(wk, begin, end, iters, wv, lane)) return;
   uint2 *s_item = s_itemb + wv * kListCap;
-  uint16_t *s_und = s_undb + wv * kListCap;
+  uint32_t *s_und = s_undb + wv * kListCap;
   unsigned long long *table = w.table + (int64_t)b * w.cap;
   uint32_t *flags = w.flags + (int64_t)b * w.nwords;
   uint32_t *slots = w.slots + (int64_t)b * w.max_voxels * w.K;
   int cnt = 0, nu = 0, claims = 0;
 
-  typename Src::Loc loc = src.locate(sb + 4 * lane);
-  bool live = MODE == 0 || !Src::kIsDepth || __any_sync(0xffffffffu, src.lane_live(loc, s_cull, 0));
-  typename Src::Pre pre = src.preload(b, live ? sb + 4 * lane : se, se);
-  int64_t tb = sb;
+  bool live = MODE == 0 || !Src::kIsDepth || src.walk_live(wk, s_cull);
+  typename Src::Pre pre = src.preload(b, wk, live);
   bool flushing = false;
   // One loop, one copy of each stage (the kernel has to stay inside the instruction cache): item passes while
-  // 32 items are waiting, exact passes while 32 undecided points are waiting, else the next tile; at the end
-  // of the strip the two lists are flushed with partial passes.  Both lists are consumed from their END.
+  // 32 items are waiting, exact passes while 32 undecided elements are waiting, else the next tile; at the end
+  // of the walk the two lists are flushed with partial passes.  Both lists are consumed from their END.
 #pragma unroll 1
   while (true) {
     if (cnt >= 32 || (flushing && nu == 0 && cnt > 0)) {
@@ -569,14 +642,13 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
       const int n = cnt < 32 ? cnt : 32;
       if (lane < n) {
         const uint2 it = s_item[cnt - n + lane];
-        const uint32_t idx = (uint32_t)sb + it.y;
         if (MODE == 0) {
-          claims += table_insert(table, flags, w, it.x, idx);
+          claims += table_insert(table, flags, w, it.x, it.y);
         } else {
           const uint32_t r = table_rank(table, w, it.x);
           if (r != kEmpty32) {
-            slot_insert(slots + (int64_t)r * w.K, w.K, idx);
-            if (point2voxel) point2voxel[(int64_t)b * w.N + idx] = (int32_t)r;
+            slot_insert(slots + (int64_t)r * w.K, w.K, it.y);
+            if (point2voxel) point2voxel[(int64_t)b * w.N + it.y] = (int32_t)r;
           }
         }
       }
@@ -585,40 +657,39 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
       continue;
     }
     if (nu >= 32 || (flushing && nu > 0)) {
-      // ---- exact pass: IEEE arithmetic of the reference for up to 32 undecided points; hits join the item list ----
+      // ---- exact pass: IEEE arithmetic of the reference for up to 32 undecided elements; hits join the item list ----
       const int n = nu < 32 ? nu : 32;
       bool in = false;
-      int lid = 0, cx, cy, cz;
+      uint32_t idx = 0;
+      int cx, cy, cz;
       if (lane < n) {
-        lid = s_und[nu - n + lane];
-        in = src.cell_exact(b, sb + lid, s_cal, g, cx, cy, cz);
+        idx = s_und[nu - n + lane];
+        in = src.cell_exact(b, idx, s_cal, g, cx, cy, cz);
       }
       const unsigned b1 = __ballot_sync(0xffffffffu, in);
-      if (in) s_item[cnt + __popc(b1 & lt)] = make_uint2(voxel_key(cx, cy, cz, g), (uint32_t)lid);
+      if (in) s_item[cnt + __popc(b1 & lt)] = make_uint2(voxel_key(cx, cy, cz, g), idx);
       cnt += __popc(b1);
       nu -= n;
       __syncwarp();
       continue;
     }
-    if (tb >= se) {
+    if (!src.walk_more(wk)) {
       if (flushing) break;
       flushing = true;
       continue;
     }
     // ---- next tile ----
-    const int64_t i0 = tb + 4 * lane;
-    const typename Src::Loc cloc = loc;
+    const typename Src::Walker cwk = wk;
     const typename Src::Pre cpre = pre;
     const bool clive = live;
-    const uint32_t l0 = (uint32_t)(tb - sb) + 4 * lane;
-    tb += kTilePoints;
-    if (tb < se) {                                          // the tile after this one: position, liveness, depth load
-      loc = src.locate(i0 + kTilePoints);
-      live = MODE == 0 || !Src::kIsDepth || __any_sync(0xffffffffu, src.lane_live(loc, s_cull, 0));
-      pre = src.preload(b, live ? i0 + kTilePoints : se, se);
+    src.walk_next(wk);
+    if (src.walk_more(wk)) {                                // the tile after this one: liveness, depth load
+      live = MODE == 0 || !Src::kIsDepth || src.walk_live(wk, s_cull);
+      pre = src.preload(b, wk, live);
     }
     if (!clive) continue;                                   // no pixel of this tile can reach a kept voxel
-    typename Src::Cursor cur = src.cursor(b, i0, se, s_cal, cpre, cloc);
+    const uint32_t l0 = src.walk_index(cwk);
+    typename Src::Cursor cur = src.cursor(b, cwk, s_cal, cpre);
     Quad qd;
     src.classify(cur, s_cal, g, qd);
     // exclusive prefix of the per-lane counts (0..4) from three ballots of the count's bit planes
@@ -627,7 +698,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
     const unsigned p0 = __ballot_sync(0xffffffffu, cin & 1u), p1 = __ballot_sync(0xffffffffu, cin & 2u),
                    p2 = __ballot_sync(0xffffffffu, cin & 4u);
     uint2 *it = s_item + cnt + (__popc(p0 & lt) + 2 * __popc(p1 & lt) + 4 * __popc(p2 & lt));
-    // the order inside the list is irrelevant: point q of the lane goes to the lane's slot #(set bits below q)
+    // the order inside the list is irrelevant: element q of the lane goes to the lane's slot #(set bits below q)
     if (in & 1u) it[0] = make_uint2(qd.key[0], l0);
     if (in & 2u) it[in & 1u] = make_uint2(qd.key[1], l0 + 1);
     if (in & 4u) it[__popc(in & 3u)] = make_uint2(qd.key[2], l0 + 2);
@@ -640,7 +711,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
       int ua = nu + __popc(u0 & lt) + 2 * __popc(u1 & lt) + 4 * __popc(u2 & lt);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if ((qd.und >> q) & 1u) s_und[ua++] = (uint16_t)(l0 + q);
+        if ((qd.und >> q) & 1u) s_und[ua++] = l0 + q;
       nu += __popc(u0) + 2 * __popc(u1) + 4 * __popc(u2);
     }
     __syncwarp();
@@ -745,11 +816,11 @@ __device__ __forceinline__ int voxel_rank(const HvWork &w, int b, uint32_t first
 
 // P2r -----------------------------------------------------------------------
 // One pass over the table, one thread per pair of entries (a 16-byte load; no loop: the dependent chain
-// entry -> rank words -> stores is hidden by thread-level parallelism).  grid (cap / 512, frames).
-// Entry {key | first point} -> {key | rank} ({key | ~0} for the voxels the reference drops); row r of the
-// slots gets its first point; coors[r] is the key decoded as (z, y, x); the kept voxels are marked in the
-// frame's bird's-eye mask (read first: after the first few hundred voxels nearly every bit is already set).
-static __global__ void __launch_bounds__(256) hv_rank_kernel(HvWork w, VoxelGrid g, int32_t *coors) {
+// entry -> rank words -> store is hidden by thread-level parallelism).  grid (cap / 512, frames).
+// Entry {key | first point} -> {key | rank} ({key | ~0} for the voxels the reference drops), written in
+// place; the kept voxels are marked in one of the frame's kBevCopies bird's-eye masks (copies: 8 M atomics
+// per step on 512 bytes per frame would serialise in L2).
+static __global__ void __launch_bounds__(256) hv_rank_kernel(HvWork w) {
   const int b = blockIdx.y + w.b0;
   const int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (s0 >= w.cap) return;
@@ -766,26 +837,19 @@ static __global__ void __launch_bounds__(256) hv_rank_kernel(HvWork w, VoxelGrid
       continue;
     }
     table[q] = (e & 0xFFFFFFFF00000000ull) | (uint32_t)r;
-    const int64_t vr = (int64_t)b * w.max_voxels + r;
-    w.slots[vr * w.K] = first;
-    int cz, cy, cx;
-    key_to_zyx(key, g, cz, cy, cx);
-    coors[vr * 3 + 0] = cz;
-    coors[vr * 3 + 1] = cy;
-    coors[vr * 3 + 2] = cx;
     if (w.bev) {
-      const uint32_t bx = (uint32_t)cx * kBevDim / (uint32_t)g.grid[0], by = (uint32_t)cy * kBevDim / (uint32_t)g.grid[1];
-      const uint32_t bit = by * kBevDim + bx;
-      uint32_t *word = w.bev + (int64_t)b * kBevWords + (bit >> 5);
-      const uint32_t m = 1u << (bit & 31);
-      if (!(__ldcg(word) & m)) atomicOr(word, m);
+      const uint32_t t = fast_div(key, w.div_gx);
+      const uint32_t cx = key - t * w.div_gx.d;
+      const uint32_t cy = t - fast_div(t, w.div_gy) * w.div_gy.d;
+      const uint32_t bit = ((cy * w.bev_ky) >> 20) * kBevDim + ((cx * w.bev_kx) >> 20);
+      atomicOr(w.bev + ((int64_t)b * kBevCopies + (blockIdx.x & (kBevCopies - 1))) * kBevWords + (bit >> 5), 1u << (bit & 31));
     }
   }
 }
 
 // P2c -----------------------------------------------------------------------
-// grid (frames), 256 threads.  For every camera and block of 2^cbshift image columns: is there a kept voxel
-// that a pixel of the block can fall into?  A pixel (u, v, z > 0) lands at the continuous cell coordinate
+// grid (cameras, frames), 256 threads.  For the camera and every block of 2^cbshift image columns: is there a
+// kept voxel that a pixel of the block can fall into?  A pixel (u, v, z > 0) lands at the continuous cell coordinate
 //   P = z * Mc (u, v, 1)^T + T,   Mc = [A B C] of the direct cell map (rd3_common.cuh), T = Th + 0.5,
 // and its reference cell is within tol(z) <= tolmax of floor(P) (the proven bound of that map), so with
 // w = Mc^-1 (P - T) = (z u, z v, z) the block's pixels fill the wedge
@@ -796,48 +860,53 @@ static __global__ void __launch_bounds__(256) hv_rank_kernel(HvWork w, VoxelGrid
 // map is singular / non-finite keeps all its blocks.
 static __global__ void __launch_bounds__(256) hv_cull_kernel(DepthSource src, VoxelGrid g, HvWork w) {
   __shared__ uint32_t s_bev[kBevWords];
-  __shared__ double s_inv[kMaxCams][9], s_T[kMaxCams][3], s_margin[kMaxCams];
-  __shared__ int s_ok[kMaxCams];
-  __shared__ uint32_t s_mask[kMaxCams];
-  const int b = blockIdx.x + w.b0;
+  __shared__ double s_inv[9], s_T[3], s_margin;
+  __shared__ int s_ok;
+  __shared__ uint32_t s_mask;
+  const int b = blockIdx.y + w.b0, cam = blockIdx.x;
   const int ncam = src.p.ncam;
-  for (int i = threadIdx.x; i < kBevWords; i += blockDim.x) s_bev[i] = w.bev[(int64_t)b * kBevWords + i];
-  if (threadIdx.x < kMaxCams) s_mask[threadIdx.x] = 0u;
-  if (threadIdx.x < ncam) {
-    const int cam = threadIdx.x;
+  for (int i = threadIdx.x; i < kBevWords; i += blockDim.x) {
+    uint32_t v = 0;
+    for (int c = 0; c < kBevCopies; ++c) v |= w.bev[((int64_t)b * kBevCopies + c) * kBevWords + i];
+    s_bev[i] = v;
+  }
+  if (threadIdx.x == 0) {
+    s_mask = 0u;
     const float *k = src.cal_table + ((int64_t)b * ncam + cam) * kCalibFloats + kCalDirect;
     double m[9];
     for (int a = 0; a < 3; ++a) {
       m[a * 3 + 0] = k[a * 4 + 0]; m[a * 3 + 1] = k[a * 4 + 1]; m[a * 3 + 2] = k[a * 4 + 2];
-      s_T[cam][a] = (double)k[a * 4 + 3] + 0.5;
+      s_T[a] = (double)k[a * 4 + 3] + 0.5;
     }
     const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
     const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
     double scale = 0.0;
     for (int i = 0; i < 9; ++i) scale = fmax(scale, fabs(m[i]));
     const double id = 1.0 / det;
-    s_inv[cam][0] = c00 * id; s_inv[cam][1] = (m[2] * m[7] - m[1] * m[8]) * id; s_inv[cam][2] = (m[1] * m[5] - m[2] * m[4]) * id;
-    s_inv[cam][3] = c01 * id; s_inv[cam][4] = (m[0] * m[8] - m[2] * m[6]) * id; s_inv[cam][5] = (m[2] * m[3] - m[0] * m[5]) * id;
-    s_inv[cam][6] = c02 * id; s_inv[cam][7] = (m[1] * m[6] - m[0] * m[7]) * id; s_inv[cam][8] = (m[0] * m[4] - m[1] * m[3]) * id;
+    s_inv[0] = c00 * id; s_inv[1] = (m[2] * m[7] - m[1] * m[8]) * id; s_inv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+    s_inv[3] = c01 * id; s_inv[4] = (m[0] * m[8] - m[2] * m[6]) * id; s_inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+    s_inv[6] = c02 * id; s_inv[7] = (m[1] * m[6] - m[0] * m[7]) * id; s_inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
     // tol(z) = 0.5 - thr(z) >= the proven bound; largest at the largest valid depth
     const double tolmax = 0.5 - ((double)src.p.zmax * (double)k[12] + (double)k[13]);
-    s_margin[cam] = 1.0 + 2.0 * tolmax;
+    s_margin = 1.0 + 2.0 * tolmax;
     bool ok = fabs(det) > 1e-12 * scale * scale * scale && isfinite(id) && tolmax >= 0.0 && tolmax < 1e6;
-    for (int i = 0; i < 9; ++i) ok = ok && isfinite(s_inv[cam][i]);
-    for (int a = 0; a < 3; ++a) ok = ok && isfinite(s_T[cam][a]);
-    s_ok[cam] = ok ? 1 : 0;
+    for (int i = 0; i < 9; ++i) ok = ok && isfinite(s_inv[i]);
+    for (int a = 0; a < 3; ++a) ok = ok && isfinite(s_T[a]);
+    s_ok = ok ? 1 : 0;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
   const int nblk = ((src.p.W - 1) >> src.cbshift) + 1;
-  const double gx = g.grid[0], gy = g.grid[1], gz = g.grid[2];
-  for (int pair = wv; pair < ncam * nblk; pair += blockDim.x >> 5) {
-    const int cam = pair / nblk, blk = pair - cam * nblk;
+  const double gz = g.grid[2];
+  // bird's-eye cell j on an axis covers the voxels i with (i * k) >> 20 == j, i.e. the cell coordinates
+  // [j 2^20 / k, (j + 1) 2^20 / k + 1)
+  const double sx = 1048576.0 / (double)w.bev_kx, sy = 1048576.0 / (double)w.bev_ky;
+  for (int blk = wv; blk < nblk; blk += blockDim.x >> 5) {
     bool hit = false;
-    if (!s_ok[cam]) {
+    if (!s_ok) {
       hit = true;
     } else {
-      const double *iv = s_inv[cam];
+      const double *iv = s_inv;
       const double u0 = (double)(blk << src.cbshift);
       double u1 = (double)(((blk + 1) << src.cbshift) - 1);
       if (u1 > (double)(src.p.W - 1)) u1 = (double)(src.p.W - 1);
@@ -851,15 +920,15 @@ static __global__ void __launch_bounds__(256) hv_cull_kernel(DepthSource src, Vo
         n[3][a] = iv[3 + a];
         n[4][a] = hm1 * iv[6 + a] - iv[3 + a];
       }
-      const double mg = s_margin[cam];
-      const double hx = 0.5 * gx / kBevDim + 1.0 + mg, hy = 0.5 * gy / kBevDim + 1.0 + mg, hz = 0.5 * gz + mg;
+      const double mg = s_margin;
+      const double hx = 0.5 * (sx + 1.0) + mg, hy = 0.5 * (sy + 1.0) + mg, hz = 0.5 * gz + mg;
       double cst[5], slack[5];
       for (int k = 0; k < 5; ++k) {
         // z part (the box spans the whole height), -n.T and the half-extent terms are the same for every cell
-        cst[k] = n[k][2] * (0.5 * gz - s_T[cam][2]) - n[k][0] * s_T[cam][0] - n[k][1] * s_T[cam][1] +
+        cst[k] = n[k][2] * (0.5 * gz - s_T[2]) - n[k][0] * s_T[0] - n[k][1] * s_T[1] +
                  fabs(n[k][0]) * hx + fabs(n[k][1]) * hy + fabs(n[k][2]) * hz;
-        slack[k] = 1e-9 * (fabs(n[k][0]) * (gx + fabs(s_T[cam][0]) + hx) + fabs(n[k][1]) * (gy + fabs(s_T[cam][1]) + hy) +
-                           fabs(n[k][2]) * (gz + fabs(s_T[cam][2]) + hz));
+        slack[k] = 1e-9 * (fabs(n[k][0]) * ((double)g.grid[0] + fabs(s_T[0]) + hx) + fabs(n[k][1]) * ((double)g.grid[1] + fabs(s_T[1]) + hy) +
+                           fabs(n[k][2]) * (gz + fabs(s_T[2]) + hz));
       }
       for (int wi = lane; wi < kBevWords && !hit; wi += 32) {
         uint32_t bits = s_bev[wi];
@@ -867,17 +936,17 @@ static __global__ void __launch_bounds__(256) hv_cull_kernel(DepthSource src, Vo
           const int bp = __ffs(bits) - 1;
           bits &= bits - 1;
           const int cell = wi * 32 + bp;
-          const double cxc = ((double)(cell % kBevDim) + 0.5) * gx / kBevDim, cyc = ((double)(cell / kBevDim) + 0.5) * gy / kBevDim;
+          const double cxc = ((double)(cell % kBevDim) + 0.5) * sx + 0.5, cyc = ((double)(cell / kBevDim) + 0.5) * sy + 0.5;
           bool out = false;
           for (int k = 0; k < 5; ++k) out = out || (cst[k] + n[k][0] * cxc + n[k][1] * cyc < -slack[k]);
           hit = !out;
         }
       }
     }
-    if (__any_sync(0xffffffffu, hit) && lane == 0) atomicOr(s_mask + cam, 1u << blk);
+    if (__any_sync(0xffffffffu, hit) && lane == 0) atomicOr(&s_mask, 1u << blk);
   }
   __syncthreads();
-  if (threadIdx.x < kMaxCams) w.cull[b * kMaxCams + threadIdx.x] = s_mask[threadIdx.x];
+  if (threadIdx.x == 0) w.cull[b * kMaxCams + cam] = s_mask;
 }
 
 // P4 ------------------------------------------------------------------------
@@ -886,8 +955,8 @@ static __global__ void __launch_bounds__(256) hv_cull_kernel(DepthSource src, Vo
 //   1. zero the tile (16-byte stores); every warp loads its share of the slot indices and
 //      ballot-compacts the non-empty ones into its own list segment (no atomics, no barrier)
 //   2. each warp gathers / re-unprojects (exact reference arithmetic) its listed items
-//   3. voxels are copied out with 16-byte stores; one thread per voxel writes the count and the
-//      HardSimpleVFE mean (slot order, one __fdiv_rn); coors were written by P2
+//   3. voxels are copied out with 16-byte stores; one thread per voxel writes coors (from the first
+//      point), the count and the HardSimpleVFE mean (slot order, one __fdiv_rn)
 template <class Src>
 __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGrid g, HvWork w, HvOut o, int V) {
   extern __shared__ float s_dyn[];
@@ -972,7 +1041,7 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
     for (int e = threadIdx.x; e < nfl; e += kEmitThreads) vout[e] = tile[e];
   }
 
-  // one thread per voxel: count and HardSimpleVFE mean
+  // one thread per voxel: coors, count and HardSimpleVFE mean
   // (voxel_encoder.py:45-46: sum over ALL K slots in slot order, then one division; the
   // slots beyond the count are zeros, so the running sum stops changing at the count --
   // except that (-0.0) + 0.0 = +0.0, which one extra "+ 0.0f" reproduces)
@@ -983,6 +1052,13 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
     while (cnt < K && si[cnt] != kEmpty32) ++cnt;
     const float *p0 = tile + v * K * C;
     const int64_t vr = (int64_t)b * w.max_voxels + r0 + v;
+    // coors from the voxel's first point (the tile holds it already): the fast path decides all but points within
+    // rounding of a cell boundary
+    int cx = 0, cy = 0, cz = 0;
+    if (voxel_coor_fast(p0[0], p0[1], p0[2], 0.0f, g, cx, cy, cz) == 2) voxel_coor(p0[0], p0[1], p0[2], g, cx, cy, cz);
+    o.coors[vr * 3 + 0] = cz;
+    o.coors[vr * 3 + 1] = cy;
+    o.coors[vr * 3 + 2] = cx;
     o.num[vr] = cnt;
     if (o.mean) {
       const float n = (float)cnt;
@@ -1038,17 +1114,20 @@ struct HvPlan {
   size_t off_table, off_slots, off_flags, off_bev, off_claims, off_cull, off_prefix, off_chunk, total;
 };
 
-inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels) {
+// `round_multiple`: a round has to be a whole number of the source's work units (image rows for depth maps)
+inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels, int64_t round_multiple = 1024) {
   const HvTuning &t = hv_tuning();
   HvPlan p;
   p.N = N; p.B = B; p.K = K; p.max_voxels = max_voxels;
   const int64_t n1 = N > 0 ? N : 1;
   // round length: at most `rounds` rounds, but a round should keep the whole GPU busy
   // (>= ~1.2 M points over all frames), so small batches use fewer, longer rounds
-  int64_t S = ceil_div(ceil_div(n1, t.rounds), 1024) * 1024;
-  const int64_t fill = ceil_div(ceil_div((int64_t)t.sm_count * 8 * 1024, B > 0 ? B : 1), 1024) * 1024;
+  const int64_t rm = round_multiple > 0 ? round_multiple : 1;
+  int64_t S = ceil_div(n1, t.rounds);
+  const int64_t fill = ceil_div((int64_t)t.sm_count * 8 * 1024, B > 0 ? B : 1);
   if (S < fill) S = fill;
   if (S < 65536) S = 65536;
+  S = ceil_div(S, rm) * rm;
   p.S = S;
   p.rounds = (int)ceil_div(n1, S);
   // the table never holds more than max_voxels + S keys (see header), nor more than N
@@ -1065,7 +1144,7 @@ inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels) {
   p.off_table = off; off += align_up((size_t)B * p.cap * 8);
   p.off_slots = off; off += align_up((size_t)B * max_voxels * K * 4);
   p.off_flags = off; off += align_up((size_t)B * p.nwords * 4);
-  p.off_bev = off; off += align_up((size_t)B * kBevWords * 4);
+  p.off_bev = off; off += align_up((size_t)B * kBevCopies * kBevWords * 4);
   p.off_claims = off; off += align_up((size_t)B * kMaxRounds * 4);
   p.off_cull = off; off += align_up((size_t)B * kMaxCams * 4);
   p.off_prefix = off; off += align_up((size_t)B * p.nwords * 4);
@@ -1082,7 +1161,7 @@ template <class Src> struct CullLaunch {
 template <> struct CullLaunch<DepthSource> {
   static bool wanted(const DepthSource &s) { return hv_tuning().cull && s.cal_table != nullptr; }
   static void run(const DepthSource &s, const VoxelGrid &g, const HvWork &w, int nb, cudaStream_t st) {
-    hv_cull_kernel<<<nb, 256, 0, st>>>(s, g, w);
+    hv_cull_kernel<<<dim3(s.p.ncam, nb), 256, 0, st>>>(s, g, w);
   }
 };
 
@@ -1104,6 +1183,11 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   w.N = p.N; w.cap = p.cap; w.cap_mask = (uint32_t)(p.cap - 1); w.log2cap = p.log2cap;
   w.direct = (volume <= (uint64_t)p.cap) ? 1 : 0;
   w.nwords = p.nwords; w.nchunks = p.nchunks; w.K = p.K; w.max_voxels = p.max_voxels;
+  w.div_gx = make_fastdiv((uint32_t)g.grid[0]);
+  w.div_gy = make_fastdiv((uint32_t)g.grid[1]);
+  w.bev_kx = (uint32_t)(((uint64_t)kBevDim << 20) / (uint64_t)g.grid[0]);
+  w.bev_ky = (uint32_t)(((uint64_t)kBevDim << 20) / (uint64_t)g.grid[1]);
+  if (p.S % src.host_round_multiple() != 0 && p.rounds > 1) return RD3_ERR_INVALID_ARGUMENT;   // plan made for another source
 
   const int C = src.host_num_feats();
 #ifndef RD3_EMIT_ITEMS
@@ -1146,7 +1230,6 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   } while (0)
   if (nl > 1) RD3_LANE_TRY(cudaEventRecord(lanes->fork, stream));
   if (status != RD3_OK) return status;
-  const int ins_span = kPassWarps * tune.ins_iters * kTilePoints, lkp_span = kPassWarps * tune.lkp_iters * kTilePoints;
   for (int l = 0; l < nl && status == RD3_OK; ++l) {
     const int b0 = (int)((int64_t)p.B * l / nl), b1 = (int)((int64_t)p.B * (l + 1) / nl);
     const int nb = b1 - b0;
@@ -1164,23 +1247,25 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
                                  (size_t)nb * p.max_voxels * p.K * 4, st));
     RD3_LANE_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords, 0, (size_t)nb * p.nwords * 4, st));
     RD3_LANE_TRY(cudaMemsetAsync(w.round_claims + (size_t)b0 * kMaxRounds, 0, (size_t)nb * kMaxRounds * 4, st));
-    if (cull) RD3_LANE_TRY(cudaMemsetAsync(w.bev + (size_t)b0 * kBevWords, 0, (size_t)nb * kBevWords * 4, st));
+    if (cull)
+      RD3_LANE_TRY(cudaMemsetAsync(w.bev + (size_t)b0 * kBevCopies * kBevWords, 0, (size_t)nb * kBevCopies * kBevWords * 4, st));
     prof_mark(st, 1);
     for (int r = 0; r < p.rounds && p.N > 0; ++r) {
       const int64_t begin = (int64_t)r * p.S;
       const int64_t end = begin + p.S < p.N ? begin + p.S : p.N;
-      dim3 grid((unsigned)ceil_div(end - begin, ins_span), nb);
-      hv_pass_kernel<Src, 0><<<grid, kPassThreads, 0, st>>>(src, g, w, nullptr, begin, end, r, tune.ins_iters);
+      // the rounds after the second mostly find their frames closed: fatter CTAs, fewer of them to retire
+      const int it = r < 2 ? tune.ins_iters : 4 * tune.ins_iters;
+      hv_pass_kernel<Src, 0><<<dim3(src.host_grid(begin, end, it), nb), kPassThreads, 0, st>>>(src, g, w, nullptr, begin, end, r, it);
     }
     prof_mark(st, 2);
     hv_flagscan_kernel<<<dim3(p.nchunks, nb), kScanThreads, 0, st>>>(w);
     scan_chunks_kernel<<<nb, 1024, 0, st>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels, b0);
     prof_mark(st, 3);
-    hv_rank_kernel<<<dim3((unsigned)ceil_div(p.cap, 512), nb), 256, 0, st>>>(w, g, out.coors);
+    hv_rank_kernel<<<dim3((unsigned)ceil_div(p.cap, 512), nb), 256, 0, st>>>(w);
     if (cull) CullLaunch<Src>::run(src, g, w, nb, st);
     prof_mark(st, 4);
     if (p.N > 0)
-      hv_pass_kernel<Src, 1><<<dim3((unsigned)ceil_div(p.N, lkp_span), nb), kPassThreads, 0, st>>>(
+      hv_pass_kernel<Src, 1><<<dim3(src.host_grid(0, p.N, tune.lkp_iters), nb), kPassThreads, 0, st>>>(
           src, g, w, out.point2voxel, 0, p.N, 0, tune.lkp_iters);
     prof_mark(st, 5);
     hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, V), nb), kEmitThreads, smem, st>>>(src, g, w, out, V);

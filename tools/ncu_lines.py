@@ -2,7 +2,7 @@
 samples per instruction) with the line table of the object it was built from (nvdisasm --print-line-info).
 The object must be the build that was profiled (same SASS).
 
-    python tools/ncu_lines.py rep.ncu-rep 3d-reconstruction-detection_b200/csrc/depth.o hv_insert_kernelINS_11DepthSource [min_instr]
+    python tools/ncu_lines.py rep.ncu-rep 3d-reconstruction-detection_b200/csrc/depth.o hv_pass_kernelINS_11DepthSourceELi1 [min_instr] [launch index]
 """
 import csv
 import io
@@ -14,9 +14,14 @@ import tempfile
 
 rep, obj, kern = sys.argv[1], os.path.abspath(sys.argv[2]), sys.argv[3]
 min_instr = float(sys.argv[4]) if len(sys.argv) > 4 else 2.0
+skip = sys.argv[5] if len(sys.argv) > 5 else "0"            # which launch of a multi-launch report
 
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", skip, "--launch-count", "1"],
+                     capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
+again = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+if len(again) > 1:                       # newer ncu prints the page once per view: keep the first
+    rows = rows[:again[1]]
 hdr, data = rows[1], rows[2:]
 iE, iS = hdr.index("Instructions Executed"), hdr.index("# Samples")
 stalls = [(i, h[6:]) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
