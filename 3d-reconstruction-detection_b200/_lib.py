@@ -131,20 +131,25 @@ def require_cuda(t, name, dtype=None):
         raise RuntimeError("%s must be %s, got %s" % (name, dtype, t.dtype))
 
 
-# grow-only scratch buffer per (device, stream)
+# grow-only scratch buffer per (device, stream).  Work on one stream is ordered, so calls on the same stream may
+# share scratch; different streams get their own.  Streams come and go (stream pools, graph captures): the
+# table keeps the most recently used _MAX_WORKSPACES entries.
 _workspaces = {}
+_MAX_WORKSPACES = 16
 
 
 def workspace(device, nbytes):
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _workspaces.get(key)
+    ws = _workspaces.pop(key, None)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
+    _workspaces[key] = ws                       # re-inserted last: dicts keep insertion order
+    while len(_workspaces) > _MAX_WORKSPACES:
+        _workspaces.pop(next(iter(_workspaces)))
     return ws
 
 
-PROFILE_STAGES = ("memset", "insert", "flags", "rank", "lookup", "emit", "meta")
+PROFILE_STAGES = ("memset", "insert", "flags", "cull", "lookup", "emit", "meta")
 
 
 def profile_enable(on=True):

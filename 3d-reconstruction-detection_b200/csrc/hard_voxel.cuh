@@ -267,7 +267,7 @@ struct DepthSource {
     const uint32_t nct = (uint32_t)((p.W + kTilePoints - 1) / kTilePoints);
     const uint32_t rg = blockIdx.x / nct;
     ct = blockIdx.x - rg * nct;
-    const uint32_t first = (uint32_t)(begin / p.W), last = (uint32_t)(end / p.W);
+    const uint32_t first = fast_div((uint32_t)begin, p.div_w), last = fast_div((uint32_t)end, p.div_w);   // < 2^30 pixels
     r0 = first + rg * (uint32_t)(kPassWarps * iters);
     r1 = r0 + (uint32_t)(kPassWarps * iters);
     if (r1 > last) r1 = last;
@@ -477,20 +477,24 @@ __device__ __forceinline__ void first_toggle(uint32_t *flags, uint32_t idx) {
   atomicXor(flags + (idx >> 5), 1u << (idx & 31));
 }
 
-// Insert (key, idx).  Slot ownership is permanent (CAS from empty); the payload
-// only ever decreases (atomicMin), so a stale read can only cause a redundant
-// atomic, never a wrong skip.  Returns 1 iff this call created the entry.
+// Insert (key, idx).  Slot ownership is permanent (CAS from empty); the payload only ever decreases
+// (atomicMin), so a stale read can only cause a redundant atomic, never a wrong skip.  Returns 1 iff this
+// call created the entry.
+// The first access is the CAS itself on entry 0 of the key's bucket: a new key into an empty bucket and a
+// repeated key whose entry leads its bucket -- the common cases -- take ONE memory round trip instead of
+// load + CAS.  Only when entry 0 belongs to another key is the bucket read (one 256-bit load) and searched.
 __device__ __forceinline__ int table_insert(unsigned long long *table, uint32_t *flags, const HvWork &w,
                                             uint32_t key, uint32_t idx) {
   const unsigned long long mine = ((unsigned long long)key << 32) | idx;
-  uint32_t slot;
-  unsigned long long e;
-  if (w.direct) {
-    slot = key;
-    e = __ldcg(table + slot);
-  } else {
+  uint32_t slot = w.direct ? key : hash_bucket_slot(key, w.log2cap);
+  unsigned long long e = atomicCAS(table + slot, kEmpty64, mine);
+  if (e == kEmpty64) {
+    first_toggle(flags, idx);
+    return 1;
+  }
+  if ((uint32_t)(e >> 32) != key) {
     // one 256-bit load finds the first entry of the bucket that holds the key or is empty
-    uint32_t s0 = hash_bucket_slot(key, w.log2cap);
+    uint32_t s0 = slot;
     while (true) {
       unsigned long long e0, e1, e2, e3;
       load_bucket(table + s0, e0, e1, e2, e3);
@@ -530,9 +534,28 @@ __device__ __forceinline__ int table_insert(unsigned long long *table, uint32_t 
   }
 }
 
-// Lookup after P2 (the table is not written any more): the voxel's rank, kEmpty32 when the key is absent or
-// its voxel was dropped (rank >= max_voxels).
-__device__ __forceinline__ uint32_t table_rank(const unsigned long long *table, const HvWork &w, uint32_t key) {
+// "the voxel of `key` was claimed": its column is marked in one of the frame's kBevCopies bird's-eye masks
+// (privatised: all claims of a frame on one 512-byte mask would serialise in L2).  The mask may hold voxels that
+// are dropped later (rank >= max_voxels): it only has to contain the kept ones.
+__device__ __forceinline__ void bev_mark(const HvWork &w, int b, uint32_t key, int copy) {
+  const uint32_t t = fast_div(key, w.div_gx);
+  const uint32_t cx = key - t * w.div_gx.d;
+  const uint32_t cy = t - fast_div(t, w.div_gy) * w.div_gy.d;
+  const uint32_t bit = ((cy * w.bev_ky) >> 20) * kBevDim + ((cx * w.bev_kx) >> 20);
+  atomicOr(w.bev + ((int64_t)b * kBevCopies + (copy & (kBevCopies - 1))) * kBevWords + (bit >> 5), 1u << (bit & 31));
+}
+
+// rank (first-occurrence order) of the voxel whose first point is `first_idx`
+__device__ __forceinline__ int voxel_rank(const HvWork &w, int b, uint32_t first_idx) {
+  const uint32_t word = first_idx >> 5;
+  const int64_t wi = (int64_t)b * w.nwords + word;
+  const uint32_t bits = __ldg(w.flags + wi) & ((1u << (first_idx & 31)) - 1u);
+  return __ldg(w.chunk_base + (int64_t)b * w.nchunks + (first_idx >> kChunkShift)) +
+         __ldg(w.wordprefix + wi) + __popc(bits);
+}
+
+// Lookup (the table is not written any more): the first point of the key's voxel, kEmpty32 when the key is absent.
+__device__ __forceinline__ uint32_t table_first(const unsigned long long *table, const HvWork &w, uint32_t key) {
   if (w.direct) return (uint32_t)__ldcg(table + key);            // empty entries read ~0 as well
   uint32_t s0 = hash_bucket_slot(key, w.log2cap);
   while (true) {
@@ -554,8 +577,9 @@ __device__ __forceinline__ uint32_t table_rank(const unsigned long long *table, 
 // strictly increasing at all times and the final content is independent of arrival order (every point is
 // offered exactly once).
 __device__ __forceinline__ void slot_insert(uint32_t *S, int K, uint32_t idx) {
-  // a (possibly stale, hence larger) copy of the last slot that is already smaller: K smaller indices exist
-  if (__ldcg(S + K - 1) < idx) return;
+  // The last slot and the first eight are requested together (one memory round trip).  A (possibly stale,
+  // hence larger) copy of the last slot that is already smaller than idx: K smaller indices exist.
+  const uint32_t last = __ldcg(S + K - 1);
   uint32_t cur = idx;
   int k = 0;
   // Skip the prefix of smaller indices with 8 independent loads at a time instead of one
@@ -564,6 +588,7 @@ __device__ __forceinline__ void slot_insert(uint32_t *S, int K, uint32_t idx) {
     uint32_t v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = (k + i < K) ? __ldcg(S + k + i) : kEmpty32;
+    if (last < idx) return;
     int i = 8;
 #pragma unroll
     for (int q = 7; q >= 0; --q) i = (v[q] < cur) ? i : q;      // first slot not smaller than cur
@@ -594,6 +619,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
   __shared__ __align__(8) uint64_t s_bar;        // completion of the calibration's TMA copy
   __shared__ uint2 s_itemb[kPassWarps * kListCap];     // (key, element index) of the in-range elements
   __shared__ uint32_t s_undb[kPassWarps * kListCap];   // indices of the undecided elements
+  __shared__ uint2 s_hitb[MODE ? kPassWarps * 64 : 1]; // lookup: (first point of the voxel, element index) of the table hits
   __shared__ uint32_t s_cull[kMaxCams];
   __shared__ int s_prev;
 
@@ -624,33 +650,53 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
   if (!src.walk_init(wk, begin, end, iters, wv, lane)) return;
   uint2 *s_item = s_itemb + wv * kListCap;
   uint32_t *s_und = s_undb + wv * kListCap;
+  uint2 *s_hit = s_hitb + (MODE ? wv * 64 : 0);
   unsigned long long *table = w.table + (int64_t)b * w.cap;
   uint32_t *flags = w.flags + (int64_t)b * w.nwords;
   uint32_t *slots = w.slots + (int64_t)b * w.max_voxels * w.K;
-  int cnt = 0, nu = 0, claims = 0;
+  int cnt = 0, nu = 0, nh = 0, claims = 0;
 
   bool live = MODE == 0 || !Src::kIsDepth || src.walk_live(wk, s_cull);
   typename Src::Pre pre = src.preload(b, wk, live);
   bool flushing = false;
-  // One loop, one copy of each stage (the kernel has to stay inside the instruction cache): item passes while
-  // 32 items are waiting, exact passes while 32 undecided elements are waiting, else the next tile; at the end
-  // of the walk the two lists are flushed with partial passes.  Both lists are consumed from their END.
+  // One loop, one copy of each stage (the kernel has to stay inside the instruction cache): hit passes while 32
+  // table hits are waiting, item passes while 32 items are waiting, exact passes while 32 undecided elements are
+  // waiting, else the next tile; at the end of the walk the lists are flushed with partial passes.  All lists are
+  // consumed from their END.
 #pragma unroll 1
   while (true) {
-    if (cnt >= 32 || (flushing && nu == 0 && cnt > 0)) {
-      // ---- item pass: MODE 0 table insert, MODE 1 table lookup -> rank -> slot row ----
-      const int n = cnt < 32 ? cnt : 32;
+    if (MODE == 1 && (nh >= 32 || (flushing && nu == 0 && cnt == 0 && nh > 0))) {
+      // ---- hit pass (dense lanes): first point -> rank (#first points before it) -> sorted insertion into the
+      //      voxel's slot row.  Voxels of rank >= max_voxels are the ones the reference drops.
+      const int n = nh < 32 ? nh : 32;
       if (lane < n) {
-        const uint2 it = s_item[cnt - n + lane];
-        if (MODE == 0) {
-          claims += table_insert(table, flags, w, it.x, it.y);
-        } else {
-          const uint32_t r = table_rank(table, w, it.x);
-          if (r != kEmpty32) {
-            slot_insert(slots + (int64_t)r * w.K, w.K, it.y);
-            if (point2voxel) point2voxel[(int64_t)b * w.N + it.y] = (int32_t)r;
-          }
+        const uint2 h = s_hit[nh - n + lane];
+        const int r = voxel_rank(w, b, h.x);
+        if (r < w.max_voxels) {
+          slot_insert(slots + (int64_t)r * w.K, w.K, h.y);
+          if (point2voxel) point2voxel[(int64_t)b * w.N + h.y] = r;
         }
+      }
+      nh -= n;
+      __syncwarp();
+      continue;
+    }
+    if (cnt >= 32 || (flushing && nu == 0 && cnt > 0)) {
+      // ---- item pass: MODE 0 table insert; MODE 1 table lookup, the hits join the hit list ----
+      const int n = cnt < 32 ? cnt : 32;
+      uint2 it = make_uint2(0u, 0u);
+      if (lane < n) it = s_item[cnt - n + lane];
+      if (MODE == 0) {
+        if (lane < n && table_insert(table, flags, w, it.x, it.y)) {
+          ++claims;
+          if (w.bev) bev_mark(w, b, it.x, (int)blockIdx.x + wv);
+        }
+      } else {
+        uint32_t first = kEmpty32;
+        if (lane < n) first = table_first(table, w, it.x);
+        const unsigned hb = __ballot_sync(0xffffffffu, first != kEmpty32);
+        if (first != kEmpty32) s_hit[nh + __popc(hb & lt)] = make_uint2(first, it.y);
+        nh += __popc(hb);
       }
       cnt -= n;
       __syncwarp();
@@ -805,51 +851,9 @@ static __global__ void __launch_bounds__(1024) scan_chunks_kernel(int32_t *chunk
   }
 }
 
-// rank (first-occurrence order) of the voxel whose first point is `first_idx`
-__device__ __forceinline__ int voxel_rank(const HvWork &w, int b, uint32_t first_idx) {
-  const uint32_t word = first_idx >> 5;
-  const int64_t wi = (int64_t)b * w.nwords + word;
-  const uint32_t bits = __ldg(w.flags + wi) & ((1u << (first_idx & 31)) - 1u);
-  return __ldg(w.chunk_base + (int64_t)b * w.nchunks + (first_idx >> kChunkShift)) +
-         __ldg(w.wordprefix + wi) + __popc(bits);
-}
-
-// P2r -----------------------------------------------------------------------
-// One pass over the table, one thread per pair of entries (a 16-byte load; no loop: the dependent chain
-// entry -> rank words -> store is hidden by thread-level parallelism).  grid (cap / 512, frames).
-// Entry {key | first point} -> {key | rank} ({key | ~0} for the voxels the reference drops), written in
-// place; the kept voxels are marked in one of the frame's kBevCopies bird's-eye masks (copies: 8 M atomics
-// per step on 512 bytes per frame would serialise in L2).
-static __global__ void __launch_bounds__(256) hv_rank_kernel(HvWork w) {
-  const int b = blockIdx.y + w.b0;
-  const int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  if (s0 >= w.cap) return;
-  unsigned long long *table = w.table + (int64_t)b * w.cap + s0;
-  const ulonglong2 ee = __ldcs(reinterpret_cast<const ulonglong2 *>(table));
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const unsigned long long e = q ? ee.y : ee.x;
-    if (e == kEmpty64) continue;
-    const uint32_t first = (uint32_t)e, key = (uint32_t)(e >> 32);
-    const int r = voxel_rank(w, b, first);
-    if (r >= w.max_voxels) {
-      table[q] = e | 0xFFFFFFFFull;
-      continue;
-    }
-    table[q] = (e & 0xFFFFFFFF00000000ull) | (uint32_t)r;
-    if (w.bev) {
-      const uint32_t t = fast_div(key, w.div_gx);
-      const uint32_t cx = key - t * w.div_gx.d;
-      const uint32_t cy = t - fast_div(t, w.div_gy) * w.div_gy.d;
-      const uint32_t bit = ((cy * w.bev_ky) >> 20) * kBevDim + ((cx * w.bev_kx) >> 20);
-      atomicOr(w.bev + ((int64_t)b * kBevCopies + (blockIdx.x & (kBevCopies - 1))) * kBevWords + (bit >> 5), 1u << (bit & 31));
-    }
-  }
-}
-
 // P2c -----------------------------------------------------------------------
-// grid (cameras, frames), 256 threads.  For the camera and every block of 2^cbshift image columns: is there a
-// kept voxel that a pixel of the block can fall into?  A pixel (u, v, z > 0) lands at the continuous cell coordinate
+// grid (cameras x column blocks, frames), one thread per word of the bird's-eye mask.  For one camera and one
+// block of 2^cbshift image columns: is there a claimed voxel that a pixel of the block can fall into?  A pixel (u, v, z > 0) lands at the continuous cell coordinate
 //   P = z * Mc (u, v, 1)^T + T,   Mc = [A B C] of the direct cell map (rd3_common.cuh), T = Th + 0.5,
 // and its reference cell is within tol(z) <= tolmax of floor(P) (the proven bound of that map), so with
 // w = Mc^-1 (P - T) = (z u, z v, z) the block's pixels fill the wedge
@@ -858,20 +862,17 @@ static __global__ void __launch_bounds__(256) hv_rank_kernel(HvWork w) {
 // one of these five planes cannot receive a pixel of the block; the largest value of a plane function over a
 // box is its value at the centre plus |n| . half-extents.  Everything is evaluated in fp64; a camera whose
 // map is singular / non-finite keeps all its blocks.
-static __global__ void __launch_bounds__(256) hv_cull_kernel(DepthSource src, VoxelGrid g, HvWork w) {
-  __shared__ uint32_t s_bev[kBevWords];
+static __global__ void __launch_bounds__(kBevWords) hv_cull_kernel(DepthSource src, VoxelGrid g, HvWork w) {
   __shared__ double s_inv[9], s_T[3], s_margin;
-  __shared__ int s_ok;
-  __shared__ uint32_t s_mask;
-  const int b = blockIdx.y + w.b0, cam = blockIdx.x;
+  __shared__ int s_ok, s_hitflag;
+  const int nblk = ((src.p.W - 1) >> src.cbshift) + 1;
+  const int b = blockIdx.y + w.b0, cam = blockIdx.x / nblk, blk = blockIdx.x - cam * nblk;
   const int ncam = src.p.ncam;
-  for (int i = threadIdx.x; i < kBevWords; i += blockDim.x) {
-    uint32_t v = 0;
-    for (int c = 0; c < kBevCopies; ++c) v |= w.bev[((int64_t)b * kBevCopies + c) * kBevWords + i];
-    s_bev[i] = v;
-  }
+  // thread t owns word t of the bird's-eye mask (OR of the privatised copies)
+  uint32_t bits = 0;
+  for (int c = 0; c < kBevCopies; ++c) bits |= __ldcg(w.bev + ((int64_t)b * kBevCopies + c) * kBevWords + threadIdx.x);
   if (threadIdx.x == 0) {
-    s_mask = 0u;
+    s_hitflag = 0;
     const float *k = src.cal_table + ((int64_t)b * ncam + cam) * kCalibFloats + kCalDirect;
     double m[9];
     for (int a = 0; a < 3; ++a) {
@@ -895,58 +896,51 @@ static __global__ void __launch_bounds__(256) hv_cull_kernel(DepthSource src, Vo
     s_ok = ok ? 1 : 0;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-  const int nblk = ((src.p.W - 1) >> src.cbshift) + 1;
-  const double gz = g.grid[2];
-  // bird's-eye cell j on an axis covers the voxels i with (i * k) >> 20 == j, i.e. the cell coordinates
-  // [j 2^20 / k, (j + 1) 2^20 / k + 1)
-  const double sx = 1048576.0 / (double)w.bev_kx, sy = 1048576.0 / (double)w.bev_ky;
-  for (int blk = wv; blk < nblk; blk += blockDim.x >> 5) {
-    bool hit = false;
-    if (!s_ok) {
-      hit = true;
-    } else {
-      const double *iv = s_inv;
-      const double u0 = (double)(blk << src.cbshift);
-      double u1 = (double)(((blk + 1) << src.cbshift) - 1);
-      if (u1 > (double)(src.p.W - 1)) u1 = (double)(src.p.W - 1);
-      const double hm1 = (double)(src.p.H - 1);
-      // plane normals n (rows: w3 | w1 - u0 w3 | u1 w3 - w1 | w2 | (H-1) w3 - w2)
-      double n[5][3];
-      for (int a = 0; a < 3; ++a) {
-        n[0][a] = iv[6 + a];
-        n[1][a] = iv[a] - u0 * iv[6 + a];
-        n[2][a] = u1 * iv[6 + a] - iv[a];
-        n[3][a] = iv[3 + a];
-        n[4][a] = hm1 * iv[6 + a] - iv[3 + a];
-      }
-      const double mg = s_margin;
-      const double hx = 0.5 * (sx + 1.0) + mg, hy = 0.5 * (sy + 1.0) + mg, hz = 0.5 * gz + mg;
-      double cst[5], slack[5];
-      for (int k = 0; k < 5; ++k) {
-        // z part (the box spans the whole height), -n.T and the half-extent terms are the same for every cell
-        cst[k] = n[k][2] * (0.5 * gz - s_T[2]) - n[k][0] * s_T[0] - n[k][1] * s_T[1] +
-                 fabs(n[k][0]) * hx + fabs(n[k][1]) * hy + fabs(n[k][2]) * hz;
-        slack[k] = 1e-9 * (fabs(n[k][0]) * ((double)g.grid[0] + fabs(s_T[0]) + hx) + fabs(n[k][1]) * ((double)g.grid[1] + fabs(s_T[1]) + hy) +
-                           fabs(n[k][2]) * (gz + fabs(s_T[2]) + hz));
-      }
-      for (int wi = lane; wi < kBevWords && !hit; wi += 32) {
-        uint32_t bits = s_bev[wi];
-        while (bits && !hit) {
-          const int bp = __ffs(bits) - 1;
-          bits &= bits - 1;
-          const int cell = wi * 32 + bp;
-          const double cxc = ((double)(cell % kBevDim) + 0.5) * sx + 0.5, cyc = ((double)(cell / kBevDim) + 0.5) * sy + 0.5;
-          bool out = false;
-          for (int k = 0; k < 5; ++k) out = out || (cst[k] + n[k][0] * cxc + n[k][1] * cyc < -slack[k]);
-          hit = !out;
-        }
-      }
+  bool hit = false;
+  if (!s_ok) {
+    hit = true;
+  } else if (bits) {
+    const double gz = g.grid[2];
+    // bird's-eye cell j on an axis covers the voxels i with (i * k) >> 20 == j, i.e. the cell coordinates
+    // [j 2^20 / k, (j + 1) 2^20 / k + 1)
+    const double sx = 1048576.0 / (double)w.bev_kx, sy = 1048576.0 / (double)w.bev_ky;
+    const double *iv = s_inv;
+    const double u0 = (double)(blk << src.cbshift);
+    double u1 = (double)(((blk + 1) << src.cbshift) - 1);
+    if (u1 > (double)(src.p.W - 1)) u1 = (double)(src.p.W - 1);
+    const double hm1 = (double)(src.p.H - 1);
+    // plane normals n (rows: w3 | w1 - u0 w3 | u1 w3 - w1 | w2 | (H-1) w3 - w2)
+    double n[5][3];
+    for (int a = 0; a < 3; ++a) {
+      n[0][a] = iv[6 + a];
+      n[1][a] = iv[a] - u0 * iv[6 + a];
+      n[2][a] = u1 * iv[6 + a] - iv[a];
+      n[3][a] = iv[3 + a];
+      n[4][a] = hm1 * iv[6 + a] - iv[3 + a];
     }
-    if (__any_sync(0xffffffffu, hit) && lane == 0) atomicOr(&s_mask, 1u << blk);
+    const double mg = s_margin;
+    const double hx = 0.5 * (sx + 1.0) + mg, hy = 0.5 * (sy + 1.0) + mg, hz = 0.5 * gz + mg;
+    double cst[5], slack[5];
+    for (int k = 0; k < 5; ++k) {
+      // z part (the box spans the whole height), -n.T and the half-extent terms are the same for every cell
+      cst[k] = n[k][2] * (0.5 * gz - s_T[2]) - n[k][0] * s_T[0] - n[k][1] * s_T[1] +
+               fabs(n[k][0]) * hx + fabs(n[k][1]) * hy + fabs(n[k][2]) * hz;
+      slack[k] = 1e-9 * (fabs(n[k][0]) * ((double)g.grid[0] + fabs(s_T[0]) + hx) + fabs(n[k][1]) * ((double)g.grid[1] + fabs(s_T[1]) + hy) +
+                         fabs(n[k][2]) * (gz + fabs(s_T[2]) + hz));
+    }
+    while (bits && !hit) {
+      const int bp = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const int cell = threadIdx.x * 32 + bp;
+      const double cxc = ((double)(cell % kBevDim) + 0.5) * sx + 0.5, cyc = ((double)(cell / kBevDim) + 0.5) * sy + 0.5;
+      bool out = false;
+      for (int k = 0; k < 5; ++k) out = out || (cst[k] + n[k][0] * cxc + n[k][1] * cyc < -slack[k]);
+      hit = !out;
+    }
   }
+  if (hit) s_hitflag = 1;
   __syncthreads();
-  if (threadIdx.x == 0) w.cull[b * kMaxCams + cam] = s_mask;
+  if (threadIdx.x == 0 && s_hitflag) atomicOr(w.cull + b * kMaxCams + cam, 1u << blk);
 }
 
 // P4 ------------------------------------------------------------------------
@@ -1161,7 +1155,8 @@ template <class Src> struct CullLaunch {
 template <> struct CullLaunch<DepthSource> {
   static bool wanted(const DepthSource &s) { return hv_tuning().cull && s.cal_table != nullptr; }
   static void run(const DepthSource &s, const VoxelGrid &g, const HvWork &w, int nb, cudaStream_t st) {
-    hv_cull_kernel<<<dim3(s.p.ncam, nb), 256, 0, st>>>(s, g, w);
+    const int nblk = ((s.p.W - 1) >> s.cbshift) + 1;
+    hv_cull_kernel<<<dim3(s.p.ncam * nblk, nb), kBevWords, 0, st>>>(s, g, w);
   }
 };
 
@@ -1247,8 +1242,10 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
                                  (size_t)nb * p.max_voxels * p.K * 4, st));
     RD3_LANE_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords, 0, (size_t)nb * p.nwords * 4, st));
     RD3_LANE_TRY(cudaMemsetAsync(w.round_claims + (size_t)b0 * kMaxRounds, 0, (size_t)nb * kMaxRounds * 4, st));
-    if (cull)
+    if (cull) {
       RD3_LANE_TRY(cudaMemsetAsync(w.bev + (size_t)b0 * kBevCopies * kBevWords, 0, (size_t)nb * kBevCopies * kBevWords * 4, st));
+      RD3_LANE_TRY(cudaMemsetAsync(w.cull + (size_t)b0 * kMaxCams, 0, (size_t)nb * kMaxCams * 4, st));
+    }
     prof_mark(st, 1);
     for (int r = 0; r < p.rounds && p.N > 0; ++r) {
       const int64_t begin = (int64_t)r * p.S;
@@ -1261,7 +1258,6 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
     hv_flagscan_kernel<<<dim3(p.nchunks, nb), kScanThreads, 0, st>>>(w);
     scan_chunks_kernel<<<nb, 1024, 0, st>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels, b0);
     prof_mark(st, 3);
-    hv_rank_kernel<<<dim3((unsigned)ceil_div(p.cap, 512), nb), 256, 0, st>>>(w);
     if (cull) CullLaunch<Src>::run(src, g, w, nb, st);
     prof_mark(st, 4);
     if (p.N > 0)

@@ -14,12 +14,14 @@ from .backproject import _prep, make_params, squeeze_head
 
 
 class DepthToVoxels(nn.Module):
-    """Batched fused front end.  Output buffers and scratch are allocated once
-    per input shape and reused, so steady-state calls allocate nothing and do
-    not synchronise with the host."""
+    """Batched fused front end.  Like the reference ops every call returns FRESH output tensors (torch's
+    caching allocator makes that cheap: no cudaMalloc in steady state, no host synchronisation).
+    ``reuse_buffers=True`` is the opt-in for callers that consume a result before the next call with the
+    same shape on the same stream (benchmarks, CUDA-graph capture): the outputs then live in buffers
+    allocated once per (shape, stream) and are overwritten by the next call."""
 
     def __init__(self, voxel_size, point_cloud_range, max_num_points, max_voxels,
-                 max_depth=None, range_filter=None, with_mean=True, with_voxels=True):
+                 max_depth=None, range_filter=None, with_mean=True, with_voxels=True, reuse_buffers=False):
         """``with_voxels=False`` skips the padded (B, max_voxels, max_points, 3) tensor -- 85 % of
         the output bytes -- for callers that only feed the sparse encoder (mean + coors + num)."""
         super().__init__()
@@ -33,19 +35,25 @@ class DepthToVoxels(nn.Module):
         self.max_depth = max_depth
         self.range_filter = range_filter
         self.with_mean = with_mean
+        self.reuse_buffers = reuse_buffers
         self._out_cache = {}
 
+    def _alloc(self, B, dev, max_voxels):
+        K = self.max_num_points
+        return dict(
+            voxels=(torch.empty((B, max_voxels, K, 3), dtype=torch.float32, device=dev)
+                    if self.with_voxels else None),
+            coors=torch.empty((B, max_voxels, 3), dtype=torch.int32, device=dev),
+            num=torch.empty((B, max_voxels), dtype=torch.int32, device=dev),
+            mean=torch.empty((B, max_voxels, 3), dtype=torch.float32, device=dev) if self.with_mean else None,
+            voxel_num=torch.empty((B,), dtype=torch.int32, device=dev))
+
     def _get_buffers(self, B, dev, max_voxels):
-        key = (B, dev, max_voxels)
+        if not self.reuse_buffers:
+            return self._alloc(B, dev, max_voxels)
+        key = (B, dev, max_voxels, torch.cuda.current_stream(dev).cuda_stream)
         if key not in self._out_cache:
-            K = self.max_num_points
-            self._out_cache[key] = dict(
-                voxels=(torch.empty((B, max_voxels, K, 3), dtype=torch.float32, device=dev)
-                        if self.with_voxels else None),
-                coors=torch.empty((B, max_voxels, 3), dtype=torch.int32, device=dev),
-                num=torch.empty((B, max_voxels), dtype=torch.int32, device=dev),
-                mean=torch.empty((B, max_voxels, 3), dtype=torch.float32, device=dev) if self.with_mean else None,
-                voxel_num=torch.empty((B,), dtype=torch.int32, device=dev))
+            self._out_cache[key] = self._alloc(B, dev, max_voxels)
         return self._out_cache[key]
 
     def forward(self, depths, intrinsics, cam2lidar_rts, confs=None, conf_thresh=None, sky_masks=None):
@@ -85,7 +93,7 @@ class DepthToVoxels(nn.Module):
 _pack_cache = {}
 
 
-def pack_sparse_inputs(result, batch_offset=0, with_num_points=False, sync=True):
+def pack_sparse_inputs(result, batch_offset=0, with_num_points=False, sync=True, reuse_buffers=False):
     """One launch instead of the per-sample slice + F.pad + torch.cat tail of
     ``_voxelize_and_encode`` (sparse_refinement.py:393-402).
 
@@ -95,7 +103,8 @@ def pack_sparse_inputs(result, batch_offset=0, with_num_points=False, sync=True)
     ``(voxel_features, num_points, coors)``.  ``sync=True`` reads sum M back (the one D2H read
     the reference's ``hard_voxelize`` return value forces per sample); ``sync=False`` returns the
     worst-case-sized buffers and a device tensor ``offsets (B+1)`` instead of the batch size.
-    The returned tensors are views of buffers reused by the next call with the same shape."""
+    Fresh tensors per call unless ``reuse_buffers=True`` (then: views of buffers that the next call with the
+    same shape on the same stream overwrites)."""
     feats, coors, num, vnum = result["voxel_mean"], result["coors"], result["num_points"], result["voxel_num"]
     if feats is None:
         raise RuntimeError("pack_sparse_inputs needs voxel_mean (DepthToVoxels(with_mean=True))")
@@ -104,13 +113,18 @@ def pack_sparse_inputs(result, batch_offset=0, with_num_points=False, sync=True)
         _lib.require_cuda(t, n, d)
     B, MV, F = feats.shape
     dev = feats.device
-    key = (B, MV, F, dev, with_num_points)
-    if key not in _pack_cache:
-        _pack_cache[key] = (torch.empty((B * MV, F), dtype=torch.float32, device=dev),
-                            torch.empty((B * MV, 4), dtype=torch.int32, device=dev),
-                            torch.empty((B * MV,), dtype=torch.int32, device=dev) if with_num_points else None,
-                            torch.empty((B + 1,), dtype=torch.int32, device=dev))
-    of, oc, on, offs = _pack_cache[key]
+    def alloc():
+        return (torch.empty((B * MV, F), dtype=torch.float32, device=dev),
+                torch.empty((B * MV, 4), dtype=torch.int32, device=dev),
+                torch.empty((B * MV,), dtype=torch.int32, device=dev) if with_num_points else None,
+                torch.empty((B + 1,), dtype=torch.int32, device=dev))
+    if reuse_buffers:
+        key = (B, MV, F, dev, with_num_points, torch.cuda.current_stream(dev).cuda_stream)
+        if key not in _pack_cache:
+            _pack_cache[key] = alloc()
+        of, oc, on, offs = _pack_cache[key]
+    else:
+        of, oc, on, offs = alloc()
     with torch.cuda.device_of(feats):
         st = _lib.lib().rd3_pack_sparse_inputs(_lib.ptr(feats), _lib.ptr(coors), _lib.ptr(num), _lib.ptr(vnum),
                                                B, MV, F, int(batch_offset), _lib.ptr(of), _lib.ptr(oc),

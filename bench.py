@@ -357,7 +357,7 @@ def main():
     alg = {
         "insert": B * npix * 4,                                 # depth read (rounds of the still open frames)
         "lookup": B * npix * 4,                                 # depth read
-        "flags": 0, "rank": 0, "memset": 0,                     # scratch-only stages
+        "flags": 0, "cull": 0, "memset": 0,                     # scratch-only stages
         "emit": M_total * K * C * 4,                            # voxels written
         "meta": M_total * (12 + 4 + 4 * F),                     # coors + num + mean written
     }

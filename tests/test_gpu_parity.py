@@ -607,6 +607,32 @@ def test_hard_simple_vfe_backward():
     assert torch.allclose(a.grad.cpu(), xr.grad, rtol=1e-6, atol=1e-7)
 
 
+def test_fused_outputs_are_fresh_unless_reuse_is_requested():
+    """Like the reference ops, a second forward must not overwrite what the first returned (pred and GT
+    voxelization in one training step); reuse_buffers=True is the explicit opt-in."""
+    c = synthetic.CONFIGS["C1"]
+    b0, b1 = synthetic.make_batch([0, 1], 56, 96), synthetic.make_batch([7, 8], 56, 96)
+    d0, d1 = ({k: v.to(DEV) for k, v in b.items()} for b in (b0, b1))
+    mod = rd3_b200.DepthToVoxels(c["voxel_size"], c["pcr"], c["max_points"], 3000, max_depth=synthetic.MAX_DEPTH).to(DEV)
+    r0 = mod(d0["depth"], d0["intrinsics"], d0["cam2lidar"])
+    keep = {k: v.clone() for k, v in r0.items()}
+    r1 = mod(d1["depth"], d1["intrinsics"], d1["cam2lidar"])
+    torch.cuda.synchronize()
+    assert r0["coors"].data_ptr() != r1["coors"].data_ptr()
+    for k in keep:
+        assert torch.equal(r0[k], keep[k]), k
+    assert not torch.equal(r0["voxel_num"], r1["voxel_num"]) or not torch.equal(r0["coors"], r1["coors"])
+    p0 = rd3_b200.pack_sparse_inputs(r0)
+    p0c = [t.clone() for t in p0[:2]]
+    rd3_b200.pack_sparse_inputs(r1)
+    assert all(torch.equal(a, b_) for a, b_ in zip(p0[:2], p0c))
+    shared = rd3_b200.DepthToVoxels(c["voxel_size"], c["pcr"], c["max_points"], 3000, max_depth=synthetic.MAX_DEPTH,
+                                    reuse_buffers=True).to(DEV)
+    s0 = shared(d0["depth"], d0["intrinsics"], d0["cam2lidar"])
+    s1 = shared(d1["depth"], d1["intrinsics"], d1["cam2lidar"])
+    assert s0["coors"].data_ptr() == s1["coors"].data_ptr()
+
+
 def test_cuda_graph_capture_of_fused_path():
     """The whole kernel sequence (incl. the internal stream lanes) is capturable: no host sync,
     no allocation inside DepthToVoxels.forward in steady state."""
@@ -614,7 +640,8 @@ def test_cuda_graph_capture_of_fused_path():
     H, W = 56, 96
     b = synthetic.make_batch([0, 1, 2], H, W)
     d = {k: v.to(DEV) for k, v in b.items()}
-    mod = rd3_b200.DepthToVoxels(c["voxel_size"], c["pcr"], c["max_points"], 3000, max_depth=synthetic.MAX_DEPTH).to(DEV)
+    mod = rd3_b200.DepthToVoxels(c["voxel_size"], c["pcr"], c["max_points"], 3000, max_depth=synthetic.MAX_DEPTH,
+                                 reuse_buffers=True).to(DEV)
     k_, m_ = d["intrinsics"].contiguous(), d["cam2lidar"].contiguous()
     ref = {k: v.clone() for k, v in mod(d["depth"], k_, m_).items()}        # warm-up allocates buffers
     torch.cuda.synchronize()

@@ -11,10 +11,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 libs = [a.split("=", 1) for a in sys.argv[1:] if "=" in a] or [["tree", ""]]
 scenes = [a for a in sys.argv[1:] if a in ("mixture", "ground")] or ["mixture", "ground"]
-for name, path in libs:
+for name, spec in libs:
     for scene in scenes:
         env = dict(os.environ)
-        path, *kv = path.split(",")                      # name=lib.so,RD3_X=1,RD3_Y=2
+        path, *kv = spec.split(",")                      # name=lib.so,RD3_X:1,RD3_Y:2
         for a in kv:
             env[a.split(":", 1)[0]] = a.split(":", 1)[1]
         if path:
