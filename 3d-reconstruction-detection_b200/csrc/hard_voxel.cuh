@@ -63,6 +63,7 @@ constexpr int kEmitThreads = RD3_EMIT_THREADS;
 constexpr int kTilePoints = 128;      // points per warp tile (4 per lane)
 constexpr int kListCap = 160;         // per-warp item / undecided lists: 31 carried + 128 new
 constexpr int kMaxRounds = 64;
+constexpr uint32_t kDummyKey = 0xFFFFFFE0u;   // + lane: 32 values no voxel key takes (make_grid: volume <= kDummyKey)
 constexpr int kBevDim = 64;           // bird's-eye mask of the kept voxels: kBevDim x kBevDim bits over the x,y grid
 constexpr int kBevWords = kBevDim * kBevDim / 32;
 constexpr int kBevCopies = 32;        // privatised copies of the mask (power of two): spreads the marking atomics
@@ -423,7 +424,8 @@ struct DepthSource {
 // ---------------------------------------------------------------------------
 struct HvWork {
   unsigned long long *table;  // [B][cap]   {key:32 | min point idx:32}, after P2 {key:32 | rank:32}; empty = ~0
-  uint32_t *slots;            // [B][max_voxels*K] sorted point indices, empty = ~0
+  uint32_t *slots;            // [B][max_voxels][K-1] sorted indices of the points after the first, empty = ~0
+  uint32_t *first_of;         // [B][max_voxels] first point of the voxel of rank r (the r-th set bit of flags)
   uint32_t *flags;            // [B][nwords] bit i: point i is the first of a voxel
   int32_t *wordprefix;        // [B][nwords] exclusive popcount prefix inside the chunk
   int32_t *chunk_base;        // [B][nchunks] totals, then exclusive bases after the chunk scan
@@ -432,6 +434,7 @@ struct HvWork {
   uint32_t *cull;             // [B][kMaxCams] live column blocks per camera, or null (nothing culled)
   FastDiv div_gx, div_gy;     // key -> (x, y) cell
   uint32_t bev_kx, bev_ky;    // bird's-eye cell of voxel column i: (i * k) >> 20, k = floor(kBevDim 2^20 / grid)
+  FastDiv div_K;              // slot item -> (voxel, slot)
   int64_t N;
   int b0;                     // first frame of the group this launch works on
   int64_t cap;
@@ -477,24 +480,22 @@ __device__ __forceinline__ void first_toggle(uint32_t *flags, uint32_t idx) {
   atomicXor(flags + (idx >> 5), 1u << (idx & 31));
 }
 
-// Insert (key, idx).  Slot ownership is permanent (CAS from empty); the payload only ever decreases
-// (atomicMin), so a stale read can only cause a redundant atomic, never a wrong skip.  Returns 1 iff this
-// call created the entry.
-// The first access is the CAS itself on entry 0 of the key's bucket: a new key into an empty bucket and a
-// repeated key whose entry leads its bucket -- the common cases -- take ONE memory round trip instead of
-// load + CAS.  Only when entry 0 belongs to another key is the bucket read (one 256-bit load) and searched.
+// Insert (key, idx).  Slot ownership is permanent (CAS from empty); the payload
+// only ever decreases (atomicMin), so a stale read can only cause a redundant
+// atomic, never a wrong skip.  Returns 1 iff this call created the entry.
+// (Measured: issuing the CAS first, without the load, is slower -- repeated keys then pay an atomic on a hot
+// entry where a load would have told them to leave.)
 __device__ __forceinline__ int table_insert(unsigned long long *table, uint32_t *flags, const HvWork &w,
                                             uint32_t key, uint32_t idx) {
   const unsigned long long mine = ((unsigned long long)key << 32) | idx;
-  uint32_t slot = w.direct ? key : hash_bucket_slot(key, w.log2cap);
-  unsigned long long e = atomicCAS(table + slot, kEmpty64, mine);
-  if (e == kEmpty64) {
-    first_toggle(flags, idx);
-    return 1;
-  }
-  if ((uint32_t)(e >> 32) != key) {
+  uint32_t slot;
+  unsigned long long e;
+  if (w.direct) {
+    slot = key;
+    e = __ldcg(table + slot);
+  } else {
     // one 256-bit load finds the first entry of the bucket that holds the key or is empty
-    uint32_t s0 = slot;
+    uint32_t s0 = hash_bucket_slot(key, w.log2cap);
     while (true) {
       unsigned long long e0, e1, e2, e3;
       load_bucket(table + s0, e0, e1, e2, e3);
@@ -653,7 +654,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
   uint2 *s_hit = s_hitb + (MODE ? wv * 64 : 0);
   unsigned long long *table = w.table + (int64_t)b * w.cap;
   uint32_t *flags = w.flags + (int64_t)b * w.nwords;
-  uint32_t *slots = w.slots + (int64_t)b * w.max_voxels * w.K;
+  uint32_t *slots = w.slots + (int64_t)b * w.max_voxels * (w.K - 1);
   int cnt = 0, nu = 0, nh = 0, claims = 0;
 
   bool live = MODE == 0 || !Src::kIsDepth || src.walk_live(wk, s_cull);
@@ -671,10 +672,13 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
       const int n = nh < 32 ? nh : 32;
       if (lane < n) {
         const uint2 h = s_hit[nh - n + lane];
-        const int r = voxel_rank(w, b, h.x);
-        if (r < w.max_voxels) {
-          slot_insert(slots + (int64_t)r * w.K, w.K, h.y);
-          if (point2voxel) point2voxel[(int64_t)b * w.N + h.y] = r;
+        // a voxel's first point is not kept in the slot rows (hv_firsts_kernel lists the first points by rank)
+        if (h.x != h.y || point2voxel) {
+          const int r = voxel_rank(w, b, h.x);
+          if (r < w.max_voxels) {
+            if (h.x != h.y && w.K > 1) slot_insert(slots + (int64_t)r * (w.K - 1), w.K - 1, h.y);
+            if (point2voxel) point2voxel[(int64_t)b * w.N + h.y] = r;
+          }
         }
       }
       nh -= n;
@@ -687,7 +691,12 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
       uint2 it = make_uint2(0u, 0u);
       if (lane < n) it = s_item[cnt - n + lane];
       if (MODE == 0) {
-        if (lane < n && table_insert(table, flags, w, it.x, it.y)) {
+        // neighbouring pixels often fall into one voxel: of the lanes holding the same key only the one with the
+        // smallest index goes to the table (the entry keeps the minimum anyway; atomics on one address would
+        // serialise in L2, where equal-address loads coalesce)
+        const unsigned grp = __match_any_sync(0xffffffffu, lane < n ? it.x : kDummyKey + lane);
+        const uint32_t lowest = __reduce_min_sync(grp, it.y);
+        if (lane < n && it.y == lowest && table_insert(table, flags, w, it.x, it.y)) {
           ++claims;
           if (w.bev) bev_mark(w, b, it.x, (int)blockIdx.x + wv);
         }
@@ -811,6 +820,23 @@ __device__ __forceinline__ void chunk_scan_store(uint32_t my_word, int *s_warp, 
   flags[wi] = my_word;
   wordprefix[wi] = base + inc - cnt;
   if (threadIdx.x == 0) chunk_total[blockIdx.x] = total;
+}
+
+// P2f -----------------------------------------------------------------------
+// After the chunk scan: the r-th set bit of the first-point flags is the first point of the voxel of rank r.
+// grid (nwords / 256, frames), one flag word per thread.
+static __global__ void __launch_bounds__(256) hv_firsts_kernel(HvWork w) {
+  const int b = blockIdx.y + w.b0;
+  const int wl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wl >= w.nwords) return;
+  uint32_t bits = w.flags[(int64_t)b * w.nwords + wl];
+  if (!bits) return;
+  int r = __ldg(w.chunk_base + (int64_t)b * w.nchunks + wl / kChunkWords) + __ldg(w.wordprefix + (int64_t)b * w.nwords + wl);
+  uint32_t *out = w.first_of + (int64_t)b * w.max_voxels;
+  while (bits && r < w.max_voxels) {
+    out[r++] = ((uint32_t)wl << 5) + (uint32_t)(__ffs(bits) - 1);
+    bits &= bits - 1;
+  }
 }
 
 // P2s -----------------------------------------------------------------------
@@ -969,7 +995,13 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
   float *tile = s_dyn;
   uint32_t *s_idx = reinterpret_cast<uint32_t *>(s_dyn + (((size_t)V * K * C + 3) & ~(size_t)3));
   uint16_t *s_list = reinterpret_cast<uint16_t *>(s_idx + (size_t)V * K);
-  const uint32_t *S = w.slots + ((int64_t)b * w.max_voxels + r0) * K;
+  const uint32_t *S = w.slots + ((int64_t)b * w.max_voxels + r0) * (K - 1);
+  const uint32_t *F1 = w.first_of + (int64_t)b * w.max_voxels + r0;
+  // slot item it = v * K + k of the CTA: k == 0 is the voxel's first point, k >= 1 column k - 1 of its slot row
+  auto slot_index = [&](int it) -> uint32_t {
+    const uint32_t v = fast_div((uint32_t)it, w.div_K), k = (uint32_t)it - v * (uint32_t)K;
+    return k ? __ldg(S + v * (uint32_t)(K - 1) + (k - 1)) : __ldg(F1 + v);
+  };
 
   // warp wv owns items [wv*per, wv*per+per): its list segment starts at the same offset
   const int per = ((items + nw - 1) / nw + 31) & ~31;
@@ -980,7 +1012,7 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int it = lo + 32 * q + lane;
-    pre[q] = it < hi ? __ldg(S + it) : kEmpty32;
+    pre[q] = it < hi ? slot_index(it) : kEmpty32;
   }
   const bool cal_async = src.stage_async(s_cal, &s_bar, b);     // one TMA bulk copy, no load / store loop
   {
@@ -1003,7 +1035,7 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
     const int it = it0 + lane;
     uint32_t idx = kEmpty32;
     if (it < hi) {
-      idx = __ldg(S + it);
+      idx = slot_index(it);
       s_idx[it] = idx;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, idx != kEmpty32);
@@ -1105,7 +1137,7 @@ struct HvPlan {
   int log2cap;
   int nwords, nchunks;
   // [table | slots] are set to 0xFF with one memset, [flags | bev | round_claims] to 0 with another
-  size_t off_table, off_slots, off_flags, off_bev, off_claims, off_cull, off_prefix, off_chunk, total;
+  size_t off_table, off_slots, off_first, off_flags, off_bev, off_claims, off_cull, off_prefix, off_chunk, total;
 };
 
 // `round_multiple`: a round has to be a whole number of the source's work units (image rows for depth maps)
@@ -1136,7 +1168,8 @@ inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels, int64_t round_mul
   p.nwords = p.nchunks * kChunkWords;
   size_t off = 0;
   p.off_table = off; off += align_up((size_t)B * p.cap * 8);
-  p.off_slots = off; off += align_up((size_t)B * max_voxels * K * 4);
+  p.off_slots = off; off += align_up((size_t)B * max_voxels * (K > 1 ? K - 1 : 1) * 4);
+  p.off_first = off; off += align_up((size_t)B * max_voxels * 4);
   p.off_flags = off; off += align_up((size_t)B * p.nwords * 4);
   p.off_bev = off; off += align_up((size_t)B * kBevCopies * kBevWords * 4);
   p.off_claims = off; off += align_up((size_t)B * kMaxRounds * 4);
@@ -1168,6 +1201,7 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   HvWork w;
   w.table = (unsigned long long *)(base + p.off_table);
   w.slots = (uint32_t *)(base + p.off_slots);
+  w.first_of = (uint32_t *)(base + p.off_first);
   w.flags = (uint32_t *)(base + p.off_flags);
   w.round_claims = (int32_t *)(base + p.off_claims);
   w.wordprefix = (int32_t *)(base + p.off_prefix);
@@ -1182,6 +1216,7 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   w.div_gy = make_fastdiv((uint32_t)g.grid[1]);
   w.bev_kx = (uint32_t)(((uint64_t)kBevDim << 20) / (uint64_t)g.grid[0]);
   w.bev_ky = (uint32_t)(((uint64_t)kBevDim << 20) / (uint64_t)g.grid[1]);
+  w.div_K = make_fastdiv((uint32_t)p.K);
   if (p.S % src.host_round_multiple() != 0 && p.rounds > 1) return RD3_ERR_INVALID_ARGUMENT;   // plan made for another source
 
   const int C = src.host_num_feats();
@@ -1238,8 +1273,9 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
     w.b0 = b0;
     prof_mark(st, 0);
     RD3_LANE_TRY(cudaMemsetAsync(w.table + (size_t)b0 * p.cap, 0xFF, (size_t)nb * p.cap * 8, st));
-    RD3_LANE_TRY(cudaMemsetAsync(w.slots + (size_t)b0 * p.max_voxels * p.K, 0xFF,
-                                 (size_t)nb * p.max_voxels * p.K * 4, st));
+    if (p.K > 1)
+      RD3_LANE_TRY(cudaMemsetAsync(w.slots + (size_t)b0 * p.max_voxels * (p.K - 1), 0xFF,
+                                   (size_t)nb * p.max_voxels * (p.K - 1) * 4, st));
     RD3_LANE_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords, 0, (size_t)nb * p.nwords * 4, st));
     RD3_LANE_TRY(cudaMemsetAsync(w.round_claims + (size_t)b0 * kMaxRounds, 0, (size_t)nb * kMaxRounds * 4, st));
     if (cull) {
@@ -1257,6 +1293,7 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
     prof_mark(st, 2);
     hv_flagscan_kernel<<<dim3(p.nchunks, nb), kScanThreads, 0, st>>>(w);
     scan_chunks_kernel<<<nb, 1024, 0, st>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels, b0);
+    hv_firsts_kernel<<<dim3((unsigned)ceil_div(p.nwords, 256), nb), 256, 0, st>>>(w);
     prof_mark(st, 3);
     if (cull) CullLaunch<Src>::run(src, g, w, nb, st);
     prof_mark(st, 4);

@@ -129,7 +129,7 @@ int make_grid(const float voxel_size[3], const float coors_range[6], VoxelGrid *
   uint64_t vol = 1;
   for (int i = 0; i < 3; ++i) {
     vol *= (uint64_t)g->grid[i];
-    if (vol > 0xFFFFFFFEull) {
+    if (vol > 0xFFFFFFDFull) {
       *volume = 0;
       return RD3_ERR_UNSUPPORTED;   // grid[] is still valid
     }
