@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("RD3_LIB_PATH") or os.path.join(_HERE, "librd3_b200.so
 
 _c = ctypes
 _vp, _i32, _i64, _sz, _f32 = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_size_t, _c.c_float
-_F3, _F6, _I3 = _c.c_float * 3, _c.c_float * 6, _c.c_int32 * 3
+_F3, _F6, _I3, _I4 = _c.c_float * 3, _c.c_float * 6, _c.c_int32 * 3, _c.c_int32 * 4
 
 
 class DepthParams(ctypes.Structure):
@@ -60,9 +60,9 @@ SIGNATURES = {
                                            _vp]),
     "rd3_voxel_occupancy": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp, _i32, _i32, _i32,
                                    _i32, _i32, _vp, _vp]),
-    "rd3_coors_extent": (_i32, [_vp, _i64, _vp, _vp]),
-    "rd3_dynamic_scatter_workspace_bytes": (_sz, [_i64, _i32, _I3]),
-    "rd3_dynamic_scatter_forward": (_i32, [_vp, _vp, _i64, _i32, _I3, _i32, _vp, _vp, _vp, _vp, _vp,
+    "rd3_coors_extent": (_i32, [_vp, _i64, _i32, _vp, _vp]),
+    "rd3_dynamic_scatter_workspace_bytes": (_sz, [_i64, _i32, _i32, _I4]),
+    "rd3_dynamic_scatter_forward": (_i32, [_vp, _vp, _i64, _i32, _i32, _I4, _i32, _vp, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _sz, _vp]),
     "rd3_dynamic_scatter_backward_workspace_bytes": (_sz, [_i64, _i32]),
     "rd3_dynamic_scatter_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32,
@@ -120,6 +120,10 @@ def f6(v):
 
 def i3(v):
     return _I3(*[int(x) for x in v])
+
+
+def i4(v):
+    return _I4(*[int(x) for x in v])
 
 
 def require_cuda(t, name, dtype=None):

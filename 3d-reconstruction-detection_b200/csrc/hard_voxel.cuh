@@ -672,7 +672,8 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
       const int n = nh < 32 ? nh : 32;
       if (lane < n) {
         const uint2 h = s_hit[nh - n + lane];
-        // a voxel's first point is not kept in the slot rows (hv_firsts_kernel lists the first points by rank)
+        // a voxel's first point is not kept in the slot rows (hv_firsts_kernel lists the first points by rank);
+        // it only gets this far when the caller wants the point -> voxel map
         if (h.x != h.y || point2voxel) {
           const int r = voxel_rank(w, b, h.x);
           if (r < w.max_voxels) {
@@ -691,12 +692,9 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
       uint2 it = make_uint2(0u, 0u);
       if (lane < n) it = s_item[cnt - n + lane];
       if (MODE == 0) {
-        // neighbouring pixels often fall into one voxel: of the lanes holding the same key only the one with the
-        // smallest index goes to the table (the entry keeps the minimum anyway; atomics on one address would
-        // serialise in L2, where equal-address loads coalesce)
-        const unsigned grp = __match_any_sync(0xffffffffu, lane < n ? it.x : kDummyKey + lane);
-        const uint32_t lowest = __reduce_min_sync(grp, it.y);
-        if (lane < n && it.y == lowest && table_insert(table, flags, w, it.x, it.y)) {
+        // (measured: electing one lane per key with __match_any_sync + __reduce_min_sync costs more than the
+        // repeated atomics it saves, in the sparse and in the dense scene)
+        if (lane < n && table_insert(table, flags, w, it.x, it.y)) {
           ++claims;
           if (w.bev) bev_mark(w, b, it.x, (int)blockIdx.x + wv);
         }
@@ -747,8 +745,17 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
     typename Src::Cursor cur = src.cursor(b, cwk, s_cal, cpre);
     Quad qd;
     src.classify(cur, s_cal, g, qd);
+    unsigned in = qd.in;
+    if (MODE == 1 && !point2voxel) {
+      // A voxel's first point is already listed by rank (hv_firsts_kernel): the lookup has nothing to add for it.
+      // Its flag bit says so without a table probe -- in the region the voxels were claimed from that is
+      // nearly every in-range pixel.
+      const uint32_t w0 = l0 >> 5, sh = l0 & 31u;
+      uint32_t fb = __ldg(flags + w0) >> sh;
+      if (sh > 28u && (int)w0 + 1 < w.nwords) fb |= __ldg(flags + w0 + 1) << (32u - sh);
+      in &= ~fb;
+    }
     // exclusive prefix of the per-lane counts (0..4) from three ballots of the count's bit planes
-    const unsigned in = qd.in;
     const unsigned cin = __popc(in);
     const unsigned p0 = __ballot_sync(0xffffffffu, cin & 1u), p1 = __ballot_sync(0xffffffffu, cin & 2u),
                    p2 = __ballot_sync(0xffffffffu, cin & 4u);
@@ -774,6 +781,35 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
   if (MODE == 0) {
     for (int d = 16; d > 0; d >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, d);
     if (lane == 0 && claims) atomicAdd(w.round_claims + b * kMaxRounds + round, claims);
+  }
+}
+
+// P0 ------------------------------------------------------------------------
+// All scratch of a sub-batch is initialised by ONE launch (six memsets cost six launches per lane): up to
+// kInitRegions word-aligned regions, each filled with its own 32-bit pattern, 16 bytes per store in the body.
+constexpr int kInitRegions = 6;
+struct HvInit {
+  uint32_t *ptr[kInitRegions];
+  unsigned long long words[kInitRegions];
+  uint32_t val[kInitRegions];
+  int n;
+};
+static __global__ void __launch_bounds__(256) hv_init_kernel(HvInit in) {
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+  for (int r = 0; r < in.n; ++r) {
+    uint32_t *p = in.ptr[r];
+    const unsigned long long n = in.words[r];
+    const uint32_t v = in.val[r];
+    unsigned long long head = ((16u - (unsigned)(reinterpret_cast<uintptr_t>(p) & 15u)) & 15u) >> 2;   // words up to 16-byte alignment
+    if (head > n) head = n;
+    const unsigned long long body = (n - head) >> 2;             // uint4 stores
+    uint4 *p4 = reinterpret_cast<uint4 *>(p + head);
+    const uint4 v4 = make_uint4(v, v, v, v);
+    for (unsigned long long i = tid; i < body; i += nthreads) p4[i] = v4;
+    const unsigned long long done = head + (body << 2);
+    if (tid < head) p[tid] = v;
+    if (tid < n - done) p[done + tid] = v;
   }
 }
 
@@ -997,22 +1033,27 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
   uint16_t *s_list = reinterpret_cast<uint16_t *>(s_idx + (size_t)V * K);
   const uint32_t *S = w.slots + ((int64_t)b * w.max_voxels + r0) * (K - 1);
   const uint32_t *F1 = w.first_of + (int64_t)b * w.max_voxels + r0;
-  // slot item it = v * K + k of the CTA: k == 0 is the voxel's first point, k >= 1 column k - 1 of its slot row
-  auto slot_index = [&](int it) -> uint32_t {
-    const uint32_t v = fast_div((uint32_t)it, w.div_K), k = (uint32_t)it - v * (uint32_t)K;
-    return k ? __ldg(S + v * (uint32_t)(K - 1) + (k - 1)) : __ldg(F1 + v);
-  };
-
   // warp wv owns items [wv*per, wv*per+per): its list segment starts at the same offset
   const int per = ((items + nw - 1) / nw + 31) & ~31;
   const int lo = wv * per, hi = min(items, lo + per);
+  // slot item it = v * K + k of the CTA: k == 0 is the voxel's first point, k >= 1 column k - 1 of its slot row.
+  // A lane visits the items lo + lane, lo + lane + 32, ...: (v, k) advance by (32 / K, 32 % K) with one carry.
+  const uint32_t stepv = 32u / (uint32_t)K, stepk = 32u % (uint32_t)K;
+  uint32_t iv = fast_div((uint32_t)(lo + lane), w.div_K);
+  uint32_t ik = (uint32_t)(lo + lane) - iv * (uint32_t)K;
+  auto slot_index = [&]() -> uint32_t { return ik ? __ldg(S + iv * (uint32_t)(K - 1) + (ik - 1)) : __ldg(F1 + iv); };
+  auto slot_advance = [&]() {
+    iv += stepv; ik += stepk;
+    if (ik >= (uint32_t)K) { ik -= (uint32_t)K; ++iv; }
+  };
   // The first 128 slot indices of the warp's share are requested up front (4 independent loads per
   // lane): one DRAM round trip instead of four dependent ones, overlapped with the calibration copy and the zero fill.
   uint32_t pre[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int it = lo + 32 * q + lane;
-    pre[q] = it < hi ? slot_index(it) : kEmpty32;
+    pre[q] = it < hi ? slot_index() : kEmpty32;
+    slot_advance();
   }
   const bool cal_async = src.stage_async(s_cal, &s_bar, b);     // one TMA bulk copy, no load / store loop
   {
@@ -1035,9 +1076,10 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
     const int it = it0 + lane;
     uint32_t idx = kEmpty32;
     if (it < hi) {
-      idx = slot_index(it);
+      idx = slot_index();
       s_idx[it] = idx;
     }
+    slot_advance();
     const unsigned bal = __ballot_sync(0xffffffffu, idx != kEmpty32);
     if (idx != kEmpty32) s_list[lo + nmine + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)it;
     nmine += __popc(bal);
@@ -1272,15 +1314,21 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
     }
     w.b0 = b0;
     prof_mark(st, 0);
-    RD3_LANE_TRY(cudaMemsetAsync(w.table + (size_t)b0 * p.cap, 0xFF, (size_t)nb * p.cap * 8, st));
-    if (p.K > 1)
-      RD3_LANE_TRY(cudaMemsetAsync(w.slots + (size_t)b0 * p.max_voxels * (p.K - 1), 0xFF,
-                                   (size_t)nb * p.max_voxels * (p.K - 1) * 4, st));
-    RD3_LANE_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords, 0, (size_t)nb * p.nwords * 4, st));
-    RD3_LANE_TRY(cudaMemsetAsync(w.round_claims + (size_t)b0 * kMaxRounds, 0, (size_t)nb * kMaxRounds * 4, st));
-    if (cull) {
-      RD3_LANE_TRY(cudaMemsetAsync(w.bev + (size_t)b0 * kBevCopies * kBevWords, 0, (size_t)nb * kBevCopies * kBevWords * 4, st));
-      RD3_LANE_TRY(cudaMemsetAsync(w.cull + (size_t)b0 * kMaxCams, 0, (size_t)nb * kMaxCams * 4, st));
+    {
+      HvInit in;
+      in.n = 0;
+      auto add = [&](void *ptr, size_t bytes, uint32_t val) {
+        in.ptr[in.n] = (uint32_t *)ptr; in.words[in.n] = bytes / 4; in.val[in.n] = val; ++in.n;
+      };
+      add(w.table + (size_t)b0 * p.cap, (size_t)nb * p.cap * 8, 0xFFFFFFFFu);
+      if (p.K > 1) add(w.slots + (size_t)b0 * p.max_voxels * (p.K - 1), (size_t)nb * p.max_voxels * (p.K - 1) * 4, 0xFFFFFFFFu);
+      add(w.flags + (size_t)b0 * p.nwords, (size_t)nb * p.nwords * 4, 0u);
+      add(w.round_claims + (size_t)b0 * kMaxRounds, (size_t)nb * kMaxRounds * 4, 0u);
+      if (cull) {
+        add(w.bev + (size_t)b0 * kBevCopies * kBevWords, (size_t)nb * kBevCopies * kBevWords * 4, 0u);
+        add(w.cull + (size_t)b0 * kMaxCams, (size_t)nb * kMaxCams * 4, 0u);
+      }
+      hv_init_kernel<<<tune.sm_count * 8, 256, 0, st>>>(in);
     }
     prof_mark(st, 1);
     for (int r = 0; r < p.rounds && p.N > 0; ++r) {

@@ -42,7 +42,7 @@ struct LaneLock {
   LaneLock();
   ~LaneLock();
 };
-int stream_lane_count();           // RD3_STREAMS (1..kMaxLanes), default 3
+int stream_lane_count();           // RD3_STREAMS (1..kMaxLanes), default 2
 
 #define RD3_CUDA_TRY(expr)                       \
   do {                                           \

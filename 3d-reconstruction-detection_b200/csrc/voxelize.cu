@@ -82,7 +82,7 @@ static int env_int(const char *name, int dflt, int lo, int hi) {
 }
 
 int stream_lane_count() {
-  static const int n = env_int("RD3_STREAMS", 3, 1, kMaxLanes);    // read once, not in the launch path
+  static const int n = env_int("RD3_STREAMS", 2, 1, kMaxLanes);    // read once, not in the launch path
   return n;
 }
 

@@ -12,7 +12,7 @@ class _dynamic_scatter(Function):
 
     @staticmethod
     def forward(ctx, feats, coors, reduce_type='max', dims=None):
-        """feats (N,C), coors (N,3) -> (voxel_feats (M,C), voxel_coors (M,3)).
+        """feats (N,C), coors (N,3|4) -> (voxel_feats (M,C), voxel_coors (M,3|4)).
         scatter_points.py:12-34."""
         results = dynamic_point_to_voxel_forward(feats, coors, reduce_type, dims)
         voxel_feats, voxel_coors, point2voxel_map, voxel_points_count = results
@@ -48,22 +48,25 @@ class DynamicScatter(nn.Module):
         vs = torch.tensor(voxel_size, dtype=torch.float32)
         g = torch.round((pcr[3:] - pcr[:3]) / vs).long().tolist()
         self._dims = [max(g[2], 1), max(g[1], 1), max(g[0], 1)]
+        self._batch_hint = 1          # samples the bitmap is sized for; grows to the largest batch seen
 
     def forward_single(self, points, coors):
         reduce = 'mean' if self.average_points else 'max'
         return dynamic_scatter(points.contiguous(), coors.contiguous(), reduce, self._dims)
 
     def forward(self, points, coors):
+        """scatter_points.py:74-99.  Batched ``coors`` (N,4) = (batch,z,y,x): the reference loops over the samples
+        with a ``torch.where`` and two host synchronisations each; here the batch column is the slowest dimension of
+        the voxel key, so the whole batch is ONE launch sequence whose output is already the reference's
+        concatenation in sample order.  The sample count is a remembered hint (checked on the device: a batch
+        that outgrows it is measured and redone), so steady state costs the single host read of M."""
         if coors.size(-1) == 3:
             return self.forward_single(points, coors)
-        batch_size = coors[-1, 0] + 1                               # scatter_points.py:86
-        voxels, voxel_coors = [], []
-        for i in range(batch_size):
-            inds = torch.where(coors[:, 0] == i)
-            voxel, voxel_coor = self.forward_single(points[inds], coors[inds][:, 1:])
-            voxel_coors.append(nn.functional.pad(voxel_coor, (1, 0), mode='constant', value=i))
-            voxels.append(voxel)
-        return torch.cat(voxels, dim=0), torch.cat(voxel_coors, dim=0)
+        reduce = 'mean' if self.average_points else 'max'
+        dims = [self._batch_hint] + self._dims
+        voxels, voxel_coors = dynamic_scatter(points.contiguous(), coors.contiguous(), reduce, dims)
+        self._batch_hint = max(self._batch_hint, dims[0])        # updated in place when the hint was exceeded
+        return voxels, voxel_coors
 
     def __repr__(self):
         return (self.__class__.__name__ + '(voxel_size=' + str(self.voxel_size) +

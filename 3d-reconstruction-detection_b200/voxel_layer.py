@@ -76,11 +76,16 @@ def dynamic_voxelize(points, coors, voxel_size, coors_range, NDim=3):
 def dynamic_point_to_voxel_forward(feats, coors, reduce_type, dims=None):
     """voxelization.h:108-121 -> scatter_points_cuda.cu:183-239.
 
-    Returns [voxel_feats (M,C), voxel_coors (M,3), point2voxel_map (N) int32,
+    Returns [voxel_feats (M,C), voxel_coors (M,ncols), point2voxel_map (N) int32,
     voxel_points_count (M) int32]; voxels in lexicographic coordinate order.
-    ``dims`` (optional, 3 ints): exclusive upper bound of valid coordinates (the
-    voxel grid); when absent or exceeded it is measured on the device first.
+    ``coors`` is (N,3), or (N,4) with the batch index in front: the whole batch is then one launch
+    sequence and the result is the reference's per-sample loop + concatenation (scatter_points.py:86-97).
+    ``dims`` (optional, ncols ints): exclusive upper bound of valid coordinates (the
+    voxel grid, with the sample count in front for (N,4)); when absent or exceeded it is measured on
+    the device first; a ``dims`` LIST is updated in place with the bounds actually used, so a caller can keep
+    them as the next call's hint.  One device->host read per call (M and the status word).
     """
+    dims_arg = dims if isinstance(dims, list) else None
     code = _reduce_code(reduce_type)
     _lib.require_cuda(feats, "feats", torch.float32)
     _lib.require_cuda(coors, "coors", torch.int32)
@@ -88,29 +93,34 @@ def dynamic_point_to_voxel_forward(feats, coors, reduce_type, dims=None):
     if N == 0:                                        # scatter_points_cuda.cu:192-196
         return [feats.clone().detach(), coors.clone().detach(),
                 coors.new_empty((0,), dtype=torch.int32), coors.new_empty((0,), dtype=torch.int32)]
-    if coors.shape[0] != N or coors.shape[1] != 3:
-        raise RuntimeError("coors must be (N, 3)")
+    ncols = coors.shape[1] if coors.dim() == 2 else 0
+    if coors.shape[0] != N or ncols not in (3, 4):
+        raise RuntimeError("coors must be (N, 3) or (N, 4)")
+    if ncols == 4 and coors.data_ptr() % 16:
+        coors = coors.clone()                         # rows are moved as 16-byte words
+    if dims is not None and len(dims) != ncols:
+        raise RuntimeError("dims must have one entry per coors column")
     L = _lib.lib()
     dev = feats.device
     with torch.cuda.device_of(feats):
         stream = _lib.stream_of(feats)
         voxel_feats = torch.empty((N, C), dtype=torch.float32, device=dev)
-        voxel_coors = torch.empty((N, 3), dtype=torch.int32, device=dev)
+        voxel_coors = torch.empty((N, ncols), dtype=torch.int32, device=dev)
         p2v = torch.empty((N,), dtype=torch.int32, device=dev)
         count = torch.empty((N,), dtype=torch.int32, device=dev)
         meta = torch.empty(2, dtype=torch.int32, device=dev)        # [M, status]
         for attempt in range(2):
             if dims is None:
-                ext = torch.empty(3, dtype=torch.int32, device=dev)
-                _lib.check(L.rd3_coors_extent(_lib.ptr(coors), N, _lib.ptr(ext), stream), "coors_extent")
-                dims = [max(int(v), 1) for v in ext.tolist()]
-            cd = _lib.i3(dims)
-            nbytes = L.rd3_dynamic_scatter_workspace_bytes(N, C, cd)
+                ext = torch.empty(4, dtype=torch.int32, device=dev)
+                _lib.check(L.rd3_coors_extent(_lib.ptr(coors), N, ncols, _lib.ptr(ext), stream), "coors_extent")
+                dims = [max(int(v), 1) for v in ext.tolist()[:ncols]]
+            cd = _lib.i4(list(dims) if ncols == 4 else [1] + list(dims))
+            nbytes = L.rd3_dynamic_scatter_workspace_bytes(N, C, ncols, cd)
             if nbytes == 0:
                 raise RuntimeError("rd3_b200.dynamic_point_to_voxel_forward: coordinate extent %s "
-                                   "too large for the bitmap path" % (dims,))
+                                   "too large for the bitmap path" % (list(dims),))
             ws = _lib.workspace(dev, nbytes)
-            st = L.rd3_dynamic_scatter_forward(_lib.ptr(feats), _lib.ptr(coors), N, C, cd, code,
+            st = L.rd3_dynamic_scatter_forward(_lib.ptr(feats), _lib.ptr(coors), N, C, ncols, cd, code,
                                                _lib.ptr(voxel_feats), _lib.ptr(voxel_coors),
                                                _lib.ptr(p2v), _lib.ptr(count), _lib.ptr(meta[0:]),
                                                _lib.ptr(meta[1:]), _lib.ptr(ws), ws.numel(), stream)
@@ -121,6 +131,8 @@ def dynamic_point_to_voxel_forward(feats, coors, reduce_type, dims=None):
             dims = None                                   # hint was too small: measure and retry
         else:
             raise RuntimeError("rd3_b200.dynamic_point_to_voxel_forward: extent retry failed")
+    if dims_arg is not None:
+        dims_arg[:] = list(dims)
     if voxel_coors.dtype != coors.dtype:
         voxel_coors = voxel_coors.to(coors.dtype)
     return [voxel_feats[:M], voxel_coors[:M], p2v, count[:M]]

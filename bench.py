@@ -366,7 +366,7 @@ def main():
     dom = max(kern, key=kern.get) if calls else "insert"
     # launches of the dominant kernel per step (insert: one per round; others: one)
     rounds = _lib.lib().rd3_hard_voxel_rounds(npix, B)
-    lanes = max(1, min(int(os.environ.get("RD3_STREAMS", "3")), 4, B))
+    lanes = max(1, min(int(os.environ.get("RD3_STREAMS", "2")), 4, B))
     dom_launches = rounds if dom == "insert" else 1
     dom_ms = stage_ms[dom] / dom_launches
     dom_achieved = alg[dom] / dom_launches / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0

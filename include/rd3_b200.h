@@ -209,23 +209,28 @@ RD3_API int rd3_pack_sparse_inputs(const float *voxel_feats, const int32_t *coor
 
 /* ---------------------------------------------------------------------------
  * dynamic_point_to_voxel_forward
- *   (voxelization.h:108-121 -> scatter_points_cuda.cu:183-239)
- *   feats (N, C) fp32, coors (N, 3) int32.  Rows with any negative component
- *   are dropped (map -1).  Voxels come out in lexicographic (c0,c1,c2) order.
- *   dims (host int32[3]): exclusive upper bound of every valid coordinate
- *   (e.g. the voxel grid (gz,gy,gx)); a valid coordinate >= dims sets
- *   *d_status (device int32[1]) to 1 and the outputs are then undefined --
- *   call rd3_coors_extent and retry.
- *   Outputs sized for the worst case: voxel_feats (N, C), voxel_coors (N, 3),
- *   point2voxel (N), voxel_count (N); d_num_voxels device int32[1].
+ *   (voxelization.h:108-121 -> scatter_points_cuda.cu:183-239; with ncols == 4 also the
+ *   per-sample loop of scatter_points.py:86-97, as ONE launch sequence)
+ *   feats (N, C) fp32, coors (N, ncols) int32, ncols 3: (c0,c1,c2), ncols 4: (batch,c0,c1,c2).
+ *   Rows with any negative component are dropped (map -1); with ncols == 4 so are rows whose
+ *   batch index exceeds coors[N-1][0] (the reference derives the batch size from the last row).
+ *   Voxels come out in lexicographic order of the ncols columns, i.e. for ncols == 4 the
+ *   concatenation of the per-sample results in sample order with the batch column in front.
+ *   dims (host int32[4], dims[0] = sample capacity, ignored for ncols == 3; dims[1..3] = exclusive
+ *   upper bounds of c0,c1,c2, e.g. the voxel grid (gz,gy,gx)); a valid coordinate >= dims (or more
+ *   samples than dims[0]) sets *d_status (device int32[1]) to 1 and the outputs are then
+ *   undefined -- call rd3_coors_extent and retry.  prod(dims) must stay below 2^32 - 32.
+ *   Outputs sized for the worst case: voxel_feats (N, C), voxel_coors (N, ncols),
+ *   point2voxel (N), voxel_count (N); d_num_voxels device int32[1].  ncols == 4: coors and
+ *   voxel_coors 16-byte aligned.  sum / mean are accumulated in fp64 and rounded once.
  * ------------------------------------------------------------------------- */
-RD3_API int rd3_coors_extent(const int32_t *coors, int64_t N, int32_t *d_extent3,
+RD3_API int rd3_coors_extent(const int32_t *coors, int64_t N, int ncols, int32_t *d_extent4,
                      rd3_stream_t stream);
 
-RD3_API size_t rd3_dynamic_scatter_workspace_bytes(int64_t N, int C, const int32_t dims[3]);
+RD3_API size_t rd3_dynamic_scatter_workspace_bytes(int64_t N, int C, int ncols, const int32_t dims[4]);
 
 RD3_API int rd3_dynamic_scatter_forward(const float *feats, const int32_t *coors, int64_t N,
-                                int C, const int32_t dims[3], int reduce_type,
+                                int C, int ncols, const int32_t dims[4], int reduce_type,
                                 float *voxel_feats, int32_t *voxel_coors,
                                 int32_t *point2voxel, int32_t *voxel_count,
                                 int32_t *d_num_voxels, int32_t *d_status,

@@ -71,8 +71,10 @@ def test_workspace_sizes_and_argument_validation_without_gpu():
     p = rd3_b200.backproject.make_params(2, 6, 504, 896, max_depth=100.0)
     assert L.rd3_unproject_workspace_bytes(ctypes.byref(p)) > 0
     assert L.rd3_depth_to_voxels_workspace_bytes(ctypes.byref(p), 10, 120000) > 2 * (a // 2)
-    assert L.rd3_dynamic_scatter_workspace_bytes(1000, 3, _lib.i3([40, 1440, 1440])) > 10 << 20
-    assert L.rd3_dynamic_scatter_workspace_bytes(1000, 3, _lib.i3([70000, 70000, 70000])) == 0  # too large
+    assert L.rd3_dynamic_scatter_workspace_bytes(1000, 3, 3, _lib.i4([1, 40, 1440, 1440])) > 10 << 20
+    assert L.rd3_dynamic_scatter_workspace_bytes(1000, 3, 4, _lib.i4([4, 40, 1440, 1440])) > 40 << 20
+    assert L.rd3_dynamic_scatter_workspace_bytes(1000, 3, 3, _lib.i4([1, 70000, 70000, 70000])) == 0  # too large
+    assert L.rd3_dynamic_scatter_workspace_bytes(1000, 3, 4, _lib.i4([64, 40, 1440, 1440])) == 0       # > 2^32 cells
     # null pointers / bad sizes are rejected before any CUDA call
     null = ctypes.c_void_p(0)
     st = L.rd3_hard_voxelize(null, 10, 3, _lib.f3([1, 1, 1]), _lib.f6([0, 0, 0, 1, 1, 1]), 5, 5, null, null, null,

@@ -487,6 +487,28 @@ def test_dynamic_scatter_batched_and_backward():
             exp[m] = tr.dynamic_point_to_voxel_backward(gout[off:off + M], feats[m], r[0], r[2], r[3], red)
             off += M
         assert torch.allclose(f.grad.cpu(), exp, rtol=1e-6, atol=1e-7)
+    # the batch is ONE launch sequence: the sample count is a hint that grows, never a host read per sample
+    ds = rd3_b200.DynamicScatter([0.32, 0.32, 6], [-74.88, -74.88, -2, 74.88, 74.88, 4], True)
+    assert ds._batch_hint == 1
+    ds(feats.to(DEV), coors4.to(DEV))
+    assert ds._batch_hint == 3
+    # UNSORTED batch column: the reference takes batch_size from the LAST row (scatter_points.py:86) and never
+    # looks at rows of a later sample; negative batch indices match no sample
+    perm = torch.randperm(N, generator=g)
+    c4 = coors4[perm].clone()
+    c4[-1, 0] = 1                                        # batch_size = 2: the rows of sample 2 are ignored
+    c4[:50, 0] = -1
+    for red, avg in (("mean", True), ("max", False)):
+        vf, vc = rd3_b200.DynamicScatter([0.32, 0.32, 6], [-74.88, -74.88, -2, 74.88, 74.88, 4], avg)(
+            feats[perm].to(DEV), c4.to(DEV))
+        rf, rc = tr.dynamic_scatter_batched(feats[perm], c4, red)
+        assert int(vc[:, 0].max()) == 1 and torch.equal(vc.cpu(), rc)
+        assert torch.allclose(vf.cpu(), rf, rtol=1e-6, atol=5e-5)
+    # the 4-column C entry returns the point -> voxel map of the whole batch (ranks of the concatenated output)
+    vf4, vc4, p2v4, cnt4 = voxel_layer.dynamic_point_to_voxel_forward(feats.to(DEV), coors4.to(DEV), "sum", [3, 9, 9, 9])
+    assert int(cnt4.sum()) == int((p2v4 >= 0).sum()) and vc4.shape[1] == 4
+    sel = (p2v4 >= 0).cpu()
+    assert torch.equal(vc4.cpu()[p2v4.cpu()[sel].long()], coors4[sel])
     # all-invalid input -> zero grad (test_dynamic_scatter.py:35-50)
     f = feats.clone().to(DEV).requires_grad_()
     neg = torch.full((N, 3), -1, dtype=torch.int32, device=DEV)
