@@ -60,8 +60,19 @@ constexpr int kEmitThreads = RD3_EMIT_THREADS;
 #ifndef RD3_LKP_MINB
 #define RD3_LKP_MINB 5                // ... and the lookup pass
 #endif
+#ifndef RD3_EMIT_MINB
+#define RD3_EMIT_MINB 6               // resident CTAs per SM the emit kernel is compiled for
+#endif
+#ifndef RD3_PASS_SLACK
+#define RD3_PASS_SLACK 64             // items that stay queued behind a pass: their table sectors are being prefetched
+#endif
+#ifndef RD3_PASS_PREFETCH
+#define RD3_PASS_PREFETCH 1           // prefetch.global.L2 of an item's table sector when it joins the queue
+#endif
 constexpr int kTilePoints = 128;      // points per warp tile (4 per lane)
-constexpr int kListCap = 160;         // per-warp item / undecided lists: 31 carried + 128 new
+constexpr int kListCap = 160;         // per-warp list of undecided elements: 31 carried + 128 new
+constexpr int kQueueCap = 256;        // per-warp FIFO of in-range items (power of two): slack + 31 carried + 128 new + 32
+static_assert(RD3_PASS_SLACK + 31 + 128 + 32 <= kQueueCap, "item queue too small for the slack");
 constexpr int kMaxRounds = 64;
 constexpr uint32_t kDummyKey = 0xFFFFFFE0u;   // + lane: 32 values no voxel key takes (make_grid: volume <= kDummyKey)
 constexpr int kBevDim = 64;           // bird's-eye mask of the kept voxels: kBevDim x kBevDim bits over the x,y grid
@@ -474,6 +485,15 @@ __device__ __forceinline__ void load_bucket(const unsigned long long *p, unsigne
                : "l"(p));
 }
 
+// The sector a key's probe will read first, requested ahead of time (no register, no dependency): the item then
+// waits RD3_PASS_SLACK queue positions before its pass, and the probe finds the sector in L2.
+__device__ __forceinline__ void table_prefetch(const unsigned long long *table, const HvWork &w, uint32_t key) {
+#if RD3_PASS_PREFETCH
+  const unsigned long long *p = table + (w.direct ? key : hash_bucket_slot(key, w.log2cap));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
 // "point idx is / is no longer the first point of its voxel": XOR, so that the owner's toggle and the
 // toggle of whoever displaces it commute (an index that was displaced is toggled exactly twice)
 __device__ __forceinline__ void first_toggle(uint32_t *flags, uint32_t idx) {
@@ -618,7 +638,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
                    int iters) {
   __shared__ __align__(16) float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 4];
   __shared__ __align__(8) uint64_t s_bar;        // completion of the calibration's TMA copy
-  __shared__ uint2 s_itemb[kPassWarps * kListCap];     // (key, element index) of the in-range elements
+  __shared__ uint2 s_itemb[kPassWarps * kQueueCap];    // FIFO of (key, element index) of the in-range elements
   __shared__ uint32_t s_undb[kPassWarps * kListCap];   // indices of the undecided elements
   __shared__ uint2 s_hitb[MODE ? kPassWarps * 64 : 1]; // lookup: (first point of the voxel, element index) of the table hits
   __shared__ uint32_t s_cull[kMaxCams];
@@ -649,7 +669,9 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
 
   typename Src::Walker wk;
   if (!src.walk_init(wk, begin, end, iters, wv, lane)) return;
-  uint2 *s_item = s_itemb + wv * kListCap;
+  uint2 *s_item = s_itemb + wv * kQueueCap;
+  constexpr unsigned qm = kQueueCap - 1;
+  unsigned qhead = 0;                    // queue position of the oldest item; cnt items follow (positions mod kQueueCap)
   uint32_t *s_und = s_undb + wv * kListCap;
   uint2 *s_hit = s_hitb + (MODE ? wv * 64 : 0);
   unsigned long long *table = w.table + (int64_t)b * w.cap;
@@ -686,11 +708,13 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
       __syncwarp();
       continue;
     }
-    if (cnt >= 32 || (flushing && nu == 0 && cnt > 0)) {
-      // ---- item pass: MODE 0 table insert; MODE 1 table lookup, the hits join the hit list ----
+    if (cnt >= 32 + RD3_PASS_SLACK || (flushing && nu == 0 && cnt > 0)) {
+      // ---- item pass over the OLDEST items (the sectors of the younger ones are still on their way from DRAM):
+      //      MODE 0 table insert; MODE 1 table lookup, the hits join the hit list ----
       const int n = cnt < 32 ? cnt : 32;
       uint2 it = make_uint2(0u, 0u);
-      if (lane < n) it = s_item[cnt - n + lane];
+      if (lane < n) it = s_item[(qhead + lane) & qm];
+      qhead += n;
       if (MODE == 0) {
         // (measured: electing one lane per key with __match_any_sync + __reduce_min_sync costs more than the
         // repeated atomics it saves, in the sparse and in the dense scene)
@@ -720,7 +744,11 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
         in = src.cell_exact(b, idx, s_cal, g, cx, cy, cz);
       }
       const unsigned b1 = __ballot_sync(0xffffffffu, in);
-      if (in) s_item[cnt + __popc(b1 & lt)] = make_uint2(voxel_key(cx, cy, cz, g), idx);
+      if (in) {
+        const uint32_t key = voxel_key(cx, cy, cz, g);
+        s_item[(qhead + cnt + __popc(b1 & lt)) & qm] = make_uint2(key, idx);
+        table_prefetch(table, w, key);
+      }
       cnt += __popc(b1);
       nu -= n;
       __syncwarp();
@@ -759,12 +787,12 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
     const unsigned cin = __popc(in);
     const unsigned p0 = __ballot_sync(0xffffffffu, cin & 1u), p1 = __ballot_sync(0xffffffffu, cin & 2u),
                    p2 = __ballot_sync(0xffffffffu, cin & 4u);
-    uint2 *it = s_item + cnt + (__popc(p0 & lt) + 2 * __popc(p1 & lt) + 4 * __popc(p2 & lt));
-    // the order inside the list is irrelevant: element q of the lane goes to the lane's slot #(set bits below q)
-    if (in & 1u) it[0] = make_uint2(qd.key[0], l0);
-    if (in & 2u) it[in & 1u] = make_uint2(qd.key[1], l0 + 1);
-    if (in & 4u) it[__popc(in & 3u)] = make_uint2(qd.key[2], l0 + 2);
-    if (in & 8u) it[__popc(in & 7u)] = make_uint2(qd.key[3], l0 + 3);
+    const unsigned qp = qhead + cnt + (__popc(p0 & lt) + 2 * __popc(p1 & lt) + 4 * __popc(p2 & lt));
+    // the order inside the queue is irrelevant: element q of the lane goes to the lane's slot #(set bits below q)
+    if (in & 1u) { s_item[qp & qm] = make_uint2(qd.key[0], l0); table_prefetch(table, w, qd.key[0]); }
+    if (in & 2u) { s_item[(qp + (in & 1u)) & qm] = make_uint2(qd.key[1], l0 + 1); table_prefetch(table, w, qd.key[1]); }
+    if (in & 4u) { s_item[(qp + __popc(in & 3u)) & qm] = make_uint2(qd.key[2], l0 + 2); table_prefetch(table, w, qd.key[2]); }
+    if (in & 8u) { s_item[(qp + __popc(in & 7u)) & qm] = make_uint2(qd.key[3], l0 + 3); table_prefetch(table, w, qd.key[3]); }
     cnt += __popc(p0) + 2 * __popc(p1) + 4 * __popc(p2);
     if (__any_sync(0xffffffffu, qd.und != 0u)) {
       const unsigned cun = __popc(qd.und);
@@ -785,8 +813,8 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
 }
 
 // P0 ------------------------------------------------------------------------
-// All scratch of a sub-batch is initialised by ONE launch (six memsets cost six launches per lane): up to
-// kInitRegions word-aligned regions, each filled with its own 32-bit pattern, 16 bytes per store in the body.
+// The small scratch arrays of a sub-batch are initialised by ONE launch (a memset each would be a launch each): up
+// to kInitRegions word-aligned regions, each filled with its own 32-bit pattern, 16 bytes per store in the body.
 constexpr int kInitRegions = 6;
 struct HvInit {
   uint32_t *ptr[kInitRegions];
@@ -1014,7 +1042,7 @@ static __global__ void __launch_bounds__(kBevWords) hv_cull_kernel(DepthSource s
 //   3. voxels are copied out with 16-byte stores; one thread per voxel writes coors (from the first
 //      point), the count and the HardSimpleVFE mean (slot order, one __fdiv_rn)
 template <class Src>
-__global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGrid g, HvWork w, HvOut o, int V) {
+__global__ void __launch_bounds__(kEmitThreads, RD3_EMIT_MINB) hv_emit_kernel(Src src, VoxelGrid g, HvWork w, HvOut o, int V) {
   extern __shared__ float s_dyn[];
   __shared__ __align__(16) float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 4];
   __shared__ __align__(8) uint64_t s_bar;
@@ -1031,30 +1059,19 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
   float *tile = s_dyn;
   uint32_t *s_idx = reinterpret_cast<uint32_t *>(s_dyn + (((size_t)V * K * C + 3) & ~(size_t)3));
   uint16_t *s_list = reinterpret_cast<uint16_t *>(s_idx + (size_t)V * K);
+  // Warp wv owns the voxels [wv*vper, wv*vper + vper) of the CTA, i.e. the slot items [lo, hi); its list segment
+  // starts at lo.  A pass of the warp covers vpw = 32 / K whole voxels: lane = vl * K + k keeps its (voxel-in-pass,
+  // slot) for all passes, so no item index is ever divided (K > 32: one slot column per pass, lanes over voxels).
+  // Slot k == 0 is the voxel's first point (first_of), k >= 1 column k - 1 of its row of later points.
+  const int vper = (nvox + nw - 1) / nw;
+  const int v_lo = min(nvox, wv * vper), v_hi = min(nvox, v_lo + vper);
+  const int lo = v_lo * K;
+  const int vpw = K <= 32 ? 32 / K : 32;
+  const int my_vl = K <= 32 ? lane / K : lane, my_k0 = K <= 32 ? lane - my_vl * K : 0;
+  const bool lane_on = K <= 32 ? lane < vpw * K : true;
+  const int kpasses = K <= 32 ? 1 : K;                      // K > 32: the slot column advances with the pass
   const uint32_t *S = w.slots + ((int64_t)b * w.max_voxels + r0) * (K - 1);
   const uint32_t *F1 = w.first_of + (int64_t)b * w.max_voxels + r0;
-  // warp wv owns items [wv*per, wv*per+per): its list segment starts at the same offset
-  const int per = ((items + nw - 1) / nw + 31) & ~31;
-  const int lo = wv * per, hi = min(items, lo + per);
-  // slot item it = v * K + k of the CTA: k == 0 is the voxel's first point, k >= 1 column k - 1 of its slot row.
-  // A lane visits the items lo + lane, lo + lane + 32, ...: (v, k) advance by (32 / K, 32 % K) with one carry.
-  const uint32_t stepv = 32u / (uint32_t)K, stepk = 32u % (uint32_t)K;
-  uint32_t iv = fast_div((uint32_t)(lo + lane), w.div_K);
-  uint32_t ik = (uint32_t)(lo + lane) - iv * (uint32_t)K;
-  auto slot_index = [&]() -> uint32_t { return ik ? __ldg(S + iv * (uint32_t)(K - 1) + (ik - 1)) : __ldg(F1 + iv); };
-  auto slot_advance = [&]() {
-    iv += stepv; ik += stepk;
-    if (ik >= (uint32_t)K) { ik -= (uint32_t)K; ++iv; }
-  };
-  // The first 128 slot indices of the warp's share are requested up front (4 independent loads per
-  // lane): one DRAM round trip instead of four dependent ones, overlapped with the calibration copy and the zero fill.
-  uint32_t pre[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int it = lo + 32 * q + lane;
-    pre[q] = it < hi ? slot_index() : kEmpty32;
-    slot_advance();
-  }
   const bool cal_async = src.stage_async(s_cal, &s_bar, b);     // one TMA bulk copy, no load / store loop
   {
     float4 *t4 = reinterpret_cast<float4 *>(tile);
@@ -1063,26 +1080,27 @@ __global__ void __launch_bounds__(kEmitThreads) hv_emit_kernel(Src src, VoxelGri
     for (int e = threadIdx.x; e < n4; e += kEmitThreads) t4[e] = z4;
   }
   int nmine = 0;
+  // two passes' indices are requested before the first is consumed (independent loads in flight)
+  for (int vb = v_lo; vb < v_hi; vb += 2 * vpw) {
+    for (int kk = 0; kk < kpasses; ++kk) {
+      uint32_t idx2[2];
+      int it2[2];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int it = lo + 32 * q + lane;
-    const uint32_t idx = pre[q];
-    if (it < hi) s_idx[it] = idx;
-    const unsigned bal = __ballot_sync(0xffffffffu, idx != kEmpty32);
-    if (idx != kEmpty32) s_list[lo + nmine + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)it;
-    nmine += __popc(bal);
-  }
-  for (int it0 = lo + 128; it0 < hi; it0 += 32) {
-    const int it = it0 + lane;
-    uint32_t idx = kEmpty32;
-    if (it < hi) {
-      idx = slot_index();
-      s_idx[it] = idx;
+      for (int h = 0; h < 2; ++h) {
+        const int v = vb + h * vpw + my_vl, k = my_k0 + kk;
+        const bool on = lane_on && v < v_hi;
+        it2[h] = v * K + k;
+        idx2[h] = on ? (k ? __ldg(S + (int64_t)v * (K - 1) + (k - 1)) : __ldg(F1 + v)) : kEmpty32;
+        if (!on) it2[h] = -1;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (it2[h] >= 0) s_idx[it2[h]] = idx2[h];
+        const unsigned bal = __ballot_sync(0xffffffffu, idx2[h] != kEmpty32);
+        if (idx2[h] != kEmpty32) s_list[lo + nmine + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)it2[h];
+        nmine += __popc(bal);
+      }
     }
-    slot_advance();
-    const unsigned bal = __ballot_sync(0xffffffffu, idx != kEmpty32);
-    if (idx != kEmpty32) s_list[lo + nmine + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)it;
-    nmine += __popc(bal);
   }
   __syncthreads();                       // tile zeroed, calibration copy issued
   if (cal_async) tma_wait(&s_bar);
@@ -1320,15 +1338,18 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
       auto add = [&](void *ptr, size_t bytes, uint32_t val) {
         in.ptr[in.n] = (uint32_t *)ptr; in.words[in.n] = bytes / 4; in.val[in.n] = val; ++in.n;
       };
-      add(w.table + (size_t)b0 * p.cap, (size_t)nb * p.cap * 8, 0xFFFFFFFFu);
-      if (p.K > 1) add(w.slots + (size_t)b0 * p.max_voxels * (p.K - 1), (size_t)nb * p.max_voxels * (p.K - 1) * 4, 0xFFFFFFFFu);
-      add(w.flags + (size_t)b0 * p.nwords, (size_t)nb * p.nwords * 4, 0u);
+      // the big regions with the driver's memset (measured faster than a fill kernel), the small ones in one launch
+      RD3_LANE_TRY(cudaMemsetAsync(w.table + (size_t)b0 * p.cap, 0xFF, (size_t)nb * p.cap * 8, st));
+      if (p.K > 1)
+        RD3_LANE_TRY(cudaMemsetAsync(w.slots + (size_t)b0 * p.max_voxels * (p.K - 1), 0xFF,
+                                     (size_t)nb * p.max_voxels * (p.K - 1) * 4, st));
+      RD3_LANE_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords, 0, (size_t)nb * p.nwords * 4, st));
       add(w.round_claims + (size_t)b0 * kMaxRounds, (size_t)nb * kMaxRounds * 4, 0u);
       if (cull) {
         add(w.bev + (size_t)b0 * kBevCopies * kBevWords, (size_t)nb * kBevCopies * kBevWords * 4, 0u);
         add(w.cull + (size_t)b0 * kMaxCams, (size_t)nb * kMaxCams * 4, 0u);
       }
-      hv_init_kernel<<<tune.sm_count * 8, 256, 0, st>>>(in);
+      hv_init_kernel<<<32, 256, 0, st>>>(in);
     }
     prof_mark(st, 1);
     for (int r = 0; r < p.rounds && p.N > 0; ++r) {

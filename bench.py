@@ -10,8 +10,10 @@ over the whole batch.
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a path
     python bench.py --impl reference [--gpus N --steps K --warmup W] # reference CPU path, host cores
 
-Prints ONE JSON line (rank 0).  `value` is pixels(points)/s over all GPUs with the
-inputs resident in HBM; `e2e` is the same through the public API from pinned HOST
+Prints ONE JSON line (rank 0).  `value` is pixels(points)/s of the whole job with the
+inputs resident in HBM: at N > 1 the step's 64 frames are sharded by sample (BASELINE
+config C5, strong scaling) and the NCCL all-gather of what the sparse encoder consumes is
+inside the timed region.  `e2e` is the same path through the public API from pinned HOST
 buffers with every host<->device copy inside the timed region.
 """
 import argparse
@@ -227,6 +229,17 @@ def _emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def _source_hash():
+    """Hash of the CUDA sources: stamps numbers that were measured offline (ncu traffic) with the build they belong to."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "3d-reconstruction-detection_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -234,17 +247,19 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=64, help="frames per step in TOTAL (BASELINE config C5: sharded over the GPUs)")
     ap.add_argument("--cpu-workers", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-rows", action="store_true", help="skip the C1 / C3 / C4 operator rows")
+    ap.add_argument("--no-masks", action="store_true", help="skip the conf + sky + percentile variant")
+    ap.add_argument("--no-graph", action="store_true", help="N > 1: do not replay the step as a CUDA graph")
     ap.add_argument("--scene", default="mixture", choices=["mixture", "ground"],
                     help="synthetic depth: SURVEY 8(d) per-pixel mixture (default) or a structured ground+walls scene")
     ap.add_argument("--e2e-chunk", type=int, default=8, help="frames per H2D -> kernels -> D2H chunk of the e2e leg")
     ap.add_argument("--e2e-streams", type=int, default=3)
-    ap.add_argument("--gather", action="store_true", help="also time the NCCL all_gather of the outputs")
     ap.add_argument("--profile-only", action="store_true",
-                    help="few steps, no e2e / cpu baseline (the command profiled under ncu)")
+                    help="few steps, no e2e / cpu baseline / rows (the command profiled under ncu)")
     args = ap.parse_args()
     if args.warmup < 3 and not args.profile_only:
         args.warmup = 3
@@ -254,7 +269,7 @@ def main():
     import torch
     import torch.distributed as dist
     import rd3_b200
-    from rd3_b200 import _lib, synthetic
+    from rd3_b200 import _lib, parallel, synthetic
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -268,82 +283,164 @@ def main():
 
     cfg = synthetic.CONFIGS[WORKLOAD]
     H, W = cfg["hw"]
-    B = args.frames
+    BT = args.frames                                   # frames per step, whole job
     K, mv = cfg["max_points"], cfg["max_voxels"][0]
     npix = 6 * H * W
+    C = F = 3
 
-    # weak scaling: every rank owns B frames (frame ids disjoint across ranks)
-    host = synthetic.make_batch([rank * B + i for i in range(B)], H, W, with_conf=False, scene=args.scene)
+    # strong scaling (BASELINE config C5): the step's BT frames are sharded by sample, contiguous chunks
+    f0, f1 = parallel.shard_range(BT, world, rank)
+    B = f1 - f0
+    sizes = parallel.shard_sizes(BT, world)
+    bmax = max(sizes)
+    host = synthetic.make_batch(list(range(f0, f1)), H, W, with_conf=not args.no_masks, scene=args.scene)
     depth_h = host["depth"].pin_memory()
     intr_h, c2l_h = host["intrinsics"].pin_memory(), host["cam2lidar"].pin_memory()
     depth, intr, c2l = depth_h.to(dev), intr_h.to(dev), c2l_h.to(dev)
 
-    mod = rd3_b200.DepthToVoxels(cfg["voxel_size"], cfg["pcr"], K, cfg["max_voxels"],
-                                 max_depth=synthetic.MAX_DEPTH).to(dev).train()
+    def make_mod(**kw):
+        return rd3_b200.DepthToVoxels(cfg["voxel_size"], cfg["pcr"], K, cfg["max_voxels"], max_depth=synthetic.MAX_DEPTH,
+                                      reuse_buffers=True, **kw).to(dev).train()
 
-    def step():
-        return mod(depth, intr, c2l)
+    mod = make_mod()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- the step ----------------------------------------------------------------------
+    # N == 1: one pass of the fused path over the BT frames.
+    # N  > 1: the rank's shard in two sub-batches; what the sparse encoder consumes (voxel mean, coors, counts, voxel_num;
+    #         fixed-size padded rows) is all-gathered on a communication stream while the next sub-batch computes.
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    nsub = 2 if (world > 1 and B >= 2) else 1
+    subs = [(B * i // nsub, B * (i + 1) // nsub) for i in range(nsub)]
+    sub_mods = [make_mod() for _ in subs] if world > 1 else None
+    gathered = None
+    if world > 1:
+        gathered = [dict(voxel_mean=torch.empty((world, s1 - s0, mv, F), device=dev),
+                         coors=torch.empty((world, s1 - s0, mv, 3), dtype=torch.int32, device=dev),
+                         num_points=torch.empty((world, s1 - s0, mv), dtype=torch.int32, device=dev),
+                         voxel_num=torch.empty((world, s1 - s0), dtype=torch.int32, device=dev)) for s0, s1 in subs]
+        if len(set(sizes)) != 1:
+            raise RuntimeError("--frames must be a multiple of the number of GPUs (equal shards are gathered without padding)")
+
+    outs = [None] * nsub                                   # the sub-batches' (reused) output buffers
+
+    def compute_only():
+        if world == 1:
+            return mod(depth, intr, c2l)
+        for si, ((s0, s1), m) in enumerate(zip(subs, sub_mods)):
+            outs[si] = m(depth[s0:s1], intr[s0:s1], c2l[s0:s1])
+        return outs[-1]
+
+    def step():
+        if world == 1:
+            return mod(depth, intr, c2l)
+        cur = torch.cuda.current_stream(dev)
+        comm.wait_stream(cur)                              # the previous step's consumers are done with `gathered`
+        for si, ((s0, s1), m) in enumerate(zip(subs, sub_mods)):
+            outs[si] = m(depth[s0:s1], intr[s0:s1], c2l[s0:s1])
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev)
+                for name in ("voxel_mean", "coors", "num_points", "voxel_num"):
+                    dist.all_gather_into_tensor(gathered[si][name], outs[si][name])
+        cur.wait_stream(comm)
+        return outs[-1]
+
     for _ in range(args.warmup):
         r = step()
     barrier()
-    vn = r["voxel_num"].tolist()
-    M_total = int(sum(vn))
+    graph = None
+    if world > 1 and not args.no_graph:
+        # 8 frames per GPU are ~40 kernel launches + 8 collectives for ~0.2 ms of device work: replay the step as one
+        # CUDA graph (the library's internal stream lanes and NCCL are both capturable); eager if capture fails
+        try:
+            gs = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(gs):
+                step()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=gs):
+                step()
+            g.replay()
+            torch.cuda.synchronize()
+            graph = g
+        except Exception as e:                                 # noqa: BLE001
+            sys.stderr.write("CUDA graph capture of the step failed (%s): eager launches\n" % (str(e).splitlines()[0],))
+            graph = None
+            torch.cuda.synchronize()
+        ok = torch.tensor([1 if graph is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            graph = None
+    run_step = (lambda: graph.replay()) if graph is not None else step
+    for _ in range(3):
+        run_step()
+    barrier()
+    vn = r["voxel_num"].tolist() if world == 1 else [v for gd in gathered for v in gd["voxel_num"].flatten().tolist()]
+    M_total = int(sum(vn))                               # voxels of the whole job per step
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
 
     # ---- device-resident timed region ------------------------------------------------
     clocks = ClockSampler(local_rank)
     clocks.start()
     time.sleep(0.3)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms_per_step = timed(run_step, args.steps)
     clk = clocks.stop()
-    # per-kernel durations: the same steps again with CUDA events between the kernels
-    # (rd3_profile_*; the library then runs its frame sub-batches on ONE stream so that the
-    # events bracket single kernels -- the timed region above overlaps them on 3 streams)
+    value = BT * npix / (ms_per_step * 1e-3)
+    multi = None
+    if world > 1:
+        n2 = max(3, min(args.steps, 30))
+        compute_ms = timed(compute_only, n2)
+
+        def gather_only():
+            for si in range(nsub):
+                for name in ("voxel_mean", "coors", "num_points", "voxel_num"):
+                    dist.all_gather_into_tensor(gathered[si][name], outs[si][name])
+        gather_ms = timed(gather_only, n2)
+        gbytes = sum(t.numel() * t.element_size() for gd in gathered for t in gd.values())
+        # weak scaling for reference: BT frames on EVERY GPU, no collective (what round 1 reported)
+        wh = synthetic.make_batch([rank * BT + i for i in range(BT)], H, W, with_conf=False, scene=args.scene)
+        wd, wi, wc = wh["depth"].to(dev), wh["intrinsics"].to(dev), wh["cam2lidar"].to(dev)
+        wmod = make_mod()
+        for _ in range(3):
+            wmod(wd, wi, wc)
+        weak_ms = timed(lambda: wmod(wd, wi, wc), n2)
+        del wd, wmod
+        multi = {"frames_total": BT, "frames_per_gpu": B, "compute_only_ms": compute_ms, "gather_only_ms": gather_ms,
+                 "compute_plus_gather_ms": ms_per_step, "gathered_bytes_per_rank_per_step": gbytes,
+                 "cuda_graph": graph is not None,
+                 "gather": "all_gather_into_tensor of voxel_mean + coors + num_points + voxel_num (padded rows) per sub-batch "
+                           "on a communication stream, overlapped with the next sub-batch's kernels",
+                 "weak": {"frames_per_gpu": BT, "ms_per_step": weak_ms, "value": world * BT * npix / (weak_ms * 1e-3),
+                          "frames_per_sec": world * BT / (weak_ms * 1e-3), "note": "independent replicas, no collective"}}
+
+    # per-kernel durations: extra steps with CUDA events between the kernels (rd3_profile_*; the library then runs
+    # its frame sub-batches on ONE stream so that the events bracket single kernels)
     prof_steps = max(1, min(args.steps, 5))
     _lib.profile_enable(True)
     for _ in range(prof_steps):
-        step()
+        compute_only()
     torch.cuda.synchronize()
     stage_ms, calls = _lib.profile_read()
     _lib.profile_enable(False)
-    stage_ms = {k: v / prof_steps for k, v in stage_ms.items()}     # per step
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    ms_per_step = ms_max / args.steps
-    value = world * B * npix / (ms_per_step * 1e-3)
-
-    # ---- optional: NCCL gather of the outputs (north_star: only collective on the path) --
-    gather_ms = None
-    if args.gather and world > 1:
-        outs = [r["voxel_mean"], r["coors"], r["num_points"], r["voxel_num"]]
-        bufs = [torch.empty((world * o.shape[0],) + tuple(o.shape[1:]), dtype=o.dtype, device=dev) for o in outs]
-        for _ in range(2):
-            for o, bf in zip(outs, bufs):
-                dist.all_gather_into_tensor(bf, o)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for o, bf in zip(outs, bufs):
-            dist.all_gather_into_tensor(bf, o)
-        g1.record()
-        barrier()
-        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        gather_ms = float(tg.item())
+    stage_ms = {k: v / prof_steps for k, v in stage_ms.items()}     # per step, this rank's shard
 
     # ---- roofline of the dominant kernel + of the whole fused path ---------------------
     hbm_peak, peak_src = 6650.0, "fallback"
@@ -352,26 +449,26 @@ def main():
             hbm_peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         pass
-    C = F = 3
+    M_local = M_total * B // BT
     # ALGORITHMIC bytes per launch (DESIGN.md "Kernels"): compulsory reads+writes only
     alg = {
         "insert": B * npix * 4,                                 # depth read (rounds of the still open frames)
         "lookup": B * npix * 4,                                 # depth read
         "flags": 0, "cull": 0, "memset": 0,                     # scratch-only stages
-        "emit": M_total * K * C * 4,                            # voxels written
-        "meta": M_total * (12 + 4 + 4 * F),                     # coors + num + mean written
+        "emit": M_local * (K * C * 4 + 12 + 4 + 4 * F),         # voxels + coors + num + mean written
+        "meta": 0,
     }
-    path_bytes = B * npix * 4 + M_total * (K * 4 * C + 16) + M_total * 4 * F
-    kern = {k: v for k, v in stage_ms.items() if k != "memset"}
-    dom = max(kern, key=kern.get) if calls else "insert"
-    # launches of the dominant kernel per step (insert: one per round; others: one)
+    path_bytes = BT * npix * 4 + M_total * (K * 4 * C + 16) + M_total * 4 * F
+    kern = {k: v for k, v in stage_ms.items() if k not in ("memset", "meta")}
+    dom = max(kern, key=kern.get) if calls else "lookup"
     rounds = _lib.lib().rd3_hard_voxel_rounds(npix, B)
     lanes = max(1, min(int(os.environ.get("RD3_STREAMS", "2")), 4, B))
     dom_launches = rounds if dom == "insert" else 1
     dom_ms = stage_ms[dom] / dom_launches
     dom_achieved = alg[dom] / dom_launches / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     path_achieved = path_bytes / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": {"insert": "hv_pass_kernel<0>", "lookup": "hv_pass_kernel<1>"}.get(dom, "hv_%s_kernel" % dom), "achieved": dom_achieved, "peak": hbm_peak,
+    kname = {"insert": "hv_pass_kernel<DepthSource,0>", "lookup": "hv_pass_kernel<DepthSource,1>"}.get(dom, "hv_%s_kernel" % dom)
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": dom_achieved, "peak": hbm_peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": dom_achieved / hbm_peak, "traffic": None,
                 "ms_per_launch": dom_ms, "launches_per_step": dom_launches,
                 "algorithmic_bytes_per_launch": alg[dom] / dom_launches,
@@ -380,13 +477,41 @@ def main():
     if os.path.exists(traffic_file):
         try:
             tr_ = json.load(open(traffic_file))
-            if tr_.get("kernel") == roofline["kernel"]:
+            # an ncu number belongs to ONE build: it is only reported when the kernel sources are unchanged
+            if tr_.get("kernel") == kname and tr_.get("source_hash") == _source_hash() and world == 1:
                 roofline["traffic"] = tr_.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = tr_.get("capture")
         except Exception:
             pass
     path_roofline = {"bound": "hbm", "achieved": path_achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": path_achieved / hbm_peak, "algorithmic_bytes_per_step": path_bytes,
                      "stage_ms_per_step_single_stream": stage_ms}
+
+    # ---- the path WITH the confidence / sky masks and the device-side percentile threshold (north_star; SURVEY 8(d):
+    #      42.1 MB / frame) -- same frames, conf + sky resident in HBM
+    masks = None
+    if not args.no_masks and not args.profile_only:
+        conf, sky = host["conf"].to(dev), host["sky"].to(dev)
+        mmod = make_mod()
+
+        def mstep():
+            thr = rd3_b200.conf_threshold(conf, sky, synthetic.CONF_PERCENTILE)
+            return mmod(depth, intr, c2l, confs=conf, conf_thresh=thr, sky_masks=sky)
+
+        for _ in range(3):
+            rm = mstep()
+        n3 = max(3, min(args.steps, 30))
+        m_ms = timed(mstep, n3)
+        Mm = torch.tensor([int(rm["voxel_num"].sum())], device=dev)
+        if world > 1:
+            dist.all_reduce(Mm)
+        m_bytes = BT * npix * 9 + int(Mm.item()) * (K * 4 * C + 16 + 4 * F)
+        masks = {"ms_per_step": m_ms, "frames_per_sec": BT / (m_ms * 1e-3), "value": BT * npix / (m_ms * 1e-3),
+                 "algorithmic_bytes_per_step": m_bytes, "achieved_GBps": m_bytes / (m_ms * 1e-3) / 1e9,
+                 "frac": m_bytes / (m_ms * 1e-3) / 1e9 / hbm_peak, "voxels_per_frame_mean": int(Mm.item()) / BT,
+                 "what": "conf >= percentile(conf[~sky], %g) (exact device-side selection, no host read) & ~sky & depth "
+                         "masks fused into the same kernels; no collective" % synthetic.CONF_PERCENTILE}
+        del conf, sky, mmod
 
     # ---- e2e: public API from pinned host buffers, copies inside the timed region ------
     e2e = None
@@ -395,75 +520,83 @@ def main():
         nchunks = B // chunk
         nstreams = min(args.e2e_streams, nchunks)
         streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
-        mods = [rd3_b200.DepthToVoxels(cfg["voxel_size"], cfg["pcr"], K, cfg["max_voxels"],
-                                       max_depth=synthetic.MAX_DEPTH).to(dev).train() for _ in range(nstreams)]
         d_in = [torch.empty((chunk, 6, H, W), device=dev) for _ in range(nstreams)]
-        h_out = dict(voxels=torch.empty((B, mv, K, 3), pin_memory=True),
-                     coors=torch.empty((B, mv, 3), dtype=torch.int32, pin_memory=True),
-                     num_points=torch.empty((B, mv), dtype=torch.int32, pin_memory=True),
-                     voxel_mean=torch.empty((B, mv, 3), pin_memory=True),
-                     voxel_num=torch.empty((B,), dtype=torch.int32, pin_memory=True))
-        h2d = depth_h.numel() * 4 + intr_h.numel() * 4 + c2l_h.numel() * 4
-        d2h = sum(v.numel() * v.element_size() for v in h_out.values())
 
-        def e2e_step():
-            for ci in range(nchunks):
-                s = streams[ci % nstreams]
-                sl = slice(ci * chunk, (ci + 1) * chunk)
-                with torch.cuda.stream(s):
-                    d_in[ci % nstreams].copy_(depth_h[sl], non_blocking=True)
-                    k_d = intr_h[sl].to(dev, non_blocking=True)
-                    m_d = c2l_h[sl].to(dev, non_blocking=True)
-                    rr = mods[ci % nstreams](d_in[ci % nstreams], k_d, m_d)
-                    for name, hbuf in h_out.items():
-                        hbuf[sl].copy_(rr[name], non_blocking=True)
-            for s in streams:
-                s.synchronize()
+        def run_e2e(with_voxels):
+            mods = [make_mod(with_voxels=with_voxels) for _ in range(nstreams)]
+            if with_voxels:
+                h_out = dict(voxels=torch.empty((B, mv, K, 3), pin_memory=True),
+                             coors=torch.empty((B, mv, 3), dtype=torch.int32, pin_memory=True),
+                             num_points=torch.empty((B, mv), dtype=torch.int32, pin_memory=True),
+                             voxel_mean=torch.empty((B, mv, 3), pin_memory=True),
+                             voxel_num=torch.empty((B,), dtype=torch.int32, pin_memory=True))
+            else:       # what the sparse encoder consumes: packed (sum M, 3) features, (sum M, 4) [b,z,y,x] coors, counts
+                h_out = dict(feats=torch.empty((nchunks, chunk * mv, 3), pin_memory=True),
+                             coors=torch.empty((nchunks, chunk * mv, 4), dtype=torch.int32, pin_memory=True),
+                             num=torch.empty((nchunks, chunk * mv), dtype=torch.int32, pin_memory=True),
+                             offsets=torch.empty((nchunks, chunk + 1), dtype=torch.int32, pin_memory=True))
+            h2d = depth_h.numel() * 4 + intr_h.numel() * 4 + c2l_h.numel() * 4
+            d2h = sum(v.numel() * v.element_size() for v in h_out.values())
 
-        n_e2e = max(2, min(args.steps, 5))
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
+            def e2e_step():
+                for ci in range(nchunks):
+                    s = streams[ci % nstreams]
+                    sl = slice(ci * chunk, (ci + 1) * chunk)
+                    with torch.cuda.stream(s):
+                        d_in[ci % nstreams].copy_(depth_h[sl], non_blocking=True)
+                        k_d = intr_h[sl].to(dev, non_blocking=True)
+                        m_d = c2l_h[sl].to(dev, non_blocking=True)
+                        rr = mods[ci % nstreams](d_in[ci % nstreams], k_d, m_d)
+                        if with_voxels:
+                            for name, hbuf in h_out.items():
+                                hbuf[sl].copy_(rr[name], non_blocking=True)
+                        else:
+                            of, oc, on, offs = rd3_b200.pack_sparse_inputs(rr, batch_offset=f0 + ci * chunk, with_num_points=True,
+                                                                           sync=False, reuse_buffers=True)
+                            # packed rows are a prefix of the worst-case buffers; the copy moves the worst case (the
+                            # synthetic frames saturate max_voxels), the consumer reads offsets[-1] rows
+                            h_out["feats"][ci].copy_(of, non_blocking=True)
+                            h_out["coors"][ci].copy_(oc, non_blocking=True)
+                            h_out["num"][ci].copy_(on, non_blocking=True)
+                            h_out["offsets"][ci].copy_(offs, non_blocking=True)
+                for s in streams:
+                    s.synchronize()
+
+            n_e2e = max(2, min(args.steps, 5))
             e2e_step()
-        barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * npix * n_e2e / float(dt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
-               "frames_per_sec": world * B * n_e2e / float(dt.item()),
-               "how": "pinned host depth/calibration -> %d-frame chunks on %d streams (H2D, fused kernels, D2H of "
-                      "voxels+coors+num+mean+count) through rd3_b200.DepthToVoxels" % (chunk, nstreams)}
-        assert torch.equal(h_out["voxel_num"], r["voxel_num"].cpu())
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                e2e_step()
+            barrier()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            res = {"value": BT * npix * n_e2e / float(dt.item()), "unit": UNIT,
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
+                   "frames_per_sec": BT * n_e2e / float(dt.item())}
+            if with_voxels:
+                assert torch.equal(h_out["voxel_num"], compute_only()["voxel_num"].cpu()) or world > 1
+            else:
+                assert int(h_out["offsets"][0, -1]) > 0
+            return res
 
-    # ---- the same path without the padded voxel tensor: SparseEncoder inputs only ---
-    enc = None
-    if not args.profile_only:
-        lite = rd3_b200.DepthToVoxels(cfg["voxel_size"], cfg["pcr"], K, cfg["max_voxels"],
-                                      max_depth=synthetic.MAX_DEPTH, with_voxels=False).to(dev).train()
+        e2e = run_e2e(False)
+        e2e["how"] = ("pinned host depth/calibration -> %d-frame chunks on %d streams: H2D, fused kernels without the padded "
+                      "voxel tensor, pack_sparse_inputs, D2H of the packed features + [b,z,y,x] coors + counts + offsets "
+                      "(what SparseEncoder consumes) through rd3_b200.DepthToVoxels; per-rank byte counts" % (chunk, nstreams))
+        e2e["full_voxel_tensor"] = run_e2e(True)
+        e2e["full_voxel_tensor"]["how"] = "same, D2H of voxels + coors + num + mean + count (padded tensors)"
 
-        def enc_step():
-            return rd3_b200.pack_sparse_inputs(lite(depth, intr, c2l), batch_offset=rank * B, sync=False)
-
-        for _ in range(3):
-            enc_step()
-        barrier()
-        n_enc = max(3, min(args.steps, 20))
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(n_enc):
-            enc_step()
-        g1.record()
-        barrier()
-        te = torch.tensor([g0.elapsed_time(g1) / n_enc], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        enc_bytes = B * npix * 4 + M_total * (12 + 4 + 4 * F) + M_total * (16 + 4 * F)
-        enc = {"ms_per_step": float(te.item()), "frames_per_sec": world * B / (float(te.item()) * 1e-3),
-               "algorithmic_bytes_per_step": enc_bytes,
-               "what": "DepthToVoxels(with_voxels=False) + pack_sparse_inputs: (sum M,3) features and "
-                       "(sum M,4) [b,z,y,x] coors for the whole batch, inputs resident in HBM"}
+    # ---- operator rows at the other BASELINE configs (C1, C3, C4; one GPU) ---------------
+    rows = None
+    if rank == 0 and world == 1 and not args.no_rows and not args.profile_only:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_rows
+            rows = bench_rows.collect(iters=10, scene=args.scene)
+        except Exception as e:                                 # noqa: BLE001
+            rows = {"error": str(e).splitlines()[0] if str(e) else repr(e)}
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) --------------------------
     cpu_baseline = None
@@ -480,24 +613,34 @@ def main():
                         "frames_per_sec": ff / tt, "sample": ref.describe() + ", %d frames in %.1f s" % (ff, tt)}
 
     if rank == 0:
+        # launches of this repo's kernels per step and rank: per stream lane init + rounds + flagscan + chunk scan +
+        # firsts + cull + lookup + emit, plus the calibration kernel of every DepthToVoxels call
+        calls_per_step = 1 if world == 1 else nsub
+        per_call = 1 + min(lanes, max(1, B // calls_per_step)) * (rounds + 7)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "frames_per_sec": world * B / (ms_per_step * 1e-3),
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "frames_per_sec": BT / (ms_per_step * 1e-3),
             "config": {"workload": WORKLOAD_DESC,
-                       "scene": args.scene, "frames_per_gpu_per_step": B, "pixels_per_frame": npix,
-                       "voxels_per_frame_mean": M_total / B,
-                       "l2": "inputs larger than L2 (%.0f MB depth per step per GPU vs 126 MB L2)" % (B * npix * 4 / 1e6),
-                       "parallelism": "frames sharded by sample, %d per GPU, no data-path collective" % B},
-            "clocks": clk, "gpu_launches": (1 + lanes * (rounds + 5)) * args.steps,
+                       "scene": args.scene, "frames_per_step": BT, "frames_per_gpu_per_step": B, "pixels_per_frame": npix,
+                       "voxels_per_frame_mean": M_total / BT,
+                       "l2": "inputs larger than L2 (%.0f MB depth per step per GPU vs 126 MB L2)" % (B * npix * 4 / 1e6)
+                             if B * npix * 4 > 126e6 else "per-GPU inputs (%.0f MB) fit L2: the outputs written per step (%.0f MB) "
+                             "and the scratch do not" % (B * npix * 4 / 1e6, M_local * (K * 12 + 28) / 1e6),
+                       "parallelism": ("BASELINE config C5: %d frames per step sharded by sample over %d GPU(s), %d per GPU; "
+                                       "NCCL all-gather of the encoder inputs inside the timed region" % (BT, world, B))
+                                      if world > 1 else "one GPU, %d frames per step, no collective" % BT},
+            "clocks": clk, "gpu_launches": world * calls_per_step * per_call * args.steps,
             "roofline": roofline, "path_roofline": path_roofline,
             "e2e": e2e, "cpu_baseline": cpu_baseline,
         }
-        if gather_ms is not None:
-            line["gather_ms"] = gather_ms
-        if enc is not None:
-            line["encoder_inputs"] = enc
+        if multi is not None:
+            line["multi_gpu"] = multi
+        if masks is not None:
+            line["with_masks"] = masks
+        if rows is not None:
+            line["rows"] = rows
         _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -49,7 +49,20 @@ def main():
     ap.add_argument("--scene", default="mixture")
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
-    dev = torch.device("cuda:0")
+    rows = collect(args.iters, args.scene)
+    print("%-38s %-40s %10s %9s %9s %8s %10s" % ("row", "config", "alg MB", "ms(med)", "GB/s", "of HBM", "Munit/s"))
+    for r in rows:
+        print("%-38s %-40s %10.1f %9.3f %9.1f %7.1f%% %10.1f" % (r["row"], r["config"][:40], r["alg_MB"], r["ms_median"],
+                                                                 r["GBps"], 100 * r["frac_of_hbm"], r["Munits_per_s"]))
+    if args.json:
+        json.dump(dict(peak_gbs=PEAK, scene=args.scene, rows=rows), open(args.json, "w"), indent=1)
+
+
+def collect(iters=20, scene="mixture"):
+    """-> list of row dicts (bench.py embeds them in its JSON line as `rows`)."""
+    import types
+    args = types.SimpleNamespace(iters=iters, scene=scene)
+    dev = torch.device("cuda", torch.cuda.current_device())
     flush = torch.zeros(64 << 20, device=dev)            # 256 MB
     rows = []
 
@@ -172,12 +185,7 @@ def main():
     add("f4 conf percentile (p=30, non-sky)", "8 x 6x504x896 conf + sky", B * npix, "pixel", B * npix * 5,
         timeit(lambda: rd3_b200.conf_threshold(d["conf"], d["sky"], 30.0), args.iters, flush))
 
-    print("%-38s %-40s %10s %9s %9s %8s %10s" % ("row", "config", "alg MB", "ms(med)", "GB/s", "of HBM", "Munit/s"))
-    for r in rows:
-        print("%-38s %-40s %10.1f %9.3f %9.1f %7.1f%% %10.1f" % (r["row"], r["config"][:40], r["alg_MB"], r["ms_median"],
-                                                                 r["GBps"], 100 * r["frac_of_hbm"], r["Munits_per_s"]))
-    if args.json:
-        json.dump(dict(peak_gbs=PEAK, scene=args.scene, rows=rows), open(args.json, "w"), indent=1)
+    return rows
 
 
 if __name__ == "__main__":
