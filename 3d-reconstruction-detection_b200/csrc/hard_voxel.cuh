@@ -63,16 +63,8 @@ constexpr int kEmitThreads = RD3_EMIT_THREADS;
 #ifndef RD3_EMIT_MINB
 #define RD3_EMIT_MINB 6               // resident CTAs per SM the emit kernel is compiled for
 #endif
-#ifndef RD3_PASS_SLACK
-#define RD3_PASS_SLACK 64             // items that stay queued behind a pass: their table sectors are being prefetched
-#endif
-#ifndef RD3_PASS_PREFETCH
-#define RD3_PASS_PREFETCH 1           // prefetch.global.L2 of an item's table sector when it joins the queue
-#endif
 constexpr int kTilePoints = 128;      // points per warp tile (4 per lane)
-constexpr int kListCap = 160;         // per-warp list of undecided elements: 31 carried + 128 new
-constexpr int kQueueCap = 256;        // per-warp FIFO of in-range items (power of two): slack + 31 carried + 128 new + 32
-static_assert(RD3_PASS_SLACK + 31 + 128 + 32 <= kQueueCap, "item queue too small for the slack");
+constexpr int kListCap = 160;         // per-warp item / undecided lists: 31 carried + 128 new
 constexpr int kMaxRounds = 64;
 constexpr uint32_t kDummyKey = 0xFFFFFFE0u;   // + lane: 32 values no voxel key takes (make_grid: volume <= kDummyKey)
 constexpr int kBevDim = 64;           // bird's-eye mask of the kept voxels: kBevDim x kBevDim bits over the x,y grid
@@ -445,7 +437,7 @@ struct HvWork {
   uint32_t *cull;             // [B][kMaxCams] live column blocks per camera, or null (nothing culled)
   FastDiv div_gx, div_gy;     // key -> (x, y) cell
   uint32_t bev_kx, bev_ky;    // bird's-eye cell of voxel column i: (i * k) >> 20, k = floor(kBevDim 2^20 / grid)
-  FastDiv div_K;              // slot item -> (voxel, slot)
+  FastDiv div_Km1;            // slot-row word -> voxel
   int64_t N;
   int b0;                     // first frame of the group this launch works on
   int64_t cap;
@@ -483,15 +475,6 @@ __device__ __forceinline__ void load_bucket(const unsigned long long *p, unsigne
   asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
                : "=l"(e0), "=l"(e1), "=l"(e2), "=l"(e3)
                : "l"(p));
-}
-
-// The sector a key's probe will read first, requested ahead of time (no register, no dependency): the item then
-// waits RD3_PASS_SLACK queue positions before its pass, and the probe finds the sector in L2.
-__device__ __forceinline__ void table_prefetch(const unsigned long long *table, const HvWork &w, uint32_t key) {
-#if RD3_PASS_PREFETCH
-  const unsigned long long *p = table + (w.direct ? key : hash_bucket_slot(key, w.log2cap));
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#endif
 }
 
 // "point idx is / is no longer the first point of its voxel": XOR, so that the owner's toggle and the
@@ -638,7 +621,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
                    int iters) {
   __shared__ __align__(16) float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 4];
   __shared__ __align__(8) uint64_t s_bar;        // completion of the calibration's TMA copy
-  __shared__ uint2 s_itemb[kPassWarps * kQueueCap];    // FIFO of (key, element index) of the in-range elements
+  __shared__ uint2 s_itemb[kPassWarps * kListCap];     // (key, element index) of the in-range elements
   __shared__ uint32_t s_undb[kPassWarps * kListCap];   // indices of the undecided elements
   __shared__ uint2 s_hitb[MODE ? kPassWarps * 64 : 1]; // lookup: (first point of the voxel, element index) of the table hits
   __shared__ uint32_t s_cull[kMaxCams];
@@ -669,9 +652,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
 
   typename Src::Walker wk;
   if (!src.walk_init(wk, begin, end, iters, wv, lane)) return;
-  uint2 *s_item = s_itemb + wv * kQueueCap;
-  constexpr unsigned qm = kQueueCap - 1;
-  unsigned qhead = 0;                    // queue position of the oldest item; cnt items follow (positions mod kQueueCap)
+  uint2 *s_item = s_itemb + wv * kListCap;
   uint32_t *s_und = s_undb + wv * kListCap;
   uint2 *s_hit = s_hitb + (MODE ? wv * 64 : 0);
   unsigned long long *table = w.table + (int64_t)b * w.cap;
@@ -708,13 +689,13 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
       __syncwarp();
       continue;
     }
-    if (cnt >= 32 + RD3_PASS_SLACK || (flushing && nu == 0 && cnt > 0)) {
-      // ---- item pass over the OLDEST items (the sectors of the younger ones are still on their way from DRAM):
-      //      MODE 0 table insert; MODE 1 table lookup, the hits join the hit list ----
+    if (cnt >= 32 || (flushing && nu == 0 && cnt > 0)) {
+      // ---- item pass: MODE 0 table insert; MODE 1 table lookup, the hits join the hit list ----
+      // (measured and dropped: a FIFO with 32 / 64 items of slack whose table sectors are prefetched into L2 when
+      // they join the queue -- insert +3 %, lookup +3 %)
       const int n = cnt < 32 ? cnt : 32;
       uint2 it = make_uint2(0u, 0u);
-      if (lane < n) it = s_item[(qhead + lane) & qm];
-      qhead += n;
+      if (lane < n) it = s_item[cnt - n + lane];
       if (MODE == 0) {
         // (measured: electing one lane per key with __match_any_sync + __reduce_min_sync costs more than the
         // repeated atomics it saves, in the sparse and in the dense scene)
@@ -744,11 +725,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
         in = src.cell_exact(b, idx, s_cal, g, cx, cy, cz);
       }
       const unsigned b1 = __ballot_sync(0xffffffffu, in);
-      if (in) {
-        const uint32_t key = voxel_key(cx, cy, cz, g);
-        s_item[(qhead + cnt + __popc(b1 & lt)) & qm] = make_uint2(key, idx);
-        table_prefetch(table, w, key);
-      }
+      if (in) s_item[cnt + __popc(b1 & lt)] = make_uint2(voxel_key(cx, cy, cz, g), idx);
       cnt += __popc(b1);
       nu -= n;
       __syncwarp();
@@ -787,12 +764,12 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
     const unsigned cin = __popc(in);
     const unsigned p0 = __ballot_sync(0xffffffffu, cin & 1u), p1 = __ballot_sync(0xffffffffu, cin & 2u),
                    p2 = __ballot_sync(0xffffffffu, cin & 4u);
-    const unsigned qp = qhead + cnt + (__popc(p0 & lt) + 2 * __popc(p1 & lt) + 4 * __popc(p2 & lt));
-    // the order inside the queue is irrelevant: element q of the lane goes to the lane's slot #(set bits below q)
-    if (in & 1u) { s_item[qp & qm] = make_uint2(qd.key[0], l0); table_prefetch(table, w, qd.key[0]); }
-    if (in & 2u) { s_item[(qp + (in & 1u)) & qm] = make_uint2(qd.key[1], l0 + 1); table_prefetch(table, w, qd.key[1]); }
-    if (in & 4u) { s_item[(qp + __popc(in & 3u)) & qm] = make_uint2(qd.key[2], l0 + 2); table_prefetch(table, w, qd.key[2]); }
-    if (in & 8u) { s_item[(qp + __popc(in & 7u)) & qm] = make_uint2(qd.key[3], l0 + 3); table_prefetch(table, w, qd.key[3]); }
+    uint2 *it = s_item + cnt + (__popc(p0 & lt) + 2 * __popc(p1 & lt) + 4 * __popc(p2 & lt));
+    // the order inside the list is irrelevant: element q of the lane goes to the lane's slot #(set bits below q)
+    if (in & 1u) it[0] = make_uint2(qd.key[0], l0);
+    if (in & 2u) it[in & 1u] = make_uint2(qd.key[1], l0 + 1);
+    if (in & 4u) it[__popc(in & 3u)] = make_uint2(qd.key[2], l0 + 2);
+    if (in & 8u) it[__popc(in & 7u)] = make_uint2(qd.key[3], l0 + 3);
     cnt += __popc(p0) + 2 * __popc(p1) + 4 * __popc(p2);
     if (__any_sync(0xffffffffu, qd.und != 0u)) {
       const unsigned cun = __popc(qd.und);
@@ -1034,11 +1011,14 @@ static __global__ void __launch_bounds__(kBevWords) hv_cull_kernel(DepthSource s
 }
 
 // P4 ------------------------------------------------------------------------
-// A CTA owns V consecutive voxels (~1024 slot items).  dynamic smem: tile[V*K*C] floats
-// (padded to 16 B) + idx[V*K] u32 + list[V*K] u16.
-//   1. zero the tile (16-byte stores); every warp loads its share of the slot indices and
-//      ballot-compacts the non-empty ones into its own list segment (no atomics, no barrier)
-//   2. each warp gathers / re-unprojects (exact reference arithmetic) its listed items
+// A CTA owns V consecutive voxels (~1024 slot items).  dynamic smem: tile[V*K*C] floats (padded to 16 B) +
+// sidx[V*(K-1)] u32 (the slot rows, flat) + first[V] u32 + list[V*(K-1)] u16.
+//   1. zero the tile (16-byte stores); the voxels' first points are loaded (one per thread); every warp loads its
+//      share of the FLAT slot rows (4 independent coalesced loads per lane up front) and ballot-compacts the
+//      non-empty ones into its own list segment (no atomics, no barrier) -- rows are mostly empty, and only a
+//      listed item ever needs its (voxel, slot) position
+//   2. every voxel's first point and the listed items are gathered / re-unprojected (exact reference arithmetic)
+//      into the tile
 //   3. voxels are copied out with 16-byte stores; one thread per voxel writes coors (from the first
 //      point), the count and the HardSimpleVFE mean (slot order, one __fdiv_rn)
 template <class Src>
@@ -1051,27 +1031,31 @@ __global__ void __launch_bounds__(kEmitThreads, RD3_EMIT_MINB) hv_emit_kernel(Sr
   const int r0 = blockIdx.x * V;
   if (r0 >= vn) return;
   const int C = src.num_feats();
-  const int K = w.K;
+  const int K = w.K, Km1 = K - 1;
   const int nvox = min(V, vn - r0);
   const int items = nvox * K;
+  const int nS = nvox * Km1;                        // slot-row words of the CTA
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
   constexpr int nw = kEmitThreads / 32;
   float *tile = s_dyn;
-  uint32_t *s_idx = reinterpret_cast<uint32_t *>(s_dyn + (((size_t)V * K * C + 3) & ~(size_t)3));
-  uint16_t *s_list = reinterpret_cast<uint16_t *>(s_idx + (size_t)V * K);
-  // Warp wv owns the voxels [wv*vper, wv*vper + vper) of the CTA, i.e. the slot items [lo, hi); its list segment
-  // starts at lo.  A pass of the warp covers vpw = 32 / K whole voxels: lane = vl * K + k keeps its (voxel-in-pass,
-  // slot) for all passes, so no item index is ever divided (K > 32: one slot column per pass, lanes over voxels).
-  // Slot k == 0 is the voxel's first point (first_of), k >= 1 column k - 1 of its row of later points.
-  const int vper = (nvox + nw - 1) / nw;
-  const int v_lo = min(nvox, wv * vper), v_hi = min(nvox, v_lo + vper);
-  const int lo = v_lo * K;
-  const int vpw = K <= 32 ? 32 / K : 32;
-  const int my_vl = K <= 32 ? lane / K : lane, my_k0 = K <= 32 ? lane - my_vl * K : 0;
-  const bool lane_on = K <= 32 ? lane < vpw * K : true;
-  const int kpasses = K <= 32 ? 1 : K;                      // K > 32: the slot column advances with the pass
-  const uint32_t *S = w.slots + ((int64_t)b * w.max_voxels + r0) * (K - 1);
+  uint32_t *s_sidx = reinterpret_cast<uint32_t *>(s_dyn + (((size_t)V * K * C + 3) & ~(size_t)3));
+  uint32_t *s_first = s_sidx + (size_t)V * (Km1 > 0 ? Km1 : 1);
+  uint16_t *s_list = reinterpret_cast<uint16_t *>(s_first + V);
+  const uint32_t *S = w.slots + ((int64_t)b * w.max_voxels + r0) * Km1;
   const uint32_t *F1 = w.first_of + (int64_t)b * w.max_voxels + r0;
+
+  // warp wv owns the slot words [wv*per, wv*per+per): its list segment starts at the same offset
+  const int per = ((nS + nw - 1) / nw + 31) & ~31;
+  const int lo = wv * per, hi = min(nS, lo + per);
+  // The first 128 slot words of the warp's share are requested up front (4 independent loads per
+  // lane): one DRAM round trip instead of four dependent ones, overlapped with the calibration copy and the zero fill.
+  uint32_t pre[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int j = lo + 32 * q + lane;
+    pre[q] = j < hi ? __ldg(S + j) : kEmpty32;
+  }
+  uint32_t myfirst = threadIdx.x < nvox ? __ldg(F1 + threadIdx.x) : kEmpty32;
   const bool cal_async = src.stage_async(s_cal, &s_bar, b);     // one TMA bulk copy, no load / store loop
   {
     float4 *t4 = reinterpret_cast<float4 *>(tile);
@@ -1079,34 +1063,38 @@ __global__ void __launch_bounds__(kEmitThreads, RD3_EMIT_MINB) hv_emit_kernel(Sr
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int e = threadIdx.x; e < n4; e += kEmitThreads) t4[e] = z4;
   }
+  if (threadIdx.x < nvox) s_first[threadIdx.x] = myfirst;
+  for (int v = threadIdx.x + kEmitThreads; v < nvox; v += kEmitThreads) s_first[v] = __ldg(F1 + v);
   int nmine = 0;
-  // two passes' indices are requested before the first is consumed (independent loads in flight)
-  for (int vb = v_lo; vb < v_hi; vb += 2 * vpw) {
-    for (int kk = 0; kk < kpasses; ++kk) {
-      uint32_t idx2[2];
-      int it2[2];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int v = vb + h * vpw + my_vl, k = my_k0 + kk;
-        const bool on = lane_on && v < v_hi;
-        it2[h] = v * K + k;
-        idx2[h] = on ? (k ? __ldg(S + (int64_t)v * (K - 1) + (k - 1)) : __ldg(F1 + v)) : kEmpty32;
-        if (!on) it2[h] = -1;
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (it2[h] >= 0) s_idx[it2[h]] = idx2[h];
-        const unsigned bal = __ballot_sync(0xffffffffu, idx2[h] != kEmpty32);
-        if (idx2[h] != kEmpty32) s_list[lo + nmine + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)it2[h];
-        nmine += __popc(bal);
-      }
-    }
+  for (int q = 0; q < 4; ++q) {
+    const int j = lo + 32 * q + lane;
+    const uint32_t idx = pre[q];
+    if (j < hi) s_sidx[j] = idx;
+    const unsigned bal = __ballot_sync(0xffffffffu, idx != kEmpty32);
+    if (idx != kEmpty32) s_list[lo + nmine + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)j;
+    nmine += __popc(bal);
   }
-  __syncthreads();                       // tile zeroed, calibration copy issued
+  for (int j0 = lo + 128; j0 < hi; j0 += 32) {
+    const int j = j0 + lane;
+    uint32_t idx = kEmpty32;
+    if (j < hi) {
+      idx = __ldg(S + j);
+      s_sidx[j] = idx;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, idx != kEmpty32);
+    if (idx != kEmpty32) s_list[lo + nmine + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)j;
+    nmine += __popc(bal);
+  }
+  __syncthreads();                       // tile zeroed, first points staged, calibration copy issued
   if (cal_async) tma_wait(&s_bar);
-  for (int j = lane; j < nmine; j += 32) {
-    const int it = s_list[lo + j];
-    src.gather(b, s_idx[it], s_cal, tile + it * C);
+  // first points: every voxel has one (slot 0 of its tile row)
+  for (int v = threadIdx.x; v < nvox; v += kEmitThreads) src.gather(b, s_first[v], s_cal, tile + (size_t)v * K * C);
+  // later points: the listed slot words; word j = v * (K-1) + (k-1) is slot item v * K + k = j + v + 1
+  for (int t = lane; t < nmine; t += 32) {
+    const int j = s_list[lo + t];
+    const int v = (int)fast_div((uint32_t)j, w.div_Km1);
+    src.gather(b, s_sidx[j], s_cal, tile + (size_t)(j + v + 1) * C);
   }
   __syncthreads();
 
@@ -1133,9 +1121,9 @@ __global__ void __launch_bounds__(kEmitThreads, RD3_EMIT_MINB) hv_emit_kernel(Sr
   // except that (-0.0) + 0.0 = +0.0, which one extra "+ 0.0f" reproduces)
   const int F = o.F;
   for (int v = threadIdx.x; v < nvox; v += kEmitThreads) {
-    const uint32_t *si = s_idx + v * K;
-    int cnt = 0;
-    while (cnt < K && si[cnt] != kEmpty32) ++cnt;
+    const uint32_t *si = s_sidx + v * Km1;
+    int cnt = 1;                                   // the first point, then the non-empty prefix of the slot row
+    while (cnt < K && si[cnt - 1] != kEmpty32) ++cnt;
     const float *p0 = tile + v * K * C;
     const int64_t vr = (int64_t)b * w.max_voxels + r0 + v;
     // coors from the voxel's first point (the tile holds it already): the fast path decides all but points within
@@ -1276,7 +1264,7 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   w.div_gy = make_fastdiv((uint32_t)g.grid[1]);
   w.bev_kx = (uint32_t)(((uint64_t)kBevDim << 20) / (uint64_t)g.grid[0]);
   w.bev_ky = (uint32_t)(((uint64_t)kBevDim << 20) / (uint64_t)g.grid[1]);
-  w.div_K = make_fastdiv((uint32_t)p.K);
+  w.div_Km1 = make_fastdiv((uint32_t)(p.K > 1 ? p.K - 1 : 1));
   if (p.S % src.host_round_multiple() != 0 && p.rounds > 1) return RD3_ERR_INVALID_ARGUMENT;   // plan made for another source
 
   const int C = src.host_num_feats();
@@ -1287,8 +1275,8 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   if (V < 1) V = 1;
   if (V > 32 * RD3_EMIT_ITEMS) V = 32 * RD3_EMIT_ITEMS;
   while (V > 1 && (size_t)V * p.K * (C + 1) * 4 > 10 * 1024 * RD3_EMIT_ITEMS) V /= 2;
-  const size_t smem = align_up((size_t)V * p.K * C * 4, 16) + (size_t)V * p.K * 4 +
-                      align_up((size_t)V * p.K * 2, 16) + (size_t)V * 4;
+  const size_t smem = align_up((size_t)V * p.K * C * 4, 16) + (size_t)V * p.K * 4 + (size_t)V * 4 +
+                      align_up((size_t)V * p.K * 2, 16) + 64;
   if (smem > 200 * 1024) return RD3_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
     RD3_CUDA_TRY(cudaFuncSetAttribute(hv_emit_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize,
