@@ -61,7 +61,7 @@ constexpr int kEmitThreads = RD3_EMIT_THREADS;
 #define RD3_LKP_MINB 5                // ... and the lookup pass
 #endif
 #ifndef RD3_EMIT_MINB
-#define RD3_EMIT_MINB 6               // resident CTAs per SM the emit kernel is compiled for
+#define RD3_EMIT_MINB 8               // resident CTAs per SM the emit kernel is compiled for
 #endif
 constexpr int kTilePoints = 128;      // points per warp tile (4 per lane)
 constexpr int kListCap = 160;         // per-warp item / undecided lists: 31 carried + 128 new

@@ -53,18 +53,28 @@ __global__ void __launch_bounds__(kSelThreads) sel_hist_kernel(const float *__re
   __syncthreads();
   const int64_t lo = (int64_t)blockIdx.x * kSelChunk;
   const int64_t hi = lo + kSelChunk < npix ? lo + kSelChunk : npix;
-  for (int64_t i = lo + threadIdx.x; i < hi; i += kSelThreads) {
-    const uint32_t k = sel_key(__ldg(conf + (int64_t)b * npix + i));
-    const bool ns = sky ? __ldg(sky + (int64_t)b * npix + i) == 0
-                        : (sky_prob ? !(__ldg(sky_prob + (int64_t)b * npix + i) >= sky_thr) : true);
+  const int lane = threadIdx.x & 31;
+  // the loop bound is rounded up to whole warps: every lane takes part in the warp votes of PASS 0
+  const int64_t hi32 = lo + ((hi - lo + 31) & ~(int64_t)31);
+  for (int64_t i = lo + threadIdx.x; i < hi32; i += kSelThreads) {
+    const bool on = i < hi;
+    const uint32_t k = on ? sel_key(__ldg(conf + (int64_t)b * npix + i)) : 0u;
+    const bool ns = on && (sky ? __ldg(sky + (int64_t)b * npix + i) == 0
+                               : (sky_prob ? !(__ldg(sky_prob + (int64_t)b * npix + i) >= sky_thr) : true));
     if (PASS == 0) {
-      if (ns) atomicAdd(&s_h[0][k >> 21], 1u);
-      atomicAdd(&s_h[1][k >> 21], 1u);
-      if (k == 0xFFFFFFFFu) {                               // np.percentile of data with a NaN is NaN
+      // Confidences cluster in a handful of the top-11-bit bins (conf = 1 + exp(x): four exponents), so 32 plain
+      // shared-memory atomics of a warp would serialise on a few addresses.  Lanes holding the same bin are
+      // counted by ONE lane (__match_any_sync); absent lanes get bins of their own.
+      const uint32_t bin = on ? (k >> 21) : (kSelBins + lane);
+      const unsigned g_all = __match_any_sync(0xffffffffu, bin);
+      const unsigned g_ns = __match_any_sync(0xffffffffu, ns ? bin : (kSelBins + lane));
+      if (on && lane == __ffs(g_all) - 1) atomicAdd(&s_h[1][bin], (uint32_t)__popc(g_all));
+      if (ns && lane == __ffs(g_ns) - 1) atomicAdd(&s_h[0][bin], (uint32_t)__popc(g_ns));
+      if (on && k == 0xFFFFFFFFu) {                         // np.percentile of data with a NaN is NaN
         if (ns) nanflag[2 * b] = 1u;
         nanflag[2 * b + 1] = 1u;
       }
-    } else if (ns || use_all) {
+    } else if (ns || (on && use_all)) {
       if (PASS == 1) {
         if ((k >> 21) == (p0 >> 21)) atomicAdd(&s_h[0][(k >> 10) & 2047u], 1u);
         if ((k >> 21) == (p1 >> 21)) atomicAdd(&s_h[1][(k >> 10) & 2047u], 1u);
