@@ -433,6 +433,7 @@ struct HvWork {
   int32_t *wordprefix;        // [B][nwords] exclusive popcount prefix inside the chunk
   int32_t *chunk_base;        // [B][nchunks] totals, then exclusive bases after the chunk scan
   int32_t *round_claims;      // [B][kMaxRounds] voxels claimed per insert round
+  int32_t *scan_done;         // [B] CTAs of hv_count_kernel that have finished (the last one scans the chunk totals)
   uint32_t *bev;              // [B][kBevCopies][kBevWords] bird's-eye masks of the kept voxels (OR of the copies), or null
   uint32_t *cull;             // [B][kMaxCams] live column blocks per camera, or null (nothing culled)
   FastDiv div_gx, div_gy;     // key -> (x, y) cell
@@ -819,25 +820,51 @@ static __global__ void __launch_bounds__(256) hv_init_kernel(HvInit in) {
 }
 
 // P2a -----------------------------------------------------------------------
-// grid (nchunks, B), kScanThreads threads, one flag word each.
-static __global__ void __launch_bounds__(kScanThreads) hv_flagscan_kernel(HvWork w) {
-  __shared__ int s_warp[kScanThreads / 32];
+// First-point flags -> chunk totals -> (by the frame's LAST CTA to finish: no second launch, no spinning)
+// exclusive chunk bases and voxel_num.  grid (ceil(nchunks / 4), frames), 256 threads: a CTA owns 4 chunks of
+// kChunkWords flag words, 64 threads per chunk, one 16-byte load per thread.
+static __global__ void __launch_bounds__(256) hv_count_kernel(HvWork w, int32_t *voxel_num) {
+  __shared__ int s_part[8];
+  __shared__ int s_last, s_carry;
+  __shared__ int s_warp[8];
   const int b = blockIdx.y + w.b0;
-  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-  const int64_t wi = (int64_t)b * w.nwords + (int64_t)blockIdx.x * kChunkWords + threadIdx.x;
-  const int cnt = __popc(w.flags[wi]);
-  const int inc = warp_inclusive_scan(cnt);
-  if (lane == 31) s_warp[wv] = inc;
-  __syncthreads();
-  int base = 0, total = 0;
-#pragma unroll
-  for (int k = 0; k < kScanThreads / 32; ++k) {
-    const int t = s_warp[k];
-    if (k < wv) base += t;
-    total += t;
+  const int t = threadIdx.x, lane = t & 31, wv = t >> 5;
+  const int c = blockIdx.x * 4 + (t >> 6);
+  int cnt = 0;
+  if (c < w.nchunks) {
+    const uint4 f = __ldcs(reinterpret_cast<const uint4 *>(w.flags + (int64_t)b * w.nwords + (int64_t)c * kChunkWords) + (t & 63));
+    cnt = __popc(f.x) + __popc(f.y) + __popc(f.z) + __popc(f.w);
   }
-  w.wordprefix[wi] = base + inc - cnt;
-  if (threadIdx.x == 0) w.chunk_base[(int64_t)b * w.nchunks + blockIdx.x] = total;
+  for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if (lane == 0) s_part[wv] = cnt;
+  __syncthreads();
+  int32_t *cb = w.chunk_base + (int64_t)b * w.nchunks;
+  if ((t & 63) == 0 && c < w.nchunks) cb[c] = s_part[wv] + s_part[wv + 1];
+  __threadfence();                                   // the totals are visible before the ticket is taken
+  __syncthreads();
+  if (t == 0) s_last = atomicAdd(w.scan_done + b, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // the last CTA of the frame: exclusive scan of the chunk totals in place
+  if (t == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < w.nchunks; base += 256) {
+    const int i = base + t;
+    const int v = (i < w.nchunks) ? __ldcg(cb + i) : 0;
+    const int inc = warp_inclusive_scan(v);
+    if (lane == 31) s_warp[wv] = inc;
+    __syncthreads();
+    int before = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) before += (k < wv) ? s_warp[k] : 0;
+    const int excl = s_carry + before + inc - v;
+    if (i < w.nchunks) cb[i] = excl;
+    __syncthreads();
+    if (t == 255) s_carry = excl + v;
+    __syncthreads();
+  }
+  if (t == 0) voxel_num[b] = s_carry < w.max_voxels ? s_carry : w.max_voxels;
 }
 
 // Shared tail of the ordered-flag kernels (depth.cu): lane L of warp wv holds the
@@ -864,19 +891,37 @@ __device__ __forceinline__ void chunk_scan_store(uint32_t my_word, int *s_warp, 
 }
 
 // P2f -----------------------------------------------------------------------
-// After the chunk scan: the r-th set bit of the first-point flags is the first point of the voxel of rank r.
-// grid (nwords / 256, frames), one flag word per thread.
-static __global__ void __launch_bounds__(256) hv_firsts_kernel(HvWork w) {
-  const int b = blockIdx.y + w.b0;
-  const int wl = blockIdx.x * blockDim.x + threadIdx.x;
-  if (wl >= w.nwords) return;
-  uint32_t bits = w.flags[(int64_t)b * w.nwords + wl];
-  if (!bits) return;
-  int r = __ldg(w.chunk_base + (int64_t)b * w.nchunks + wl / kChunkWords) + __ldg(w.wordprefix + (int64_t)b * w.nwords + wl);
+// After the chunk bases are known, for 4 chunks per CTA (64 threads per chunk, 4 flag words per thread): the
+// exclusive popcount prefix of every word inside its chunk (what voxel_rank adds to the chunk base), and the list
+// of first points by rank -- the r-th set bit of the flags is the first point of the voxel of rank r.
+__device__ __forceinline__ void firsts_block(const HvWork &w, int b, int blk) {
+  __shared__ int s_fw[8];
+  const int t = threadIdx.x, lane = t & 31, wv = t >> 5;
+  const int c = blk * 4 + (t >> 6);
+  const bool on = c < w.nchunks;
+  const int64_t w0 = (int64_t)b * w.nwords + (int64_t)(on ? c : 0) * kChunkWords + (t & 63) * 4;
+  uint4 f = make_uint4(0u, 0u, 0u, 0u);
+  if (on) f = __ldg(reinterpret_cast<const uint4 *>(w.flags + w0));
+  const int c0 = __popc(f.x), c1 = __popc(f.y), c2 = __popc(f.z), c3 = __popc(f.w);
+  const int mine = c0 + c1 + c2 + c3;
+  const int inc = warp_inclusive_scan(mine);
+  if (lane == 31) s_fw[wv] = inc;
+  __syncthreads();
+  if (!on) return;
+  const int p0 = inc - mine + ((wv & 1) ? s_fw[wv - 1] : 0);           // two warps per chunk
+  *reinterpret_cast<int4 *>(w.wordprefix + w0) = make_int4(p0, p0 + c0, p0 + c0 + c1, p0 + c0 + c1 + c2);
+  if (!mine) return;
+  int r = __ldg(w.chunk_base + (int64_t)b * w.nchunks + c) + p0;
   uint32_t *out = w.first_of + (int64_t)b * w.max_voxels;
-  while (bits && r < w.max_voxels) {
-    out[r++] = ((uint32_t)wl << 5) + (uint32_t)(__ffs(bits) - 1);
-    bits &= bits - 1;
+  const uint32_t wl = (uint32_t)(c * kChunkWords + (t & 63) * 4);
+  const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t bits = fw[q];
+    while (bits && r < w.max_voxels) {
+      out[r++] = ((wl + q) << 5) + (uint32_t)(__ffs(bits) - 1);
+      bits &= bits - 1;
+    }
   }
 }
 
@@ -929,15 +974,16 @@ static __global__ void __launch_bounds__(1024) scan_chunks_kernel(int32_t *chunk
 // one of these five planes cannot receive a pixel of the block; the largest value of a plane function over a
 // box is its value at the centre plus |n| . half-extents.  Everything is evaluated in fp64; a camera whose
 // map is singular / non-finite keeps all its blocks.
-static __global__ void __launch_bounds__(kBevWords) hv_cull_kernel(DepthSource src, VoxelGrid g, HvWork w) {
+__device__ __forceinline__ void cull_block(const DepthSource &src, const VoxelGrid &g, const HvWork &w, int b, int pair) {
   __shared__ double s_inv[9], s_T[3], s_margin;
   __shared__ int s_ok, s_hitflag;
   const int nblk = ((src.p.W - 1) >> src.cbshift) + 1;
-  const int b = blockIdx.y + w.b0, cam = blockIdx.x / nblk, blk = blockIdx.x - cam * nblk;
+  const int cam = pair / nblk, blk = pair - cam * nblk;
   const int ncam = src.p.ncam;
-  // thread t owns word t of the bird's-eye mask (OR of the privatised copies)
+  // thread t < kBevWords owns word t of the bird's-eye mask (OR of the privatised copies)
   uint32_t bits = 0;
-  for (int c = 0; c < kBevCopies; ++c) bits |= __ldcg(w.bev + ((int64_t)b * kBevCopies + c) * kBevWords + threadIdx.x);
+  if (threadIdx.x < kBevWords)
+    for (int c = 0; c < kBevCopies; ++c) bits |= __ldcg(w.bev + ((int64_t)b * kBevCopies + c) * kBevWords + threadIdx.x);
   if (threadIdx.x == 0) {
     s_hitflag = 0;
     const float *k = src.cal_table + ((int64_t)b * ncam + cam) * kCalibFloats + kCalDirect;
@@ -1008,6 +1054,18 @@ static __global__ void __launch_bounds__(kBevWords) hv_cull_kernel(DepthSource s
   if (hit) s_hitflag = 1;
   __syncthreads();
   if (threadIdx.x == 0 && s_hitflag) atomicOr(w.cull + b * kMaxCams + cam, 1u << blk);
+}
+
+// P2f + P2c in ONE launch (both only need the chunk bases): grid (ncull + ceil(nchunks / 4), frames), 256 threads;
+// the first ncull CTAs of a frame (depth source with culling: cameras x column blocks, else 0) decide a cull bit each.
+template <class Src>
+__global__ void __launch_bounds__(256) hv_post_kernel(Src src, VoxelGrid g, HvWork w, int ncull) {
+  const int b = blockIdx.y + w.b0;
+  if ((int)blockIdx.x < ncull) {
+    if constexpr (Src::kIsDepth) cull_block(src, g, w, b, (int)blockIdx.x);
+    return;
+  }
+  firsts_block(w, b, (int)blockIdx.x - ncull);
 }
 
 // P4 ------------------------------------------------------------------------
@@ -1185,7 +1243,7 @@ struct HvPlan {
   int log2cap;
   int nwords, nchunks;
   // [table | slots] are set to 0xFF with one memset, [flags | bev | round_claims] to 0 with another
-  size_t off_table, off_slots, off_first, off_flags, off_bev, off_claims, off_cull, off_prefix, off_chunk, total;
+  size_t off_table, off_slots, off_first, off_flags, off_bev, off_claims, off_done, off_cull, off_prefix, off_chunk, total;
 };
 
 // `round_multiple`: a round has to be a whole number of the source's work units (image rows for depth maps)
@@ -1221,6 +1279,7 @@ inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels, int64_t round_mul
   p.off_flags = off; off += align_up((size_t)B * p.nwords * 4);
   p.off_bev = off; off += align_up((size_t)B * kBevCopies * kBevWords * 4);
   p.off_claims = off; off += align_up((size_t)B * kMaxRounds * 4);
+  p.off_done = off; off += align_up((size_t)B * 4);
   p.off_cull = off; off += align_up((size_t)B * kMaxCams * 4);
   p.off_prefix = off; off += align_up((size_t)B * p.nwords * 4);
   p.off_chunk = off; off += align_up((size_t)B * p.nchunks * 4);
@@ -1231,14 +1290,11 @@ inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels, int64_t round_mul
 // culling needs the precomputed calibration table and more than one column block or camera to pay off
 template <class Src> struct CullLaunch {
   static bool wanted(const Src &) { return false; }
-  static void run(const Src &, const VoxelGrid &, const HvWork &, int, cudaStream_t) {}
+  static int blocks(const Src &) { return 0; }
 };
 template <> struct CullLaunch<DepthSource> {
   static bool wanted(const DepthSource &s) { return hv_tuning().cull && s.cal_table != nullptr; }
-  static void run(const DepthSource &s, const VoxelGrid &g, const HvWork &w, int nb, cudaStream_t st) {
-    const int nblk = ((s.p.W - 1) >> s.cbshift) + 1;
-    hv_cull_kernel<<<dim3(s.p.ncam * nblk, nb), kBevWords, 0, st>>>(s, g, w);
-  }
+  static int blocks(const DepthSource &s) { return s.p.ncam * (((s.p.W - 1) >> s.cbshift) + 1); }
 };
 
 template <class Src>
@@ -1252,6 +1308,7 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   w.first_of = (uint32_t *)(base + p.off_first);
   w.flags = (uint32_t *)(base + p.off_flags);
   w.round_claims = (int32_t *)(base + p.off_claims);
+  w.scan_done = (int32_t *)(base + p.off_done);
   w.wordprefix = (int32_t *)(base + p.off_prefix);
   w.chunk_base = (int32_t *)(base + p.off_chunk);
   const bool cull = CullLaunch<Src>::wanted(src) && g.fast_ok;
@@ -1333,6 +1390,7 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
                                      (size_t)nb * p.max_voxels * (p.K - 1) * 4, st));
       RD3_LANE_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords, 0, (size_t)nb * p.nwords * 4, st));
       add(w.round_claims + (size_t)b0 * kMaxRounds, (size_t)nb * kMaxRounds * 4, 0u);
+      add(w.scan_done + b0, (size_t)nb * 4, 0u);
       if (cull) {
         add(w.bev + (size_t)b0 * kBevCopies * kBevWords, (size_t)nb * kBevCopies * kBevWords * 4, 0u);
         add(w.cull + (size_t)b0 * kMaxCams, (size_t)nb * kMaxCams * 4, 0u);
@@ -1348,11 +1406,12 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
       hv_pass_kernel<Src, 0><<<dim3(src.host_grid(begin, end, it), nb), kPassThreads, 0, st>>>(src, g, w, nullptr, begin, end, r, it);
     }
     prof_mark(st, 2);
-    hv_flagscan_kernel<<<dim3(p.nchunks, nb), kScanThreads, 0, st>>>(w);
-    scan_chunks_kernel<<<nb, 1024, 0, st>>>(w.chunk_base, w.nchunks, out.voxel_num, w.max_voxels, b0);
-    hv_firsts_kernel<<<dim3((unsigned)ceil_div(p.nwords, 256), nb), 256, 0, st>>>(w);
+    hv_count_kernel<<<dim3((unsigned)ceil_div(p.nchunks, 4), nb), 256, 0, st>>>(w, out.voxel_num);
     prof_mark(st, 3);
-    if (cull) CullLaunch<Src>::run(src, g, w, nb, st);
+    {
+      const int ncull = cull ? CullLaunch<Src>::blocks(src) : 0;
+      hv_post_kernel<Src><<<dim3((unsigned)(ncull + ceil_div(p.nchunks, 4)), nb), 256, 0, st>>>(src, g, w, ncull);
+    }
     prof_mark(st, 4);
     if (p.N > 0)
       hv_pass_kernel<Src, 1><<<dim3(src.host_grid(0, p.N, tune.lkp_iters), nb), kPassThreads, 0, st>>>(

@@ -1,3 +1,3 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-python tools/ab.py cur=ab_libs/cur.so e8=ab_libs/e8.so e4=ab_libs/e4.so
+python tools/ab.py cur=ab_libs/cur.so cur_s1=ab_libs/cur.so,RD3_STREAMS:1 cur_s3=ab_libs/cur.so,RD3_STREAMS:3
