@@ -1068,8 +1068,9 @@ __device__ __forceinline__ void cull_block(const DepthSource &src, const VoxelGr
 
 // P2f + P2c in ONE launch (both only need the chunk bases): grid (ncull + ceil(nchunks / 4), frames), 256 threads;
 // the first ncull CTAs of a frame (depth source with culling: cameras x column blocks, else 0) decide a cull bit each.
+// (compiled for 8 CTAs per SM: the cull part's fp64 plane set would otherwise cap the whole launch at 3)
 template <class Src>
-__global__ void __launch_bounds__(256) hv_post_kernel(Src src, VoxelGrid g, HvWork w, int ncull) {
+__global__ void __launch_bounds__(256, 8) hv_post_kernel(Src src, VoxelGrid g, HvWork w, int ncull) {
   const int b = blockIdx.y + w.b0;
   if ((int)blockIdx.x < ncull) {
     if constexpr (Src::kIsDepth) cull_block(src, g, w, b, (int)blockIdx.x);
@@ -1157,9 +1158,15 @@ __global__ void __launch_bounds__(kEmitThreads, RD3_EMIT_MINB) hv_emit_kernel(Sr
   __syncthreads();                       // tile zeroed, first points staged, calibration copy issued
   if (cal_async) tma_wait(&s_bar);
   // first points: every voxel has one (slot 0 of its tile row)
-  // (interleaved over the warps: with ~100 voxels per CTA a plain thread index would leave half of the warps idle
-  // while the others run the exact unprojection)
-  for (int v = lane * nw + wv; v < nvox; v += kEmitThreads) src.gather(b, s_first[v], s_cal, tile + (size_t)v * K * C);
+  // (a block of voxels per warp: with ~100 voxels per CTA a plain thread index would leave half of the warps idle
+  // while the others run the exact unprojection; consecutive voxels per lane keep the tile stores conflict-free)
+  {
+    const int vpw = (nvox + nw - 1) / nw;
+    for (int v0 = 0; v0 < vpw; v0 += 32) {
+      const int v = wv * vpw + v0 + lane;
+      if (v0 + lane < vpw && v < nvox) src.gather(b, s_first[v], s_cal, tile + (size_t)v * K * C);
+    }
+  }
   // later points: the listed slot words; word j = v * (K-1) + (k-1) is slot item v * K + k = j + v + 1
   for (int t = lane; t < nmine; t += 32) {
     const int j = s_list[lo + t];

@@ -655,6 +655,21 @@ def test_fused_outputs_are_fresh_unless_reuse_is_requested():
     assert s0["coors"].data_ptr() == s1["coors"].data_ptr()
 
 
+def test_nccl_gather_matches_single_process():
+    """frames sharded by sample over 2 GPUs, outputs all-gathered with NCCL == the single-GPU result,
+    bit for bit (unequal shards included).  Needs two GPUs; the gloo twin runs on the CPU (test_host_logic.py)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import subprocess
+    import sys
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "nccl_gather_worker.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617", worker],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
 def test_cuda_graph_capture_of_fused_path():
     """The whole kernel sequence (incl. the internal stream lanes) is capturable: no host sync,
     no allocation inside DepthToVoxels.forward in steady state."""
