@@ -196,6 +196,9 @@ static int make_depth_source(const float *depth, const float *intrinsics, const 
   d.div_hw = make_fastdiv((uint32_t)d.HW);
   d.div_w = make_fastdiv((uint32_t)d.W);
   src->vec_ok = ((p->W & 3) == 0) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0);
+  src->mask_vec_ok = ((p->W & 3) == 0) && (!conf || (reinterpret_cast<uintptr_t>(conf) & 15) == 0) &&
+                     (!sky || (reinterpret_cast<uintptr_t>(sky) & 3) == 0) &&
+                     (!src->sky_prob || (reinterpret_cast<uintptr_t>(src->sky_prob) & 15) == 0);
   src->div_h = make_fastdiv((uint32_t)p->H);
   src->cbshift = 7;                                  // culling: blocks of >= 128 image columns, at most 32 per row
   while (((p->W - 1) >> src->cbshift) >= 32) ++src->cbshift;

@@ -61,7 +61,7 @@ constexpr int kEmitThreads = RD3_EMIT_THREADS;
 #define RD3_LKP_MINB 5                // ... and the lookup pass
 #endif
 #ifndef RD3_EMIT_MINB
-#define RD3_EMIT_MINB 8               // resident CTAs per SM the emit kernel is compiled for
+#define RD3_EMIT_MINB 5               // resident CTAs per SM the emit kernel is compiled for (shared memory allows 5 at K*C = 30)
 #endif
 constexpr int kTilePoints = 128;      // points per warp tile (4 per lane)
 constexpr int kListCap = 160;         // per-warp item / undecided lists: 31 carried + 128 new
@@ -70,6 +70,8 @@ constexpr uint32_t kDummyKey = 0xFFFFFFE0u;   // + lane: 32 values no voxel key 
 constexpr int kBevDim = 64;           // bird's-eye mask of the kept voxels: kBevDim x kBevDim bits over the x,y grid
 constexpr int kBevWords = kBevDim * kBevDim / 32;
 constexpr int kBevCopies = 32;        // privatised copies of the mask (power of two): spreads the marking atomics
+constexpr int kLocalIters = 16;       // insert pass: a warp whose strip has at most this many tiles keeps the first-point
+                                      // bits of its own points in shared memory (4 words per tile) and flushes them once
 
 // ---------------------------------------------------------------------------
 // packed fp32 pairs (FFMA2 / FADD2 on sm_100a: two IEEE-rounded results per issue slot)
@@ -138,12 +140,16 @@ struct PointsSource {
 
   struct Walker {
     int64_t cur, end;     // first element of the warp's current tile, end of its strip
+    int64_t cur0;         // first element of the strip
     int lane;
   };
+  // element index of position lp (tile number * 128 + offset) of the warp's strip
+  __device__ __forceinline__ uint32_t strip_index(const Walker &k, uint32_t lp) const { return (uint32_t)k.cur0 + lp; }
   __device__ __forceinline__ bool cta_live(const HvCull &, int, int64_t, int64_t, int) const { return true; }
   __device__ __forceinline__ bool walk_init(Walker &k, int64_t begin, int64_t end, int iters, int wv, int lane) const {
     const int64_t strip = (int64_t)iters * kTilePoints;
     k.cur = begin + ((int64_t)blockIdx.x * kPassWarps + wv) * strip;
+    k.cur0 = k.cur;
     k.end = k.cur + strip < end ? k.cur + strip : end;
     k.lane = lane;
     return k.cur < end;
@@ -202,6 +208,7 @@ struct DepthSource {
   DepthParams p;
   CellRange rg;            // range filter in cell units (fused path); on = 0 when the grid test implies it
   int vec_ok;              // 16-byte aligned float4 loads of 4 pixels of a row are legal (W % 4 == 0, aligned base)
+  int mask_vec_ok;         // ... and the same for the conf / sky / sky_prob maps (16 / 4 / 16-byte loads)
   int cbshift;             // culling: image columns are grouped in blocks of 2^cbshift (>= 128, <= 32 blocks)
   FastDiv div_h;           // global row -> camera
   static constexpr bool kIsDepth = true;
@@ -260,6 +267,7 @@ struct DepthSource {
 
   struct Walker {
     uint32_t gr, gr_end;   // global image row (cam * H + v) of the warp's current tile, end of its rows
+    uint32_t gr0, c0;      // first row of the strip, first column of the tile
     uint32_t cam, v;       // the same row as (camera, row)
     uint32_t u;            // the lane's first column (fixed)
     uint32_t blk;          // culling block of the column tile
@@ -292,6 +300,8 @@ struct DepthSource {
     uint32_t r0, r1, ct;
     cta_rows(begin, end, iters, r0, r1, ct);
     k.gr = r0 + (uint32_t)(wv * iters);
+    k.gr0 = k.gr;
+    k.c0 = ct * kTilePoints;
     k.gr_end = k.gr + (uint32_t)iters < r1 ? k.gr + (uint32_t)iters : r1;
     k.cam = fast_div(k.gr, div_h);
     k.v = k.gr - k.cam * (uint32_t)p.H;
@@ -310,6 +320,10 @@ struct DepthSource {
     return (s_cull[k.cam] >> k.blk) & 1u;
   }
   __device__ __forceinline__ uint32_t walk_index(const Walker &k) const { return k.gr * (uint32_t)p.W + k.u; }
+  // pixel index of position lp (row of the strip * 128 + column offset inside the tile)
+  __device__ __forceinline__ uint32_t strip_index(const Walker &k, uint32_t lp) const {
+    return (k.gr0 + (lp >> 7)) * (uint32_t)p.W + k.c0 + (lp & 127u);
+  }
   __device__ __forceinline__ int walk_npx(const Walker &k) const { return k.npx; }
 
   // The depth load does not depend on the calibration: the load of the NEXT tile is issued before the
@@ -344,11 +358,31 @@ struct DepthSource {
 #pragma unroll
     for (int q = 0; q < 4; ++q) c.valid |= ((c.z[q] > 0.0f) & (c.z[q] <= p.zmax)) ? (1u << q) : 0u;
     c.valid &= (1u << k.npx) - 1u;
-    if (p.use_masks) {
+    if (p.use_masks && c.valid) {
       const int64_t gi = (int64_t)b * p.npix + walk_index(k);
+      if (vec_ok && k.npx == 4 && mask_vec_ok) {
+        // the 4 pixels' confidences with one 16-byte load, their sky bytes with one 4-byte load
+        unsigned keep = 0xFu;
+        if (p.use_conf) {
+          const float thr = p.conf_thresh_dev ? __ldg(p.conf_thresh_dev + b) : p.conf_thresh;
+          const float4 cf = __ldg(reinterpret_cast<const float4 *>(conf + gi));
+          keep = (cf.x >= thr ? 1u : 0u) | (cf.y >= thr ? 2u : 0u) | (cf.z >= thr ? 4u : 0u) | (cf.w >= thr ? 8u : 0u);
+        }
+        if (p.use_sky) {
+          if (sky) {
+            const uint32_t sb = __ldg(reinterpret_cast<const uint32_t *>(sky + gi));
+            keep &= ((sb & 0xFFu) ? 0u : 1u) | ((sb & 0xFF00u) ? 0u : 2u) | ((sb & 0xFF0000u) ? 0u : 4u) | ((sb & 0xFF000000u) ? 0u : 8u);
+          } else {
+            const float4 sp = __ldg(reinterpret_cast<const float4 *>(sky_prob + gi));
+            keep &= (sp.x >= sky_thr ? 0u : 1u) | (sp.y >= sky_thr ? 0u : 2u) | (sp.z >= sky_thr ? 0u : 4u) | (sp.w >= sky_thr ? 0u : 8u);
+          }
+        }
+        c.valid &= keep;
+      } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (((c.valid >> q) & 1u) && !depth_ok(c.z[q], gi + q, b)) c.valid &= ~(1u << q);
+        for (int q = 0; q < 4; ++q)
+          if (((c.valid >> q) & 1u) && !depth_ok(c.z[q], gi + q, b)) c.valid &= ~(1u << q);
+      }
     }
     c.cam = k.cam;
     c.uf = (float)k.u;
@@ -436,6 +470,9 @@ struct HvWork {
   int32_t *scan_done;         // [B] CTAs of hv_count_kernel that have finished (the last one scans the chunk totals)
   uint32_t *bev;              // [B][kBevCopies][kBevWords] bird's-eye masks of the kept voxels (OR of the copies), or null
   uint32_t *cull;             // [B][kMaxCams] live column blocks per camera, or null (nothing culled)
+  uint32_t *filter;           // [B][fwords] one bit per hashed voxel key: set when the key is claimed.  The lookup pass asks
+                              // this L2-resident bitmap before it touches the table (a miss there is a DRAM sector)
+  uint32_t *later;            // [B][lwords] bit r: the voxel of rank r has points after its first one (its slot row is in use)
   FastDiv div_gx, div_gy;     // key -> (x, y) cell
   uint32_t bev_kx, bev_ky;    // bird's-eye cell of voxel column i: (i * k) >> 20, k = floor(kBevDim 2^20 / grid)
   FastDiv div_Km1;            // slot-row word -> voxel
@@ -445,6 +482,8 @@ struct HvWork {
   uint32_t cap_mask;
   int log2cap;
   int direct;                 // grid volume <= cap: slot = key, no probing
+  int fshift;                 // filter bit of a key: (key * 2654435769u) >> fshift
+  int fwords, lwords;
   int nwords;                 // multiple of kChunkWords
   int nchunks;
   int K;                      // max_points
@@ -486,10 +525,14 @@ __device__ __forceinline__ void first_toggle(uint32_t *flags, uint32_t idx) {
 
 // Insert (key, idx).  Slot ownership is permanent (CAS from empty); the payload
 // only ever decreases (atomicMin), so a stale read can only cause a redundant
-// atomic, never a wrong skip.  Returns 1 iff this call created the entry.
+// atomic, never a wrong skip.  Returns 1 iff this call created the entry, 2 iff it lowered the entry's index, else 0:
+// in both cases `idx` became the first point of its voxel and the CALLER toggles its flag bit (the insert pass keeps
+// the bits of its own points in shared memory); the displaced holder's bit is toggled here.
 // (Measured: issuing the CAS first, without the load, is slower -- repeated keys then pay an atomic on a hot
 // entry where a load would have told them to leave.)
-__device__ __forceinline__ int table_insert(unsigned long long *table, uint32_t *flags, const HvWork &w,
+__device__ __forceinline__ uint32_t filter_bit(uint32_t key, int fshift) { return (key * 2654435769u) >> fshift; }
+
+__device__ __forceinline__ int table_insert(unsigned long long *table, uint32_t *flags, uint32_t *filter, const HvWork &w,
                                             uint32_t key, uint32_t idx) {
   const unsigned long long mine = ((unsigned long long)key << 32) | idx;
   uint32_t slot;
@@ -519,7 +562,10 @@ __device__ __forceinline__ int table_insert(unsigned long long *table, uint32_t 
     if (e == kEmpty64) {
       const unsigned long long old = atomicCAS(table + slot, kEmpty64, mine);
       if (old == kEmpty64) {
-        first_toggle(flags, idx);
+        if (filter) {
+          const uint32_t fb = filter_bit(key, w.fshift);
+          atomicOr(filter + (fb >> 5), 1u << (fb & 31));
+        }
         return 1;
       }
       e = old;
@@ -528,8 +574,8 @@ __device__ __forceinline__ int table_insert(unsigned long long *table, uint32_t 
       if ((uint32_t)e > idx) {
         const unsigned long long old = atomicMin(table + slot, mine);
         if ((uint32_t)old > idx) {     // this point is the voxel's first one now, the previous holder is not
-          first_toggle(flags, idx);
           first_toggle(flags, (uint32_t)old);
+          return 2;
         }
       }
       return 0;
@@ -542,12 +588,11 @@ __device__ __forceinline__ int table_insert(unsigned long long *table, uint32_t 
 // "the voxel of `key` was claimed": its column is marked in one of the frame's kBevCopies bird's-eye masks
 // (privatised: all claims of a frame on one 512-byte mask would serialise in L2).  The mask may hold voxels that
 // are dropped later (rank >= max_voxels): it only has to contain the kept ones.
-__device__ __forceinline__ void bev_mark(const HvWork &w, int b, uint32_t key, int copy) {
+__device__ __forceinline__ uint32_t bev_bit(const HvWork &w, uint32_t key) {
   const uint32_t t = fast_div(key, w.div_gx);
   const uint32_t cx = key - t * w.div_gx.d;
   const uint32_t cy = t - fast_div(t, w.div_gy) * w.div_gy.d;
-  const uint32_t bit = ((cy * w.bev_ky) >> 20) * kBevDim + ((cx * w.bev_kx) >> 20);
-  atomicOr(w.bev + ((int64_t)b * kBevCopies + (copy & (kBevCopies - 1))) * kBevWords + (bit >> 5), 1u << (bit & 31));
+  return ((cy * w.bev_ky) >> 20) * kBevDim + ((cx * w.bev_kx) >> 20);
 }
 
 // rank (first-occurrence order) of the voxel whose first point is `first_idx`
@@ -581,7 +626,7 @@ __device__ __forceinline__ uint32_t table_first(const unsigned long long *table,
 // the row: a value reaches slot k only after losing against the slots before it, so the non-empty prefix is
 // strictly increasing at all times and the final content is independent of arrival order (every point is
 // offered exactly once).
-__device__ __forceinline__ void slot_insert(uint32_t *S, int K, uint32_t idx) {
+__device__ __forceinline__ void slot_insert(uint32_t *S, int K, uint32_t idx, uint32_t *later, int r) {
   // The last slot and the first eight are requested together (one memory round trip).  A (possibly stale,
   // hence larger) copy of the last slot that is already smaller than idx: K smaller indices exist.
   const uint32_t last = __ldcg(S + K - 1);
@@ -602,7 +647,11 @@ __device__ __forceinline__ void slot_insert(uint32_t *S, int K, uint32_t idx) {
   }
   for (; k < K; ++k) {
     const uint32_t old = atomicMin(S + k, cur);
-    if (old == kEmpty32) return;
+    if (old == kEmpty32) {
+      // word 0 leaves the empty state exactly once per row: that inserter tells the emit kernel to read the row
+      if (k == 0) atomicOr(later + (r >> 5), 1u << (r & 31));
+      return;
+    }
     if (old > cur) cur = old;            // displaced a larger index: carry it on
   }
 }
@@ -627,6 +676,10 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
   __shared__ uint2 s_hitb[MODE ? kPassWarps * 64 : 1]; // lookup: (first point of the voxel, element index) of the table hits
   __shared__ uint32_t s_cull[kMaxCams];
   __shared__ int s_prev;
+  // insert: per warp, the first-point bits of the strip's own points (4 words per tile) and the bird's-eye marks of its
+  // claims; both reach global memory once, at the end of the walk, with one atomic per non-zero word
+  __shared__ uint32_t s_lflagb[MODE == 0 ? kPassWarps * kLocalIters * 4 : 1];
+  __shared__ uint32_t s_lbevb[MODE == 0 ? kPassWarps * kBevWords : 1];
 
   const int b = blockIdx.y + w.b0;
   const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
@@ -647,6 +700,11 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
     if (s_prev >= w.max_voxels) return;
   }
   if (MODE == 1 && Src::kIsDepth && tid < kMaxCams) s_cull[tid] = w.cull ? __ldg(w.cull + b * kMaxCams + tid) : 0xFFFFFFFFu;
+  if (MODE == 0) {
+    for (int i = tid; i < kPassWarps * kLocalIters * 4; i += kPassThreads) s_lflagb[i] = 0u;
+    if (w.bev)
+      for (int i = tid; i < kPassWarps * kBevWords; i += kPassThreads) s_lbevb[i] = 0u;
+  }
   const bool cal_async = src.stage_async(s_cal, &s_bar, b);
   __syncthreads();
   if (cal_async) tma_wait(&s_bar);
@@ -659,6 +717,15 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
   unsigned long long *table = w.table + (int64_t)b * w.cap;
   uint32_t *flags = w.flags + (int64_t)b * w.nwords;
   uint32_t *slots = w.slots + (int64_t)b * w.max_voxels * (w.K - 1);
+  uint32_t *filter = w.filter ? w.filter + (int64_t)b * w.fwords : nullptr;
+  uint32_t *later = w.later + (int64_t)b * w.lwords;
+  uint32_t *s_lflag = s_lflagb + (MODE == 0 ? wv * kLocalIters * 4 : 0);
+  uint32_t *s_lbev = s_lbevb + (MODE == 0 ? wv * kBevWords : 0);
+  // insert with a short strip: list entries hold the POSITION inside the strip (tile number * 128 + offset), which
+  // addresses the warp's local flag words directly; the element index is rebuilt from it when the table needs it
+  const bool local = MODE == 0 && iters <= kLocalIters;
+  const typename Src::Walker wk0 = wk;
+  uint32_t tno = 0;                                               // tiles walked so far
   int cnt = 0, nu = 0, nh = 0, claims = 0;
 
   bool live = MODE == 0 || !Src::kIsDepth || src.walk_live(wk, s_cull);
@@ -681,7 +748,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
         if (h.x != h.y || point2voxel) {
           const int r = voxel_rank(w, b, h.x);
           if (r < w.max_voxels) {
-            if (h.x != h.y && w.K > 1) slot_insert(slots + (int64_t)r * (w.K - 1), w.K - 1, h.y);
+            if (h.x != h.y && w.K > 1) slot_insert(slots + (int64_t)r * (w.K - 1), w.K - 1, h.y, later, r);
             if (point2voxel) point2voxel[(int64_t)b * w.N + h.y] = r;
           }
         }
@@ -700,9 +767,20 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
       if (MODE == 0) {
         // (measured: electing one lane per key with __match_any_sync + __reduce_min_sync costs more than the
         // repeated atomics it saves, in the sparse and in the dense scene)
-        if (lane < n && table_insert(table, flags, w, it.x, it.y)) {
-          ++claims;
-          if (w.bev) bev_mark(w, b, it.x, (int)blockIdx.x + wv);
+        if (lane < n) {
+          const uint32_t idx = local ? src.strip_index(wk0, it.y) : it.y;
+          const int r = table_insert(table, flags, filter, w, it.x, idx);
+          if (r) {                                               // this point is (for now) the first of its voxel
+            if (local) atomicXor(s_lflag + (it.y >> 5), 1u << (it.y & 31));
+            else first_toggle(flags, idx);
+          }
+          if (r == 1) {
+            ++claims;
+            if (w.bev) {
+              const uint32_t bb = bev_bit(w, it.x);
+              atomicOr(s_lbev + (bb >> 5), 1u << (bb & 31));
+            }
+          }
         }
       } else {
         uint32_t first = kEmpty32;
@@ -723,7 +801,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
       int cx, cy, cz;
       if (lane < n) {
         idx = s_und[nu - n + lane];
-        in = src.cell_exact(b, idx, s_cal, g, cx, cy, cz);
+        in = src.cell_exact(b, local ? src.strip_index(wk0, idx) : idx, s_cal, g, cx, cy, cz);
       }
       const unsigned b1 = __ballot_sync(0xffffffffu, in);
       if (in) s_item[cnt + __popc(b1 & lt)] = make_uint2(voxel_key(cx, cy, cz, g), idx);
@@ -748,10 +826,23 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
     }
     if (!clive) continue;                                   // no pixel of this tile can reach a kept voxel
     const uint32_t l0 = src.walk_index(cwk);
+    const uint32_t e0 = local ? (tno << 7) + 4u * (uint32_t)lane : l0;    // what the lists hold for the lane's first element
+    ++tno;
     typename Src::Cursor cur = src.cursor(b, cwk, s_cal, cpre);
     Quad qd;
     src.classify(cur, s_cal, g, qd);
     unsigned in = qd.in;
+    if (MODE == 1 && filter) {
+      // Has the key been claimed at all?  One bit per hashed key in a bitmap that stays in L2 (512 KB per frame against
+      // a table of several MB): nearly every pixel whose voxel is not kept leaves here instead of costing a table sector.
+      uint32_t fw[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t fb = filter_bit(qd.key[q], w.fshift);
+        fw[q] = ((in >> q) & 1u) ? (__ldg(filter + (fb >> 5)) >> (fb & 31)) & 1u : 0u;
+      }
+      in = fw[0] | (fw[1] << 1) | (fw[2] << 2) | (fw[3] << 3);
+    }
     if (MODE == 1 && !point2voxel) {
       // A voxel's first point is already listed by rank (hv_firsts_kernel): the lookup has nothing to add for it.
       // Its flag bit says so without a table probe -- in the region the voxels were claimed from that is
@@ -767,10 +858,10 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
                    p2 = __ballot_sync(0xffffffffu, cin & 4u);
     uint2 *it = s_item + cnt + (__popc(p0 & lt) + 2 * __popc(p1 & lt) + 4 * __popc(p2 & lt));
     // the order inside the list is irrelevant: element q of the lane goes to the lane's slot #(set bits below q)
-    if (in & 1u) it[0] = make_uint2(qd.key[0], l0);
-    if (in & 2u) it[in & 1u] = make_uint2(qd.key[1], l0 + 1);
-    if (in & 4u) it[__popc(in & 3u)] = make_uint2(qd.key[2], l0 + 2);
-    if (in & 8u) it[__popc(in & 7u)] = make_uint2(qd.key[3], l0 + 3);
+    if (in & 1u) it[0] = make_uint2(qd.key[0], e0);
+    if (in & 2u) it[in & 1u] = make_uint2(qd.key[1], e0 + 1);
+    if (in & 4u) it[__popc(in & 3u)] = make_uint2(qd.key[2], e0 + 2);
+    if (in & 8u) it[__popc(in & 7u)] = make_uint2(qd.key[3], e0 + 3);
     cnt += __popc(p0) + 2 * __popc(p1) + 4 * __popc(p2);
     if (__any_sync(0xffffffffu, qd.und != 0u)) {
       const unsigned cun = __popc(qd.und);
@@ -779,12 +870,32 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
       int ua = nu + __popc(u0 & lt) + 2 * __popc(u1 & lt) + 4 * __popc(u2 & lt);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if ((qd.und >> q) & 1u) s_und[ua++] = l0 + q;
+        if ((qd.und >> q) & 1u) s_und[ua++] = e0 + q;
       nu += __popc(u0) + 2 * __popc(u1) + 4 * __popc(u2);
     }
     __syncwarp();
   }
   if (MODE == 0) {
+    __syncwarp();
+    if (local) {
+      // local flag word j = 32 consecutive elements of the strip starting at position 32 j
+      for (uint32_t j = lane; j < tno * 4u; j += 32) {
+        const uint32_t bits = s_lflag[j];
+        if (bits) {
+          const uint32_t pos = src.strip_index(wk0, j << 5);
+          const uint32_t sh = pos & 31u;
+          atomicXor(flags + (pos >> 5), bits << sh);
+          if (sh && (bits >> (32u - sh))) atomicXor(flags + (pos >> 5) + 1, bits >> (32u - sh));
+        }
+      }
+    }
+    if (w.bev) {
+      uint32_t *gb = w.bev + ((int64_t)b * kBevCopies + ((blockIdx.x + wv) & (kBevCopies - 1))) * kBevWords;
+      for (int j = lane; j < kBevWords; j += 32) {
+        const uint32_t bits = s_lbev[j];
+        if (bits) atomicOr(gb + j, bits);
+      }
+    }
     for (int d = 16; d > 0; d >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, d);
     if (lane == 0 && claims) atomicAdd(w.round_claims + b * kMaxRounds + round, claims);
   }
@@ -1080,129 +1191,107 @@ __global__ void __launch_bounds__(256, 8) hv_post_kernel(Src src, VoxelGrid g, H
 }
 
 // P4 ------------------------------------------------------------------------
-// A CTA owns V consecutive voxels (~1024 slot items).  dynamic smem: tile[V*K*C] floats (padded to 16 B) +
-// sidx[V*(K-1)] u32 (the slot rows, flat) + first[V] u32 + list[V*(K-1)] u16.
-//   1. zero the tile (16-byte stores); the voxels' first points are loaded (one per thread); every warp loads its
-//      share of the FLAT slot rows (4 independent coalesced loads per lane up front) and ballot-compacts the
-//      non-empty ones into its own list segment (no atomics, no barrier) -- rows are mostly empty, and only a
-//      listed item ever needs its (voxel, slot) position
-//   2. every voxel's first point and the listed items are gathered / re-unprojected (exact reference arithmetic)
-//      into the tile
-//   3. voxels are copied out with 16-byte stores; one thread per voxel writes coors (from the first
-//      point), the count and the HardSimpleVFE mean (slot order, one __fdiv_rn)
+// A warp owns `vpw` consecutive voxels (ranks), vpw = 32 unless the rows are very long (then a power of two below);
+// lane groups of 32 / vpw lanes share a voxel.  No block barrier after the calibration copy.
+// dynamic smem per warp: tile[vpw*K*C] floats (the voxels' rows exactly as they lie in the output) + the list of the
+// later points (idx u32, position u16: vpw * K <= 10 K by the shared-memory limit).
+//   1. the tile is zeroed (16-byte stores); the voxel's first point is requested; the voxels whose `later` bit is set
+//      walk their slot rows (sorted, non-empty prefix; the lanes of a group take consecutive words) and ballot-compact
+//      (point, position) into the warp's list -- a voxel without later points never touches its row
+//   2. first points (one per voxel) and listed points (dense over the lanes) are gathered / re-unprojected with the
+//      reference's exact arithmetic into the tile
+//   3. the tile is copied out with 16-byte stores (the warp's rows are one contiguous block of the output); one lane
+//      per voxel writes coors (from the first point), the count and the HardSimpleVFE mean (slot order, one __fdiv_rn)
 template <class Src>
-__global__ void __launch_bounds__(kEmitThreads, RD3_EMIT_MINB) hv_emit_kernel(Src src, VoxelGrid g, HvWork w, HvOut o, int V) {
-  extern __shared__ float s_dyn[];
+__global__ void __launch_bounds__(kEmitThreads, RD3_EMIT_MINB) hv_emit_kernel(Src src, VoxelGrid g, HvWork w, HvOut o, int wbytes,
+                                                                              int lg_vpw) {
+  extern __shared__ __align__(16) unsigned char s_dynb[];
   __shared__ __align__(16) float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 4];
   __shared__ __align__(8) uint64_t s_bar;
   const int b = blockIdx.y + w.b0;
   const int vn = o.voxel_num[b];
-  const int r0 = blockIdx.x * V;
-  if (r0 >= vn) return;
-  const int C = src.num_feats();
-  const int K = w.K, Km1 = K - 1;
-  const int nvox = min(V, vn - r0);
-  const int items = nvox * K;
-  const int nS = nvox * Km1;                        // slot-row words of the CTA
+  const int vpw = 1 << lg_vpw;
+  const int nwarps = (int)blockDim.x >> 5;
+  const int r0c = blockIdx.x * nwarps * vpw;
+  if (r0c >= vn) return;
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-  constexpr int nw = kEmitThreads / 32;
-  float *tile = s_dyn;
-  uint32_t *s_sidx = reinterpret_cast<uint32_t *>(s_dyn + (((size_t)V * K * C + 3) & ~(size_t)3));
-  uint32_t *s_first = s_sidx + (size_t)V * (Km1 > 0 ? Km1 : 1);
-  uint16_t *s_list = reinterpret_cast<uint16_t *>(s_first + V);
-  const uint32_t *S = w.slots + ((int64_t)b * w.max_voxels + r0) * Km1;
-  const uint32_t *F1 = w.first_of + (int64_t)b * w.max_voxels + r0;
-
-  // warp wv owns the slot words [wv*per, wv*per+per): its list segment starts at the same offset
-  const int per = ((nS + nw - 1) / nw + 31) & ~31;
-  const int lo = wv * per, hi = min(nS, lo + per);
-  // The first 128 slot words of the warp's share are requested up front (4 independent loads per
-  // lane): one DRAM round trip instead of four dependent ones, overlapped with the calibration copy and the zero fill.
-  uint32_t pre[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int j = lo + 32 * q + lane;
-    pre[q] = j < hi ? __ldg(S + j) : kEmpty32;
-  }
-  uint32_t myfirst = threadIdx.x < nvox ? __ldg(F1 + threadIdx.x) : kEmpty32;
+  const unsigned lt = (1u << lane) - 1u;
   const bool cal_async = src.stage_async(s_cal, &s_bar, b);     // one TMA bulk copy, no load / store loop
-  {
+  const int r0 = r0c + wv * vpw;                                 // a multiple of vpw: the warp's voxels share one `later` word
+  const int nv = vn - r0 < vpw ? vn - r0 : vpw;
+  const int lg_lpv = 5 - lg_vpw;                                 // lanes per voxel
+  const int vl = lane >> lg_lpv, sub = lane & ((1 << lg_lpv) - 1);
+  const bool live = vl < nv;
+  const int v = r0 + vl;
+  const int C = src.num_feats();
+  const int K = w.K, Km1 = K - 1, KC = K * C;
+  float *tile = reinterpret_cast<float *>(s_dynb + (size_t)wv * wbytes);
+  uint32_t *l_idx = reinterpret_cast<uint32_t *>(tile + ((vpw * KC + 3) & ~3));
+  uint16_t *l_pos = reinterpret_cast<uint16_t *>(l_idx + vpw * (Km1 > 0 ? Km1 : 1));
+  uint32_t first = kEmpty32, lw = 0;
+  if (nv > 0) {
+    if (live) first = __ldg(w.first_of + (int64_t)b * w.max_voxels + v);
+    lw = __ldg(w.later + (int64_t)b * w.lwords + (r0 >> 5)) >> (r0 & 31);
     float4 *t4 = reinterpret_cast<float4 *>(tile);
-    const int n4 = (items * C + 3) >> 2;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e = threadIdx.x; e < n4; e += kEmitThreads) t4[e] = z4;
+    const int n4 = (vpw * KC + 3) >> 2;
+    for (int e = lane; e < n4; e += 32) t4[e] = z4;
   }
-  if (threadIdx.x < nvox) s_first[threadIdx.x] = myfirst;
-  for (int v = threadIdx.x + kEmitThreads; v < nvox; v += kEmitThreads) s_first[v] = __ldg(F1 + v);
-  int nmine = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int j = lo + 32 * q + lane;
-    const uint32_t idx = pre[q];
-    if (j < hi) s_sidx[j] = idx;
-    const unsigned bal = __ballot_sync(0xffffffffu, idx != kEmpty32);
-    if (idx != kEmpty32) s_list[lo + nmine + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)j;
-    nmine += __popc(bal);
-  }
-  for (int j0 = lo + 128; j0 < hi; j0 += 32) {
-    const int j = j0 + lane;
-    uint32_t idx = kEmpty32;
-    if (j < hi) {
-      idx = __ldg(S + j);
-      s_sidx[j] = idx;
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, idx != kEmpty32);
-    if (idx != kEmpty32) s_list[lo + nmine + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)j;
-    nmine += __popc(bal);
-  }
-  __syncthreads();                       // tile zeroed, first points staged, calibration copy issued
+  __syncthreads();                       // calibration copy issued (and the tile zeroed, as far as this warp goes)
   if (cal_async) tma_wait(&s_bar);
-  // first points: every voxel has one (slot 0 of its tile row)
-  // (a block of voxels per warp: with ~100 voxels per CTA a plain thread index would leave half of the warps idle
-  // while the others run the exact unprojection; consecutive voxels per lane keep the tile stores conflict-free)
+  if (nv <= 0) return;
+
+  // slot rows of the voxels that have later points: the group's lanes take the words k0 + sub
+  int cnt = 0, n = 0;
   {
-    const int vpw = (nvox + nw - 1) / nw;
-    for (int v0 = 0; v0 < vpw; v0 += 32) {
-      const int v = wv * vpw + v0 + lane;
-      if (v0 + lane < vpw && v < nvox) src.gather(b, s_first[v], s_cal, tile + (size_t)v * K * C);
+    bool open = live && ((lw >> vl) & 1u);
+    const uint32_t *row = w.slots + ((int64_t)b * w.max_voxels + v) * Km1;
+    for (int k0 = 0; k0 < Km1; k0 += 1 << lg_lpv) {
+      if (!__any_sync(0xffffffffu, open)) break;
+      const int k = k0 + sub;
+      const uint32_t wd = (open && k < Km1) ? __ldg(row + k) : kEmpty32;
+      const bool has = wd != kEmpty32;
+      const unsigned bal = __ballot_sync(0xffffffffu, has);
+      if (has) {
+        const int q = n + __popc(bal & lt);
+        l_idx[q] = wd;
+        l_pos[q] = (uint16_t)(vl * K + k + 1);
+        ++cnt;
+      }
+      n += __popc(bal);
+      // the row is a non-empty prefix: the group goes on only while its last word was in use
+      open = __shfl_sync(0xffffffffu, has, (vl << lg_lpv) + (1 << lg_lpv) - 1);
+    }
+    for (int d = 1; d < (1 << lg_lpv); d <<= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    cnt += 1;                                                    // the first point
+  }
+  __syncwarp();
+  if (live && sub == 0) src.gather(b, first, s_cal, tile + vl * KC);
+  for (int t = lane; t < n; t += 32) src.gather(b, l_idx[t], s_cal, tile + (size_t)l_pos[t] * C);
+  __syncwarp();
+
+  // voxels: the warp's nv rows are nv*K*C contiguous floats (skipped when the caller only wants coors / num / mean)
+  if (o.voxels) {
+    float *vout = o.voxels + ((int64_t)b * w.max_voxels + r0) * KC;
+    const int nfl = nv * KC;
+    if ((reinterpret_cast<uintptr_t>(vout) & 15) == 0) {
+      const float4 *t4 = reinterpret_cast<const float4 *>(tile);
+      float4 *v4 = reinterpret_cast<float4 *>(vout);
+      const int n4 = nfl >> 2;
+      for (int e = lane; e < n4; e += 32) v4[e] = t4[e];
+      for (int e = (nfl & ~3) + lane; e < nfl; e += 32) vout[e] = tile[e];
+    } else {
+      for (int e = lane; e < nfl; e += 32) vout[e] = tile[e];
     }
   }
-  // later points: the listed slot words; word j = v * (K-1) + (k-1) is slot item v * K + k = j + v + 1
-  for (int t = lane; t < nmine; t += 32) {
-    const int j = s_list[lo + t];
-    const int v = (int)fast_div((uint32_t)j, w.div_Km1);
-    src.gather(b, s_sidx[j], s_cal, tile + (size_t)(j + v + 1) * C);
-  }
-  __syncthreads();
 
-  // voxels: contiguous nvox*K*C floats (skipped when the caller only wants coors / num / mean)
-  float *vout = o.voxels + ((int64_t)b * w.max_voxels + r0) * K * C;
-  const int nfl = o.voxels ? items * C : 0;
-  if ((reinterpret_cast<uintptr_t>(vout) & 15) == 0) {
-    const float4 *t4 = reinterpret_cast<const float4 *>(tile);
-    float4 *v4 = reinterpret_cast<float4 *>(vout);
-    const int n4 = nfl >> 2;
-#ifdef RD3_EMIT_STCS
-    for (int e = threadIdx.x; e < n4; e += kEmitThreads) __stcs(v4 + e, t4[e]);
-#else
-    for (int e = threadIdx.x; e < n4; e += kEmitThreads) v4[e] = t4[e];
-#endif
-    for (int e = (nfl & ~3) + threadIdx.x; e < nfl; e += kEmitThreads) vout[e] = tile[e];
-  } else {
-    for (int e = threadIdx.x; e < nfl; e += kEmitThreads) vout[e] = tile[e];
-  }
-
-  // one thread per voxel: coors, count and HardSimpleVFE mean
+  // one lane per voxel: coors, count and HardSimpleVFE mean
   // (voxel_encoder.py:45-46: sum over ALL K slots in slot order, then one division; the
   // slots beyond the count are zeros, so the running sum stops changing at the count --
   // except that (-0.0) + 0.0 = +0.0, which one extra "+ 0.0f" reproduces)
-  const int F = o.F;
-  for (int v = threadIdx.x; v < nvox; v += kEmitThreads) {
-    const uint32_t *si = s_sidx + v * Km1;
-    int cnt = 1;                                   // the first point, then the non-empty prefix of the slot row
-    while (cnt < K && si[cnt - 1] != kEmpty32) ++cnt;
-    const float *p0 = tile + v * K * C;
-    const int64_t vr = (int64_t)b * w.max_voxels + r0 + v;
+  if (live && sub == 0) {
+    const float *p0 = tile + vl * KC;
+    const int64_t vr = (int64_t)b * w.max_voxels + v;
     // coors from the voxel's first point (the tile holds it already): the fast path decides all but points within
     // rounding of a cell boundary
     int cx = 0, cy = 0, cz = 0;
@@ -1212,7 +1301,8 @@ __global__ void __launch_bounds__(kEmitThreads, RD3_EMIT_MINB) hv_emit_kernel(Sr
     o.coors[vr * 3 + 2] = cx;
     o.num[vr] = cnt;
     if (o.mean) {
-      const float n = (float)cnt;
+      const int F = o.F;
+      const float nf = (float)cnt;
       float *mo = o.mean + vr * F;
       if (F == 3) {
         float sx = 0.0f, sy = 0.0f, sz = 0.0f;
@@ -1223,16 +1313,16 @@ __global__ void __launch_bounds__(kEmitThreads, RD3_EMIT_MINB) hv_emit_kernel(Sr
           sz = __fadd_rn(sz, p[2]);
         }
         if (cnt < K) { sx = __fadd_rn(sx, 0.0f); sy = __fadd_rn(sy, 0.0f); sz = __fadd_rn(sz, 0.0f); }
-        mo[0] = __fdiv_rn(sx, n);
-        mo[1] = __fdiv_rn(sy, n);
-        mo[2] = __fdiv_rn(sz, n);
+        mo[0] = __fdiv_rn(sx, nf);
+        mo[1] = __fdiv_rn(sy, nf);
+        mo[2] = __fdiv_rn(sz, nf);
       } else {
         for (int f = 0; f < F; ++f) {
           float sacc = 0.0f;
           const float *p = p0 + f;
           for (int k = 0; k < cnt; ++k, p += C) sacc = __fadd_rn(sacc, *p);
           if (cnt < K) sacc = __fadd_rn(sacc, 0.0f);
-          mo[f] = __fdiv_rn(sacc, n);
+          mo[f] = __fdiv_rn(sacc, nf);
         }
       }
     }
@@ -1247,6 +1337,7 @@ struct HvTuning {           // read once from the environment (experiments); def
   int load_pct;             // worst-case load factor of the table in percent (RD3_TABLE_LOAD_PCT)
   int ins_iters, lkp_iters; // tiles per warp strip (RD3_INS_ITERS, RD3_LKP_ITERS)
   int cull;                 // RD3_CULL=0 disables the camera / column-block culling
+  int filter;               // RD3_FILTER=0 disables the key filter of the lookup pass
   int sm_count;
 };
 const HvTuning &hv_tuning();
@@ -1262,7 +1353,9 @@ struct HvPlan {
   int log2cap;
   int nwords, nchunks;
   // [table | slots] are set to 0xFF with one memset, [flags | bev | round_claims] to 0 with another
-  size_t off_table, off_slots, off_first, off_flags, off_bev, off_claims, off_done, off_cull, off_prefix, off_chunk, total;
+  int fshift, fwords, lwords;
+  size_t off_table, off_slots, off_first, off_flags, off_bev, off_claims, off_done, off_cull, off_prefix, off_chunk,
+      off_filter, off_later, total;
 };
 
 // `round_multiple`: a round has to be a whole number of the source's work units (image rows for depth maps)
@@ -1302,6 +1395,14 @@ inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels, int64_t round_mul
   p.off_cull = off; off += align_up((size_t)B * kMaxCams * 4);
   p.off_prefix = off; off += align_up((size_t)B * p.nwords * 4);
   p.off_chunk = off; off += align_up((size_t)B * p.nchunks * 4);
+  // key filter: ~16 bits per key the table can hold, 2^12 .. 2^22 bits (512 KB) per frame
+  int lf = 12;
+  while (lf < 22 && ((int64_t)1 << lf) < 16 * keys) ++lf;
+  p.fshift = 32 - lf;
+  p.fwords = 1 << (lf - 5);
+  p.lwords = (int)ceil_div(max_voxels, 32);
+  p.off_filter = off; off += align_up((size_t)B * p.fwords * 4);
+  p.off_later = off; off += align_up((size_t)B * p.lwords * 4);
   p.total = off;
   return p;
 }
@@ -1330,6 +1431,9 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   w.scan_done = (int32_t *)(base + p.off_done);
   w.wordprefix = (int32_t *)(base + p.off_prefix);
   w.chunk_base = (int32_t *)(base + p.off_chunk);
+  w.filter = tune.filter ? (uint32_t *)(base + p.off_filter) : nullptr;
+  w.later = (uint32_t *)(base + p.off_later);
+  w.fshift = p.fshift; w.fwords = p.fwords; w.lwords = p.lwords;
   const bool cull = CullLaunch<Src>::wanted(src) && g.fast_ok;
   w.bev = cull ? (uint32_t *)(base + p.off_bev) : nullptr;
   w.cull = cull ? (uint32_t *)(base + p.off_cull) : nullptr;
@@ -1344,16 +1448,19 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   if (p.S % src.host_round_multiple() != 0 && p.rounds > 1) return RD3_ERR_INVALID_ARGUMENT;   // plan made for another source
 
   const int C = src.host_num_feats();
-#ifndef RD3_EMIT_ITEMS
-#define RD3_EMIT_ITEMS 4             // slot items per thread of an emit CTA: amortises the CTA prologue
-#endif
-  int V = RD3_EMIT_ITEMS * kEmitThreads / p.K;
-  if (V < 1) V = 1;
-  if (V > 32 * RD3_EMIT_ITEMS) V = 32 * RD3_EMIT_ITEMS;
-  while (V > 1 && (size_t)V * p.K * (C + 1) * 4 > 10 * 1024 * RD3_EMIT_ITEMS) V /= 2;
-  const size_t smem = align_up((size_t)V * p.K * C * 4, 16) + (size_t)V * p.K * 4 + (size_t)V * 4 +
-                      align_up((size_t)V * p.K * 2, 16) + 64;
-  if (smem > 200 * 1024) return RD3_ERR_UNSUPPORTED;
+  // emit: per-warp shared memory = the rows of the warp's vpw voxels + the list of their later points.  vpw = 32 unless
+  // that exceeds ~12 KB per warp (long rows: max_points 100+), then the largest power of two that fits; as many warps per
+  // CTA (<= kEmitThreads / 32) as fit ~96 KB
+  const int Km1p = p.K > 1 ? p.K - 1 : 1;
+  auto emit_wbytes = [&](int vpw) { return align_up((size_t)vpw * p.K * C * 4, 16) + (size_t)vpw * Km1p * 6; };
+  int lg_vpw = 5;
+  while (lg_vpw > 0 && emit_wbytes(1 << lg_vpw) > 12 * 1024) --lg_vpw;
+  const size_t wbytes = align_up(emit_wbytes(1 << lg_vpw), 16);
+  if (wbytes > 200 * 1024) return RD3_ERR_UNSUPPORTED;
+  int emit_warps = (int)((96 * 1024) / wbytes);
+  if (emit_warps < 1) emit_warps = 1;
+  if (emit_warps > kEmitThreads / 32) emit_warps = kEmitThreads / 32;
+  const size_t smem = wbytes * emit_warps;
   if (smem > 48 * 1024)
     RD3_CUDA_TRY(cudaFuncSetAttribute(hv_emit_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
@@ -1408,6 +1515,8 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
         RD3_LANE_TRY(cudaMemsetAsync(w.slots + (size_t)b0 * p.max_voxels * (p.K - 1), 0xFF,
                                      (size_t)nb * p.max_voxels * (p.K - 1) * 4, st));
       RD3_LANE_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords, 0, (size_t)nb * p.nwords * 4, st));
+      if (w.filter) RD3_LANE_TRY(cudaMemsetAsync(w.filter + (size_t)b0 * p.fwords, 0, (size_t)nb * p.fwords * 4, st));
+      add(w.later + (size_t)b0 * p.lwords, (size_t)nb * p.lwords * 4, 0u);
       add(w.round_claims + (size_t)b0 * kMaxRounds, (size_t)nb * kMaxRounds * 4, 0u);
       add(w.scan_done + b0, (size_t)nb * 4, 0u);
       if (cull) {
@@ -1436,7 +1545,8 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
       hv_pass_kernel<Src, 1><<<dim3(src.host_grid(0, p.N, tune.lkp_iters), nb), kPassThreads, 0, st>>>(
           src, g, w, out.point2voxel, 0, p.N, 0, tune.lkp_iters);
     prof_mark(st, 5);
-    hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, V), nb), kEmitThreads, smem, st>>>(src, g, w, out, V);
+    hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, (emit_warps << lg_vpw)), nb), 32 * emit_warps, smem, st>>>(
+        src, g, w, out, (int)wbytes, lg_vpw);
     prof_mark(st, 6);
     prof_mark(st, 7);
   }
