@@ -18,7 +18,7 @@ namespace rd3 {
 // (has_grid) it also holds the direct pixel->cell map and its error-bound constants
 // (rd3_common.cuh: pixel_key_fast), derived in fp64 and rounded once.
 __global__ void calib_kernel(const float *intr, const float *c2l, int ncam, int H, int W,
-                             VoxelGrid g, int has_grid, CellRange rg, float *table) {
+                             VoxelGrid g, int has_grid, CellRange rg, float *table, double *cull_cal, float zmax) {
   __shared__ float s_cal[kMaxCams * kCalibFloats];
   const int b = blockIdx.x;
   const float *Kb = intr + (int64_t)b * ncam * 9;
@@ -53,6 +53,35 @@ __global__ void calib_kernel(const float *intr, const float *c2l, int ncam, int 
     const double eps2 = 1.1920928955078125e-7;   // 2^-23
     k[12] = __double2float_rd(-(Qc * 1.000001) * eps2);
     k[13] = __double2float_rd(0.5 - (Pc * 1.000001) * eps2 - 9.5367431640625e-7);
+    if (cull_cal) {
+      // culling test of the lookup pass (hard_voxel.cuh: cull_block): inverse of the direct cell map Mc = [A B C],
+      // T = Th + 0.5 and the margin 1 + 2 tolmax, in fp64.  A singular / non-finite map keeps all its blocks (ok = 0).
+      double *cc = cull_cal + ((int64_t)b * ncam + cam) * kCullDoubles;
+      double m[9], T[3];
+      for (int a = 0; a < 3; ++a) {
+        m[a * 3 + 0] = k[a * 4 + 0]; m[a * 3 + 1] = k[a * 4 + 1]; m[a * 3 + 2] = k[a * 4 + 2];
+        T[a] = (double)k[a * 4 + 3] + 0.5;
+      }
+      const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+      const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+      double scale = 0.0;
+      for (int i = 0; i < 9; ++i) scale = fmax(scale, fabs(m[i]));
+      const double id = 1.0 / det;
+      double inv[9];
+      inv[0] = c00 * id; inv[1] = (m[2] * m[7] - m[1] * m[8]) * id; inv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+      inv[3] = c01 * id; inv[4] = (m[0] * m[8] - m[2] * m[6]) * id; inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+      inv[6] = c02 * id; inv[7] = (m[1] * m[6] - m[0] * m[7]) * id; inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+      // tol(z) = 0.5 - thr(z) >= the proven bound; largest at the largest valid depth
+      const double tolmax = 0.5 - ((double)zmax * (double)k[12] + (double)k[13]);
+      bool ok = fabs(det) > 1e-12 * scale * scale * scale && isfinite(id) && tolmax >= 0.0 && tolmax < 1e6;
+      for (int i = 0; i < 9; ++i) ok = ok && isfinite(inv[i]);
+      for (int a = 0; a < 3; ++a) ok = ok && isfinite(T[a]);
+      for (int i = 0; i < 9; ++i) cc[i] = inv[i];
+      for (int a = 0; a < 3; ++a) cc[9 + a] = T[a];
+      cc[12] = 1.0 + 2.0 * tolmax;
+      cc[13] = ok ? 1.0 : 0.0;
+      cc[14] = cc[15] = 0.0;
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < ncam * kCalibFloats; i += blockDim.x)
@@ -180,6 +209,7 @@ static int make_depth_source(const float *depth, const float *intrinsics, const 
   src->intr = intrinsics;
   src->c2l = cam2lidar;
   src->cal_table = nullptr;
+  src->cull_cal = nullptr;
   src->rg.on = 0;
   DepthParams &d = src->p;
   d.ncam = p->ncam; d.H = p->H; d.W = p->W; d.HW = p->H * p->W; d.npix = (int32_t)npix;
@@ -243,7 +273,7 @@ size_t rd3_depth_to_voxels_workspace_bytes(const rd3_depth_params *p, int max_po
                                            int max_voxels) {
   if (!p || p->B <= 0 || max_points <= 0 || max_voxels <= 0) return 0;
   return hv_plan((int64_t)p->ncam * p->H * p->W, p->B, max_points, max_voxels, p->W).total +
-         align_up((size_t)p->B * p->ncam * kCalibFloats * 4);
+         align_up((size_t)p->B * p->ncam * kCalibFloats * 4) + align_up((size_t)p->B * p->ncam * kCullDoubles * 8);
 }
 
 int rd3_depth_to_voxels(const float *depth, const float *intrinsics, const float *cam2lidar,
@@ -266,8 +296,10 @@ int rd3_depth_to_voxels(const float *depth, const float *intrinsics, const float
   if (st != RD3_OK) return st;
   const HvPlan plan = hv_plan(src.p.npix, p->B, max_points, max_voxels, p->W);
   const size_t cal_bytes = align_up((size_t)p->B * p->ncam * kCalibFloats * 4);
-  if (workspace_bytes < plan.total + cal_bytes) return RD3_ERR_WORKSPACE;
+  const size_t cull_bytes = align_up((size_t)p->B * p->ncam * kCullDoubles * 8);
+  if (workspace_bytes < plan.total + cal_bytes + cull_bytes) return RD3_ERR_WORKSPACE;
   float *cal_table = (float *)((char *)workspace + plan.total);
+  double *cull_cal = (double *)((char *)workspace + plan.total + cal_bytes);
   // inclusive range filter in cell units minus 0.5 (pixel_key_fast works on h = f' - 0.5).  When the voxel grid's
   // own test implies every plane of the filter (the usual case: the filter box contains the grid), the fast
   // path does not look at it at all; the exact path still applies it literally.
@@ -277,8 +309,9 @@ int rd3_depth_to_voxels(const float *depth, const float *intrinsics, const float
     src.rg.hi[a] = (float)(((double)p->range[3 + a] - (double)g.lo[a]) / (double)g.vs[a] - 0.5);
   }
   calib_kernel<<<p->B, 128, 0, (cudaStream_t)stream>>>(intrinsics, cam2lidar, p->ncam, p->H, p->W, g, 1,
-                                                       src.rg, cal_table);
+                                                       src.rg, cal_table, cull_cal, src.p.zmax);
   src.cal_table = cal_table;
+  src.cull_cal = cull_cal;
   HvOut out{voxels, coors, num_points_per_voxel, voxel_mean, d_voxel_num, nullptr,
             voxel_mean ? 3 : 0};
   return hv_run(src, g, vol, plan, workspace, out, (cudaStream_t)stream);

@@ -61,7 +61,7 @@ constexpr int kEmitThreads = RD3_EMIT_THREADS;
 #define RD3_LKP_MINB 5                // ... and the lookup pass
 #endif
 #ifndef RD3_EMIT_MINB
-#define RD3_EMIT_MINB 5               // resident CTAs per SM the emit kernel is compiled for (shared memory allows 5 at K*C = 30)
+#define RD3_EMIT_MINB 6               // resident CTAs per SM the emit kernel is compiled for (shared memory allows 6 at K*C = 30)
 #endif
 constexpr int kTilePoints = 128;      // points per warp tile (4 per lane)
 constexpr int kListCap = 160;         // per-warp item / undecided lists: 31 carried + 128 new
@@ -69,7 +69,9 @@ constexpr int kMaxRounds = 64;
 constexpr uint32_t kDummyKey = 0xFFFFFFE0u;   // + lane: 32 values no voxel key takes (make_grid: volume <= kDummyKey)
 constexpr int kBevDim = 64;           // bird's-eye mask of the kept voxels: kBevDim x kBevDim bits over the x,y grid
 constexpr int kBevWords = kBevDim * kBevDim / 32;
+constexpr int kCullDoubles = 16;      // per camera: inverse of the direct cell map [9], T [3], margin, ok
 constexpr int kBevCopies = 32;        // privatised copies of the mask (power of two): spreads the marking atomics
+constexpr int kEmitList = 96;         // emit: entries of a warp's list of later points (worked off when it could overflow)
 constexpr int kLocalIters = 16;       // insert pass: a warp whose strip has at most this many tiles keeps the first-point
                                       // bits of its own points in shared memory (4 words per tile) and flushes them once
 
@@ -145,10 +147,10 @@ struct PointsSource {
   };
   // element index of position lp (tile number * 128 + offset) of the warp's strip
   __device__ __forceinline__ uint32_t strip_index(const Walker &k, uint32_t lp) const { return (uint32_t)k.cur0 + lp; }
-  __device__ __forceinline__ bool cta_live(const HvCull &, int, int64_t, int64_t, int) const { return true; }
-  __device__ __forceinline__ bool walk_init(Walker &k, int64_t begin, int64_t end, int iters, int wv, int lane) const {
+  __device__ __forceinline__ bool cta_live(const HvCull &, int, int64_t, int64_t, int, int) const { return true; }
+  __device__ __forceinline__ bool walk_init(Walker &k, int64_t begin, int64_t end, int iters, int bx, int wv, int lane) const {
     const int64_t strip = (int64_t)iters * kTilePoints;
-    k.cur = begin + ((int64_t)blockIdx.x * kPassWarps + wv) * strip;
+    k.cur = begin + ((int64_t)bx * kPassWarps + wv) * strip;
     k.cur0 = k.cur;
     k.end = k.cur + strip < end ? k.cur + strip : end;
     k.lane = lane;
@@ -194,6 +196,12 @@ struct PointsSource {
     const float *p = pts + ((int64_t)b * N + i) * C;
     for (int c = 0; c < C; ++c) dst[c] = __ldg(p + c);
   }
+  // a voxel's first point, listed by the post kernel: nothing to carry besides the index
+  static constexpr bool kCarryFirst = false;
+  __device__ __forceinline__ float first_payload(int, uint32_t) const { return 0.0f; }
+  __device__ __forceinline__ void gather_first(int b, uint32_t i, float, const float *s_cal, float *dst) const {
+    gather(b, i, s_cal, dst);
+  }
 };
 
 struct DepthSource {
@@ -205,6 +213,7 @@ struct DepthSource {
   const float *intr;       // (B, ncam, 9)
   const float *c2l;        // (B, ncam, 16)
   const float *cal_table;  // (B, ncam, kCalibFloats) precomputed by calib_kernel, or null
+  const double *cull_cal;  // (B, ncam, kCullDoubles) inverse cell map per camera for the culling test (calib_kernel), or null
   DepthParams p;
   CellRange rg;            // range filter in cell units (fused path); on = 0 when the grid test implies it
   int vec_ok;              // 16-byte aligned float4 loads of 4 pixels of a row are legal (W % 4 == 0, aligned base)
@@ -273,22 +282,22 @@ struct DepthSource {
     uint32_t blk;          // culling block of the column tile
     int npx;               // columns u .. u + npx - 1 exist (0 for lanes right of the image)
   };
-  // rows [r0, r1) of the CTA blockIdx.x for the element range [begin, end)
-  __device__ __forceinline__ void cta_rows(int64_t begin, int64_t end, int iters, uint32_t &r0, uint32_t &r1,
+  // rows [r0, r1) of the CTA bx for the element range [begin, end)
+  __device__ __forceinline__ void cta_rows(int64_t begin, int64_t end, int iters, uint32_t bx, uint32_t &r0, uint32_t &r1,
                                            uint32_t &ct) const {
     const uint32_t nct = (uint32_t)((p.W + kTilePoints - 1) / kTilePoints);
-    const uint32_t rg = blockIdx.x / nct;
-    ct = blockIdx.x - rg * nct;
+    const uint32_t rg = bx / nct;
+    ct = bx - rg * nct;
     const uint32_t first = fast_div((uint32_t)begin, p.div_w), last = fast_div((uint32_t)end, p.div_w);   // < 2^30 pixels
     r0 = first + rg * (uint32_t)(kPassWarps * iters);
     r1 = r0 + (uint32_t)(kPassWarps * iters);
     if (r1 > last) r1 = last;
   }
   // lookup pass: can any row of this CTA's column tile reach a kept voxel?  (before the prologue: one or two loads)
-  __device__ __forceinline__ bool cta_live(const HvCull &c, int b, int64_t begin, int64_t end, int iters) const {
+  __device__ __forceinline__ bool cta_live(const HvCull &c, int b, int64_t begin, int64_t end, int iters, int bx) const {
     if (!c.mask) return true;
     uint32_t r0, r1, ct;
-    cta_rows(begin, end, iters, r0, r1, ct);
+    cta_rows(begin, end, iters, (uint32_t)bx, r0, r1, ct);
     if (r0 >= r1) return false;
     const uint32_t blk = (ct * kTilePoints) >> cbshift;
     const uint32_t c0 = fast_div(r0, div_h), c1 = fast_div(r1 - 1, div_h);
@@ -296,9 +305,9 @@ struct DepthSource {
     for (uint32_t cam = c0; cam <= c1; ++cam) m |= __ldg(c.mask + b * kMaxCams + cam);
     return (m >> blk) & 1u;
   }
-  __device__ __forceinline__ bool walk_init(Walker &k, int64_t begin, int64_t end, int iters, int wv, int lane) const {
+  __device__ __forceinline__ bool walk_init(Walker &k, int64_t begin, int64_t end, int iters, int bx, int wv, int lane) const {
     uint32_t r0, r1, ct;
-    cta_rows(begin, end, iters, r0, r1, ct);
+    cta_rows(begin, end, iters, (uint32_t)bx, r0, r1, ct);
     k.gr = r0 + (uint32_t)(wv * iters);
     k.gr0 = k.gr;
     k.c0 = ct * kTilePoints;
@@ -454,6 +463,15 @@ struct DepthSource {
   __device__ __forceinline__ void gather(int b, int64_t i, const float *s_cal, float *dst) const {
     point(b, i, s_cal, dst[0], dst[1], dst[2]);
   }
+  // a voxel's first point: the post kernel stores its depth next to its index (its warps have the latency to spare),
+  // so the emit kernel's first points do not start with two dependent DRAM round trips
+  static constexpr bool kCarryFirst = true;
+  __device__ __forceinline__ float first_payload(int b, uint32_t i) const { return __ldg(depth + (int64_t)b * p.npix + i); }
+  __device__ __forceinline__ void gather_first(int, uint32_t i, float d, const float *s_cal, float *dst) const {
+    uint32_t cam, v, u;
+    pixel_cvu(i, cam, v, u);
+    unproject_point(d, (int)u, (int)v, s_cal + cam * kCalibFloats, p, dst[0], dst[1], dst[2]);
+  }
 };
 
 // ---------------------------------------------------------------------------
@@ -463,6 +481,7 @@ struct HvWork {
   unsigned long long *table;  // [B][cap]   {key:32 | min point idx:32}, after P2 {key:32 | rank:32}; empty = ~0
   uint32_t *slots;            // [B][max_voxels][K-1] sorted indices of the points after the first, empty = ~0
   uint32_t *first_of;         // [B][max_voxels] first point of the voxel of rank r (the r-th set bit of flags)
+  float *first_z;             // [B][max_voxels] its depth (depth source only)
   uint32_t *flags;            // [B][nwords] bit i: point i is the first of a voxel
   int32_t *wordprefix;        // [B][nwords] exclusive popcount prefix inside the chunk
   int32_t *chunk_base;        // [B][nchunks] totals, then exclusive bases after the chunk scan
@@ -470,9 +489,9 @@ struct HvWork {
   int32_t *scan_done;         // [B] CTAs of hv_count_kernel that have finished (the last one scans the chunk totals)
   uint32_t *bev;              // [B][kBevCopies][kBevWords] bird's-eye masks of the kept voxels (OR of the copies), or null
   uint32_t *cull;             // [B][kMaxCams] live column blocks per camera, or null (nothing culled)
-  uint32_t *filter;           // [B][fwords] one bit per hashed voxel key: set when the key is claimed.  The lookup pass asks
-                              // this L2-resident bitmap before it touches the table (a miss there is a DRAM sector)
   uint32_t *later;            // [B][lwords] bit r: the voxel of rank r has points after its first one (its slot row is in use)
+  int32_t *p2v;               // [B][N] point -> voxel map or null
+  const int32_t *vnum;        // [B] voxel_num (valid after the count kernel)
   FastDiv div_gx, div_gy;     // key -> (x, y) cell
   uint32_t bev_kx, bev_ky;    // bird's-eye cell of voxel column i: (i * k) >> 20, k = floor(kBevDim 2^20 / grid)
   FastDiv div_Km1;            // slot-row word -> voxel
@@ -482,8 +501,7 @@ struct HvWork {
   uint32_t cap_mask;
   int log2cap;
   int direct;                 // grid volume <= cap: slot = key, no probing
-  int fshift;                 // filter bit of a key: (key * 2654435769u) >> fshift
-  int fwords, lwords;
+  int lwords;
   int nwords;                 // multiple of kChunkWords
   int nchunks;
   int K;                      // max_points
@@ -530,9 +548,7 @@ __device__ __forceinline__ void first_toggle(uint32_t *flags, uint32_t idx) {
 // the bits of its own points in shared memory); the displaced holder's bit is toggled here.
 // (Measured: issuing the CAS first, without the load, is slower -- repeated keys then pay an atomic on a hot
 // entry where a load would have told them to leave.)
-__device__ __forceinline__ uint32_t filter_bit(uint32_t key, int fshift) { return (key * 2654435769u) >> fshift; }
-
-__device__ __forceinline__ int table_insert(unsigned long long *table, uint32_t *flags, uint32_t *filter, const HvWork &w,
+__device__ __forceinline__ int table_insert(unsigned long long *table, uint32_t *flags, const HvWork &w,
                                             uint32_t key, uint32_t idx) {
   const unsigned long long mine = ((unsigned long long)key << 32) | idx;
   uint32_t slot;
@@ -561,13 +577,7 @@ __device__ __forceinline__ int table_insert(unsigned long long *table, uint32_t 
   while (true) {                       // `e` may be stale: the atomics decide
     if (e == kEmpty64) {
       const unsigned long long old = atomicCAS(table + slot, kEmpty64, mine);
-      if (old == kEmpty64) {
-        if (filter) {
-          const uint32_t fb = filter_bit(key, w.fshift);
-          atomicOr(filter + (fb >> 5), 1u << (fb & 31));
-        }
-        return 1;
-      }
+      if (old == kEmpty64) return 1;
       e = old;
     }
     if ((uint32_t)(e >> 32) == key) {
@@ -668,7 +678,7 @@ __device__ __forceinline__ void slot_insert(uint32_t *S, int K, uint32_t idx, ui
 template <class Src, int MODE>
 __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MINB)
     hv_pass_kernel(Src src, VoxelGrid g, HvWork w, int32_t *point2voxel, int64_t begin, int64_t end, int round,
-                   int iters) {
+                   int iters, int nfz) {
   __shared__ __align__(16) float s_cal[Src::kIsDepth ? kMaxCams * kCalibFloats : 4];
   __shared__ __align__(8) uint64_t s_bar;        // completion of the calibration's TMA copy
   __shared__ uint2 s_itemb[kPassWarps * kListCap];     // (key, element index) of the in-range elements
@@ -684,10 +694,33 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
   const int b = blockIdx.y + w.b0;
   const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
   const unsigned lt = (1u << lane) - 1u;
+  if (MODE == 1 && Src::kCarryFirst && (int)blockIdx.x < nfz) {
+    // The first nfz CTAs of every frame fetch what the emit kernel needs of the voxels' first points besides their
+    // index (depth source: the depth value): 1024 ranks per CTA, four independent loads per thread.  These CTAs wait
+    // for memory while the lookup CTAs around them issue instructions; in the emit kernel the same two dependent
+    // round trips would stall every warp.
+    const int vn = __ldg(w.vnum + b);
+    uint32_t idx[4];
+    float z[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = (int)blockIdx.x * 1024 + j * kPassThreads + tid;
+      idx[j] = r < vn ? __ldg(w.first_of + (int64_t)b * w.max_voxels + r) : kEmpty32;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z[j] = idx[j] != kEmpty32 ? src.first_payload(b, idx[j]) : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = (int)blockIdx.x * 1024 + j * kPassThreads + tid;
+      if (r < vn) w.first_z[(int64_t)b * w.max_voxels + r] = z[j];
+    }
+    return;
+  }
+  const int bx = (int)blockIdx.x - (MODE == 1 ? nfz : 0);
   if (MODE == 1) {
     // a column tile no kept voxel can be seen from: nothing to do, nothing to stage
     HvCull cl{w.cull};
-    if (!src.cta_live(cl, b, begin, end, iters)) return;
+    if (!src.cta_live(cl, b, begin, end, iters, bx)) return;
   } else {
     // voxels claimed by the previous rounds: once max_voxels exist the frame is closed
     if (wv == 0) {
@@ -710,14 +743,13 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
   if (cal_async) tma_wait(&s_bar);
 
   typename Src::Walker wk;
-  if (!src.walk_init(wk, begin, end, iters, wv, lane)) return;
+  if (!src.walk_init(wk, begin, end, iters, bx, wv, lane)) return;
   uint2 *s_item = s_itemb + wv * kListCap;
   uint32_t *s_und = s_undb + wv * kListCap;
   uint2 *s_hit = s_hitb + (MODE ? wv * 64 : 0);
   unsigned long long *table = w.table + (int64_t)b * w.cap;
   uint32_t *flags = w.flags + (int64_t)b * w.nwords;
   uint32_t *slots = w.slots + (int64_t)b * w.max_voxels * (w.K - 1);
-  uint32_t *filter = w.filter ? w.filter + (int64_t)b * w.fwords : nullptr;
   uint32_t *later = w.later + (int64_t)b * w.lwords;
   uint32_t *s_lflag = s_lflagb + (MODE == 0 ? wv * kLocalIters * 4 : 0);
   uint32_t *s_lbev = s_lbevb + (MODE == 0 ? wv * kBevWords : 0);
@@ -743,12 +775,12 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
       const int n = nh < 32 ? nh : 32;
       if (lane < n) {
         const uint2 h = s_hit[nh - n + lane];
-        // a voxel's first point is not kept in the slot rows (hv_firsts_kernel lists the first points by rank);
-        // it only gets this far when the caller wants the point -> voxel map
-        if (h.x != h.y || point2voxel) {
+        // a voxel's first point is not kept in the slot rows (the post kernel lists the first points by rank and
+        // writes their point -> voxel entries); one only gets this far through the exact path
+        if (h.x != h.y) {
           const int r = voxel_rank(w, b, h.x);
           if (r < w.max_voxels) {
-            if (h.x != h.y && w.K > 1) slot_insert(slots + (int64_t)r * (w.K - 1), w.K - 1, h.y, later, r);
+            if (w.K > 1) slot_insert(slots + (int64_t)r * (w.K - 1), w.K - 1, h.y, later, r);
             if (point2voxel) point2voxel[(int64_t)b * w.N + h.y] = r;
           }
         }
@@ -769,7 +801,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
         // repeated atomics it saves, in the sparse and in the dense scene)
         if (lane < n) {
           const uint32_t idx = local ? src.strip_index(wk0, it.y) : it.y;
-          const int r = table_insert(table, flags, filter, w, it.x, idx);
+          const int r = table_insert(table, flags, w, it.x, idx);
           if (r) {                                               // this point is (for now) the first of its voxel
             if (local) atomicXor(s_lflag + (it.y >> 5), 1u << (it.y & 31));
             else first_toggle(flags, idx);
@@ -832,21 +864,10 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
     Quad qd;
     src.classify(cur, s_cal, g, qd);
     unsigned in = qd.in;
-    if (MODE == 1 && filter) {
-      // Has the key been claimed at all?  One bit per hashed key in a bitmap that stays in L2 (512 KB per frame against
-      // a table of several MB): nearly every pixel whose voxel is not kept leaves here instead of costing a table sector.
-      uint32_t fw[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t fb = filter_bit(qd.key[q], w.fshift);
-        fw[q] = ((in >> q) & 1u) ? (__ldg(filter + (fb >> 5)) >> (fb & 31)) & 1u : 0u;
-      }
-      in = fw[0] | (fw[1] << 1) | (fw[2] << 2) | (fw[3] << 3);
-    }
-    if (MODE == 1 && !point2voxel) {
-      // A voxel's first point is already listed by rank (hv_firsts_kernel): the lookup has nothing to add for it.
-      // Its flag bit says so without a table probe -- in the region the voxels were claimed from that is
-      // nearly every in-range pixel.
+    if (MODE == 1) {
+      // A voxel's first point is already listed by rank and mapped (post kernel): the lookup has nothing to add for
+      // it.  Its flag bit says so without a table probe -- in the region the voxels were claimed from that is nearly
+      // every in-range pixel.
       const uint32_t w0 = l0 >> 5, sh = l0 & 31u;
       uint32_t fb = __ldg(flags + w0) >> sh;
       if (sh > 28u && (int)w0 + 1 < w.nwords) fb |= __ldg(flags + w0 + 1) << (32u - sh);
@@ -890,7 +911,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
       }
     }
     if (w.bev) {
-      uint32_t *gb = w.bev + ((int64_t)b * kBevCopies + ((blockIdx.x + wv) & (kBevCopies - 1))) * kBevWords;
+      uint32_t *gb = w.bev + ((int64_t)b * kBevCopies + ((bx + wv) & (kBevCopies - 1))) * kBevWords;
       for (int j = lane; j < kBevWords; j += 32) {
         const uint32_t bits = s_lbev[j];
         if (bits) atomicOr(gb + j, bits);
@@ -904,7 +925,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
 // P0 ------------------------------------------------------------------------
 // The small scratch arrays of a sub-batch are initialised by ONE launch (a memset each would be a launch each): up
 // to kInitRegions word-aligned regions, each filled with its own 32-bit pattern, 16 bytes per store in the body.
-constexpr int kInitRegions = 6;
+constexpr int kInitRegions = 8;
 struct HvInit {
   uint32_t *ptr[kInitRegions];
   unsigned long long words[kInitRegions];
@@ -1005,7 +1026,8 @@ __device__ __forceinline__ void chunk_scan_store(uint32_t my_word, int *s_warp, 
 // After the chunk bases are known, for 4 chunks per CTA (64 threads per chunk, 4 flag words per thread): the
 // exclusive popcount prefix of every word inside its chunk (what voxel_rank adds to the chunk base), and the list
 // of first points by rank -- the r-th set bit of the flags is the first point of the voxel of rank r.
-__device__ __forceinline__ void firsts_block(const HvWork &w, int b, int blk) {
+template <class Src>
+__device__ __forceinline__ void firsts_block(const Src &psrc, const HvWork &w, int b, int blk) {
   __shared__ int s_fw[8];
   const int t = threadIdx.x, lane = t & 31, wv = t >> 5;
   const int c = blk * 4 + (t >> 6);
@@ -1040,7 +1062,11 @@ __device__ __forceinline__ void firsts_block(const HvWork &w, int b, int blk) {
       const uint32_t I = __shfl_sync(0xffffffffu, wl + q, src);
       if ((W >> lane) & 1u) {
         const int pos = R + __popc(W & lt);
-        if (pos < w.max_voxels) out[pos] = (I << 5) + (uint32_t)lane;
+        if (pos < w.max_voxels) {
+          const uint32_t idx = (I << 5) + (uint32_t)lane;
+          out[pos] = idx;
+          if (w.p2v) w.p2v[(int64_t)b * w.N + idx] = pos;          // point -> voxel map of the first points
+        }
       }
     }
   }
@@ -1097,6 +1123,7 @@ static __global__ void __launch_bounds__(1024) scan_chunks_kernel(int32_t *chunk
 // map is singular / non-finite keeps all its blocks.
 __device__ __forceinline__ void cull_block(const DepthSource &src, const VoxelGrid &g, const HvWork &w, int b, int pair) {
   __shared__ double s_inv[9], s_T[3], s_margin;
+  __shared__ double s_pl[5][4];          // per plane: normal x, y | constant | slack
   __shared__ int s_ok, s_hitflag;
   const int nblk = ((src.p.W - 1) >> src.cbshift) + 1;
   const int cam = pair / nblk, blk = pair - cam * nblk;
@@ -1105,70 +1132,60 @@ __device__ __forceinline__ void cull_block(const DepthSource &src, const VoxelGr
   uint32_t bits = 0;
   if (threadIdx.x < kBevWords)
     for (int c = 0; c < kBevCopies; ++c) bits |= __ldcg(w.bev + ((int64_t)b * kBevCopies + c) * kBevWords + threadIdx.x);
-  if (threadIdx.x == 0) {
-    s_hitflag = 0;
-    const float *k = src.cal_table + ((int64_t)b * ncam + cam) * kCalibFloats + kCalDirect;
-    double m[9];
-    for (int a = 0; a < 3; ++a) {
-      m[a * 3 + 0] = k[a * 4 + 0]; m[a * 3 + 1] = k[a * 4 + 1]; m[a * 3 + 2] = k[a * 4 + 2];
-      s_T[a] = (double)k[a * 4 + 3] + 0.5;
-    }
-    const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
-    const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
-    double scale = 0.0;
-    for (int i = 0; i < 9; ++i) scale = fmax(scale, fabs(m[i]));
-    const double id = 1.0 / det;
-    s_inv[0] = c00 * id; s_inv[1] = (m[2] * m[7] - m[1] * m[8]) * id; s_inv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
-    s_inv[3] = c01 * id; s_inv[4] = (m[0] * m[8] - m[2] * m[6]) * id; s_inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
-    s_inv[6] = c02 * id; s_inv[7] = (m[1] * m[6] - m[0] * m[7]) * id; s_inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
-    // tol(z) = 0.5 - thr(z) >= the proven bound; largest at the largest valid depth
-    const double tolmax = 0.5 - ((double)src.p.zmax * (double)k[12] + (double)k[13]);
-    s_margin = 1.0 + 2.0 * tolmax;
-    bool ok = fabs(det) > 1e-12 * scale * scale * scale && isfinite(id) && tolmax >= 0.0 && tolmax < 1e6;
-    for (int i = 0; i < 9; ++i) ok = ok && isfinite(s_inv[i]);
-    for (int a = 0; a < 3; ++a) ok = ok && isfinite(s_T[a]);
-    s_ok = ok ? 1 : 0;
+  if (threadIdx.x < kCullDoubles) {
+    // inverse map, T and margin of this camera: worked out once per frame by calib_kernel (fp64)
+    const double v = src.cull_cal[((int64_t)b * ncam + cam) * kCullDoubles + threadIdx.x];
+    if (threadIdx.x < 9) s_inv[threadIdx.x] = v;
+    else if (threadIdx.x < 12) s_T[threadIdx.x - 9] = v;
+    else if (threadIdx.x == 12) s_margin = v;
+    else if (threadIdx.x == 13) s_ok = v != 0.0 ? 1 : 0;
+    if (threadIdx.x == 0) s_hitflag = 0;
   }
   __syncthreads();
-  bool hit = false;
-  if (!s_ok) {
-    hit = true;
-  } else if (bits) {
+  // The five planes (normal, constant with the box half-extents folded in, rounding slack) are the same for every cell:
+  // threads 0..4 work them out into shared memory, so that no thread carries 25 doubles in registers.
+  //   rows: w3 | w1 - u0 w3 | u1 w3 - w1 | w2 | (H-1) w3 - w2
+  // bird's-eye cell j on an axis covers the voxels i with (i * k) >> 20 == j, i.e. the cell coordinates
+  // [j 2^20 / k, (j + 1) 2^20 / k + 1)
+  const double sx = 1048576.0 / (double)w.bev_kx, sy = 1048576.0 / (double)w.bev_ky;
+  if (s_ok && threadIdx.x < 5) {
+    const int k = threadIdx.x;
     const double gz = g.grid[2];
-    // bird's-eye cell j on an axis covers the voxels i with (i * k) >> 20 == j, i.e. the cell coordinates
-    // [j 2^20 / k, (j + 1) 2^20 / k + 1)
-    const double sx = 1048576.0 / (double)w.bev_kx, sy = 1048576.0 / (double)w.bev_ky;
     const double *iv = s_inv;
     const double u0 = (double)(blk << src.cbshift);
     double u1 = (double)(((blk + 1) << src.cbshift) - 1);
     if (u1 > (double)(src.p.W - 1)) u1 = (double)(src.p.W - 1);
     const double hm1 = (double)(src.p.H - 1);
-    // plane normals n (rows: w3 | w1 - u0 w3 | u1 w3 - w1 | w2 | (H-1) w3 - w2)
-    double n[5][3];
+    double n[3];
     for (int a = 0; a < 3; ++a) {
-      n[0][a] = iv[6 + a];
-      n[1][a] = iv[a] - u0 * iv[6 + a];
-      n[2][a] = u1 * iv[6 + a] - iv[a];
-      n[3][a] = iv[3 + a];
-      n[4][a] = hm1 * iv[6 + a] - iv[3 + a];
+      n[a] = k == 0 ? iv[6 + a]
+           : k == 1 ? iv[a] - u0 * iv[6 + a]
+           : k == 2 ? u1 * iv[6 + a] - iv[a]
+           : k == 3 ? iv[3 + a]
+                    : hm1 * iv[6 + a] - iv[3 + a];
     }
     const double mg = s_margin;
     const double hx = 0.5 * (sx + 1.0) + mg, hy = 0.5 * (sy + 1.0) + mg, hz = 0.5 * gz + mg;
-    double cst[5], slack[5];
-    for (int k = 0; k < 5; ++k) {
-      // z part (the box spans the whole height), -n.T and the half-extent terms are the same for every cell
-      cst[k] = n[k][2] * (0.5 * gz - s_T[2]) - n[k][0] * s_T[0] - n[k][1] * s_T[1] +
-               fabs(n[k][0]) * hx + fabs(n[k][1]) * hy + fabs(n[k][2]) * hz;
-      slack[k] = 1e-9 * (fabs(n[k][0]) * ((double)g.grid[0] + fabs(s_T[0]) + hx) + fabs(n[k][1]) * ((double)g.grid[1] + fabs(s_T[1]) + hy) +
-                         fabs(n[k][2]) * (gz + fabs(s_T[2]) + hz));
-    }
+    // z part (the box spans the whole height), -n.T and the half-extent terms are the same for every cell
+    s_pl[k][0] = n[0];
+    s_pl[k][1] = n[1];
+    s_pl[k][2] = n[2] * (0.5 * gz - s_T[2]) - n[0] * s_T[0] - n[1] * s_T[1] + fabs(n[0]) * hx + fabs(n[1]) * hy + fabs(n[2]) * hz;
+    s_pl[k][3] = 1e-9 * (fabs(n[0]) * ((double)g.grid[0] + fabs(s_T[0]) + hx) + fabs(n[1]) * ((double)g.grid[1] + fabs(s_T[1]) + hy) +
+                         fabs(n[2]) * (gz + fabs(s_T[2]) + hz));
+  }
+  __syncthreads();
+  bool hit = false;
+  if (!s_ok) {
+    hit = true;
+  } else {
     while (bits && !hit) {
       const int bp = __ffs(bits) - 1;
       bits &= bits - 1;
       const int cell = threadIdx.x * 32 + bp;
       const double cxc = ((double)(cell % kBevDim) + 0.5) * sx + 0.5, cyc = ((double)(cell / kBevDim) + 0.5) * sy + 0.5;
       bool out = false;
-      for (int k = 0; k < 5; ++k) out = out || (cst[k] + n[k][0] * cxc + n[k][1] * cyc < -slack[k]);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) out = out || (s_pl[k][2] + s_pl[k][0] * cxc + s_pl[k][1] * cyc < -s_pl[k][3]);
       hit = !out;
     }
   }
@@ -1187,14 +1204,14 @@ __global__ void __launch_bounds__(256, 8) hv_post_kernel(Src src, VoxelGrid g, H
     if constexpr (Src::kIsDepth) cull_block(src, g, w, b, (int)blockIdx.x);
     return;
   }
-  firsts_block(w, b, (int)blockIdx.x - ncull);
+  firsts_block(src, w, b, (int)blockIdx.x - ncull);
 }
 
 // P4 ------------------------------------------------------------------------
 // A warp owns `vpw` consecutive voxels (ranks), vpw = 32 unless the rows are very long (then a power of two below);
 // lane groups of 32 / vpw lanes share a voxel.  No block barrier after the calibration copy.
 // dynamic smem per warp: tile[vpw*K*C] floats (the voxels' rows exactly as they lie in the output) + the list of the
-// later points (idx u32, position u16: vpw * K <= 10 K by the shared-memory limit).
+// later points (kEmitList entries: idx u32, position u16 -- vpw * K <= 10 K by the shared-memory limit).
 //   1. the tile is zeroed (16-byte stores); the voxel's first point is requested; the voxels whose `later` bit is set
 //      walk their slot rows (sorted, non-empty prefix; the lanes of a group take consecutive words) and ballot-compact
 //      (point, position) into the warp's list -- a voxel without later points never touches its row
@@ -1227,10 +1244,14 @@ __global__ void __launch_bounds__(kEmitThreads, RD3_EMIT_MINB) hv_emit_kernel(Sr
   const int K = w.K, Km1 = K - 1, KC = K * C;
   float *tile = reinterpret_cast<float *>(s_dynb + (size_t)wv * wbytes);
   uint32_t *l_idx = reinterpret_cast<uint32_t *>(tile + ((vpw * KC + 3) & ~3));
-  uint16_t *l_pos = reinterpret_cast<uint16_t *>(l_idx + vpw * (Km1 > 0 ? Km1 : 1));
+  uint16_t *l_pos = reinterpret_cast<uint16_t *>(l_idx + kEmitList);
   uint32_t first = kEmpty32, lw = 0;
+  float firstz = 0.0f;
   if (nv > 0) {
-    if (live) first = __ldg(w.first_of + (int64_t)b * w.max_voxels + v);
+    if (live) {
+      first = __ldg(w.first_of + (int64_t)b * w.max_voxels + v);
+      if (Src::kCarryFirst) firstz = __ldg(w.first_z + (int64_t)b * w.max_voxels + v);
+    }
     lw = __ldg(w.later + (int64_t)b * w.lwords + (r0 >> 5)) >> (r0 & 31);
     float4 *t4 = reinterpret_cast<float4 *>(tile);
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1241,32 +1262,49 @@ __global__ void __launch_bounds__(kEmitThreads, RD3_EMIT_MINB) hv_emit_kernel(Sr
   if (cal_async) tma_wait(&s_bar);
   if (nv <= 0) return;
 
-  // slot rows of the voxels that have later points: the group's lanes take the words k0 + sub
+  // slot rows of the voxels that have later points: the group's lanes take the words k0 + sub, three steps at a time
+  // (a row is one or two sectors: its words cost one round trip, not one each).  The list holds kEmitList entries:
+  // it is worked off whenever another round of words might not fit.
   int cnt = 0, n = 0;
   {
     bool open = live && ((lw >> vl) & 1u);
     const uint32_t *row = w.slots + ((int64_t)b * w.max_voxels + v) * Km1;
-    for (int k0 = 0; k0 < Km1; k0 += 1 << lg_lpv) {
+    const int lpv = 1 << lg_lpv;
+    for (int k0 = 0; k0 < Km1; k0 += 3 * lpv) {
       if (!__any_sync(0xffffffffu, open)) break;
-      const int k = k0 + sub;
-      const uint32_t wd = (open && k < Km1) ? __ldg(row + k) : kEmpty32;
-      const bool has = wd != kEmpty32;
-      const unsigned bal = __ballot_sync(0xffffffffu, has);
-      if (has) {
-        const int q = n + __popc(bal & lt);
-        l_idx[q] = wd;
-        l_pos[q] = (uint16_t)(vl * K + k + 1);
-        ++cnt;
+      uint32_t wd[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int k = k0 + j * lpv + sub;
+        wd[j] = (open && k < Km1) ? __ldg(row + k) : kEmpty32;
       }
-      n += __popc(bal);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int k = k0 + j * lpv + sub;
+        const bool has = wd[j] != kEmpty32;
+        const unsigned bal = __ballot_sync(0xffffffffu, has);
+        if (n + __popc(bal) > kEmitList) {                       // warp-uniform
+          __syncwarp();
+          for (int t = lane; t < n; t += 32) src.gather(b, l_idx[t], s_cal, tile + (size_t)l_pos[t] * C);
+          __syncwarp();
+          n = 0;
+        }
+        if (has) {
+          const int q = n + __popc(bal & lt);
+          l_idx[q] = wd[j];
+          l_pos[q] = (uint16_t)(vl * K + k + 1);
+          ++cnt;
+        }
+        n += __popc(bal);
+      }
       // the row is a non-empty prefix: the group goes on only while its last word was in use
-      open = __shfl_sync(0xffffffffu, has, (vl << lg_lpv) + (1 << lg_lpv) - 1);
+      open = __shfl_sync(0xffffffffu, wd[2] != kEmpty32, (vl << lg_lpv) + lpv - 1);
     }
-    for (int d = 1; d < (1 << lg_lpv); d <<= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    for (int d = 1; d < lpv; d <<= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
     cnt += 1;                                                    // the first point
   }
   __syncwarp();
-  if (live && sub == 0) src.gather(b, first, s_cal, tile + vl * KC);
+  if (live && sub == 0) src.gather_first(b, first, firstz, s_cal, tile + vl * KC);
   for (int t = lane; t < n; t += 32) src.gather(b, l_idx[t], s_cal, tile + (size_t)l_pos[t] * C);
   __syncwarp();
 
@@ -1337,7 +1375,6 @@ struct HvTuning {           // read once from the environment (experiments); def
   int load_pct;             // worst-case load factor of the table in percent (RD3_TABLE_LOAD_PCT)
   int ins_iters, lkp_iters; // tiles per warp strip (RD3_INS_ITERS, RD3_LKP_ITERS)
   int cull;                 // RD3_CULL=0 disables the camera / column-block culling
-  int filter;               // RD3_FILTER=0 disables the key filter of the lookup pass
   int sm_count;
 };
 const HvTuning &hv_tuning();
@@ -1353,9 +1390,9 @@ struct HvPlan {
   int log2cap;
   int nwords, nchunks;
   // [table | slots] are set to 0xFF with one memset, [flags | bev | round_claims] to 0 with another
-  int fshift, fwords, lwords;
-  size_t off_table, off_slots, off_first, off_flags, off_bev, off_claims, off_done, off_cull, off_prefix, off_chunk,
-      off_filter, off_later, total;
+  int lwords;
+  size_t off_table, off_slots, off_first, off_firstz, off_flags, off_bev, off_claims, off_done, off_cull, off_prefix, off_chunk,
+      off_later, total;
 };
 
 // `round_multiple`: a round has to be a whole number of the source's work units (image rows for depth maps)
@@ -1388,6 +1425,7 @@ inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels, int64_t round_mul
   p.off_table = off; off += align_up((size_t)B * p.cap * 8);
   p.off_slots = off; off += align_up((size_t)B * max_voxels * (K > 1 ? K - 1 : 1) * 4);
   p.off_first = off; off += align_up((size_t)B * max_voxels * 4);
+  p.off_firstz = off; off += align_up((size_t)B * max_voxels * 4);
   p.off_flags = off; off += align_up((size_t)B * p.nwords * 4);
   p.off_bev = off; off += align_up((size_t)B * kBevCopies * kBevWords * 4);
   p.off_claims = off; off += align_up((size_t)B * kMaxRounds * 4);
@@ -1395,13 +1433,7 @@ inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels, int64_t round_mul
   p.off_cull = off; off += align_up((size_t)B * kMaxCams * 4);
   p.off_prefix = off; off += align_up((size_t)B * p.nwords * 4);
   p.off_chunk = off; off += align_up((size_t)B * p.nchunks * 4);
-  // key filter: ~16 bits per key the table can hold, 2^12 .. 2^22 bits (512 KB) per frame
-  int lf = 12;
-  while (lf < 22 && ((int64_t)1 << lf) < 16 * keys) ++lf;
-  p.fshift = 32 - lf;
-  p.fwords = 1 << (lf - 5);
   p.lwords = (int)ceil_div(max_voxels, 32);
-  p.off_filter = off; off += align_up((size_t)B * p.fwords * 4);
   p.off_later = off; off += align_up((size_t)B * p.lwords * 4);
   p.total = off;
   return p;
@@ -1413,7 +1445,7 @@ template <class Src> struct CullLaunch {
   static int blocks(const Src &) { return 0; }
 };
 template <> struct CullLaunch<DepthSource> {
-  static bool wanted(const DepthSource &s) { return hv_tuning().cull && s.cal_table != nullptr; }
+  static bool wanted(const DepthSource &s) { return hv_tuning().cull && s.cal_table != nullptr && s.cull_cal != nullptr; }
   static int blocks(const DepthSource &s) { return s.p.ncam * (((s.p.W - 1) >> s.cbshift) + 1); }
 };
 
@@ -1426,14 +1458,16 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   w.table = (unsigned long long *)(base + p.off_table);
   w.slots = (uint32_t *)(base + p.off_slots);
   w.first_of = (uint32_t *)(base + p.off_first);
+  w.first_z = (float *)(base + p.off_firstz);
   w.flags = (uint32_t *)(base + p.off_flags);
   w.round_claims = (int32_t *)(base + p.off_claims);
   w.scan_done = (int32_t *)(base + p.off_done);
   w.wordprefix = (int32_t *)(base + p.off_prefix);
   w.chunk_base = (int32_t *)(base + p.off_chunk);
-  w.filter = tune.filter ? (uint32_t *)(base + p.off_filter) : nullptr;
   w.later = (uint32_t *)(base + p.off_later);
-  w.fshift = p.fshift; w.fwords = p.fwords; w.lwords = p.lwords;
+  w.lwords = p.lwords;
+  w.p2v = out.point2voxel;
+  w.vnum = out.voxel_num;
   const bool cull = CullLaunch<Src>::wanted(src) && g.fast_ok;
   w.bev = cull ? (uint32_t *)(base + p.off_bev) : nullptr;
   w.cull = cull ? (uint32_t *)(base + p.off_cull) : nullptr;
@@ -1451,8 +1485,7 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   // emit: per-warp shared memory = the rows of the warp's vpw voxels + the list of their later points.  vpw = 32 unless
   // that exceeds ~12 KB per warp (long rows: max_points 100+), then the largest power of two that fits; as many warps per
   // CTA (<= kEmitThreads / 32) as fit ~96 KB
-  const int Km1p = p.K > 1 ? p.K - 1 : 1;
-  auto emit_wbytes = [&](int vpw) { return align_up((size_t)vpw * p.K * C * 4, 16) + (size_t)vpw * Km1p * 6; };
+  auto emit_wbytes = [&](int vpw) { return align_up((size_t)vpw * p.K * C * 4, 16) + (size_t)kEmitList * 6; };
   int lg_vpw = 5;
   while (lg_vpw > 0 && emit_wbytes(1 << lg_vpw) > 12 * 1024) --lg_vpw;
   const size_t wbytes = align_up(emit_wbytes(1 << lg_vpw), 16);
@@ -1515,7 +1548,6 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
         RD3_LANE_TRY(cudaMemsetAsync(w.slots + (size_t)b0 * p.max_voxels * (p.K - 1), 0xFF,
                                      (size_t)nb * p.max_voxels * (p.K - 1) * 4, st));
       RD3_LANE_TRY(cudaMemsetAsync(w.flags + (size_t)b0 * p.nwords, 0, (size_t)nb * p.nwords * 4, st));
-      if (w.filter) RD3_LANE_TRY(cudaMemsetAsync(w.filter + (size_t)b0 * p.fwords, 0, (size_t)nb * p.fwords * 4, st));
       add(w.later + (size_t)b0 * p.lwords, (size_t)nb * p.lwords * 4, 0u);
       add(w.round_claims + (size_t)b0 * kMaxRounds, (size_t)nb * kMaxRounds * 4, 0u);
       add(w.scan_done + b0, (size_t)nb * 4, 0u);
@@ -1531,7 +1563,7 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
       const int64_t end = begin + p.S < p.N ? begin + p.S : p.N;
       // the rounds after the second mostly find their frames closed: fatter CTAs, fewer of them to retire
       const int it = r < 2 ? tune.ins_iters : 4 * tune.ins_iters;
-      hv_pass_kernel<Src, 0><<<dim3(src.host_grid(begin, end, it), nb), kPassThreads, 0, st>>>(src, g, w, nullptr, begin, end, r, it);
+      hv_pass_kernel<Src, 0><<<dim3(src.host_grid(begin, end, it), nb), kPassThreads, 0, st>>>(src, g, w, nullptr, begin, end, r, it, 0);
     }
     prof_mark(st, 2);
     hv_count_kernel<<<dim3((unsigned)ceil_div(p.nchunks, 4), nb), 256, 0, st>>>(w, out.voxel_num);
@@ -1541,9 +1573,11 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
       hv_post_kernel<Src><<<dim3((unsigned)(ncull + ceil_div(p.nchunks, 4)), nb), 256, 0, st>>>(src, g, w, ncull);
     }
     prof_mark(st, 4);
-    if (p.N > 0)
-      hv_pass_kernel<Src, 1><<<dim3(src.host_grid(0, p.N, tune.lkp_iters), nb), kPassThreads, 0, st>>>(
-          src, g, w, out.point2voxel, 0, p.N, 0, tune.lkp_iters);
+    if (p.N > 0) {
+      const int nfz = Src::kCarryFirst ? (int)ceil_div(p.max_voxels, 1024) : 0;
+      hv_pass_kernel<Src, 1><<<dim3(nfz + src.host_grid(0, p.N, tune.lkp_iters), nb), kPassThreads, 0, st>>>(
+          src, g, w, out.point2voxel, 0, p.N, 0, tune.lkp_iters, nfz);
+    }
     prof_mark(st, 5);
     hv_emit_kernel<Src><<<dim3((unsigned)ceil_div(p.max_voxels, (emit_warps << lg_vpw)), nb), 32 * emit_warps, smem, st>>>(
         src, g, w, out, (int)wbytes, lg_vpw);

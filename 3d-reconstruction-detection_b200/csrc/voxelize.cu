@@ -94,7 +94,6 @@ const HvTuning &hv_tuning() {
     v.ins_iters = env_int("RD3_INS_ITERS", 4, 1, 64);
     v.lkp_iters = env_int("RD3_LKP_ITERS", 8, 1, 64);
     v.cull = env_int("RD3_CULL", 1, 0, 1);
-    v.filter = env_int("RD3_FILTER", 1, 0, 1);
     v.sm_count = 148;                                              // B200; replaced by the device's own count when one is visible
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) == cudaSuccess &&

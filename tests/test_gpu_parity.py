@@ -700,6 +700,30 @@ def test_cuda_graph_capture_of_fused_path():
         assert torch.equal(out["voxels"][i, :m], ref["voxels"][i, :m])
 
 
+def test_reused_buffers_alternating_scenes():
+    """DepthToVoxels(reuse_buffers=True) over alternating dense / sparse scenes (and another max_voxels on the same
+    module): nothing of an earlier call may survive in the scratch or the reused outputs."""
+    c = synthetic.CONFIGS["C1"]
+    H, W = 56, 96
+    batches = [synthetic.make_batch([0, 1, 2], H, W, scene="ground"), synthetic.make_batch([3, 4, 5], H, W),
+               synthetic.make_batch([6, 7, 8], H, W, scene="ground")]
+    keep = rd3_b200.DepthToVoxels(c["voxel_size"], c["pcr"], c["max_points"], (3000, 700), max_depth=synthetic.MAX_DEPTH,
+                                  reuse_buffers=True).to(DEV)
+    fresh = rd3_b200.DepthToVoxels(c["voxel_size"], c["pcr"], c["max_points"], (3000, 700), max_depth=synthetic.MAX_DEPTH).to(DEV)
+    for rep in range(2):
+        for bi, b in enumerate(batches):
+            for train in (True, False) if bi == 1 else (True,):
+                keep.train(train); fresh.train(train)
+                d = {k: v.to(DEV) for k, v in b.items()}
+                a = keep(d["depth"], d["intrinsics"], d["cam2lidar"])
+                r = fresh(d["depth"], d["intrinsics"], d["cam2lidar"])
+                vn = r["voxel_num"].tolist()
+                assert a["voxel_num"].tolist() == vn
+                for i, m in enumerate(vn):
+                    for k in ("coors", "num_points", "voxels", "voxel_mean"):
+                        assert torch.equal(a[k][i, :m], r[k][i, :m]), (rep, bi, train, i, k)
+
+
 # ----------------------------------------------------------------------------------------------
 # SURVEY 8(f)3: pillar encoders, gather side
 # ----------------------------------------------------------------------------------------------

@@ -19,8 +19,8 @@ for name, spec in libs:
             env[a.split(":", 1)[0]] = a.split(":", 1)[1]
         if path:
             env["RD3_LIB_PATH"] = os.path.join(ROOT, path)
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "30", "--warmup", "5",
-                            "--no-cpu-baseline", "--no-e2e", "--scene", scene],
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "50", "--warmup", "5",
+                            "--no-cpu-baseline", "--no-e2e", "--no-rows", "--no-masks", "--scene", scene],
                            capture_output=True, text=True, env=env)
         line = [l for l in r.stdout.splitlines() if l.startswith("{")]
         if not line:
