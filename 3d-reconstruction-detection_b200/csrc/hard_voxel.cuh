@@ -68,6 +68,7 @@ constexpr int kListCap = 160;         // per-warp item / undecided lists: 31 car
 constexpr int kMaxRounds = 64;
 constexpr uint32_t kDummyKey = 0xFFFFFFE0u;   // + lane: 32 values no voxel key takes (make_grid: volume <= kDummyKey)
 constexpr int kBevDim = 64;           // bird's-eye mask of the kept voxels: kBevDim x kBevDim bits over the x,y grid
+                                      // (128 x 128 culls 2 more of 13 column blocks, but marking and testing it costs more: measured)
 constexpr int kBevWords = kBevDim * kBevDim / 32;
 constexpr int kCullDoubles = 16;      // per camera: inverse of the direct cell map [9], T [3], margin, ok
 constexpr int kBevCopies = 32;        // privatised copies of the mask (power of two): spreads the marking atomics
@@ -1128,10 +1129,17 @@ __device__ __forceinline__ void cull_block(const DepthSource &src, const VoxelGr
   const int nblk = ((src.p.W - 1) >> src.cbshift) + 1;
   const int cam = pair / nblk, blk = pair - cam * nblk;
   const int ncam = src.p.ncam;
-  // thread t < kBevWords owns word t of the bird's-eye mask (OR of the privatised copies)
-  uint32_t bits = 0;
-  if (threadIdx.x < kBevWords)
-    for (int c = 0; c < kBevCopies; ++c) bits |= __ldcg(w.bev + ((int64_t)b * kBevCopies + c) * kBevWords + threadIdx.x);
+  // thread t owns the words t, t + 256, ... of the bird's-eye mask (OR of the privatised copies)
+  constexpr int kWordsPerThread = (kBevWords + 255) / 256;
+  uint32_t bitsw[kWordsPerThread];
+#pragma unroll
+  for (int j = 0; j < kWordsPerThread; ++j) {
+    const int wi = threadIdx.x + 256 * j;
+    uint32_t v = 0;
+    if (wi < kBevWords)
+      for (int c = 0; c < kBevCopies; ++c) v |= __ldcg(w.bev + ((int64_t)b * kBevCopies + c) * kBevWords + wi);
+    bitsw[j] = v;
+  }
   if (threadIdx.x < kCullDoubles) {
     // inverse map, T and margin of this camera: worked out once per frame by calib_kernel (fp64)
     const double v = src.cull_cal[((int64_t)b * ncam + cam) * kCullDoubles + threadIdx.x];
@@ -1178,15 +1186,19 @@ __device__ __forceinline__ void cull_block(const DepthSource &src, const VoxelGr
   if (!s_ok) {
     hit = true;
   } else {
-    while (bits && !hit) {
-      const int bp = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const int cell = threadIdx.x * 32 + bp;
-      const double cxc = ((double)(cell % kBevDim) + 0.5) * sx + 0.5, cyc = ((double)(cell / kBevDim) + 0.5) * sy + 0.5;
-      bool out = false;
 #pragma unroll
-      for (int k = 0; k < 5; ++k) out = out || (s_pl[k][2] + s_pl[k][0] * cxc + s_pl[k][1] * cyc < -s_pl[k][3]);
-      hit = !out;
+    for (int j = 0; j < kWordsPerThread; ++j) {
+      uint32_t bits = bitsw[j];
+      while (bits && !hit) {
+        const int bp = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int cell = (threadIdx.x + 256 * j) * 32 + bp;
+        const double cxc = ((double)(cell % kBevDim) + 0.5) * sx + 0.5, cyc = ((double)(cell / kBevDim) + 0.5) * sy + 0.5;
+        bool out = false;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) out = out || (s_pl[k][2] + s_pl[k][0] * cxc + s_pl[k][1] * cyc < -s_pl[k][3]);
+        hit = !out;
+      }
     }
   }
   if (hit) s_hitflag = 1;
