@@ -998,6 +998,17 @@ static __global__ void __launch_bounds__(256) hv_count_kernel(HvWork w, int32_t 
     __syncthreads();
   }
   if (t == 0) voxel_num[b] = s_carry < w.max_voxels ? s_carry : w.max_voxels;
+  if (w.bev) {
+    // the privatised bird's-eye masks of the frame are folded into copy 0 once, here, instead of by each of the
+    // frame's cull CTAs
+    uint32_t *m = w.bev + (int64_t)b * kBevCopies * kBevWords;
+    for (int i = t; i < kBevWords; i += 256) {
+      uint32_t v = 0;
+#pragma unroll 8
+      for (int c = 0; c < kBevCopies; ++c) v |= __ldcg(m + c * kBevWords + i);
+      m[i] = v;
+    }
+  }
 }
 
 // Shared tail of the ordered-flag kernels (depth.cu): lane L of warp wv holds the
@@ -1129,15 +1140,14 @@ __device__ __forceinline__ void cull_block(const DepthSource &src, const VoxelGr
   const int nblk = ((src.p.W - 1) >> src.cbshift) + 1;
   const int cam = pair / nblk, blk = pair - cam * nblk;
   const int ncam = src.p.ncam;
-  // thread t owns the words t, t + 256, ... of the bird's-eye mask (OR of the privatised copies)
+  // thread t owns the words t, t + 256, ... of the bird's-eye mask
   constexpr int kWordsPerThread = (kBevWords + 255) / 256;
   uint32_t bitsw[kWordsPerThread];
 #pragma unroll
   for (int j = 0; j < kWordsPerThread; ++j) {
     const int wi = threadIdx.x + 256 * j;
     uint32_t v = 0;
-    if (wi < kBevWords)
-      for (int c = 0; c < kBevCopies; ++c) v |= __ldcg(w.bev + ((int64_t)b * kBevCopies + c) * kBevWords + wi);
+    if (wi < kBevWords) v = __ldg(w.bev + (int64_t)b * kBevCopies * kBevWords + wi);      // folded by the count kernel
     bitsw[j] = v;
   }
   if (threadIdx.x < kCullDoubles) {

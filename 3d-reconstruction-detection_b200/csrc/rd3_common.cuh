@@ -37,10 +37,11 @@ struct StreamLanes {
 };
 StreamLanes *get_stream_lanes();   // nullptr if creation failed
 // The lanes (streams + events) of a device are shared by every call on it: host threads that
-// enqueue concurrently take this lock for the duration of their enqueue (no device wait inside).
+// enqueue concurrently on the SAME device take its lock for the duration of their enqueue (no device wait inside).
 struct LaneLock {
   LaneLock();
   ~LaneLock();
+  int dev;
 };
 int stream_lane_count();           // RD3_STREAMS (1..kMaxLanes), default 2
 

@@ -53,11 +53,16 @@ struct LaneSet {
   StreamLanes lanes;
 };
 LaneSet g_lanes[64];
-std::mutex g_lane_mutex;
+std::mutex g_lane_mutex[64];      // one per device: enqueues on different GPUs of one process do not wait for each other
+int lane_mutex_index() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  return dev;
+}
 }  // namespace
 
-LaneLock::LaneLock() { g_lane_mutex.lock(); }
-LaneLock::~LaneLock() { g_lane_mutex.unlock(); }
+LaneLock::LaneLock() : dev(lane_mutex_index()) { g_lane_mutex[dev].lock(); }
+LaneLock::~LaneLock() { g_lane_mutex[dev].unlock(); }
 
 StreamLanes *get_stream_lanes() {
   int dev = 0;

@@ -55,10 +55,18 @@ RD3_API const char *rd3_status_string(int status);
 /* cudaGetErrorString of the last CUDA failure seen by this library (host string). */
 RD3_API const char *rd3_last_cuda_error(void);
 
-/* Per-stage timing of the hard-voxel pipeline (rd3_hard_voxelize and
+/* Process-wide state of the library (everything else lives in the caller's workspace):
+ *   - per device, up to 3 internal non-blocking streams + fork / join events ("lanes"): the hard-voxel pipeline
+ *     runs the frames of a batch in sub-batches on them, forked from and joined to the caller's stream.  Host
+ *     threads that enqueue on the same device are serialised by a per-device lock for the duration of the
+ *     enqueue (no device wait inside).  RD3_STREAMS=1..4 sets the number of sub-batches (default 2).
+ *   - the stage profiler below (off by default; while it is on, one lane is used and calls must not overlap).
+ *   - the last CUDA error string.
+ *
+ * Per-stage timing of the hard-voxel pipeline (rd3_hard_voxelize and
  * rd3_depth_to_voxels) with CUDA events recorded on the launching stream between
- * its kernels.  Stages: 0 memset, 1 insert, 2 flags, 3 chunk scan, 4 slots,
- * 5 emit, 6 meta.  rd3_profile_enable(1) resets the counters; rd3_profile_read
+ * its kernels.  Stages: 0 memset, 1 insert rounds, 2 count (flags -> voxel_num), 3 post (first points, cull
+ * bits), 4 lookup, 5 emit, 6 meta.  rd3_profile_enable(1) resets the counters; rd3_profile_read
  * waits for the recorded events and returns the summed milliseconds per stage
  * (host double[7]) and the number of calls covered (at most 1024). */
 #define RD3_PROFILE_STAGES 7

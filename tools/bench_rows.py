@@ -128,6 +128,17 @@ def collect(iters=20, scene="mixture"):
         M = vf.shape[0]
         add("a6 DynamicScatter %s (C3)" % ("mean" if avg else "max"), "N=%d, M=%d (incl. M D2H)" % (N, M), N, "point",
             N * 28 + M * 28, timeit(lambda: ds(cloud, coors), args.iters, flush))
+    # a7 batched mode (scatter_points.py:86-97): the B frames' clouds as one (sum N, 4) [b,z,y,x] call -- one launch
+    # sequence for the batch instead of the reference's per-sample loop
+    clouds = [pts[i, :int(counts[i])] for i in range(B)]
+    bf = torch.cat(clouds).contiguous()
+    bc = torch.cat([torch.nn.functional.pad(vox_dyn(c_), (1, 0), value=i) for i, c_ in enumerate(clouds)]).contiguous()
+    for avg in (True, False):
+        ds = rd3_b200.DynamicScatter(c2["voxel_size"], c2["pcr"], avg)
+        vf, vc = ds(bf, bc)
+        Nb, Mb = bf.shape[0], vf.shape[0]
+        add("a7 DynamicScatter %s, batch of %d (C3)" % ("mean" if avg else "max", B), "sum N=%d, sum M=%d (incl. M D2H)" % (Nb, Mb),
+            Nb, "point", Nb * 32 + Mb * 32, timeit(lambda: ds(bf, bc), args.iters, flush))
     # a8 backward
     f = cloud.clone().requires_grad_()
     ds = rd3_b200.DynamicScatter(c2["voxel_size"], c2["pcr"], True)
