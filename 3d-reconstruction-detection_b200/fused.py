@@ -21,7 +21,8 @@ class DepthToVoxels(nn.Module):
     allocated once per (shape, stream) and are overwritten by the next call."""
 
     def __init__(self, voxel_size, point_cloud_range, max_num_points, max_voxels,
-                 max_depth=None, range_filter=None, with_mean=True, with_voxels=True, reuse_buffers=False):
+                 max_depth=None, range_filter=None, with_mean=True, with_voxels=True, reuse_buffers=False,
+                 flat_outputs=False):
         """``with_voxels=False`` skips the padded (B, max_voxels, max_points, 3) tensor -- 85 % of
         the output bytes -- for callers that only feed the sparse encoder (mean + coors + num)."""
         super().__init__()
@@ -36,10 +37,26 @@ class DepthToVoxels(nn.Module):
         self.range_filter = range_filter
         self.with_mean = with_mean
         self.reuse_buffers = reuse_buffers
+        self.flat_outputs = bool(flat_outputs)      # mean / coors / num / voxel_num as views of one buffer (result["flat"])
+        if self.flat_outputs and not with_mean:
+            raise ValueError("flat_outputs=True needs with_mean=True")
         self._out_cache = {}
 
     def _alloc(self, B, dev, max_voxels):
         K = self.max_num_points
+        if self.flat_outputs:
+            # what the sparse encoder consumes in ONE allocation (all 4-byte types): [mean | coors | num | voxel_num].
+            # A rank that gathers its shard's results moves them with one collective instead of four.
+            n = B * max_voxels
+            flat = torch.empty((n * 3 + n * 3 + n + B,), dtype=torch.int32, device=dev)
+            return dict(
+                voxels=(torch.empty((B, max_voxels, K, 3), dtype=torch.float32, device=dev)
+                        if self.with_voxels else None),
+                mean=flat[:n * 3].view(torch.float32).view(B, max_voxels, 3),
+                coors=flat[n * 3:n * 6].view(B, max_voxels, 3),
+                num=flat[n * 6:n * 7].view(B, max_voxels),
+                voxel_num=flat[n * 7:n * 7 + B],
+                flat=flat)
         return dict(
             voxels=(torch.empty((B, max_voxels, K, 3), dtype=torch.float32, device=dev)
                     if self.with_voxels else None),
@@ -80,8 +97,11 @@ class DepthToVoxels(nn.Module):
                                        _lib.ptr(out["voxel_num"]), _lib.ptr(ws), ws.numel(),
                                        _lib.stream_of(depths))
             _lib.check(st, "depth_to_voxels")
-        return dict(voxels=out["voxels"], coors=out["coors"], num_points=out["num"],
-                    voxel_mean=out["mean"], voxel_num=out["voxel_num"])
+        res = dict(voxels=out["voxels"], coors=out["coors"], num_points=out["num"],
+                   voxel_mean=out["mean"], voxel_num=out["voxel_num"])
+        if "flat" in out:
+            res["flat"] = out["flat"]
+        return res
 
     @staticmethod
     def to_sparse_encoder_inputs(result, batch_offset=0, with_num_points=False):

@@ -323,7 +323,7 @@ def main():
 
     def make_mod(**kw):
         return rd3_b200.DepthToVoxels(cfg["voxel_size"], cfg["pcr"], K, cfg["max_voxels"], max_depth=synthetic.MAX_DEPTH,
-                                      reuse_buffers=True, **kw).to(dev).train()
+                                      reuse_buffers=True, flat_outputs=world > 1, **kw).to(dev).train()
 
     mod = make_mod()
 
@@ -342,10 +342,12 @@ def main():
     sub_mods = [make_mod() for _ in subs] if world > 1 else None
     gathered = None
     if world > 1:
-        gathered = [dict(voxel_mean=torch.empty((world, s1 - s0, mv, F), device=dev),
-                         coors=torch.empty((world, s1 - s0, mv, 3), dtype=torch.int32, device=dev),
-                         num_points=torch.empty((world, s1 - s0, mv), dtype=torch.int32, device=dev),
-                         voxel_num=torch.empty((world, s1 - s0), dtype=torch.int32, device=dev)) for s0, s1 in subs]
+        # one flat int32 buffer per sub-batch and rank: [mean | coors | num | voxel_num] (DepthToVoxels(flat_outputs=True)),
+        # gathered with ONE collective; the views below are what a consumer reads
+        def flat_len(nb):
+            return nb * mv * 7 + nb
+        gathered_flat = [torch.empty((world, flat_len(s1 - s0)), dtype=torch.int32, device=dev) for s0, s1 in subs]
+        gathered = [dict(voxel_num=gf[:, (s1 - s0) * mv * 7:(s1 - s0) * mv * 7 + (s1 - s0)]) for gf, (s0, s1) in zip(gathered_flat, subs)]
         if len(set(sizes)) != 1:
             raise RuntimeError("--frames must be a multiple of the number of GPUs (equal shards are gathered without padding)")
 
@@ -369,8 +371,7 @@ def main():
             ev.record(cur)
             with torch.cuda.stream(comm):
                 comm.wait_event(ev)
-                for name in ("voxel_mean", "coors", "num_points", "voxel_num"):
-                    dist.all_gather_into_tensor(gathered[si][name], outs[si][name])
+                dist.all_gather_into_tensor(gathered_flat[si], outs[si]["flat"])
         cur.wait_stream(comm)
         return outs[-1]
 
@@ -434,10 +435,9 @@ def main():
 
         def gather_only():
             for si in range(nsub):
-                for name in ("voxel_mean", "coors", "num_points", "voxel_num"):
-                    dist.all_gather_into_tensor(gathered[si][name], outs[si][name])
+                dist.all_gather_into_tensor(gathered_flat[si], outs[si]["flat"])
         gather_ms = timed(gather_only, n2)
-        gbytes = sum(t.numel() * t.element_size() for gd in gathered for t in gd.values())
+        gbytes = sum(t.numel() * t.element_size() for t in gathered_flat)
         # weak scaling for reference: BT frames on EVERY GPU, no collective (what round 1 reported)
         wh = synthetic.make_batch([rank * BT + i for i in range(BT)], H, W, with_conf=False, scene=args.scene)
         wd, wi, wc = wh["depth"].to(dev), wh["intrinsics"].to(dev), wh["cam2lidar"].to(dev)
@@ -449,8 +449,9 @@ def main():
         multi = {"frames_total": BT, "frames_per_gpu": B, "compute_only_ms": compute_ms, "gather_only_ms": gather_ms,
                  "compute_plus_gather_ms": ms_per_step, "gathered_bytes_per_rank_per_step": gbytes,
                  "cuda_graph": graph is not None,
-                 "gather": "all_gather_into_tensor of voxel_mean + coors + num_points + voxel_num (padded rows) per sub-batch "
-                           "on a communication stream, overlapped with the next sub-batch's kernels",
+                 "gather": "one all_gather_into_tensor per sub-batch of the flat [voxel_mean | coors | num_points | voxel_num] "
+                           "buffer (padded rows, 28 B per voxel slot) on a communication stream, overlapped with the next "
+                           "sub-batch's kernels",
                  "weak": {"frames_per_gpu": BT, "ms_per_step": weak_ms, "value": world * BT * npix / (weak_ms * 1e-3),
                           "frames_per_sec": world * BT / (weak_ms * 1e-3), "note": "independent replicas, no collective"}}
 
@@ -506,8 +507,8 @@ def main():
                 roofline["traffic_source"] = tr_.get("capture")
         except Exception:
             pass
-    path_roofline = {"bound": "hbm", "achieved": path_achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": path_achieved / hbm_peak, "algorithmic_bytes_per_step": path_bytes,
+    path_roofline = {"bound": "hbm", "achieved": path_achieved, "peak": hbm_peak * world, "unit": "GB/s",
+                     "frac": path_achieved / (hbm_peak * world), "algorithmic_bytes_per_step": path_bytes,
                      "stage_ms_per_step_single_stream": stage_ms}
 
     # ---- the path WITH the confidence / sky masks and the device-side percentile threshold (north_star; SURVEY 8(d):
@@ -531,7 +532,7 @@ def main():
         m_bytes = BT * npix * 9 + int(Mm.item()) * (K * 4 * C + 16 + 4 * F)
         masks = {"ms_per_step": m_ms, "frames_per_sec": BT / (m_ms * 1e-3), "value": BT * npix / (m_ms * 1e-3),
                  "algorithmic_bytes_per_step": m_bytes, "achieved_GBps": m_bytes / (m_ms * 1e-3) / 1e9,
-                 "frac": m_bytes / (m_ms * 1e-3) / 1e9 / hbm_peak, "voxels_per_frame_mean": int(Mm.item()) / BT,
+                 "frac": m_bytes / (m_ms * 1e-3) / 1e9 / (hbm_peak * world), "voxels_per_frame_mean": int(Mm.item()) / BT,
                  "what": "conf >= percentile(conf[~sky], %g) (exact device-side selection, no host read) & ~sky & depth "
                          "masks fused into the same kernels; no collective" % synthetic.CONF_PERCENTILE}
         del conf, sky, mmod

@@ -700,6 +700,28 @@ def test_cuda_graph_capture_of_fused_path():
         assert torch.equal(out["voxels"][i, :m], ref["voxels"][i, :m])
 
 
+def test_flat_outputs_are_views_of_one_buffer():
+    """DepthToVoxels(flat_outputs=True): mean / coors / num / voxel_num live in ONE int32 buffer (one collective moves a
+    shard's encoder inputs); same values as the separate tensors."""
+    c = synthetic.CONFIGS["C1"]
+    b = synthetic.make_batch([0, 1, 2], 56, 96, scene="ground")
+    d = {k: v.to(DEV) for k, v in b.items()}
+    mk = lambda **kw: rd3_b200.DepthToVoxels(c["voxel_size"], c["pcr"], c["max_points"], 3000,
+                                             max_depth=synthetic.MAX_DEPTH, **kw).to(DEV)
+    a = mk(flat_outputs=True)(d["depth"], d["intrinsics"], d["cam2lidar"])
+    r = mk()(d["depth"], d["intrinsics"], d["cam2lidar"])
+    B, mv = 3, 3000
+    flat = a["flat"]
+    assert flat.dtype == torch.int32 and flat.numel() == B * mv * 7 + B
+    assert a["voxel_mean"].data_ptr() == flat.data_ptr() and a["voxel_num"].data_ptr() == flat[B * mv * 7:].data_ptr()
+    vn = r["voxel_num"].tolist()
+    assert flat[B * mv * 7:].tolist() == vn
+    for i, m in enumerate(vn):
+        for k in ("coors", "num_points", "voxels", "voxel_mean"):
+            assert torch.equal(a[k][i, :m], r[k][i, :m]), (i, k)
+        assert torch.equal(flat[:B * mv * 3].view(torch.float32).view(B, mv, 3)[i, :m], r["voxel_mean"][i, :m])
+
+
 def test_reused_buffers_alternating_scenes():
     """DepthToVoxels(reuse_buffers=True) over alternating dense / sparse scenes (and another max_voxels on the same
     module): nothing of an earlier call may survive in the scratch or the reused outputs."""
