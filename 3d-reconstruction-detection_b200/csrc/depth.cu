@@ -5,9 +5,9 @@
 // (a Python double loop over samples and cameras issuing ~15 small torch ops and
 // a boolean-mask compaction each).  Here one launch covers all samples/cameras:
 // per-camera calibration is staged in shared memory, every pixel is unprojected
-// once per pass with exactly the reference's fp32 operation order, and the
-// row-major / camera-major output order is reproduced with a ballot + popcount
-// scan instead of a stream compaction primitive.
+// once with exactly the reference's fp32 operation order, and the row-major /
+// camera-major output order is reproduced by a single-pass ordered compaction
+// (chunk counts chained by decoupled look-back).
 #include <math.h>
 
 #include "hard_voxel.cuh"
@@ -88,75 +88,197 @@ __global__ void calib_kernel(const float *intr, const float *c2l, int ncam, int 
     table[(int64_t)b * ncam * kCalibFloats + i] = s_cal[i];
 }
 
-// U1: validity flags + chunk-local exclusive prefix.  grid (nchunks, B).
-__global__ void __launch_bounds__(kScanThreads)
-    up_flags_kernel(DepthSource src, uint32_t *flags, int32_t *wordprefix, int32_t *chunk_total,
-                    int nwords, int nchunks) {
-  __shared__ float s_cal[kMaxCams * kCalibFloats];
-  __shared__ int s_warp[kScanThreads / 32];
-  const int b = blockIdx.y;
-  src.prepare(s_cal, b);
-  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-  const int word0 = blockIdx.x * kChunkWords + wv * 32;
-  uint32_t my_word = 0;
-#pragma unroll 4
-  for (int it = 0; it < 32; ++it) {
-    const int64_t i = ((int64_t)(word0 + it) << 5) + lane;
-    bool valid = false;
-    if (i < src.p.npix) {
-      const int64_t gi = (int64_t)b * src.p.npix + i;
-      const float d = __ldg(src.depth + gi);
-      if (src.depth_ok(d, gi, b)) {
-        float x, y, z;
-        valid = !src.p.use_range || src.point(b, i, s_cal, x, y, z);
-      }
-    }
-    const uint32_t bal = __ballot_sync(0xffffffffu, valid);
-    if (lane == it) my_word = bal;
-  }
-  chunk_scan_store(my_word, s_warp, flags + (int64_t)b * nwords, wordprefix + (int64_t)b * nwords,
-                   chunk_total + (int64_t)b * nchunks);
+// Ordered compaction of the valid pixels in ONE pass over the inputs (decoupled look-back; no flag pass, no re-read).
+// A CTA takes the next chunk of kUpChunk pixels of its frame from a ticket counter (so a chunk is always started
+// after every chunk before it), works out the validity of its pixels (16 per thread: four groups of 4 consecutive
+// pixels, one 16-byte load each), publishes its count, adds up the counts of the chunks before it (spinning only on
+// chunks that are already running), and writes its points at their ordered positions.  state[b][c] =
+// {flag:32 | value:32}: flag 1 = chunk total, 2 = inclusive prefix.
+constexpr int kUpChunk = 4096;
+constexpr int kUpThreads = 256;
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// U3: recompute valid pixels and write them at their ordered position.
-__global__ void __launch_bounds__(256)
-    up_write_kernel(DepthSource src, const uint32_t *__restrict__ flags,
-                    const int32_t *__restrict__ wordprefix, const int32_t *__restrict__ chunk_base,
-                    int nwords, int nchunks, float *__restrict__ out_points,
-                    int32_t *__restrict__ out_pix) {
+__global__ void __launch_bounds__(kUpThreads, 4)
+    up_single_kernel(DepthSource src, unsigned long long *state, int32_t *ticket, int nchunks,
+                     float *__restrict__ out_points, int32_t *__restrict__ out_pix, int32_t *__restrict__ counts) {
   __shared__ float s_cal[kMaxCams * kCalibFloats];
+  __shared__ int s_chunk, s_base;
+  __shared__ int s_wsum[kUpThreads / 32][4];
+  extern __shared__ __align__(16) unsigned char s_dyn[];       // per warp 4 x 128 points (+ 4 x 128 pixel indices)
   const int b = blockIdx.y;
-  src.prepare(s_cal, b);
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= src.p.npix) return;
-  const int64_t wi = (int64_t)b * nwords + (i >> 5);
-  const uint32_t word = __ldg(flags + wi);
-  const uint32_t bit = 1u << (i & 31);
-  if (!(word & bit)) return;
-  float x, y, z;
-  src.point(b, i, s_cal, x, y, z);
-  const int pos = __ldg(chunk_base + (int64_t)b * nchunks + (i >> kChunkShift)) +
-                  __ldg(wordprefix + wi) + __popc(word & (bit - 1u));
-  const int64_t o = (int64_t)b * src.p.npix + pos;
-  out_points[o * 3 + 0] = x;
-  out_points[o * 3 + 1] = y;
-  out_points[o * 3 + 2] = z;
-  if (out_pix) out_pix[o] = (int32_t)i;
+  const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+  if (tid == 0) s_chunk = atomicAdd(ticket + b, 1);
+  src.stage(s_cal, b);
+  __syncthreads();
+  const int chunk = s_chunk;
+  const int64_t fbase = (int64_t)b * src.p.npix;
+  const bool vec = src.vec_ok && (!src.p.use_masks || src.mask_vec_ok);
+  const float thr = src.p.use_conf ? (src.p.conf_thresh_dev ? __ldg(src.p.conf_thresh_dev + b) : src.p.conf_thresh) : 0.0f;
+
+  // validity of the thread's 16 pixels: group g covers pixels chunk*kUpChunk + g*1024 + tid*4 .. +3
+  float z[4][4];
+  unsigned valid[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int64_t i0 = (int64_t)chunk * kUpChunk + g * 1024 + tid * 4;
+    unsigned m = 0;
+    if (vec && i0 + 4 <= src.p.npix) {
+      const float4 t = __ldg(reinterpret_cast<const float4 *>(src.depth + fbase + i0));
+      z[g][0] = t.x; z[g][1] = t.y; z[g][2] = t.z; z[g][3] = t.w;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) m |= ((z[g][q] > 0.0f) & (z[g][q] <= src.p.zmax)) ? (1u << q) : 0u;
+      if (m && src.p.use_conf) {
+        const float4 cf = __ldg(reinterpret_cast<const float4 *>(src.conf + fbase + i0));
+        m &= (cf.x >= thr ? 1u : 0u) | (cf.y >= thr ? 2u : 0u) | (cf.z >= thr ? 4u : 0u) | (cf.w >= thr ? 8u : 0u);
+      }
+      if (m && src.p.use_sky) {
+        if (src.sky) {
+          const uint32_t sb = __ldg(reinterpret_cast<const uint32_t *>(src.sky + fbase + i0));
+          m &= ((sb & 0xFFu) ? 0u : 1u) | ((sb & 0xFF00u) ? 0u : 2u) | ((sb & 0xFF0000u) ? 0u : 4u) | ((sb & 0xFF000000u) ? 0u : 8u);
+        } else {
+          const float4 sp = __ldg(reinterpret_cast<const float4 *>(src.sky_prob + fbase + i0));
+          m &= (sp.x >= src.sky_thr ? 0u : 1u) | (sp.y >= src.sky_thr ? 0u : 2u) | (sp.z >= src.sky_thr ? 0u : 4u) |
+               (sp.w >= src.sky_thr ? 0u : 8u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        z[g][q] = 0.0f;
+        if (i0 + q < src.p.npix) {
+          z[g][q] = __ldg(src.depth + fbase + i0 + q);
+          if (src.depth_ok(z[g][q], fbase + i0 + q, b)) m |= 1u << q;
+        }
+      }
+    }
+    if (m && src.p.use_range) {                    // the inclusive range filter looks at the transformed point
+      uint32_t cam0 = 0, v0 = 0, u0 = 0;
+      if (vec) src.pixel_cvu((uint32_t)i0, cam0, v0, u0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if ((m >> q) & 1u) {
+          uint32_t cam = cam0, v = v0, u = u0 + q;
+          if (!vec) src.pixel_cvu((uint32_t)(i0 + q), cam, v, u);
+          float x, y, zz;
+          if (!unproject_point(z[g][q], (int)u, (int)v, s_cal + cam * kCalibFloats, src.p, x, y, zz)) m &= ~(1u << q);
+        }
+      }
+    }
+    valid[g] = m;
+  }
+  // ordered positions inside the chunk: groups in order, lanes in order inside a group, pixels in order inside a lane
+  int excl[4], wtot[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int c = __popc(valid[g]);
+    const int inc = warp_inclusive_scan(c);
+    excl[g] = inc - c;
+    wtot[g] = __shfl_sync(0xffffffffu, inc, 31);
+    if (lane == 31) s_wsum[wv][g] = inc;
+  }
+  __syncthreads();
+  int gbase[4], total = 0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    int before = 0, all = 0;
+#pragma unroll
+    for (int k = 0; k < kUpThreads / 32; ++k) {
+      const int t = s_wsum[k][g];
+      if (k < wv) before += t;
+      all += t;
+    }
+    gbase[g] = total + before + excl[g];
+    total += all;
+  }
+  // The chunk's count is published at once; its points are worked out into shared memory (a warp's points of one
+  // group are consecutive in the output) while the chunks before it publish theirs; only then does warp 0 look
+  // back (32 predecessors per step -- they were started earlier, so the wait is finite), and the points leave with
+  // fully coalesced 4-byte stores (lane-strided 12-byte records would touch 8x the sectors).
+  unsigned long long *st = state + (int64_t)b * nchunks;
+  if (tid == 0 && chunk > 0) st_release_u64(st + chunk, (1ull << 32) | (unsigned)total);
+  float *sp = reinterpret_cast<float *>(s_dyn) + wv * (4 * 128 * 3);
+  int32_t *sx = reinterpret_cast<int32_t *>(s_dyn) + (kUpThreads / 32) * (4 * 128 * 3) + wv * (4 * 128);
+  int wfirst[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int64_t i0 = (int64_t)chunk * kUpChunk + g * 1024 + tid * 4;
+    wfirst[g] = __shfl_sync(0xffffffffu, gbase[g], 0);                 // ordered position of the warp's first point
+    int lp = gbase[g] - wfirst[g];
+    // with 16-byte loads the group's 4 pixels lie in one image row: one index -> (camera, row, column) division
+    uint32_t cam0 = 0, v0 = 0, u0 = 0;
+    if (vec && valid[g]) src.pixel_cvu((uint32_t)i0, cam0, v0, u0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if ((valid[g] >> q) & 1u) {
+        uint32_t cam = cam0, v = v0, u = u0 + q;
+        if (!vec) src.pixel_cvu((uint32_t)(i0 + q), cam, v, u);
+        float x, y, zz;
+        unproject_point(z[g][q], (int)u, (int)v, s_cal + cam * kCalibFloats, src.p, x, y, zz);   // (the range verdict is known)
+        sp[g * 384 + lp * 3 + 0] = x;
+        sp[g * 384 + lp * 3 + 1] = y;
+        sp[g * 384 + lp * 3 + 2] = zz;
+        if (out_pix) sx[g * 128 + lp] = (int32_t)(i0 + q);
+        ++lp;
+      }
+    }
+  }
+  if (wv == 0) {
+    int base = 0;
+    if (chunk > 0) {
+      int c = chunk - 1;                                   // newest chunk of the window; lane l looks at chunk c - l
+      while (true) {
+        const int ci = c - lane;
+        const unsigned long long v = ci >= 0 ? ld_acquire_u64(st + ci) : (2ull << 32);   // before chunk 0: prefix 0
+        const unsigned f = (unsigned)(v >> 32);
+        const unsigned ready = __ballot_sync(0xffffffffu, f != 0u);
+        const unsigned incl = __ballot_sync(0xffffffffu, f == 2u);
+        const int k = incl ? __ffs(incl) - 1 : 31;         // the window counts up to its first inclusive prefix
+        const unsigned need = k == 31 ? 0xffffffffu : ((2u << k) - 1u);
+        if ((ready & need) != need) { __nanosleep(20); continue; }
+        int contrib = lane <= k ? (int)(unsigned)v : 0;
+        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+        base += contrib;
+        if (incl) break;
+        c -= 32;
+      }
+    }
+    if (lane == 0) {
+      st_release_u64(st + chunk, (2ull << 32) | (unsigned)(base + total));
+      if (chunk == nchunks - 1) counts[b] = base + total;
+      s_base = base;
+    }
+  }
+  __syncthreads();
+  const int base = s_base;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int cnt = wtot[g];
+    const int64_t o = fbase + base + wfirst[g];
+    for (int e = lane; e < cnt * 3; e += 32) out_points[o * 3 + e] = sp[g * 384 + e];
+    if (out_pix)
+      for (int e = lane; e < cnt; e += 32) out_pix[o + e] = sx[g * 128 + e];
+  }
 }
 
 struct UpPlan {
-  int nwords, nchunks;
-  size_t off_flags, off_prefix, off_chunk, total;
+  int nchunks;
+  size_t off_state, off_ticket, total;
 };
 
 static UpPlan up_plan(int B, int64_t npix) {
   UpPlan p;
-  p.nchunks = (int)ceil_div(npix > 0 ? npix : 1, kChunkPoints);
-  p.nwords = p.nchunks * kChunkWords;
+  p.nchunks = (int)ceil_div(npix > 0 ? npix : 1, kUpChunk);
   size_t off = 0;
-  p.off_flags = off; off += align_up((size_t)B * p.nwords * 4);
-  p.off_prefix = off; off += align_up((size_t)B * p.nwords * 4);
-  p.off_chunk = off; off += align_up((size_t)B * p.nchunks * 4);
+  p.off_state = off; off += align_up((size_t)B * p.nchunks * 8);     // [state | ticket] are cleared with one memset
+  p.off_ticket = off; off += align_up((size_t)B * 4);
   p.total = off;
   return p;
 }
@@ -257,15 +379,14 @@ int rd3_unproject(const float *depth, const float *intrinsics, const float *cam2
   const UpPlan plan = up_plan(p->B, src.p.npix);
   if (workspace_bytes < plan.total) return RD3_ERR_WORKSPACE;
   char *base = (char *)workspace;
-  uint32_t *flags = (uint32_t *)(base + plan.off_flags);
-  int32_t *prefix = (int32_t *)(base + plan.off_prefix);
-  int32_t *chunk = (int32_t *)(base + plan.off_chunk);
+  unsigned long long *state = (unsigned long long *)(base + plan.off_state);
+  int32_t *ticket = (int32_t *)(base + plan.off_ticket);
   cudaStream_t s = (cudaStream_t)stream;
-  up_flags_kernel<<<dim3(plan.nchunks, p->B), kScanThreads, 0, s>>>(src, flags, prefix, chunk,
-                                                                   plan.nwords, plan.nchunks);
-  scan_chunks_kernel<<<p->B, 1024, 0, s>>>(chunk, plan.nchunks, d_counts, 0x7FFFFFFF);
-  up_write_kernel<<<dim3((unsigned)ceil_div(src.p.npix, 256), p->B), 256, 0, s>>>(
-      src, flags, prefix, chunk, plan.nwords, plan.nchunks, out_points, out_pix);
+  RD3_CUDA_TRY(cudaMemsetAsync(base, 0, plan.total, s));
+  const size_t smem = (size_t)(kUpThreads / 32) * 4 * 128 * (out_pix ? 16 : 12);
+  RD3_CUDA_TRY(cudaFuncSetAttribute(up_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  up_single_kernel<<<dim3(plan.nchunks, p->B), kUpThreads, smem, s>>>(src, state, ticket, plan.nchunks, out_points,
+                                                                     out_pix, d_counts);
   return check_launch();
 }
 

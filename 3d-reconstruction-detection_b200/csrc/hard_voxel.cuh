@@ -1011,29 +1011,6 @@ static __global__ void __launch_bounds__(256) hv_count_kernel(HvWork w, int32_t 
   }
 }
 
-// Shared tail of the ordered-flag kernels (depth.cu): lane L of warp wv holds the
-// 32-bit flag word (chunk*kChunkWords + wv*32 + L).  Stores the word, its exclusive
-// popcount prefix inside the chunk, and the chunk total.
-__device__ __forceinline__ void chunk_scan_store(uint32_t my_word, int *s_warp, uint32_t *flags,
-                                                 int32_t *wordprefix, int32_t *chunk_total) {
-  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-  const int cnt = __popc(my_word);
-  const int inc = warp_inclusive_scan(cnt);
-  if (lane == 31) s_warp[wv] = inc;
-  __syncthreads();
-  int base = 0, total = 0;
-#pragma unroll
-  for (int k = 0; k < kScanThreads / 32; ++k) {
-    const int t = s_warp[k];
-    if (k < wv) base += t;
-    total += t;
-  }
-  const int64_t wi = (int64_t)blockIdx.x * kChunkWords + wv * 32 + lane;
-  flags[wi] = my_word;
-  wordprefix[wi] = base + inc - cnt;
-  if (threadIdx.x == 0) chunk_total[blockIdx.x] = total;
-}
-
 // P2f -----------------------------------------------------------------------
 // After the chunk bases are known, for 4 chunks per CTA (64 threads per chunk, 4 flag words per thread): the
 // exclusive popcount prefix of every word inside its chunk (what voxel_rank adds to the chunk base), and the list

@@ -26,10 +26,23 @@ except Exception:
     pass
 
 
-def timeit(fn, iters, flush):
+def timeit(fn, iters, flush, graph=False):
+    """Median / best CUDA-event time of fn().  graph=True: fn is captured once and the replay is timed -- what the
+    kernels take without the Python / ctypes call in front of them (sub-0.2 ms calls are otherwise host-bound)."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    if graph:
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            fn()
+        fn = g.replay
+        fn()
+        torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
         flush.add_(1.0)                       # > L2: evict between iterations
@@ -85,6 +98,8 @@ def collect(iters=20, scene="mixture"):
     pts, counts = fn()
     P = int(counts.sum())
     add("a1 unproject", "8 x 6x504x896, max_depth", B * npix, "pixel", B * npix * 4 + P * 12, timeit(fn, args.iters, flush))
+    add("a1 unproject (graph replay)", "8 x 6x504x896, max_depth", B * npix, "pixel", B * npix * 4 + P * 12,
+        timeit(fn, args.iters, flush, graph=True))
     thr = 1.4
     fn = lambda: rd3_b200.unproject_padded(d["depth"], d["intrinsics"], d["cam2lidar"], max_depth=synthetic.MAX_DEPTH,
                                            confs=d["conf"], conf_thresh=thr, sky_masks=d["sky"],
@@ -93,6 +108,8 @@ def collect(iters=20, scene="mixture"):
     P2 = int(counts2.sum())
     add("a1+a2 unproject+masks+range", "8 x 6x504x896", B * npix, "pixel", B * npix * 9 + P2 * 12,
         timeit(fn, args.iters, flush))
+    add("a1+a2 (graph replay)", "8 x 6x504x896", B * npix, "pixel", B * npix * 9 + P2 * 12,
+        timeit(fn, args.iters, flush, graph=True))
 
     # one frame's cloud for the point-array operators
     n0 = int(counts[0])
@@ -103,6 +120,8 @@ def collect(iters=20, scene="mixture"):
     vox_dyn = rd3_b200.Voxelization(c2["voxel_size"], c2["pcr"], -1)
     coors = vox_dyn(cloud)
     add("a3 dynamic_voxelize", "C3 grid 1440x1440x40, N=%d" % N, N, "point", N * 24, timeit(lambda: vox_dyn(cloud), args.iters, flush))
+    add("a3 dynamic_voxelize (graph replay)", "C3 grid 1440x1440x40, N=%d" % N, N, "point", N * 24,
+        timeit(lambda: vox_dyn(cloud), args.iters, flush, graph=True))
 
     # a4 hard voxelize (+a5 wrapper) C1/C2 grid and C4 pillars
     for name, cfg in (("C2", c2), ("C4", synthetic.CONFIGS["C4"])):

@@ -7,14 +7,10 @@ tail -8 gpurun_out/pytest.log
 B="python bench.py --steps 50 --no-rows --no-e2e --no-cpu-baseline --no-masks"
 run() { name=$1; shift; env "$@" timeout 300 $B $EXTRA > gpurun_out/sw_$name.json 2> gpurun_out/sw_$name.err; }
 run base X=1
-run l90 RD3_TABLE_LOAD_PCT=90
-run l75 RD3_TABLE_LOAD_PCT=75
 EXTRA="--scene ground" run gnd X=1
-EXTRA="--scene ground" run gnd_l90 RD3_TABLE_LOAD_PCT=90
-EXTRA="--scene ground" run gnd_l75 RD3_TABLE_LOAD_PCT=75
 python - <<'PY'
 import json,glob
-for f in ["base","l90","l75","gnd","gnd_l90","gnd_l75"]:
+for f in ["base","gnd"]:
     try:
         d=json.load(open("gpurun_out/sw_%s.json"%f))
         print("%-10s"%f, "masks", (d.get("with_masks") or {}).get("ms_per_step"), round(d["ms_per_step"],4), round(d["path_roofline"]["frac"],4), {k:round(v,3) for k,v in d["path_roofline"]["stage_ms_per_step_single_stream"].items()})
