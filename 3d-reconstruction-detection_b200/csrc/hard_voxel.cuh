@@ -67,11 +67,11 @@ constexpr int kTilePoints = 128;      // points per warp tile (4 per lane)
 constexpr int kListCap = 160;         // per-warp item / undecided lists: 31 carried + 128 new
 constexpr int kMaxRounds = 64;
 constexpr uint32_t kDummyKey = 0xFFFFFFE0u;   // + lane: 32 values no voxel key takes (make_grid: volume <= kDummyKey)
-constexpr int kBevDim = 64;           // bird's-eye mask of the kept voxels: kBevDim x kBevDim bits over the x,y grid
-                                      // (128 x 128 culls 2 more of 13 column blocks, but marking and testing it costs more: measured)
+constexpr int kBevDim = 128;          // bird's-eye mask of the kept voxels: kBevDim x kBevDim bits over the x,y grid
+                                      // (64 x 64 keeps 13 of 42 column blocks alive in the mixture scene, 128 x 128 eleven)
 constexpr int kBevWords = kBevDim * kBevDim / 32;
 constexpr int kCullDoubles = 16;      // per camera: inverse of the direct cell map [9], T [3], margin, ok
-constexpr int kBevCopies = 32;        // privatised copies of the mask (power of two): spreads the marking atomics
+constexpr int kBevCopies = 8;         // privatised copies of the mask (power of two): spreads the marking atomics
 constexpr int kEmitList = 96;         // emit: entries of a warp's list of later points (worked off when it could overflow)
 constexpr int kLocalIters = 16;       // insert pass: a warp whose strip has at most this many tiles keeps the first-point
                                       // bits of its own points in shared memory (4 words per tile) and flushes them once
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
   // insert: per warp, the first-point bits of the strip's own points (4 words per tile) and the bird's-eye marks of its
   // claims; both reach global memory once, at the end of the walk, with one atomic per non-zero word
   __shared__ uint32_t s_lflagb[MODE == 0 ? kPassWarps * kLocalIters * 4 : 1];
-  __shared__ uint32_t s_lbevb[MODE == 0 ? kPassWarps * kBevWords : 1];
+  __shared__ uint32_t s_lbev[MODE == 0 ? kBevWords : 1];   // the CTA's bird's-eye marks
 
   const int b = blockIdx.y + w.b0;
   const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
@@ -737,14 +737,16 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
   if (MODE == 0) {
     for (int i = tid; i < kPassWarps * kLocalIters * 4; i += kPassThreads) s_lflagb[i] = 0u;
     if (w.bev)
-      for (int i = tid; i < kPassWarps * kBevWords; i += kPassThreads) s_lbevb[i] = 0u;
+      for (int i = tid; i < kBevWords; i += kPassThreads) s_lbev[i] = 0u;
   }
   const bool cal_async = src.stage_async(s_cal, &s_bar, b);
   __syncthreads();
   if (cal_async) tma_wait(&s_bar);
 
   typename Src::Walker wk;
-  if (!src.walk_init(wk, begin, end, iters, bx, wv, lane)) return;
+  // (a warp whose strip lies beyond the range stays for the block barrier at the end of the insert pass)
+  const bool active = src.walk_init(wk, begin, end, iters, bx, wv, lane);
+  if (MODE == 1 && !active) return;
   uint2 *s_item = s_itemb + wv * kListCap;
   uint32_t *s_und = s_undb + wv * kListCap;
   uint2 *s_hit = s_hitb + (MODE ? wv * 64 : 0);
@@ -753,7 +755,6 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
   uint32_t *slots = w.slots + (int64_t)b * w.max_voxels * (w.K - 1);
   uint32_t *later = w.later + (int64_t)b * w.lwords;
   uint32_t *s_lflag = s_lflagb + (MODE == 0 ? wv * kLocalIters * 4 : 0);
-  uint32_t *s_lbev = s_lbevb + (MODE == 0 ? wv * kBevWords : 0);
   // insert with a short strip: list entries hold the POSITION inside the strip (tile number * 128 + offset), which
   // addresses the warp's local flag words directly; the element index is rebuilt from it when the table needs it
   const bool local = MODE == 0 && iters <= kLocalIters;
@@ -761,7 +762,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
   uint32_t tno = 0;                                               // tiles walked so far
   int cnt = 0, nu = 0, nh = 0, claims = 0;
 
-  bool live = MODE == 0 || !Src::kIsDepth || src.walk_live(wk, s_cull);
+  bool live = active && (MODE == 0 || !Src::kIsDepth || src.walk_live(wk, s_cull));
   typename Src::Pre pre = src.preload(b, wk, live);
   bool flushing = false;
   // One loop, one copy of each stage (the kernel has to stay inside the instruction cache): hit passes while 32
@@ -769,7 +770,7 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
   // waiting, else the next tile; at the end of the walk the lists are flushed with partial passes.  All lists are
   // consumed from their END.
 #pragma unroll 1
-  while (true) {
+  while (active) {
     if (MODE == 1 && (nh >= 32 || (flushing && nu == 0 && cnt == 0 && nh > 0))) {
       // ---- hit pass (dense lanes): first point -> rank (#first points before it) -> sorted insertion into the
       //      voxel's slot row.  Voxels of rank >= max_voxels are the ones the reference drops.
@@ -911,15 +912,16 @@ __global__ void __launch_bounds__(kPassThreads, MODE ? RD3_LKP_MINB : RD3_INS_MI
         }
       }
     }
+    for (int d = 16; d > 0; d >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, d);
+    if (lane == 0 && claims) atomicAdd(w.round_claims + b * kMaxRounds + round, claims);
     if (w.bev) {
-      uint32_t *gb = w.bev + ((int64_t)b * kBevCopies + ((bx + wv) & (kBevCopies - 1))) * kBevWords;
-      for (int j = lane; j < kBevWords; j += 32) {
+      __syncthreads();                                           // every warp of the CTA has made its marks
+      uint32_t *gb = w.bev + ((int64_t)b * kBevCopies + (bx & (kBevCopies - 1))) * kBevWords;
+      for (int j = tid; j < kBevWords; j += kPassThreads) {
         const uint32_t bits = s_lbev[j];
         if (bits) atomicOr(gb + j, bits);
       }
     }
-    for (int d = 16; d > 0; d >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, d);
-    if (lane == 0 && claims) atomicAdd(w.round_claims + b * kMaxRounds + round, claims);
   }
 }
 
@@ -1113,6 +1115,7 @@ static __global__ void __launch_bounds__(1024) scan_chunks_kernel(int32_t *chunk
 __device__ __forceinline__ void cull_block(const DepthSource &src, const VoxelGrid &g, const HvWork &w, int b, int pair) {
   __shared__ double s_inv[9], s_T[3], s_margin;
   __shared__ double s_pl[5][4];          // per plane: normal x, y | constant | slack
+  __shared__ float s_plf[5][4];          // the same for the fp32 per-cell test (slack widened by its error bound)
   __shared__ int s_ok, s_hitflag;
   const int nblk = ((src.p.W - 1) >> src.cbshift) + 1;
   const int cam = pair / nblk, blk = pair - cam * nblk;
@@ -1167,9 +1170,18 @@ __device__ __forceinline__ void cull_block(const DepthSource &src, const VoxelGr
     s_pl[k][2] = n[2] * (0.5 * gz - s_T[2]) - n[0] * s_T[0] - n[1] * s_T[1] + fabs(n[0]) * hx + fabs(n[1]) * hy + fabs(n[2]) * hz;
     s_pl[k][3] = 1e-9 * (fabs(n[0]) * ((double)g.grid[0] + fabs(s_T[0]) + hx) + fabs(n[1]) * ((double)g.grid[1] + fabs(s_T[1]) + hy) +
                          fabs(n[2]) * (gz + fabs(s_T[2]) + hz));
+    // The per-cell test runs in fp32 (this part's fp64 rate makes it 4x the time with a 128 x 128 mask): the slack
+    // grows by a bound of the fp32 evaluation error -- conversions of the three constants, two FMAs, the cell centre
+    // (five roundings of 2^-24 of the largest magnitude, taken as 6e-7, plus 1e-3 cells of centre error) -- so it only ever culls less.
+    const double mag = fabs(n[0]) * ((double)g.grid[0] + sx + 1.0) + fabs(n[1]) * ((double)g.grid[1] + sy + 1.0) + fabs(s_pl[k][2]);
+    s_plf[k][0] = (float)s_pl[k][0];
+    s_plf[k][1] = (float)s_pl[k][1];
+    s_plf[k][2] = (float)s_pl[k][2];
+    s_plf[k][3] = (float)((s_pl[k][3] + 6e-7 * mag + 1e-3 * (fabs(n[0]) + fabs(n[1]))) * 1.0001);
   }
   __syncthreads();
   bool hit = false;
+  const float sxf = (float)sx, syf = (float)sy;
   if (!s_ok) {
     hit = true;
   } else {
@@ -1180,10 +1192,10 @@ __device__ __forceinline__ void cull_block(const DepthSource &src, const VoxelGr
         const int bp = __ffs(bits) - 1;
         bits &= bits - 1;
         const int cell = (threadIdx.x + 256 * j) * 32 + bp;
-        const double cxc = ((double)(cell % kBevDim) + 0.5) * sx + 0.5, cyc = ((double)(cell / kBevDim) + 0.5) * sy + 0.5;
+        const float cxc = fmaf((float)(cell % kBevDim) + 0.5f, sxf, 0.5f), cyc = fmaf((float)(cell / kBevDim) + 0.5f, syf, 0.5f);
         bool out = false;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) out = out || (s_pl[k][2] + s_pl[k][0] * cxc + s_pl[k][1] * cyc < -s_pl[k][3]);
+        for (int k = 0; k < 5; ++k) out = out || (fmaf(s_plf[k][0], cxc, fmaf(s_plf[k][1], cyc, s_plf[k][2])) < -s_plf[k][3]);
         hit = !out;
       }
     }
