@@ -2,8 +2,8 @@
 # parity + env sweeps of the fused path (short benches)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
-tail -8 gpurun_out/pytest.log
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
+tail -5 gpurun_out/pytest.log
 B="python bench.py --steps 50 --no-rows --no-e2e --no-cpu-baseline --no-masks"
 run() { name=$1; shift; env "$@" timeout 300 $B $EXTRA > gpurun_out/sw_$name.json 2> gpurun_out/sw_$name.err; }
 run base X=1
