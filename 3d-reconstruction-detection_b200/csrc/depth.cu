@@ -18,8 +18,10 @@ namespace rd3 {
 // (has_grid) it also holds the direct pixel->cell map and its error-bound constants
 // (rd3_common.cuh: pixel_key_fast), derived in fp64 and rounded once.
 __global__ void calib_kernel(const float *intr, const float *c2l, int ncam, int H, int W,
-                             VoxelGrid g, int has_grid, CellRange rg, float *table, double *cull_cal, float zmax) {
+                             VoxelGrid g, int has_grid, CellRange rg, float *table, double *cull_cal, float zmax,
+                             float *cull_planes, int cbshift) {
   __shared__ float s_cal[kMaxCams * kCalibFloats];
+  __shared__ double s_cc[kMaxCams][kCullDoubles];
   const int b = blockIdx.x;
   const float *Kb = intr + (int64_t)b * ncam * 9;
   const float *Mb = c2l + (int64_t)b * ncam * 16;
@@ -81,9 +83,20 @@ __global__ void calib_kernel(const float *intr, const float *c2l, int ncam, int 
       cc[12] = 1.0 + 2.0 * tolmax;
       cc[13] = ok ? 1.0 : 0.0;
       cc[14] = cc[15] = 0.0;
+      for (int i = 0; i < kCullDoubles; ++i) s_cc[cam][i] = cc[i];
     }
   }
   __syncthreads();
+  if (has_grid && cull_cal && cull_planes) {
+    // the five wedge planes of every (camera, column block): one plane per thread and step
+    const int nblk = ((W - 1) >> cbshift) + 1;
+    for (int i = threadIdx.x; i < ncam * nblk * 5; i += blockDim.x) {
+      const int k = i % 5, pair = i / 5;
+      const int cam = pair / nblk, blk = pair - cam * nblk;
+      cull_plane_of(&s_cc[cam][0], &s_cc[cam][9], s_cc[cam][12], k, blk, cbshift, W, H, g,
+                    cull_planes + (((int64_t)b * ncam + cam) * nblk + blk) * 20 + k * 4);
+    }
+  }
   for (int i = threadIdx.x; i < ncam * kCalibFloats; i += blockDim.x)
     table[(int64_t)b * ncam * kCalibFloats + i] = s_cal[i];
 }
@@ -332,6 +345,7 @@ static int make_depth_source(const float *depth, const float *intrinsics, const 
   src->c2l = cam2lidar;
   src->cal_table = nullptr;
   src->cull_cal = nullptr;
+  src->cull_planes = nullptr;
   src->rg.on = 0;
   DepthParams &d = src->p;
   d.ncam = p->ncam; d.H = p->H; d.W = p->W; d.HW = p->H * p->W; d.npix = (int32_t)npix;
@@ -394,7 +408,8 @@ size_t rd3_depth_to_voxels_workspace_bytes(const rd3_depth_params *p, int max_po
                                            int max_voxels) {
   if (!p || p->B <= 0 || max_points <= 0 || max_voxels <= 0) return 0;
   return hv_plan((int64_t)p->ncam * p->H * p->W, p->B, max_points, max_voxels, p->W).total +
-         align_up((size_t)p->B * p->ncam * kCalibFloats * 4) + align_up((size_t)p->B * p->ncam * kCullDoubles * 8);
+         align_up((size_t)p->B * p->ncam * kCalibFloats * 4) + align_up((size_t)p->B * p->ncam * kCullDoubles * 8) +
+         align_up((size_t)p->B * p->ncam * 32 * 20 * 4);
 }
 
 int rd3_depth_to_voxels(const float *depth, const float *intrinsics, const float *cam2lidar,
@@ -418,9 +433,11 @@ int rd3_depth_to_voxels(const float *depth, const float *intrinsics, const float
   const HvPlan plan = hv_plan(src.p.npix, p->B, max_points, max_voxels, p->W);
   const size_t cal_bytes = align_up((size_t)p->B * p->ncam * kCalibFloats * 4);
   const size_t cull_bytes = align_up((size_t)p->B * p->ncam * kCullDoubles * 8);
-  if (workspace_bytes < plan.total + cal_bytes + cull_bytes) return RD3_ERR_WORKSPACE;
+  const size_t planes_bytes = align_up((size_t)p->B * p->ncam * 32 * 20 * 4);     // at most 32 column blocks per camera
+  if (workspace_bytes < plan.total + cal_bytes + cull_bytes + planes_bytes) return RD3_ERR_WORKSPACE;
   float *cal_table = (float *)((char *)workspace + plan.total);
   double *cull_cal = (double *)((char *)workspace + plan.total + cal_bytes);
+  float *cull_planes = (float *)((char *)workspace + plan.total + cal_bytes + cull_bytes);
   // inclusive range filter in cell units minus 0.5 (pixel_key_fast works on h = f' - 0.5).  When the voxel grid's
   // own test implies every plane of the filter (the usual case: the filter box contains the grid), the fast
   // path does not look at it at all; the exact path still applies it literally.
@@ -430,9 +447,10 @@ int rd3_depth_to_voxels(const float *depth, const float *intrinsics, const float
     src.rg.hi[a] = (float)(((double)p->range[3 + a] - (double)g.lo[a]) / (double)g.vs[a] - 0.5);
   }
   calib_kernel<<<p->B, 128, 0, (cudaStream_t)stream>>>(intrinsics, cam2lidar, p->ncam, p->H, p->W, g, 1,
-                                                       src.rg, cal_table, cull_cal, src.p.zmax);
+                                                       src.rg, cal_table, cull_cal, src.p.zmax, cull_planes, src.cbshift);
   src.cal_table = cal_table;
   src.cull_cal = cull_cal;
+  src.cull_planes = cull_planes;
   HvOut out{voxels, coors, num_points_per_voxel, voxel_mean, d_voxel_num, nullptr,
             voxel_mean ? 3 : 0};
   return hv_run(src, g, vol, plan, workspace, out, (cudaStream_t)stream);

@@ -215,6 +215,7 @@ struct DepthSource {
   const float *c2l;        // (B, ncam, 16)
   const float *cal_table;  // (B, ncam, kCalibFloats) precomputed by calib_kernel, or null
   const double *cull_cal;  // (B, ncam, kCullDoubles) inverse cell map per camera for the culling test (calib_kernel), or null
+  const float *cull_planes; // (B, ncam, column blocks, 5 planes, 4) the wedge planes of every (camera, column block), or null
   DepthParams p;
   CellRange rg;            // range filter in cell units (fused path); on = 0 when the grid test implies it
   int vec_ok;              // 16-byte aligned float4 loads of 4 pixels of a row are legal (W % 4 == 0, aligned base)
@@ -1101,6 +1102,43 @@ static __global__ void __launch_bounds__(1024) scan_chunks_kernel(int32_t *chunk
   }
 }
 
+// Plane k (0..4) of the viewing wedge of (camera, column block) for the cull test below, from the camera's inverse
+// cell map: rows  w3 | w1 - u0 w3 | u1 w3 - w1 | w2 | (H-1) w3 - w2.  out[0..3] = normal x, y | constant with the
+// half-extents of a bird's-eye cell folded in | slack.  Worked out in fp64 once per frame (calib_kernel); the
+// per-cell test runs in fp32 (this part's fp64 rate made it the bulk of the post kernel), so the slack carries a
+// bound of the fp32 evaluation error -- conversions of the three constants, two FMAs, the cell centre (five
+// roundings of 2^-24 of the largest magnitude, taken as 6e-7, plus 1e-3 cells of centre error): it only ever culls less.
+// A bird's-eye cell j on an axis covers the voxels i with (i * kx) >> 20 == j, i.e. the cell coordinates
+// [j 2^20 / kx, (j + 1) 2^20 / kx + 1).
+__device__ __forceinline__ void cull_plane_of(const double *iv, const double *T, double margin, int k, int blk, int cbshift,
+                                              int W, int H, const VoxelGrid &g, float *out) {
+  const double sx = 1048576.0 / (double)(uint32_t)(((uint64_t)kBevDim << 20) / (uint64_t)g.grid[0]);
+  const double sy = 1048576.0 / (double)(uint32_t)(((uint64_t)kBevDim << 20) / (uint64_t)g.grid[1]);
+  const double gz = g.grid[2];
+  const double u0 = (double)(blk << cbshift);
+  double u1 = (double)(((blk + 1) << cbshift) - 1);
+  if (u1 > (double)(W - 1)) u1 = (double)(W - 1);
+  const double hm1 = (double)(H - 1);
+  double n[3];
+  for (int a = 0; a < 3; ++a) {
+    n[a] = k == 0 ? iv[6 + a]
+         : k == 1 ? iv[a] - u0 * iv[6 + a]
+         : k == 2 ? u1 * iv[6 + a] - iv[a]
+         : k == 3 ? iv[3 + a]
+                  : hm1 * iv[6 + a] - iv[3 + a];
+  }
+  const double hx = 0.5 * (sx + 1.0) + margin, hy = 0.5 * (sy + 1.0) + margin, hz = 0.5 * gz + margin;
+  // z part (the box spans the whole height), -n.T and the half-extent terms are the same for every cell
+  const double cst = n[2] * (0.5 * gz - T[2]) - n[0] * T[0] - n[1] * T[1] + fabs(n[0]) * hx + fabs(n[1]) * hy + fabs(n[2]) * hz;
+  const double slack = 1e-9 * (fabs(n[0]) * ((double)g.grid[0] + fabs(T[0]) + hx) + fabs(n[1]) * ((double)g.grid[1] + fabs(T[1]) + hy) +
+                               fabs(n[2]) * (gz + fabs(T[2]) + hz));
+  const double mag = fabs(n[0]) * ((double)g.grid[0] + sx + 1.0) + fabs(n[1]) * ((double)g.grid[1] + sy + 1.0) + fabs(cst);
+  out[0] = (float)n[0];
+  out[1] = (float)n[1];
+  out[2] = (float)cst;
+  out[3] = (float)((slack + 6e-7 * mag + 1e-3 * (fabs(n[0]) + fabs(n[1]))) * 1.0001);
+}
+
 // P2c -----------------------------------------------------------------------
 // grid (cameras x column blocks, frames), one thread per word of the bird's-eye mask.  For one camera and one
 // block of 2^cbshift image columns: is there a claimed voxel that a pixel of the block can fall into?  A pixel (u, v, z > 0) lands at the continuous cell coordinate
@@ -1113,9 +1151,7 @@ static __global__ void __launch_bounds__(1024) scan_chunks_kernel(int32_t *chunk
 // box is its value at the centre plus |n| . half-extents.  Everything is evaluated in fp64; a camera whose
 // map is singular / non-finite keeps all its blocks.
 __device__ __forceinline__ void cull_block(const DepthSource &src, const VoxelGrid &g, const HvWork &w, int b, int pair) {
-  __shared__ double s_inv[9], s_T[3], s_margin;
-  __shared__ double s_pl[5][4];          // per plane: normal x, y | constant | slack
-  __shared__ float s_plf[5][4];          // the same for the fp32 per-cell test (slack widened by its error bound)
+  __shared__ float s_plf[5][4];          // per plane: normal x, y | constant | slack (calib_kernel: cull_planes_of)
   __shared__ int s_ok, s_hitflag;
   const int nblk = ((src.p.W - 1) >> src.cbshift) + 1;
   const int cam = pair / nblk, blk = pair - cam * nblk;
@@ -1130,58 +1166,15 @@ __device__ __forceinline__ void cull_block(const DepthSource &src, const VoxelGr
     if (wi < kBevWords) v = __ldg(w.bev + (int64_t)b * kBevCopies * kBevWords + wi);      // folded by the count kernel
     bitsw[j] = v;
   }
-  if (threadIdx.x < kCullDoubles) {
-    // inverse map, T and margin of this camera: worked out once per frame by calib_kernel (fp64)
-    const double v = src.cull_cal[((int64_t)b * ncam + cam) * kCullDoubles + threadIdx.x];
-    if (threadIdx.x < 9) s_inv[threadIdx.x] = v;
-    else if (threadIdx.x < 12) s_T[threadIdx.x - 9] = v;
-    else if (threadIdx.x == 12) s_margin = v;
-    else if (threadIdx.x == 13) s_ok = v != 0.0 ? 1 : 0;
-    if (threadIdx.x == 0) s_hitflag = 0;
+  if (threadIdx.x < 20)
+    (&s_plf[0][0])[threadIdx.x] = __ldg(src.cull_planes + (((int64_t)b * ncam + cam) * nblk + blk) * 20 + threadIdx.x);
+  if (threadIdx.x == 32) {
+    s_ok = src.cull_cal[((int64_t)b * ncam + cam) * kCullDoubles + 13] != 0.0 ? 1 : 0;
+    s_hitflag = 0;
   }
   __syncthreads();
-  // The five planes (normal, constant with the box half-extents folded in, rounding slack) are the same for every cell:
-  // threads 0..4 work them out into shared memory, so that no thread carries 25 doubles in registers.
-  //   rows: w3 | w1 - u0 w3 | u1 w3 - w1 | w2 | (H-1) w3 - w2
-  // bird's-eye cell j on an axis covers the voxels i with (i * k) >> 20 == j, i.e. the cell coordinates
-  // [j 2^20 / k, (j + 1) 2^20 / k + 1)
-  const double sx = 1048576.0 / (double)w.bev_kx, sy = 1048576.0 / (double)w.bev_ky;
-  if (s_ok && threadIdx.x < 5) {
-    const int k = threadIdx.x;
-    const double gz = g.grid[2];
-    const double *iv = s_inv;
-    const double u0 = (double)(blk << src.cbshift);
-    double u1 = (double)(((blk + 1) << src.cbshift) - 1);
-    if (u1 > (double)(src.p.W - 1)) u1 = (double)(src.p.W - 1);
-    const double hm1 = (double)(src.p.H - 1);
-    double n[3];
-    for (int a = 0; a < 3; ++a) {
-      n[a] = k == 0 ? iv[6 + a]
-           : k == 1 ? iv[a] - u0 * iv[6 + a]
-           : k == 2 ? u1 * iv[6 + a] - iv[a]
-           : k == 3 ? iv[3 + a]
-                    : hm1 * iv[6 + a] - iv[3 + a];
-    }
-    const double mg = s_margin;
-    const double hx = 0.5 * (sx + 1.0) + mg, hy = 0.5 * (sy + 1.0) + mg, hz = 0.5 * gz + mg;
-    // z part (the box spans the whole height), -n.T and the half-extent terms are the same for every cell
-    s_pl[k][0] = n[0];
-    s_pl[k][1] = n[1];
-    s_pl[k][2] = n[2] * (0.5 * gz - s_T[2]) - n[0] * s_T[0] - n[1] * s_T[1] + fabs(n[0]) * hx + fabs(n[1]) * hy + fabs(n[2]) * hz;
-    s_pl[k][3] = 1e-9 * (fabs(n[0]) * ((double)g.grid[0] + fabs(s_T[0]) + hx) + fabs(n[1]) * ((double)g.grid[1] + fabs(s_T[1]) + hy) +
-                         fabs(n[2]) * (gz + fabs(s_T[2]) + hz));
-    // The per-cell test runs in fp32 (this part's fp64 rate makes it 4x the time with a 128 x 128 mask): the slack
-    // grows by a bound of the fp32 evaluation error -- conversions of the three constants, two FMAs, the cell centre
-    // (five roundings of 2^-24 of the largest magnitude, taken as 6e-7, plus 1e-3 cells of centre error) -- so it only ever culls less.
-    const double mag = fabs(n[0]) * ((double)g.grid[0] + sx + 1.0) + fabs(n[1]) * ((double)g.grid[1] + sy + 1.0) + fabs(s_pl[k][2]);
-    s_plf[k][0] = (float)s_pl[k][0];
-    s_plf[k][1] = (float)s_pl[k][1];
-    s_plf[k][2] = (float)s_pl[k][2];
-    s_plf[k][3] = (float)((s_pl[k][3] + 6e-7 * mag + 1e-3 * (fabs(n[0]) + fabs(n[1]))) * 1.0001);
-  }
-  __syncthreads();
+  const float sxf = 1048576.0f / (float)w.bev_kx, syf = 1048576.0f / (float)w.bev_ky;
   bool hit = false;
-  const float sxf = (float)sx, syf = (float)sy;
   if (!s_ok) {
     hit = true;
   } else {
@@ -1456,7 +1449,7 @@ template <class Src> struct CullLaunch {
   static int blocks(const Src &) { return 0; }
 };
 template <> struct CullLaunch<DepthSource> {
-  static bool wanted(const DepthSource &s) { return hv_tuning().cull && s.cal_table != nullptr && s.cull_cal != nullptr; }
+  static bool wanted(const DepthSource &s) { return hv_tuning().cull && s.cal_table != nullptr && s.cull_cal != nullptr && s.cull_planes != nullptr; }
   static int blocks(const DepthSource &s) { return s.p.ncam * (((s.p.W - 1) >> s.cbshift) + 1); }
 };
 
