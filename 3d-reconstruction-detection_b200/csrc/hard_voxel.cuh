@@ -491,6 +491,8 @@ struct HvWork {
   int32_t *scan_done;         // [B] CTAs of hv_count_kernel that have finished (the last one scans the chunk totals)
   uint32_t *bev;              // [B][kBevCopies][kBevWords] bird's-eye masks of the kept voxels (OR of the copies), or null
   uint32_t *cull;             // [B][kMaxCams] live column blocks per camera, or null (nothing culled)
+  uint16_t *bev_list;         // [B][kBevDim^2] the marked cells of the folded mask (count kernel), bev_count[B] of them
+  int32_t *bev_count;
   uint32_t *later;            // [B][lwords] bit r: the voxel of rank r has points after its first one (its slot row is in use)
   int32_t *p2v;               // [B][N] point -> voxel map or null
   const int32_t *vnum;        // [B] voxel_num (valid after the count kernel)
@@ -1002,14 +1004,46 @@ static __global__ void __launch_bounds__(256) hv_count_kernel(HvWork w, int32_t 
   }
   if (t == 0) voxel_num[b] = s_carry < w.max_voxels ? s_carry : w.max_voxels;
   if (w.bev) {
-    // the privatised bird's-eye masks of the frame are folded into copy 0 once, here, instead of by each of the
-    // frame's cull CTAs
-    uint32_t *m = w.bev + (int64_t)b * kBevCopies * kBevWords;
-    for (int i = t; i < kBevWords; i += 256) {
-      uint32_t v = 0;
+    // The privatised bird's-eye masks of the frame are folded once, here, and the marked cells are LISTED: the cull
+    // CTAs then share the cells evenly among their threads (a thread that owned mask words walked up to 64 cells of a
+    // dense word while its neighbours had none).  Thread t folds the words [t * per, t * per + per).
+    static_assert(kBevWords % 256 == 0, "mask words per thread");
+    constexpr int per = kBevWords / 256;
+    const uint32_t *m = w.bev + (int64_t)b * kBevCopies * kBevWords;
+    uint32_t v[per];
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < per; ++j) {
+      uint32_t x = 0;
 #pragma unroll 8
-      for (int c = 0; c < kBevCopies; ++c) v |= __ldcg(m + c * kBevWords + i);
-      m[i] = v;
+      for (int k = 0; k < kBevCopies; ++k) x |= __ldcg(m + k * kBevWords + t * per + j);
+      v[j] = x;
+      c += __popc(x);
+    }
+    const int inc = warp_inclusive_scan(c);
+    __syncthreads();                                   // s_warp is free again
+    if (lane == 31) s_warp[wv] = inc;
+    __syncthreads();
+    int pos = inc - c;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pos += (k < wv) ? s_warp[k] : 0;
+    uint16_t *list = w.bev_list + (int64_t)b * kBevDim * kBevDim;
+    if (t == 255) w.bev_count[b] = pos + c;
+    // expansion one word at a time with the WARP (lane L owns bit L: consecutive list positions, coalesced stores);
+    // empty words are skipped by vote
+    const unsigned ltm = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < per; ++j) {
+      unsigned nz = __ballot_sync(0xffffffffu, v[j] != 0u);
+      while (nz) {
+        const int src = __ffs(nz) - 1;
+        nz &= nz - 1;
+        const uint32_t W = __shfl_sync(0xffffffffu, v[j], src);
+        const int P = __shfl_sync(0xffffffffu, pos, src);
+        const int T = __shfl_sync(0xffffffffu, t * per + j, src);
+        if ((W >> lane) & 1u) list[P + __popc(W & ltm)] = (uint16_t)(T * 32 + lane);
+      }
+      pos += __popc(v[j]);
     }
   }
 }
@@ -1156,16 +1190,6 @@ __device__ __forceinline__ void cull_block(const DepthSource &src, const VoxelGr
   const int nblk = ((src.p.W - 1) >> src.cbshift) + 1;
   const int cam = pair / nblk, blk = pair - cam * nblk;
   const int ncam = src.p.ncam;
-  // thread t owns the words t, t + 256, ... of the bird's-eye mask
-  constexpr int kWordsPerThread = (kBevWords + 255) / 256;
-  uint32_t bitsw[kWordsPerThread];
-#pragma unroll
-  for (int j = 0; j < kWordsPerThread; ++j) {
-    const int wi = threadIdx.x + 256 * j;
-    uint32_t v = 0;
-    if (wi < kBevWords) v = __ldg(w.bev + (int64_t)b * kBevCopies * kBevWords + wi);      // folded by the count kernel
-    bitsw[j] = v;
-  }
   if (threadIdx.x < 20)
     (&s_plf[0][0])[threadIdx.x] = __ldg(src.cull_planes + (((int64_t)b * ncam + cam) * nblk + blk) * 20 + threadIdx.x);
   if (threadIdx.x == 32) {
@@ -1178,19 +1202,16 @@ __device__ __forceinline__ void cull_block(const DepthSource &src, const VoxelGr
   if (!s_ok) {
     hit = true;
   } else {
+    // the frame's marked cells (listed by the count kernel), shared evenly among the threads
+    const int ncell = __ldg(w.bev_count + b);
+    const uint16_t *list = w.bev_list + (int64_t)b * kBevDim * kBevDim;
+    for (int i = threadIdx.x; i < ncell && !hit; i += 256) {
+      const int cell = __ldg(list + i);
+      const float cxc = fmaf((float)(cell % kBevDim) + 0.5f, sxf, 0.5f), cyc = fmaf((float)(cell / kBevDim) + 0.5f, syf, 0.5f);
+      bool out = false;
 #pragma unroll
-    for (int j = 0; j < kWordsPerThread; ++j) {
-      uint32_t bits = bitsw[j];
-      while (bits && !hit) {
-        const int bp = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const int cell = (threadIdx.x + 256 * j) * 32 + bp;
-        const float cxc = fmaf((float)(cell % kBevDim) + 0.5f, sxf, 0.5f), cyc = fmaf((float)(cell / kBevDim) + 0.5f, syf, 0.5f);
-        bool out = false;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) out = out || (fmaf(s_plf[k][0], cxc, fmaf(s_plf[k][1], cyc, s_plf[k][2])) < -s_plf[k][3]);
-        hit = !out;
-      }
+      for (int k = 0; k < 5; ++k) out = out || (fmaf(s_plf[k][0], cxc, fmaf(s_plf[k][1], cyc, s_plf[k][2])) < -s_plf[k][3]);
+      hit = !out;
     }
   }
   if (hit) s_hitflag = 1;
@@ -1396,7 +1417,7 @@ struct HvPlan {
   // [table | slots] are set to 0xFF with one memset, [flags | bev | round_claims] to 0 with another
   int lwords;
   size_t off_table, off_slots, off_first, off_firstz, off_flags, off_bev, off_claims, off_done, off_cull, off_prefix, off_chunk,
-      off_later, total;
+      off_later, off_bevlist, off_bevcount, total;
 };
 
 // `round_multiple`: a round has to be a whole number of the source's work units (image rows for depth maps)
@@ -1439,6 +1460,8 @@ inline HvPlan hv_plan(int64_t N, int B, int K, int max_voxels, int64_t round_mul
   p.off_chunk = off; off += align_up((size_t)B * p.nchunks * 4);
   p.lwords = (int)ceil_div(max_voxels, 32);
   p.off_later = off; off += align_up((size_t)B * p.lwords * 4);
+  p.off_bevlist = off; off += align_up((size_t)B * kBevDim * kBevDim * 2);
+  p.off_bevcount = off; off += align_up((size_t)B * 4);
   p.total = off;
   return p;
 }
@@ -1475,6 +1498,8 @@ int hv_run(const Src &src, const VoxelGrid &g, uint64_t volume, const HvPlan &p,
   const bool cull = CullLaunch<Src>::wanted(src) && g.fast_ok;
   w.bev = cull ? (uint32_t *)(base + p.off_bev) : nullptr;
   w.cull = cull ? (uint32_t *)(base + p.off_cull) : nullptr;
+  w.bev_list = (uint16_t *)(base + p.off_bevlist);
+  w.bev_count = (int32_t *)(base + p.off_bevcount);
   w.N = p.N; w.cap = p.cap; w.cap_mask = (uint32_t)(p.cap - 1); w.log2cap = p.log2cap;
   w.direct = (volume <= (uint64_t)p.cap) ? 1 : 0;
   w.nwords = p.nwords; w.nchunks = p.nchunks; w.K = p.K; w.max_voxels = p.max_voxels;
