@@ -335,75 +335,120 @@ def main():
     # ---- the step ----------------------------------------------------------------------
     # N == 1: one pass of the fused path over the BT frames.
     # N  > 1: the rank's shard in two sub-batches; what the sparse encoder consumes (voxel mean, coors, counts, voxel_num;
-    #         fixed-size padded rows) is all-gathered on a communication stream while the next sub-batch computes.
+    #         fixed-size padded rows) is all-gathered on a communication stream while the next sub-batch -- of this step or
+    #         of the next one -- computes.  Two sets of output / gather buffers alternate from step to step, so a step's
+    #         gather only has to be finished when its buffers come up again two steps later; PIPE steps are replayed as
+    #         one CUDA graph.
+    PIPE = 4
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
-    nsub = 2 if (world > 1 and B >= 2) else 1
+    # two sub-batches overlap a step's own gather with its own kernels; with few frames per GPU a call is latency-bound
+    # (~14 dependent launches) and one sub-batch per step is faster -- its gather then overlaps the NEXT step's kernels
+    nsub = 2 if (world > 1 and B >= 16) else 1
     subs = [(B * i // nsub, B * (i + 1) // nsub) for i in range(nsub)]
-    sub_mods = [make_mod() for _ in subs] if world > 1 else None
+    sub_mods = [[make_mod() for _ in subs] for _p in range(2)] if world > 1 else None
     gathered = None
     if world > 1:
         # one flat int32 buffer per sub-batch and rank: [mean | coors | num | voxel_num] (DepthToVoxels(flat_outputs=True)),
         # gathered with ONE collective; the views below are what a consumer reads
         def flat_len(nb):
             return nb * mv * 7 + nb
-        gathered_flat = [torch.empty((world, flat_len(s1 - s0)), dtype=torch.int32, device=dev) for s0, s1 in subs]
-        gathered = [dict(voxel_num=gf[:, (s1 - s0) * mv * 7:(s1 - s0) * mv * 7 + (s1 - s0)]) for gf, (s0, s1) in zip(gathered_flat, subs)]
+        gathered_flat = [[torch.empty((world, flat_len(s1 - s0)), dtype=torch.int32, device=dev) for s0, s1 in subs]
+                         for _p in range(2)]
+        gathered = [dict(voxel_num=gf[:, (s1 - s0) * mv * 7:(s1 - s0) * mv * 7 + (s1 - s0)])
+                    for gf, (s0, s1) in zip(gathered_flat[0], subs)]
         if len(set(sizes)) != 1:
             raise RuntimeError("--frames must be a multiple of the number of GPUs (equal shards are gathered without padding)")
 
-    outs = [None] * nsub                                   # the sub-batches' (reused) output buffers
+    outs = [[None] * nsub, [None] * nsub]                  # the sub-batches' (reused) output buffers, per buffer set
+    gdone = [None, None]                                   # per buffer set: its last gather has finished
 
     def compute_only():
         if world == 1:
             return mod(depth, intr, c2l)
-        for si, ((s0, s1), m) in enumerate(zip(subs, sub_mods)):
-            outs[si] = m(depth[s0:s1], intr[s0:s1], c2l[s0:s1])
-        return outs[-1]
+        for si, ((s0, s1), m) in enumerate(zip(subs, sub_mods[0])):
+            outs[0][si] = m(depth[s0:s1], intr[s0:s1], c2l[s0:s1])
+        return outs[0][-1]
 
-    def step():
-        if world == 1:
-            return mod(depth, intr, c2l)
+    def step_p(p):
+        """One step on buffer set p: sub-batch kernels on the current stream, each followed by its all-gather on the
+        communication stream.  Nothing waits for the gathers here."""
         cur = torch.cuda.current_stream(dev)
-        comm.wait_stream(cur)                              # the previous step's consumers are done with `gathered`
-        for si, ((s0, s1), m) in enumerate(zip(subs, sub_mods)):
-            outs[si] = m(depth[s0:s1], intr[s0:s1], c2l[s0:s1])
+        if gdone[p] is not None:
+            cur.wait_event(gdone[p])                       # the set's previous gather has read the buffers written below
+        for si, ((s0, s1), m) in enumerate(zip(subs, sub_mods[p])):
+            outs[p][si] = m(depth[s0:s1], intr[s0:s1], c2l[s0:s1])
             ev = torch.cuda.Event()
             ev.record(cur)
             with torch.cuda.stream(comm):
                 comm.wait_event(ev)
-                dist.all_gather_into_tensor(gathered_flat[si], outs[si]["flat"])
-        cur.wait_stream(comm)
-        return outs[-1]
+                dist.all_gather_into_tensor(gathered_flat[p][si], outs[p][si]["flat"])
+        gdone[p] = torch.cuda.Event()
+        gdone[p].record(comm)
+        return outs[p][-1]
+
+    def join():
+        torch.cuda.current_stream(dev).wait_stream(comm)
+
+    step_count = [0]
+
+    def step():
+        if world == 1:
+            return mod(depth, intr, c2l)
+        r_ = step_p(step_count[0] & 1)
+        step_count[0] += 1
+        return r_
 
     for _ in range(args.warmup):
         r = step()
+    if world > 1:
+        join()
     barrier()
     graph = None
     if world > 1 and not args.no_graph:
-        # 8 frames per GPU are ~40 kernel launches + 8 collectives for ~0.2 ms of device work: replay the step as one
-        # CUDA graph (the library's internal stream lanes and NCCL are both capturable); eager if capture fails
+        # 8 frames per GPU are ~40 kernel launches + 2 collectives for ~0.2 ms of device work: PIPE steps are replayed as
+        # one CUDA graph (the library's internal stream lanes and NCCL are both capturable); eager if capture fails
         try:
             gs = torch.cuda.Stream(device=dev)
             with torch.cuda.stream(gs):
-                step()
+                for k in range(PIPE):
+                    step_p(k & 1)
+                join()
             torch.cuda.synchronize()
+            gdone[0] = gdone[1] = None                         # no event from outside the capture
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=gs):
-                step()
+                for k in range(PIPE):
+                    step_p(k & 1)
+                join()
+            gdone[0] = gdone[1] = None
             g.replay()
             torch.cuda.synchronize()
             graph = g
         except Exception as e:                                 # noqa: BLE001
             sys.stderr.write("CUDA graph capture of the step failed (%s): eager launches\n" % (str(e).splitlines()[0],))
             graph = None
+            gdone[0] = gdone[1] = None
             torch.cuda.synchronize()
         ok = torch.tensor([1 if graph is not None else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             graph = None
-    run_step = (lambda: graph.replay()) if graph is not None else step
-    for _ in range(3):
-        run_step()
+
+    def run_steps(k):
+        """exactly k steps, gathers included (the stream is joined with the communication stream at the end)"""
+        if world == 1:
+            for _ in range(k):
+                mod(depth, intr, c2l)
+            return
+        if graph is not None:
+            for _ in range(k // PIPE):
+                graph.replay()
+            k = k % PIPE
+        for _ in range(k):
+            step()
+        join()
+
+    run_steps(3 if world == 1 else PIPE + 1)
     barrier()
     vn = r["voxel_num"].tolist() if world == 1 else [v for gd in gathered for v in gd["voxel_num"].flatten().tolist()]
     M_total = int(sum(vn))                               # voxels of the whole job per step
@@ -425,7 +470,7 @@ def main():
     clocks = ClockSampler(local_rank)
     clocks.start()
     time.sleep(0.3)
-    ms_per_step = timed(run_step, args.steps)
+    ms_per_step = timed(lambda: run_steps(args.steps), 1) / args.steps
     clk = clocks.stop()
     value = BT * npix / (ms_per_step * 1e-3)
     multi = None
@@ -435,9 +480,9 @@ def main():
 
         def gather_only():
             for si in range(nsub):
-                dist.all_gather_into_tensor(gathered_flat[si], outs[si]["flat"])
+                dist.all_gather_into_tensor(gathered_flat[0][si], outs[0][si]["flat"])
         gather_ms = timed(gather_only, n2)
-        gbytes = sum(t.numel() * t.element_size() for t in gathered_flat)
+        gbytes = sum(t.numel() * t.element_size() for t in gathered_flat[0])
         # weak scaling for reference: BT frames on EVERY GPU, no collective (what round 1 reported)
         wh = synthetic.make_batch([rank * BT + i for i in range(BT)], H, W, with_conf=False, scene=args.scene)
         wd, wi, wc = wh["depth"].to(dev), wh["intrinsics"].to(dev), wh["cam2lidar"].to(dev)
@@ -450,8 +495,8 @@ def main():
                  "compute_plus_gather_ms": ms_per_step, "gathered_bytes_per_rank_per_step": gbytes,
                  "cuda_graph": graph is not None,
                  "gather": "one all_gather_into_tensor per sub-batch of the flat [voxel_mean | coors | num_points | voxel_num] "
-                           "buffer (padded rows, 28 B per voxel slot) on a communication stream, overlapped with the next "
-                           "sub-batch's kernels",
+                           "buffer (padded rows, 28 B per voxel slot) on a communication stream, overlapped with the kernels of "
+                           "the next sub-batch (of this step or the next: two buffer sets, %d steps per graph replay)" % PIPE,
                  "weak": {"frames_per_gpu": BT, "ms_per_step": weak_ms, "value": world * BT * npix / (weak_ms * 1e-3),
                           "frames_per_sec": world * BT / (weak_ms * 1e-3), "note": "independent replicas, no collective"}}
 
@@ -497,13 +542,22 @@ def main():
                 "ms_per_launch": dom_ms, "launches_per_step": dom_launches,
                 "algorithmic_bytes_per_launch": alg[dom] / dom_launches,
                 "how": "CUDA events between the kernels of %d extra steps with the frame sub-batches on one stream" % prof_steps}
+    if dom == "insert":
+        roofline["note"] = ("the insert pass is %d launches over consecutive pixel ranges; a frame whose earlier rounds claimed "
+                            "max_voxels voxels is closed and its CTAs of the later rounds return at once, so the average "
+                            "launch is much shorter than the first one" % rounds)
+    # second opinion: the other two heavy kernels on the same scale (algorithmic bytes of one launch / its duration)
+    roofline["others"] = {k: {"ms_per_step": stage_ms[k], "achieved": alg[k] / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else 0.0,
+                              "frac": alg[k] / (stage_ms[k] * 1e-3) / 1e9 / hbm_peak if stage_ms[k] > 0 else 0.0}
+                          for k in ("insert", "lookup", "emit") if k != dom}
     traffic_file = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(traffic_file):
         try:
             tr_ = json.load(open(traffic_file))
             # an ncu number belongs to ONE build: it is only reported when the kernel sources are unchanged
-            if tr_.get("kernel") == kname and tr_.get("source_hash") == _source_hash() and world == 1:
-                roofline["traffic"] = tr_.get("dram_bytes_per_launch")
+            ent = (tr_.get("kernels") or {}).get(kname)
+            if ent and tr_.get("source_hash") == _source_hash() and world == 1:
+                roofline["traffic"] = ent.get("dram_bytes_per_launch")
                 roofline["traffic_source"] = tr_.get("capture")
         except Exception:
             pass

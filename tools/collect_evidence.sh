@@ -22,11 +22,19 @@ out=subprocess.run(["ncu","-i","gpurun_out/r2_all.ncu-rep","--page","raw","--csv
 rows=list(csv.reader(io.StringIO(out))); h=rows[0]; u=rows[1]
 i_n=h.index("Kernel Name"); i_r=h.index("dram__bytes_read.sum"); i_w=h.index("dram__bytes_write.sum")
 tob=lambda v,unit: float(v.replace(",",""))*{"byte":1,"Kbyte":1e3,"Mbyte":1e6,"Gbyte":1e9}[unit]
+ins=[]; kern={}
 for r in rows[2:]:
+    tot=tob(r[i_r],u[i_r])+tob(r[i_w],u[i_w])
     if "hv_pass_kernel" in r[i_n] and "1>" in r[i_n]:
-        rd=tob(r[i_r],u[i_r]); wr=tob(r[i_w],u[i_w])
-        d={"kernel":"hv_pass_kernel<DepthSource,1>","dram_bytes_per_launch":rd+wr,"dram_read":rd,"dram_write":wr,
-           "capture":"profiles/r2_kernels_full.txt: ncu --set full --clock-control none, one lookup launch over 64 frames (bench.py --profile-only, RD3_STREAMS=1)",
-           "source_hash":b._source_hash()}
-        json.dump(d,open('profiles/dominant_kernel_traffic.json','w'),indent=1); print(d)
+        kern["hv_pass_kernel<DepthSource,1>"]={"dram_bytes_per_launch":tot,"launches":1}
+    elif "hv_pass_kernel" in r[i_n] and "0>" in r[i_n]:
+        ins.append(tot)
+    elif "hv_emit_kernel" in r[i_n]:
+        kern["hv_emit_kernel"]={"dram_bytes_per_launch":tot,"launches":1}
+if ins:   # the insert rounds of one step (the capture holds one step): average per launch, like bench.py's per-launch time
+    kern["hv_pass_kernel<DepthSource,0>"]={"dram_bytes_per_launch":sum(ins)/len(ins),"launches":len(ins),"note":"average over the step's insert rounds; round 1 alone: %.0f bytes" % ins[0]}
+d={"kernels":kern,
+   "capture":"profiles/r2_kernels_full.txt: ncu --set full --clock-control none, the launches of one step over 64 frames (bench.py --profile-only, RD3_STREAMS=1)",
+   "source_hash":b._source_hash()}
+json.dump(d,open('profiles/dominant_kernel_traffic.json','w'),indent=1); print(d)
 PY
