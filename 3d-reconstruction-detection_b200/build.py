@@ -26,6 +26,32 @@ def _newest_source():
     return t
 
 
+SASS_HASH = os.path.join(HERE, "librd3_b200.sass_md5")
+
+
+def _write_sass_hash(objs):
+    """md5 of the machine code (cuobjdump -sass without addresses / line info): the stamp that ties numbers measured
+    offline (ncu traffic in profiles/) to a build.  Comment-only edits of the sources leave it unchanged."""
+    import hashlib
+    import re
+    cuobjdump = os.path.join(os.path.dirname(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")), "cuobjdump")
+    h = hashlib.md5()
+    try:
+        for o in objs:
+            out = subprocess.run([cuobjdump, "-sass", o], capture_output=True, text=True, check=True).stdout
+            for line in out.splitlines():
+                m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?);", line)
+                if m:
+                    h.update(m.group(1).encode())
+                elif "Function :" in line:
+                    h.update(line.strip().encode())
+        with open(SASS_HASH, "w") as f:
+            f.write(h.hexdigest()[:16] + "\n")
+    except Exception:                                  # noqa: BLE001  (no cuobjdump: bench.py falls back to a source hash)
+        if os.path.exists(SASS_HASH):
+            os.remove(SASS_HASH)
+
+
 def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source():
         return LIB
@@ -46,6 +72,7 @@ def build(force=False, verbose=False):
     subprocess.check_call(cmd)
     with open(os.path.join(HERE, "csrc", "ptxas.log"), "w") as f:
         f.write("\n".join(logs))
+    _write_sass_hash(objs)
     if verbose:
         sys.stderr.write("\n".join(logs))
     return LIB

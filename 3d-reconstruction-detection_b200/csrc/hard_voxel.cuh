@@ -17,21 +17,22 @@
 //        claimed max_voxels voxels is CLOSED: its CTAs of the later rounds return at once (voxels
 //        first seen after that point have rank >= max_voxels and the reference drops them), so the
 //        table never holds more than max_voxels + S keys, whatever N is.
-//   P2 rank    flag scan (per-chunk popcount prefix, chunk totals -> voxel_num), then one pass over
-//        the table: entry -> rank r = #first-points before its first point; the entry becomes
-//        {key | r} (or {key | ~0} when r >= max_voxels), slot row r gets its first point, coors[r]
-//        is decoded from the key, and (depth source) the voxel is marked in a 64x64 bird's-eye mask.
-//   P2c cull   (depth source) per camera and block of image columns: can a pixel of this block reach
-//        any marked bird's-eye cell?  Exact plane test of the block's viewing wedge against the cells,
-//        widened by the proven error bound of the pixel->cell map.  Pseudo point clouds are camera-major,
-//        so with max_voxels reached early most cameras cannot contribute any more.
+//   P2 count   (`hv_count_kernel`) per-chunk popcount of the flags; the frame's last CTA scans the chunk totals
+//        (-> voxel_num) and lists the marked cells of the 128 x 128 bird's-eye mask the claims left behind.
+//      post    (`hv_post_kernel`, one launch) word prefixes + the list of first points by rank (the r-th set flag
+//        is the first point of voxel r: rank = popcount prefix, no pass over the table) + their point -> voxel
+//        entries; and P2c cull (depth source): per camera and block of image columns, can a pixel of this block
+//        reach any marked bird's-eye cell?  Plane test of the block's viewing wedge against the cells, widened by
+//        the proven error bound of the pixel->cell map.  Pseudo point clouds are camera-major, so with max_voxels
+//        reached early most cameras cannot contribute any more.
 //   P3 lookup  (`hv_pass_kernel<Src, 1>`, ONE launch over all points, frame-major so that a frame's
 //        table and slot rows stay in L2): tiles whose column blocks are all culled are skipped without
-//        reading their depth; every other point: cell -> table -> rank -> sorted insertion of its index
-//        into S[r][0..K) (atomicMin cascade keeping the K smallest indices; a full row rejects a later
-//        point with one load).
-//   P4 emit    a CTA owns V voxels: gathers (or re-unprojects exactly) the slot points into a
-//        shared-memory tile, writes voxels (coalesced), count and the HardSimpleVFE mean.
+//        reading their depth; every other point: first-point flag (nothing to add) -> cell -> table -> rank ->
+//        sorted insertion of its index into S[r][0..K-1) (atomicMin cascade keeping the smallest indices; a full
+//        row rejects a later point with one load).  Its leading CTAs fetch the depths of the first points.
+//   P4 emit    one lane per voxel, a warp per 32 consecutive ranks: gathers (or re-unprojects exactly) the first
+//        point and the slot points into a warp-private shared-memory tile, writes voxels (coalesced), coors,
+//        count and the HardSimpleVFE mean.
 //
 // A warp of the pass kernels owns a STRIP of `iters` consecutive 128-point tiles: the depth of the next
 // tile is in flight while the current one is classified; in-range keys are appended to a per-warp list that

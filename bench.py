@@ -230,14 +230,18 @@ def _emit(line):
 
 
 def _source_hash():
-    """Hash of the CUDA sources: stamps numbers that were measured offline (ncu traffic) with the build they belong to."""
+    """Stamp of the build that numbers measured offline (ncu traffic) belong to: the md5 of the machine code that
+    build.py writes next to the library (unchanged by comment-only edits); a hash of the CUDA sources if it is missing."""
     import hashlib
+    f = os.path.join(ROOT, "3d-reconstruction-detection_b200", "librd3_b200.sass_md5")
+    if os.path.exists(f):
+        return "sass:" + open(f).read().strip()
     h = hashlib.sha256()
     d = os.path.join(ROOT, "3d-reconstruction-detection_b200", "csrc")
     for f in sorted(os.listdir(d)):
         if f.endswith((".cu", ".cuh")):
             h.update(open(os.path.join(d, f), "rb").read())
-    return h.hexdigest()[:16]
+    return "src:" + h.hexdigest()[:16]
 
 
 def _shutdown_process_group(dist):
