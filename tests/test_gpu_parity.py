@@ -587,6 +587,37 @@ def test_fused_randomized(seed):
             assert np.array_equal(c2, oc) and np.array_equal(n2, on) and np.array_equal(bits(v2), bits(ov))
 
 
+@pytest.mark.parametrize("mv,masks", [(2500, False), (400, True)])
+def test_fused_many_frames_per_lane(mv, masks):
+    """The benchmark's batch shape in small: 24 frames = 12 per stream lane, frames of both scenes interleaved (so that
+    the frames of one launch close in different insert rounds), every frame bit for bit against the oracle."""
+    c = synthetic.CONFIGS["C1"]
+    H, W, B = 60, 104, 24
+    frames = [synthetic.make_frame(100 + i, H, W, scene="ground" if i % 3 == 1 else "mixture") for i in range(B)]
+    b = {k: torch.stack([f[k] for f in frames]) for k in frames[0]}
+    d = {k: v.to(DEV) for k, v in b.items()}
+    rf = synthetic.FILTER_RANGE if masks else None
+    thr = 1.4 if masks else None
+    mod = rd3_b200.DepthToVoxels(c["voxel_size"], c["pcr"], c["max_points"], mv, max_depth=synthetic.MAX_DEPTH,
+                                 range_filter=rf).to(DEV)
+    r = mod(d["depth"], d["intrinsics"], d["cam2lidar"], confs=d["conf"] if masks else None, conf_thresh=thr,
+            sky_masks=d["sky"] if masks else None)
+    vn = r["voxel_num"].cpu().numpy()
+    assert len(set(vn.tolist())) > 1 or vn[0] == mv
+    for i in range(B):
+        okw = dict(max_depth=synthetic.MAX_DEPTH)
+        if masks:
+            okw.update(conf=b["conf"][i].numpy(), conf_thresh=thr, sky=b["sky"][i].numpy(), range_filter=rf)
+        pts = oracle.unproject(b["depth"][i].numpy(), b["intrinsics"][i].numpy(), b["cam2lidar"][i].numpy(), **okw)
+        ov, oc, on = oracle.hard_voxelize(pts, list(c["voxel_size"]), list(c["pcr"]), c["max_points"], mv)
+        m = int(vn[i])
+        assert m == len(oc), (i, m, len(oc))
+        assert np.array_equal(r["coors"][i, :m].cpu().numpy(), oc), i
+        assert np.array_equal(r["num_points"][i, :m].cpu().numpy(), on), i
+        assert np.array_equal(bits(r["voxels"][i, :m].cpu().numpy()), bits(ov)), i
+        assert np.array_equal(bits(r["voxel_mean"][i, :m].cpu().numpy()), bits(oracle.hard_simple_vfe(ov, on, 3))), i
+
+
 def test_cell_boundary_stress():
     """Depth planes chosen so that many unprojected points land (to rounding) ON voxel boundaries:
     the reciprocal fast path must hand every such pixel to the exact arithmetic."""
