@@ -62,6 +62,48 @@ def gather_voxel_outputs(result, num_frames_total=None, group=None):
     return out
 
 
+def flat_layout(num_frames, max_voxels, feat_dim=3):
+    """Element offsets of the regions of ``DepthToVoxels(flat_outputs=True)``'s int32 buffer for ``num_frames`` frames:
+    dict name -> (start, stop, shape, dtype), plus ``total`` under the key ``None``."""
+    n = int(num_frames) * int(max_voxels)
+    return {"voxel_mean": (0, n * feat_dim, (num_frames, max_voxels, feat_dim), torch.float32),
+            "coors": (n * feat_dim, n * feat_dim + n * 3, (num_frames, max_voxels, 3), torch.int32),
+            "num_points": (n * feat_dim + n * 3, n * feat_dim + n * 4, (num_frames, max_voxels), torch.int32),
+            "voxel_num": (n * feat_dim + n * 4, n * feat_dim + n * 4 + num_frames, (num_frames,), torch.int32),
+            None: n * feat_dim + n * 4 + num_frames}
+
+
+def gather_flat_outputs(result, max_voxels, out=None, group=None, async_op=False):
+    """ONE collective for what the sparse encoder consumes of every rank's shard: all-gathers ``result["flat"]``
+    (``DepthToVoxels(flat_outputs=True)``: mean | coors | num | voxel_num of this rank's frames; equal shards on all
+    ranks) into ``out`` (world, flat) -- allocated when None -- and returns ``(views, work)``: ``views`` is the same dict
+    as ``gather_voxel_outputs`` gives (frames in global order, no copy: they alias ``out``), ``work`` the async handle
+    or None.  bench.py times this pattern with two buffer sets on a communication stream."""
+    flat = result["flat"]
+    b_local = result["voxel_num"].shape[0]
+    lay = flat_layout(b_local, max_voxels, result["voxel_mean"].shape[-1])
+    if flat.numel() != lay[None]:
+        raise ValueError("result['flat'] has %d elements, the layout for %d frames x %d voxels has %d"
+                         % (flat.numel(), b_local, max_voxels, lay[None]))
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if out is None:
+        out = flat.new_empty((world, flat.numel()))
+    work = None
+    if world == 1:
+        out[0].copy_(flat)
+    else:
+        work = dist.all_gather_into_tensor(out.view(-1), flat, group=group, async_op=async_op)
+    views = {}
+    for name in ("voxel_mean", "coors", "num_points", "voxel_num"):
+        a, b, shape, dtype = lay[name]
+        v = out[:, a:b]
+        if dtype != torch.int32:
+            v = v.view(dtype)
+        views[name] = v.reshape((world * shape[0],) + tuple(shape[1:]))     # rank-major == global frame order
+    views["voxels"] = None
+    return views, (work if async_op else None)
+
+
 def to_sparse_encoder_inputs(result, batch_offset=0):
     """(voxel_features (sum M, F), coors (sum M, 4) [b,z,y,x], batch_size) of a (gathered)
     result: the cat + F.pad(coor, (1,0), value=i) of sparse_refinement.py:393-402 as one kernel

@@ -75,6 +75,55 @@ def _gloo_worker(rank, world, port, total, q):
     dist.destroy_process_group()
 
 
+def _fake_flat_result(frame_ids, mv=7):
+    """what DepthToVoxels(flat_outputs=True) returns, on the CPU: views of one int32 buffer"""
+    r = _fake_result(frame_ids, mv=mv)
+    B, MV, F = r["voxel_mean"].shape
+    lay = parallel.flat_layout(B, MV, F)
+    flat = torch.empty(lay[None], dtype=torch.int32)
+    out = {"voxels": None, "flat": flat}
+    for name in ("voxel_mean", "coors", "num_points", "voxel_num"):
+        a, b, shape, dtype = lay[name]
+        v = flat[a:b].view(dtype).view(shape)
+        v.copy_(r[name])
+        out[name] = v
+    return out, MV
+
+
+def _gloo_flat_worker(rank, world, port, total, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = parallel.shard_range(total, world, rank)
+    local, MV = _fake_flat_result(list(range(lo, hi)))
+    views, _ = parallel.gather_flat_outputs(local, MV)
+    ref = _fake_result(list(range(total)), mv=MV)
+    ok = all(torch.equal(views[k], ref[k]) for k in ("voxel_mean", "coors", "num_points", "voxel_num"))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_flat_gather_is_one_collective_with_the_same_result():
+    total = 6                                      # equal shards (3 + 3): the flat buffers have one size
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_flat_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+    # single process: a copy, same views
+    local, MV = _fake_flat_result([0, 1, 2])
+    views, work = parallel.gather_flat_outputs(local, MV)
+    assert work is None and torch.equal(views["coors"], local["coors"]) and torch.equal(views["voxel_mean"], local["voxel_mean"])
+    with pytest.raises(ValueError):
+        parallel.gather_flat_outputs(dict(local, flat=local["flat"][:-1]), MV)
+
+
 @pytest.mark.parametrize("total", [4, 5])
 def test_gloo_world2_gather_matches_single_process(total):
     ctx = mp.get_context("spawn")
