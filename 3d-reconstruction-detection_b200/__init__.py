@@ -25,7 +25,7 @@ from .voxel_encoder import (DynamicSimpleVFE, HardSimpleVFE, HardVoxelOccupancyV
 from .backproject import (DepthToPointsMixin, backproject_depth_to_points,  # noqa: F401
                           conf_threshold, unproject_padded)
 from .fused import DepthToVoxels, pack_sparse_inputs  # noqa: F401
-from .parallel import gather_voxel_outputs, shard_range, shard_sizes  # noqa: F401
+from .parallel import gather_flat_outputs, gather_voxel_outputs, shard_range, shard_sizes  # noqa: F401
 from .patch import patch_mmdet3d  # noqa: F401
 from .pipelines import FilterPointByRange, VoxelDownsample  # noqa: F401
 from .pillar import (PillarDecorator, PointPillarsScatter, map_voxel_center_to_point,  # noqa: F401
