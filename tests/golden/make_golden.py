@@ -14,6 +14,7 @@ Sources of truth:
                               pillar_encoder.py:104-146 and pillar_scatter.py:39-102 (ibid.)
 
     python tests/golden/make_golden.py pillar      # only (re)generate pillar.npz
+    python tests/golden/make_golden.py real        # only (re)generate real_cloud.npz
 """
 import os
 import sys
@@ -59,9 +60,43 @@ def pillar(ref):
     np.savez_compressed(os.path.join(OUT, "pillar.npz"), **d)
 
 
+def read_pcd_xyz(path):
+    """xyz of a binary .pcd with FIELDS x y z rgb (the pseudo point clouds the reference ships under output/)"""
+    raw = open(path, "rb").read()
+    head, _, body = raw.partition(b"DATA binary\n")
+    fields = [l.split()[1:] for l in head.decode().splitlines() if l.startswith("FIELDS")][0]
+    npts = [int(l.split()[1]) for l in head.decode().splitlines() if l.startswith("POINTS")][0]
+    a = np.frombuffer(body, dtype=np.float32, count=npts * len(fields)).reshape(npts, len(fields))
+    return np.ascontiguousarray(a[:, :3])
+
+
+def real_cloud(ref):
+    """6. a REAL pseudo point cloud of the reference (output/sample_0_points.pcd, 40 000 points produced by its own
+    DA3 -> unprojection -> FPS pipeline) through the reference's own CPU op: the C2 grid, a coarse grid
+    with both truncations active, the pillar grid, and dynamic voxelization.  The padded voxel tensor is kept as per-voxel sums."""
+    path = "/root/reference/output/sample_0_points.pcd"
+    pts = read_pcd_xyz(path)
+    d = dict(points=pts, source=os.path.basename(path))
+    for tag, vs, pcr, mp, mv in (("c2", [0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3], 10, 120000),
+                                 ("coarse", [0.5, 0.5, 0.5], [-54, -54, -5, 54, 54, 3], 2, 3000),
+                                 ("c4", [0.2, 0.2, 8.0], [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], 20, 30000)):
+        v, c, n = tr.voxelization_forward(ref, torch.from_numpy(pts), vs, pcr, mp, mv)
+        d[tag + "_cfg"] = np.array(vs + pcr + [mp, mv], dtype=np.float64)
+        d[tag + "_coors"], d[tag + "_num"] = c.numpy(), n.numpy()
+        d[tag + "_voxels_sum"] = v.sum(dim=1).numpy()
+        d[tag + "_first"] = v[:, 0].numpy()                      # slot 0 of every voxel: its first point, bit for bit
+    d["dyn_coors"] = tr.voxelization_forward(ref, torch.from_numpy(pts), [0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3],
+                                             -1, -1).numpy()
+    np.savez_compressed(os.path.join(OUT, "real_cloud.npz"), **d)
+
+
 def main():
     ref = oracle.ref_voxel_layer()
     assert ref is not None, "build oracle/_ref first (python oracle/build_ref.py)"
+    if sys.argv[1:] == ["real"]:
+        real_cloud(ref)
+        print("real_cloud.npz", os.path.getsize(os.path.join(OUT, "real_cloud.npz")))
+        return
     if sys.argv[1:] == ["pillar"]:
         pillar(ref)
         print("pillar.npz", os.path.getsize(os.path.join(OUT, "pillar.npz")))
@@ -106,6 +141,7 @@ def main():
         d["voxel_coors"], d["map"], d["count"] = rc.numpy(), rm.numpy(), rn.numpy()
     np.savez_compressed(os.path.join(OUT, "dynamic_scatter.npz"), **d)
     pillar(ref)
+    real_cloud(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

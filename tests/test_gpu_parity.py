@@ -128,6 +128,22 @@ def test_hard_golden_adversarial():
     assert np.array_equal(dyn.cpu().numpy(), g["dyn_coors"])
 
 
+def test_hard_real_reference_cloud():
+    """golden/real_cloud.npz: one of the pseudo point clouds the reference ships (output/sample_0_points.pcd) through
+    the reference's own CPU op -- C2 grid, a coarse grid with both truncations active, the pillar grid, dynamic."""
+    g = np.load(os.path.join(GOLD, "real_cloud.npz"))
+    pts = g["points"]
+    for tag in ("c2", "coarse", "c4"):
+        cfg = g[tag + "_cfg"]
+        vs, pcr, mp, mv = cfg[:3].tolist(), cfg[3:9].tolist(), int(cfg[9]), int(cfg[10])
+        v, c, n = gpu_hard(pts, vs, pcr, mp, mv)
+        assert np.array_equal(c, g[tag + "_coors"]) and np.array_equal(n, g[tag + "_num"]), tag
+        assert np.array_equal(bits(v[:, 0]), bits(g[tag + "_first"])), tag
+        assert np.allclose(v.sum(axis=1), g[tag + "_voxels_sum"], rtol=1e-5, atol=1e-4), tag
+    dyn = rd3_b200.Voxelization([0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3], -1)(torch.from_numpy(pts).to(DEV))
+    assert np.array_equal(dyn.cpu().numpy(), g["dyn_coors"])
+
+
 @pytest.mark.parametrize("vs,pcr,mp,mv", CASES)
 def test_hard_adversarial(vs, pcr, mp, mv):
     pts = _adversarial_points(60000, pcr, vs, seed=mp + 1)

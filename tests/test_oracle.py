@@ -91,6 +91,27 @@ def test_c_oracle_matches_reference_op(ref_layer, vs, pcr, mp, mv):
     assert np.array_equal(oracle.grid_size(vs, pcr), g)
 
 
+def test_c_oracle_on_a_real_reference_cloud():
+    """golden/real_cloud.npz: one of the pseudo point clouds the reference ships (output/sample_0_points.pcd, 40 000
+    points out of its own DA3 -> unprojection -> FPS pipeline) through the reference's own CPU op (oracle/_ref), made
+    by tests/golden/make_golden.py.  The C restatement must reproduce it: coordinates, counts, first points bit for
+    bit, slot sums."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "real_cloud.npz"))
+    pts = g["points"]
+    assert pts.shape == (40000, 3) and np.isfinite(pts).all()
+    for tag in ("c2", "coarse", "c4"):
+        cfg = g[tag + "_cfg"]
+        vs, pcr, mp, mv = cfg[:3].tolist(), cfg[3:9].tolist(), int(cfg[9]), int(cfg[10])
+        v, c, n = oracle.hard_voxelize(pts, vs, pcr, mp, mv)
+        assert np.array_equal(c, g[tag + "_coors"]) and np.array_equal(n, g[tag + "_num"]), tag
+        assert np.array_equal(v[:, 0].view(np.uint32), np.ascontiguousarray(g[tag + "_first"]).view(np.uint32)), tag
+        assert np.allclose(v.sum(axis=1), g[tag + "_voxels_sum"], rtol=1e-5, atol=1e-4), tag
+    assert g["coarse_num"].max() == 2 and len(g["coarse_num"]) == 3000        # both truncations were active
+    dc = oracle.dynamic_voxelize(pts, [0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3])
+    assert np.array_equal(dc, g["dyn_coors"])
+    assert (g["dyn_coors"][:, 0] < 0).any()                                 # the cloud has points outside the grid (z up to 6 m)
+
+
 def test_hard_consistent_with_dynamic():
     """test_voxelize.py:50-59 logic: every hard voxel's points are the points dynamic
     voxelization maps to that coordinate, in point order."""
